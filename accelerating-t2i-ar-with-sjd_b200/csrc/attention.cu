@@ -1,0 +1,269 @@
+// Jacobi draft-window attention over the static KV cache (decode-shaped, split-KV).
+// For every CFG row b, kv head and 128-key chunk one CTA streams the K/V chunk once into shared memory
+// (cp.async, zero-filled past the end) and every warp runs flash-style online softmax for one 16-query
+// tile of one query head (mma.sync m16n8k16 bf16, fp32 accumulate).  The Jacobi window mask of the
+// reference — key j visible to window query i iff  kv_lo[b] <= j <= kv_len + i — is evaluated from
+// indices; no mask tensor exists (reference builds [2B,1,W,T+W] additive masks:
+// scheduler/jacobi_iteration_lumina_mgpt.py:1256-1336, consumed by SDPA at
+// lumina_mgpt/model/chameleon/modeling_chameleon.py:567-574; llamagen/llamagen.py:269-273).
+// A second kernel merges the per-chunk partials (log-sum-exp combine) into the bf16 attention output.
+#include "common.cuh"
+
+namespace sjd {
+
+constexpr int kAttnChunk = 128;   // keys per CTA
+constexpr int kAttnSub = 64;      // keys per online-softmax step
+constexpr int kAttnMaxRows = 8;   // CFG rows supported by the descriptor
+
+struct AttnParams {
+  const __nv_bfloat16* q;   // [rows*W][H][Dh]
+  const __nv_bfloat16* k;   // layer base: [rows][Hkv][Lmax][Dh]
+  const __nv_bfloat16* v;
+  float* part_o;            // [chunks][rows][H][W][Dh]
+  float* part_ml;           // [chunks][rows][H][W][2]
+  __nv_bfloat16* out;       // [rows*W][H*Dh]
+  int rows, W, H, Hkv, Lmax;
+  int kv_len;               // keys cached before this window
+  int kv_lo[kAttnMaxRows];  // first visible key per row
+  int n_chunks;
+  float scale_log2e;        // softmax scale * log2(e)
+};
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                                  uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int DH>
+__global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
+  constexpr int ROWB = DH * 2 + 16;  // padded smem row (bytes): conflict-free ldmatrix
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kAttnChunk * ROWB;
+
+  const int chunk = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int T = p.kv_len + p.W;
+  const int key0 = chunk * kAttnChunk;
+  const int nkeys = min(kAttnChunk, T - key0);
+  const int G = p.H / p.Hkv;
+  const int tiles_per_head = (p.W + 15) >> 4;
+  const int n_tiles = G * tiles_per_head;
+  const int lo = p.kv_lo[b];
+
+  const bool chunk_live = (key0 + nkeys > lo);  // some key of the chunk may be visible
+  if (chunk_live) {
+    const __nv_bfloat16* kg = p.k + (size_t(b) * p.Hkv + hkv) * size_t(p.Lmax) * DH + size_t(key0) * DH;
+    const __nv_bfloat16* vg = p.v + (size_t(b) * p.Hkv + hkv) * size_t(p.Lmax) * DH + size_t(key0) * DH;
+    constexpr int VEC_PER_ROW = DH / 8;
+    for (int idx = threadIdx.x; idx < kAttnChunk * VEC_PER_ROW; idx += blockDim.x) {
+      const int r = idx / VEC_PER_ROW, c = idx - r * VEC_PER_ROW;
+      const int nb = r < nkeys ? 16 : 0;
+      const size_t goff = size_t(r < nkeys ? r : 0) * DH + c * 8;
+      cp_async_16(smem_u32(sK + r * ROWB + c * 16), kg + goff, nb);
+      cp_async_16(smem_u32(sV + r * ROWB + c * 16), vg + goff, nb);
+    }
+    cp_async_wait_all();
+  }
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  for (int tile = warp; tile < n_tiles; tile += nwarps) {
+    const int hq = hkv * G + tile / tiles_per_head;
+    const int i0 = (tile % tiles_per_head) * 16;
+    const int r0 = i0 + g, r1 = i0 + g + 8;  // query indices of this thread's two rows
+    float o[DH / 8][4];
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    if (chunk_live) {
+      // Q fragments straight from global memory
+      uint32_t qf[DH / 16][4];
+      const __nv_bfloat16* q0 = p.q + (size_t(b * p.W + r0) * p.H + hq) * DH;
+      const __nv_bfloat16* q1 = p.q + (size_t(b * p.W + r1) * p.H + hq) * DH;
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const int c = kk * 16 + t * 2;
+        qf[kk][0] = r0 < p.W ? *reinterpret_cast<const uint32_t*>(q0 + c) : 0u;
+        qf[kk][1] = r1 < p.W ? *reinterpret_cast<const uint32_t*>(q1 + c) : 0u;
+        qf[kk][2] = r0 < p.W ? *reinterpret_cast<const uint32_t*>(q0 + c + 8) : 0u;
+        qf[kk][3] = r1 < p.W ? *reinterpret_cast<const uint32_t*>(q1 + c + 8) : 0u;
+      }
+      for (int sub = 0; sub < nkeys; sub += kAttnSub) {
+        // causal skip: every key of this sub-block is beyond the last query of the tile
+        if (key0 + sub > p.kv_len + min(i0 + 15, p.W - 1)) break;
+        float s[kAttnSub / 8][4];
+#pragma unroll
+        for (int n = 0; n < kAttnSub / 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) {
+#pragma unroll
+          for (int np = 0; np < kAttnSub / 16; ++np) {
+            // matrices: (keys 0-7,d 0-7) (keys 0-7,d 8-15) (keys 8-15,d 0-7) (keys 8-15,d 8-15)
+            const int key = sub + np * 16 + (lane & 7) + ((lane >> 4) << 3);
+            const int dof = kk * 16 + (((lane >> 3) & 1) << 3);
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(smem_u32(sK + key * ROWB + dof * 2), b0, b1, b2, b3);
+            mma_bf16_16816(s[np * 2], qf[kk], b0, b1);
+            mma_bf16_16816(s[np * 2 + 1], qf[kk], b2, b3);
+          }
+        }
+        // mask + online softmax (scores scaled into log2 domain)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int n = 0; n < kAttnSub / 8; ++n) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = key0 + sub + n * 8 + t * 2 + (e & 1);
+            const int qi = (e < 2) ? r0 : r1;
+            const bool ok = (j >= lo) && (j <= p.kv_len + qi) && (j < T) && (qi < p.W);
+            const float val = ok ? s[n][e] * p.scale_log2e : -INFINITY;
+            s[n][e] = val;
+            if (e < 2) mx0 = fmaxf(mx0, val); else mx1 = fmaxf(mx1, val);
+          }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0, ms1 = (mn1 == -INFINITY) ? 0.f : mn1;
+        const float a0 = exp2f(m0 - ms0), a1 = exp2f(m1 - ms1);  // m == -inf -> 0
+        m0 = mn0; m1 = mn1;
+        l0 *= a0; l1 *= a1;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
+        float ps0 = 0.f, ps1 = 0.f;
+        uint32_t pf[kAttnSub / 16][4];
+#pragma unroll
+        for (int n = 0; n < kAttnSub / 8; ++n) {
+          const float e0 = exp2f(s[n][0] - ms0), e1 = exp2f(s[n][1] - ms0);
+          const float e2 = exp2f(s[n][2] - ms1), e3 = exp2f(s[n][3] - ms1);
+          // probabilities enter P*V as bf16, like the reference's bf16 SDPA
+          const uint32_t p01 = pack_bf16(e0, e1), p23 = pack_bf16(e2, e3);
+          const __nv_bfloat162 v01 = *reinterpret_cast<const __nv_bfloat162*>(&p01);
+          const __nv_bfloat162 v23 = *reinterpret_cast<const __nv_bfloat162*>(&p23);
+          ps0 += __low2float(v01) + __high2float(v01);
+          ps1 += __low2float(v23) + __high2float(v23);
+          pf[n >> 1][(n & 1) * 2 + 0] = p01;
+          pf[n >> 1][(n & 1) * 2 + 1] = p23;
+        }
+        l0 += ps0; l1 += ps1;
+#pragma unroll
+        for (int kk = 0; kk < kAttnSub / 16; ++kk) {
+#pragma unroll
+          for (int dp = 0; dp < DH / 16; ++dp) {
+            // trans matrices: (keys 0-7,d 0-7) (keys 8-15,d 0-7) (keys 0-7,d 8-15) (keys 8-15,d 8-15)
+            const int key = sub + kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+            const int dof = dp * 16 + ((lane >> 4) << 3);
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4_trans(smem_u32(sV + key * ROWB + dof * 2), b0, b1, b2, b3);
+            mma_bf16_16816(o[dp * 2], pf[kk], b0, b1);
+            mma_bf16_16816(o[dp * 2 + 1], pf[kk], b2, b3);
+          }
+        }
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    }
+    // write partials
+    const size_t base = ((size_t(chunk) * p.rows + b) * p.H + hq) * size_t(p.W);
+    if (r0 < p.W) {
+      float* po = p.part_o + (base + r0) * DH;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) *reinterpret_cast<float2*>(po + n * 8 + t * 2) = make_float2(o[n][0], o[n][1]);
+      if (t == 0) { p.part_ml[(base + r0) * 2] = m0; p.part_ml[(base + r0) * 2 + 1] = l0; }
+    }
+    if (r1 < p.W) {
+      float* po = p.part_o + (base + r1) * DH;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) *reinterpret_cast<float2*>(po + n * 8 + t * 2) = make_float2(o[n][2], o[n][3]);
+      if (t == 0) { p.part_ml[(base + r1) * 2] = m1; p.part_ml[(base + r1) * 2 + 1] = l1; }
+    }
+  }
+}
+
+// One warp per (row b, head, query i): merge chunk partials, normalise, write bf16.
+template <int DH>
+__global__ void __launch_bounds__(256) attn_combine_kernel(AttnParams p) {
+  const int widx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int total = p.rows * p.H * p.W;
+  if (widx >= total) return;
+  const int i = widx % p.W, h = (widx / p.W) % p.H, b = widx / (p.W * p.H);
+  const size_t stride = size_t(p.rows) * p.H * p.W;  // per chunk
+  const size_t idx = (size_t(b) * p.H + h) * p.W + i;
+  float mmax = -INFINITY;
+  for (int c = 0; c < p.n_chunks; ++c) mmax = fmaxf(mmax, p.part_ml[(c * stride + idx) * 2]);
+  constexpr int PER = DH / 32;
+  float acc[PER];
+#pragma unroll
+  for (int e = 0; e < PER; ++e) acc[e] = 0.f;
+  float lsum = 0.f;
+  if (mmax != -INFINITY) {
+    for (int c = 0; c < p.n_chunks; ++c) {
+      const float m = p.part_ml[(c * stride + idx) * 2];
+      if (m == -INFINITY) continue;
+      const float w = exp2f(m - mmax);
+      lsum += w * p.part_ml[(c * stride + idx) * 2 + 1];
+      const float* po = p.part_o + (c * stride + idx) * DH;
+#pragma unroll
+      for (int e = 0; e < PER; ++e) acc[e] += w * po[lane + 32 * e];
+    }
+  }
+  const float inv = lsum > 0.f ? 1.f / lsum : 0.f;  // fully masked query (CFG hidden prefix) -> 0
+  __nv_bfloat16* dst = p.out + (size_t(b * p.W + i) * p.H + h) * DH;
+#pragma unroll
+  for (int e = 0; e < PER; ++e) dst[lane + 32 * e] = __float2bfloat16_rn(acc[e] * inv);
+}
+
+int attn_launch(const AttnParams& p, int head_dim, cudaStream_t stream) {
+  const int G = p.H / p.Hkv;
+  const int n_tiles = G * ((p.W + 15) / 16);
+  int nwarps = n_tiles < 8 ? n_tiles : 8;
+  dim3 grid(p.n_chunks, p.Hkv, p.rows);
+  const int total = p.rows * p.H * p.W;
+  dim3 cgrid((total + 7) / 8);
+  if (head_dim == 128) {
+    constexpr int smem = 2 * kAttnChunk * (128 * 2 + 16);
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(attn_window_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+    attn_window_kernel<128><<<grid, nwarps * 32, smem, stream>>>(p);
+    attn_combine_kernel<128><<<cgrid, 256, 0, stream>>>(p);
+  } else if (head_dim == 64) {
+    constexpr int smem = 2 * kAttnChunk * (64 * 2 + 16);
+    attn_window_kernel<64><<<grid, nwarps * 32, smem, stream>>>(p);
+    attn_combine_kernel<64><<<cgrid, 256, 0, stream>>>(p);
+  } else {
+    return -3;
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -6;
+}
+
+}  // namespace sjd

@@ -1,0 +1,307 @@
+// Speculative-Jacobi verify step: everything the reference does between "logits are back" and
+// "how many draft tokens survived" — CFG mix, grammar mask, top-k, softmax, sampling, probabilistic
+// accept/reject scan, residual resample, prefix match — as two launches with no host round trip and
+// no Python loop.  Restates, on device:
+//   sampling_logits2tokens                 scheduler/jacobi_iteration_lumina_mgpt.py:82-132
+//   MultiTokensVLLogitsProcessor           scheduler/logit_processor_3dim.py:45-155   (as allow-range + forced ids)
+//   MultiTokensInterleavedTopKLogitsWarper scheduler/logit_processor_3dim.py:158-204  (scores < k-th largest removed)
+//   SpeculativeSampler.__call__            scheduler/jacobi_iteration_lumina_mgpt.py:247-315
+//   reject_sampling_single_token           :209-241, get_reject_sampling_logits :203-207
+//   find_first_misaligned_token_inds       :317-333 ('jacobi' scheme)
+// torch.multinomial(p, 1) is argmax(p / Exp(1)) and torch.rand feeds the accept test; the noise tensors are
+// produced by the caller with the same torch.Generator calls the reference makes, so token streams are
+// reproducible against it.  The arithmetic deliberately avoids FMA contraction where the reference rounds
+// between operations (CFG mix), and uses IEEE division like torch.
+#include "common.cuh"
+
+namespace sjd {
+
+constexpr int kVerifyThreads = 1024;
+constexpr int kHistBins = 2048;
+
+struct VerifyParams {
+  const float* logits;   // [(has_uncond ? 2 : 1) * W][V]; cond rows first
+  int W, V;
+  int has_uncond;        // logits carry the CFG-uncond rows
+  int apply_cfg;         // mix g*(c-u)+u (else cond rows only: CFG disabled outside an image)
+  float guidance;
+  float temperature;     // scores / temperature when != 1
+  int allow_lo, allow_hi;  // ids outside [lo,hi) -> -inf; disabled when hi <= lo
+  const int* forced;     // [W] forced token id per window position, or -1
+  int top_k;             // 0 = off
+  int do_sample;         // 0 = argmax
+  int scheme;            // 0 = speculative_jacobi, 1 = jacobi
+  const int* draft;      // [W] window ids ([0] = last accepted token)
+  const int* q_row;      // [W] row of p_prev holding the draft distribution, -1 = one-hot at draft[i]
+  const float* p_prev;   // [Wcap][V]
+  float* p_cur;          // [Wcap][V] out: probabilities of this trip
+  const float* noise_e1; // [W][V]  Exp(1) noise of torch.multinomial
+  const float* noise_u;  // [W]     torch.rand values at (i, draft[i])
+  const float* noise_e2; // [V]     Exp(1) noise of the residual multinomial
+  int eoi_token;         // if an accepted draft equals this id the residual is processed in text mode
+  int text_top_k;
+  float* resid;          // [V] scratch
+  int* next_tokens;      // [W] scratch: tokens sampled from p_cur
+  int* out_tokens;       // [W] tokens after accept / resample
+  int* out_info;         // [4] matched, rejected(0/1), first_reject, reserved
+};
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+  if (f == 0.f) return 0x80000000u;  // -0 == +0 for "<"
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct BlockScratch {
+  uint32_t hist[kHistBins];
+  float redf[32];
+  int redi[32];
+  uint32_t sel_bin;
+  uint32_t sel_above;
+};
+
+// k-th largest key among the finite entries of row[0..V); caller guarantees k <= #finite.
+__device__ uint32_t block_kth_key(const float* __restrict__ row, int V, int k, BlockScratch& sc) {
+  uint32_t prefix = 0, mask = 0;
+  uint32_t remaining = uint32_t(k);
+  const int shifts[3] = {21, 10, 0};
+  const int nbits[3] = {11, 11, 10};
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = shifts[pass];
+    const uint32_t nb = 1u << nbits[pass];
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) sc.hist[i] = 0;
+    __syncthreads();
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float f = row[v];
+      if (f == -INFINITY) continue;
+      const uint32_t key = f2key(f);
+      if ((key & mask) == prefix) atomicAdd(&sc.hist[(key >> shift) & (nb - 1)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const uint32_t lane = threadIdx.x;
+      const uint32_t per = nb / 32;
+      const uint32_t hi = nb - lane * per;  // exclusive top of this lane's chunk (lane 0 = largest keys)
+      uint32_t csum = 0;
+      for (uint32_t j = 0; j < per; ++j) csum += sc.hist[hi - 1 - j];
+      uint32_t incl = csum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= uint32_t(o)) incl += t;
+      }
+      const uint32_t excl = incl - csum;
+      const bool mine = (excl < remaining) && (incl >= remaining);
+      if (mine) {
+        uint32_t run = excl;
+        for (uint32_t j = 0; j < per; ++j) {
+          const uint32_t c = sc.hist[hi - 1 - j];
+          if (run + c >= remaining) {
+            sc.sel_bin = hi - 1 - j;
+            sc.sel_above = run;
+            break;
+          }
+          run += c;
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= sc.sel_bin << shift;
+    mask |= (nb - 1) << shift;
+    remaining -= sc.sel_above;
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__device__ __forceinline__ float block_max(float v, BlockScratch& sc) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sc.redf[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = (threadIdx.x & 31) < (blockDim.x >> 5) ? sc.redf[threadIdx.x & 31] : -INFINITY;
+  return warp_max(t);
+}
+__device__ __forceinline__ float block_sumf(float v, BlockScratch& sc) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sc.redf[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = (threadIdx.x & 31) < (blockDim.x >> 5) ? sc.redf[threadIdx.x & 31] : 0.f;
+  return warp_sum(t);
+}
+__device__ __forceinline__ int block_sumi(int v, BlockScratch& sc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sc.redi[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = (threadIdx.x & 31) < (blockDim.x >> 5) ? sc.redi[threadIdx.x & 31] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+// argmax with lowest-index tie break
+__device__ __forceinline__ int block_argmax(float v, int idx, BlockScratch& sc) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { sc.redf[threadIdx.x >> 5] = v; sc.redi[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  const bool in = (threadIdx.x & 31) < (blockDim.x >> 5);
+  v = in ? sc.redf[threadIdx.x & 31] : -INFINITY;
+  idx = in ? sc.redi[threadIdx.x & 31] : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  return idx;
+}
+
+// Shared tail: row[] holds processed scores (grammar applied). Applies top-k, softmax (in place -> probabilities)
+// and draws the token.  Returns the token (valid in every thread).
+__device__ int block_topk_softmax_sample(float* __restrict__ row, int V, int top_k, int do_sample,
+                                         const float* __restrict__ noise_e, BlockScratch& sc) {
+  float mx = -INFINITY;
+  int nfin = 0;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float f = row[v];
+    mx = fmaxf(mx, f);
+    nfin += (f != -INFINITY);
+  }
+  mx = block_max(mx, sc);
+  nfin = block_sumi(nfin, sc);
+  float thr = -INFINITY;  // scores < thr are removed
+  if (top_k > 0 && top_k < V && nfin > top_k) {
+    const uint32_t key = block_kth_key(row, V, top_k, sc);
+    const uint32_t u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+    thr = __uint_as_float(u);
+  }
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float f = row[v];
+    if (f >= thr && f != -INFINITY) sum += expf(f - mx);
+  }
+  sum = block_sumf(sum, sc);
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float f = row[v];
+    const bool keep = (f >= thr && f != -INFINITY);
+    const float pr = keep ? expf(f - mx) / sum : 0.f;
+    row[v] = pr;
+    float val;
+    if (do_sample) val = pr / noise_e[v];
+    else val = keep ? f : -INFINITY;
+    if (val > best) { best = val; besti = v; }  // ascending v per thread keeps the lowest index on ties
+  }
+  return block_argmax(best, besti, sc);
+}
+
+// One CTA per window position.
+__global__ void __launch_bounds__(kVerifyThreads) verify_rows_kernel(VerifyParams p) {
+  __shared__ BlockScratch sc;
+  const int i = blockIdx.x;
+  const int V = p.V;
+  const float* c = p.logits + size_t(i) * V;
+  const float* u = p.logits + size_t(p.W + i) * V;
+  float* row = p.p_cur + size_t(i) * V;
+  const int forced = p.forced ? p.forced[i] : -1;
+  const bool ranged = p.allow_hi > p.allow_lo;
+  const bool mix = p.has_uncond && p.apply_cfg;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    float s = c[v];
+    if (mix) {
+      const float uu = u[v];
+      s = __fadd_rn(__fmul_rn(p.guidance, __fsub_rn(s, uu)), uu);
+    }
+    if (forced >= 0) s = (v == forced) ? 0.f : -INFINITY;
+    else if (ranged && (v < p.allow_lo || v >= p.allow_hi)) s = -INFINITY;
+    if (p.temperature != 1.f) s = s / p.temperature;
+    row[v] = s;
+  }
+  __syncthreads();
+  const int tok = block_topk_softmax_sample(row, V, p.top_k, p.do_sample, p.noise_e1 + size_t(i) * V, sc);
+  if (threadIdx.x == 0) p.next_tokens[i] = tok;
+}
+
+// Single CTA: accept scan over the window, prefix match, residual resample at the first rejection.
+__global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyParams p) {
+  __shared__ BlockScratch sc;
+  __shared__ int s_first;
+  __shared__ int s_text_mode;
+  const int W = p.W, V = p.V;
+  if (threadIdx.x == 0) { s_first = W; s_text_mode = 0; }
+  __syncthreads();
+  const int i = threadIdx.x;
+  if (i >= 1 && i < W) {
+    const int x = p.draft[i];
+    bool accept;
+    if (p.scheme == 0) {
+      const float px = p.p_cur[size_t(i - 1) * V + x];
+      const int qr = p.q_row[i];
+      const float qx = qr < 0 ? 1.f : p.p_prev[size_t(qr) * V + x];
+      accept = p.noise_u[i] < fminf(px / qx, 1.f);
+    } else {
+      accept = (x == p.next_tokens[i - 1]);
+    }
+    if (!accept) atomicMin(&s_first, i);
+  }
+  __syncthreads();
+  const int first = s_first;
+  const bool rejected = (p.scheme == 0) && (first < W);
+  if (p.scheme == 0) {
+    if (i < W) {
+      int tok;
+      if (i < first - 1) tok = p.draft[i + 1];          // accepted drafts
+      else tok = p.next_tokens[i];                      // fresh samples (position first-1 is overwritten below)
+      p.out_tokens[i] = tok;
+      if (i >= 1 && i <= first - 1 && p.draft[i] == p.eoi_token) s_text_mode = 1;
+    }
+  } else if (i < W) {
+    p.out_tokens[i] = p.next_tokens[i];
+  }
+  __syncthreads();
+  if (rejected) {
+    const int j = first - 1;  // window position being resampled
+    const float* a = p.p_cur + size_t(j) * V;
+    const int qr = p.q_row[first];
+    const float* b = qr < 0 ? nullptr : p.p_prev + size_t(qr) * V;
+    const int xd = p.draft[first];
+    const bool text = s_text_mode != 0;
+    const int forced = (!text && p.forced) ? p.forced[j] : -1;
+    const bool ranged = !text && (p.allow_hi > p.allow_lo);
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float q = b ? b[v] : (v == xd ? 1.f : 0.f);
+      float s = logf(fmaxf(__fsub_rn(a[v], q), 0.f));
+      if (forced >= 0) s = (v == forced) ? 0.f : -INFINITY;
+      else if (ranged && (v < p.allow_lo || v >= p.allow_hi)) s = -INFINITY;
+      if (p.temperature != 1.f) s = s / p.temperature;
+      p.resid[v] = s;
+    }
+    __syncthreads();
+    const int tok = block_topk_softmax_sample(p.resid, V, text ? p.text_top_k : p.top_k, 1, p.noise_e2, sc);
+    if (threadIdx.x == 0) p.out_tokens[j] = tok;
+  }
+  if (threadIdx.x == 0) {
+    p.out_info[0] = first;
+    p.out_info[1] = rejected ? 1 : 0;
+    p.out_info[2] = first;
+    p.out_info[3] = s_text_mode;
+  }
+}
+
+int verify_launch(const VerifyParams& p, cudaStream_t stream) {
+  if (p.W < 1 || p.W > kVerifyThreads) return -3;
+  verify_rows_kernel<<<p.W, kVerifyThreads, 0, stream>>>(p);
+  verify_accept_kernel<<<1, kVerifyThreads, 0, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -6;
+}
+
+}  // namespace sjd

@@ -1,0 +1,152 @@
+/* sjd_b200.h — C ABI of the B200-native Speculative Jacobi Decoding hot path.
+ *
+ * The reference (tyshiwo1/Accelerating-T2I-AR-with-SJD) has no FFI: its "plugin API" is Python
+ * class-swapping (scheduler/jacobi_iteration_lumina_mgpt.py:1340-1346).  This library sits UNDER the
+ * Python mirror of that API (accelerating-t2i-ar-with-sjd_b200/hf_api.py): every entry point below replaces
+ * a stretch of PyTorch-eager code of the reference's per-iteration hot loop, cited per function.
+ *
+ * Conventions: plain pointers and sizes; all device pointers are CUDA device memory of the current
+ * device; `stream` is a cudaStream_t passed as void*; functions return 0 on success or a negative
+ * SJD_E* code, never throw, and (except *_create) never allocate.  A context is thread-compatible,
+ * not thread-safe.  bf16 buffers are raw uint16 storage.
+ */
+#ifndef SJD_B200_H_
+#define SJD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SJD_OK 0
+#define SJD_E_DRIVER (-1)   /* driver entry point / tensor-map encode failed */
+#define SJD_E_TMAP (-2)
+#define SJD_E_ARG (-3)      /* bad shape / argument */
+#define SJD_E_SMEM (-4)
+#define SJD_E_ATTR (-5)
+#define SJD_E_LAUNCH (-6)   /* kernel launch failed; see sjd_last_error() */
+#define SJD_E_ALLOC (-7)
+#define SJD_E_STATE (-8)    /* weights missing, wrong call order */
+
+#define SJD_MAX_ROWS 8      /* CFG rows per context (reference uses 2: cond + uncond) */
+#define SJD_MAX_TOKENS 256  /* token rows per forward call (rows * window) */
+
+/* Library identification / diagnostics. */
+int sjd_version(void);
+const char* sjd_last_error(void);
+int sjd_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone weight-streaming GEMM  Y[M,N] = X[M,K] * W[N,K]^T  (bf16 in, fp32 accumulate).
+ * Replaces nn.Linear -> cuBLAS in the reference forward (modeling_chameleon.py:527-529,579,193-195,1560;
+ * llamagen/llamagen.py:248,277,200,332).  `x` must have at least m_tile rows (m_tile = M rounded up to 16,
+ * <= 256).  Partial tiles land in `ws` (sjd_gemm_workspace_bytes); sjd_gemm_reduce_* finish them.
+ * grid_limit <= 0 means one CTA per SM.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sjd_gemm_workspace_bytes(int N, int K, int m_tile, int grid_limit);
+int sjd_gemm_bf16(const void* w, int N, int K, const void* x, int x_rows, int m_tile, void* ws, int grid_limit,
+                  void* stream);
+int sjd_gemm_reduce_bf16(const void* ws, int N, int K, int m_tile, int grid_limit, void* out_bf16, int M,
+                         void* stream);
+int sjd_gemm_reduce_f32(const void* ws, int N, int K, int m_tile, int grid_limit, float* out_f32, int M,
+                        int round_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Verify step (one call per Jacobi iteration).  Replaces sampling_logits2tokens
+ * (scheduler/jacobi_iteration_lumina_mgpt.py:82-132), the 3-D logits processors
+ * (scheduler/logit_processor_3dim.py:45-204; HF TopKLogitsWarper for LlamaGen/Emu3),
+ * SpeculativeSampler.__call__ (:247-315) incl. residual resampling (:203-241), and
+ * prefix_matching_next_tokens / find_first_misaligned_token_inds (:317-376).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sjd_verify_args {
+  const float* logits;    /* [(has_uncond ? 2 : 1) * W][V] fp32, cond rows first */
+  int32_t W, V;
+  int32_t has_uncond;     /* logits carry CFG-uncond rows */
+  int32_t apply_cfg;      /* 1: g*(c-u)+u ; 0: cond only (check_is_force_no_cfg, :70-80) */
+  float guidance;
+  float temperature;
+  int32_t allow_lo, allow_hi; /* grammar: ids outside [lo,hi) suppressed; off when hi <= lo */
+  const int32_t* forced;  /* [W] forced id per window position (EOL/EOI/...), -1 = free; may be NULL */
+  int32_t top_k;          /* 0 = off; ties with the k-th largest are kept (scores < kth removed) */
+  int32_t do_sample;      /* 0: argmax */
+  int32_t scheme;         /* 0: 'speculative_jacobi', 1: 'jacobi' (:1032-1048) */
+  const int32_t* draft;   /* [W] window ids, [0] = last accepted token */
+  const int32_t* q_row;   /* [W] row of p_prev with the draft's distribution; -1: one-hot (fresh random draft) */
+  const float* p_prev;    /* [>=W][V] probabilities written by the previous call */
+  float* p_cur;           /* [>=W][V] out: probabilities of this call */
+  const float* noise_e1;  /* [W][V] Exp(1) noise == torch.multinomial's (q = empty_like(p).exponential_()) */
+  const float* noise_u;   /* [W] torch.rand([1,W,V])[0, i, draft[i]] */
+  const float* noise_e2;  /* [V] Exp(1) noise of the residual multinomial (consumed only on rejection) */
+  int32_t eoi_token;      /* accepted draft == eoi -> residual processed in text mode; -1 = never */
+  int32_t text_top_k;
+  float* resid;           /* [V] scratch */
+  int32_t* next_tokens;   /* [W] scratch */
+  int32_t* out_tokens;    /* [W] tokens after accept/resample: first `matched` are final, rest are next drafts */
+  int32_t* out_info;      /* [4]: matched, rejected, first_reject, residual_text_mode */
+} sjd_verify_args;
+
+int sjd_verify(const sjd_verify_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model context: the fused transformer stack of the draft-window forward with a static KV cache.
+ * Replaces `outputs = self(**model_inputs)` (scheduler/jacobi_iteration_lumina_mgpt.py:1107) for the
+ * Chameleon/Lumina (modeling_chameleon.py:1494-1591), LlamaGen (llamagen/llamagen.py:297-337 via
+ * llamagen_solver.py:234-295) and Emu3 (emu3/mllm/modeling_emu3.py:1140-1278) decoder stacks, the mask
+ * builders (_update_causal_mask, :1256-1336) and the KV roll-back (delete_false_key_value, :47-54 —
+ * here roll-back is just a smaller kv_len on the next call).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sjd_model_cfg {
+  int32_t n_layers, d_model, n_heads, n_kv_heads, head_dim, d_ff, vocab;
+  float rms_eps;
+  int32_t qk_norm;           /* 1: per-head LayerNorm on q,k (Chameleon) */
+  int32_t rope_interleaved;  /* 0: rotate-half (Chameleon, Emu3); 1: adjacent pairs (LlamaGen 2-D RoPE) */
+  int32_t rows;              /* CFG rows held in the KV cache (1 or 2) */
+  int32_t max_len;           /* KV cache capacity per row (tokens) */
+  int32_t n_rope_pos;        /* rows of the rope tables */
+  int32_t logits_round_bf16; /* 1: round logits through bf16 like a bf16 lm_head */
+} sjd_model_cfg;
+
+typedef struct sjd_layer_weights {   /* device pointers, bf16, nn.Linear layout [out, in] */
+  const void* attn_norm;   /* [d] */
+  const void* wqkv;        /* [(H + 2*Hkv) * Dh, d]  rows: q heads, k heads, v heads */
+  const void* q_norm_w; const void* q_norm_b;  /* [H, Dh] or NULL */
+  const void* k_norm_w; const void* k_norm_b;  /* [Hkv, Dh] or NULL */
+  const void* wo;          /* [d, H*Dh] */
+  const void* ffn_norm;    /* [d] */
+  const void* w_gate_up;   /* [2*d_ff, d]  rows: gate then up */
+  const void* w_down;      /* [d, d_ff] */
+} sjd_layer_weights;
+
+typedef struct sjd_ctx sjd_ctx;
+
+int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out);
+void sjd_ctx_destroy(sjd_ctx* ctx);
+size_t sjd_ctx_device_bytes(const sjd_ctx* ctx);
+int sjd_ctx_set_layer(sjd_ctx* ctx, int layer, const sjd_layer_weights* w);
+/* embed: [vocab, d] bf16 (may be NULL if every forward passes embeddings); final_norm [d]; lm_head [vocab, d];
+ * rope_cos/sin: fp32 [n_rope_pos, head_dim/2]. */
+int sjd_ctx_set_globals(sjd_ctx* ctx, const void* embed, const void* final_norm, const void* lm_head,
+                        const float* rope_cos, const float* rope_sin);
+
+typedef struct sjd_forward_args {
+  int32_t W;                 /* tokens per row in this call; rows*W <= SJD_MAX_TOKENS */
+  const int32_t* ids;        /* device [rows*W] token ids (row-major), or NULL when embeds is given */
+  const void* embeds;        /* device bf16 [rows*W, d] input embeddings, or NULL */
+  const int32_t* rope_pos;   /* device [rows*W] index into the rope tables */
+  const int32_t* cache_pos;  /* device [rows*W] KV slot written by each token */
+  int32_t kv_len;            /* keys already valid in the cache; this call's tokens sit at kv_len .. kv_len+W-1 */
+  int32_t kv_lo[SJD_MAX_ROWS]; /* first visible key per row (CFG hidden prefix / left padding) */
+  int32_t n_logit_tokens;    /* logits for the last n tokens of every row (0 < n <= W) */
+  float* logits;             /* device out [rows * n_logit_tokens, vocab] fp32, row b first */
+} sjd_forward_args;
+
+int sjd_ctx_forward(sjd_ctx* ctx, const sjd_forward_args* a, void* stream);
+/* counts kernel launches issued by this library since load (bench.py's gpu_launches) */
+uint64_t sjd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SJD_B200_H_ */
