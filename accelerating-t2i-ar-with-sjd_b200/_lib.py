@@ -136,6 +136,8 @@ def lib() -> C.CDLL:
     L.sjd_ctx_set_globals.argtypes = [C.c_void_p] * 6
     L.sjd_ctx_forward.restype = C.c_int
     L.sjd_ctx_forward.argtypes = [C.c_void_p, C.POINTER(ForwardArgs), C.c_void_p]
+    L.sjd_ctx_gemm_only.restype = C.c_int
+    L.sjd_ctx_gemm_only.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     _lib = L
     return L
 

@@ -355,4 +355,25 @@ int sjd_ctx_forward(sjd_ctx* c, const sjd_forward_args* a, void* stream) {
   return 0;
 }
 
+// Launch only the GEMMs of one window forward (same weights, activation buffers and launch order as
+// sjd_ctx_forward) — used by bench.py to time the dominant kernel in isolation for the roofline line.
+int sjd_ctx_gemm_only(sjd_ctx* c, int W, void* stream) {
+  if (!c || W < 1 || c->cfg.rows * W > SJD_MAX_TOKENS) return fail(SJD_E_ARG, "sjd_ctx_gemm_only: bad args");
+  if (!c->lm_head.ok) return fail(SJD_E_STATE, "sjd_ctx_gemm_only: globals not set");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int m_tile = round16(c->cfg.rows * W), mi = m_tile / 16;
+  if (ensure_xmaps(c, m_tile)) return fail(SJD_E_TMAP, "activation tensor maps");
+  StreamK sk;
+  int rc = 0;
+  for (auto& L : c->layers) {
+    if (!L.set) return fail(SJD_E_STATE, "sjd_ctx_gemm_only: layer weights not set");
+    rc |= run_gemm(c, L.qkv, c->xmap_xn[mi], m_tile, &sk, s);
+    rc |= run_gemm(c, L.o, c->xmap_attn[mi], m_tile, &sk, s);
+    rc |= run_gemm(c, L.gate_up, c->xmap_xn[mi], m_tile, &sk, s);
+    rc |= run_gemm(c, L.down, c->xmap_act[mi], m_tile, &sk, s);
+  }
+  rc |= run_gemm(c, c->lm_head, c->xmap_xn[mi], m_tile, &sk, s);
+  return rc ? fail(SJD_E_LAUNCH, "sjd_ctx_gemm_only") : 0;
+}
+
 }  // extern "C"

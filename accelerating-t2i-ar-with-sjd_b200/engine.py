@@ -60,3 +60,355 @@ def verify_call(logits: torch.Tensor, W: int, V: int, desc: dict, draft: torch.T
         h = info.cpu()
         res["matched"], res["rejected"] = int(h[0]), bool(h[1])
     return res
+
+
+# =====================================================================================================
+# The SJD decode loop (host control only: integers, a few pinned-memory copies and two C calls per
+# Jacobi iteration).  Mirrors JacobiSampler._sample (scheduler/jacobi_iteration_lumina_mgpt.py:912-1249):
+#   window = [last accepted | carried-over drafts | fresh random drafts]   (:606-740, :470-596)
+#   forward over the static KV cache, CFG rows batched                        (:1086-1107)
+#   verify on device (sjd_verify)                                             (:1113-1140)
+#   next window size rule                                                     (:1142-1144)
+#   append matched tokens, keep unmatched as drafts, roll the cache back      (:1146-1160, :378-430)
+# =====================================================================================================
+import random as _random
+import time as _time
+from dataclasses import dataclass, field
+
+import numpy as _np
+
+from .model import DeviceStack
+
+
+class LuminaGrammarState:
+    """Incremental host-side state of the Chameleon/Lumina image grammar that the reference recomputes from
+    input_ids every iteration (scheduler/logit_processor_3dim.py:84-155, :190-204): image tokens 4..8195 only,
+    forced end-of-line every (w+1) tokens, forced end-of-image after h rows; CFG off outside an image
+    (check_is_force_no_cfg, scheduler/jacobi_iteration_lumina_mgpt.py:70-80)."""
+
+    def __init__(self, image_start=8197, image_end=8196, eol=8803, grid_base=8804, allow=(4, 8196),
+                 image_top_k=2000, text_top_k=10):
+        self.image_start, self.image_end, self.eol, self.grid_base = image_start, image_end, eol, grid_base
+        self.allow, self.image_top_k, self.text_top_k = allow, image_top_k, text_top_k
+        self.eoi_token = image_end
+        self.reset()
+
+    def reset(self):
+        self.n_start = self.n_end = 0
+        self.since_start: list[int] = []   # tokens after the last image-start token
+        self.h = self.w = None
+
+    def observe(self, tokens):
+        for t in tokens:
+            if t == self.image_start:
+                self.n_start += 1
+                self.since_start = []
+                continue
+            if t == self.image_end:
+                self.n_end += 1
+            self.since_start.append(t)
+
+    @property
+    def no_cfg(self) -> bool:
+        return self.n_start == self.n_end
+
+    def describe(self, n: int) -> dict:
+        in_img = self.n_start == self.n_end + 1
+        d = {"allow": None, "forced": [-1] * n, "top_k": self.image_top_k if in_img else self.text_top_k}
+        if self.n_start == self.n_end:
+            self.h = self.w = None
+            return d
+        if not in_img or len(self.since_start) < 2:
+            return d
+        if self.h is None:
+            self.h = (self.since_start[0] - self.grid_base) * 2
+            self.w = (self.since_start[1] - self.grid_base) * 2
+        tokenlen = len(self.since_start) - 2
+        d["allow"] = self.allow
+        for line_len, tok in ((self.w + 1, self.eol), ((self.w + 1) * self.h + 1, self.image_end)):
+            lo_, hi_ = tokenlen + 1, tokenlen + n
+            first = -(-lo_ // line_len)  # ceil
+            for mult in range(first, hi_ // line_len + 1):
+                pos = line_len * mult - (tokenlen + 1)
+                if 0 <= pos < n:
+                    d["forced"][pos] = tok
+        return d
+
+
+class PlainTopKState:
+    """No grammar: HF TopKLogitsWarper(k) [+ TopPLogitsWarper3d(1.0), a no-op] — LlamaGen
+    (llamagen/llamagen_solver.py:458-470)."""
+    eoi_token = -1
+    text_top_k = 0
+    no_cfg = False
+
+    def __init__(self, top_k=0):
+        self.top_k = top_k
+
+    def reset(self):
+        pass
+
+    def observe(self, tokens):
+        pass
+
+    def describe(self, n: int) -> dict:
+        return {"allow": None, "forced": [-1] * n, "top_k": self.top_k}
+
+
+@dataclass
+class SJDParams:
+    """Same names and defaults as the reference's _init_new_params (jacobi_iteration_lumina_mgpt.py:865-910)."""
+    jacobi_loop_interval_l: int = 1
+    jacobi_loop_interval_r: int = (768 // 16) ** 2 + 768 // 16
+    max_num_new_tokens: int = 16
+    guidance_scale: float = 3.0
+    seed: int | None = 42
+    multi_token_init_scheme: str = "random"
+    do_cfg: bool = True
+    prefix_token_sampler_scheme: str = "speculative_jacobi"
+
+
+@dataclass
+class SJDStats:
+    nfe: int = 0
+    new_tokens: int = 0
+    t_inner: float = 0.0
+    trace: list = field(default_factory=list)   # per trip (W, matched, rejected)
+    h2d_bytes: int = 0                          # pinned-host -> device bytes copied by the loop
+    d2h_bytes: int = 0                          # device -> pinned-host bytes (accepted tokens, counters)
+
+
+def set_seed(seed: int):
+    """jacobi_iteration_lumina_mgpt.py:36-45"""
+    _random.seed(seed)
+    _np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+class NoiseSource:
+    """Noise in the exact order/shape the reference draws it from its torch.Generator
+    (SURVEY Appendix B): exponential_ [W,V] for multinomial, rand [1,W,V] for the accept test and, only when a
+    draft was rejected, exponential_ [1,V] for the residual multinomial."""
+
+    def __init__(self, seed: int | None, device, gen_device=None):
+        """gen_device: where the torch.Generator lives (default: the compute device, like the reference's
+        torch.Generator(input_ids.device), :1023).  'cpu' reproduces a CPU run of the reference bit for bit."""
+        self.device = torch.device(device)
+        self.gen_device = torch.device(gen_device) if gen_device is not None else self.device
+        self.g = torch.Generator(self.gen_device).manual_seed(seed) if seed is not None else None
+
+    def multinomial_noise(self, W, V):
+        e = torch.empty((W, V), dtype=torch.float32, device=self.gen_device).exponential_(1.0, generator=self.g)
+        return e.to(self.device)
+
+    def accept_noise(self, W, V, draft_dev):
+        rs = torch.rand((1, W, V), dtype=torch.float32, device=self.gen_device, generator=self.g)
+        u = rs[0].gather(1, draft_dev.to(self.gen_device).long()[:, None]).squeeze(1)
+        return u.to(self.device).contiguous()
+
+    def residual_noise_speculative(self, V):
+        """Draw the residual noise but remember how to un-draw it when no rejection happened."""
+        gen = self.g
+        if gen is None:
+            gen = (torch.cuda.default_generators[self.gen_device.index or 0] if self.gen_device.type == "cuda"
+                   else torch.default_generator)
+        state = gen.get_state()
+        e2 = torch.empty((1, V), dtype=torch.float32, device=self.gen_device).exponential_(1.0, generator=self.g)
+        return e2.to(self.device), (gen, state)
+
+    @staticmethod
+    def undo(token):
+        gen, state = token
+        gen.set_state(state)
+
+
+class SJDEngine:
+    """One prompt, `rows` CFG rows (cond [+ uncond]) — the reference's effective batch."""
+
+    def __init__(self, stack: DeviceStack, params: SJDParams, grammar, img_vocab: torch.Tensor,
+                 noise_factory=None):
+        self.stack, self.p, self.grammar = stack, params, grammar
+        self.img_vocab = img_vocab.cpu().long()
+        self.dev = stack.device
+        self.V = stack.shape.vocab
+        self.rows = stack.rows
+        Wmax = _lib.SJD_MAX_TOKENS // self.rows
+        self.Wmax = Wmax
+        self.pbuf = [torch.zeros(Wmax, self.V, dtype=torch.float32, device=self.dev) for _ in range(2)]
+        n_i32 = 3 * _lib.SJD_MAX_TOKENS + 3 * Wmax + 16
+        self.h_stage = torch.empty(n_i32, dtype=torch.int32).pin_memory()
+        self.d_stage = torch.empty(n_i32, dtype=torch.int32, device=self.dev)
+        self.d_out = torch.empty(4 + Wmax, dtype=torch.int32, device=self.dev)
+        self.h_out = torch.empty(4 + Wmax, dtype=torch.int32).pin_memory()
+        self.d_nxt = torch.empty(Wmax, dtype=torch.int32, device=self.dev)
+        self.resid = torch.empty(self.V, dtype=torch.float32, device=self.dev)
+        self.noise_factory = noise_factory or NoiseSource
+        self.lib = _lib.lib()
+        self.stats = SJDStats()
+
+    # -- one forward over `tokens` per row starting at cache slot kv_len -----------------------------------
+    def _forward(self, row_tokens, kv_len, kv_lo, n_logit, embeds=None):
+        rows, W = self.rows, len(row_tokens[0])
+        M = rows * W
+        hs = self.h_stage
+        flat = [t for r in row_tokens for t in r]
+        hs[:M] = torch.tensor(flat, dtype=torch.int32)
+        pos = list(range(kv_len, kv_len + W))
+        rp = []
+        for b in range(rows):
+            rp += [max(t - kv_lo[b], 0) for t in pos]
+        hs[M:2 * M] = torch.tensor(rp, dtype=torch.int32)
+        hs[2 * M:3 * M] = torch.tensor(pos * rows, dtype=torch.int32)
+        self.d_stage[:3 * M].copy_(hs[:3 * M], non_blocking=True)
+        self.stats.h2d_bytes += 12 * M
+        ds = self.d_stage
+        return self.stack.forward(W, ds[M:2 * M], ds[2 * M:3 * M], kv_len, kv_lo,
+                                  ids=None if embeds is not None else ds[:M], embeds=embeds, n_logit_tokens=n_logit)
+
+    @torch.no_grad()
+    def generate(self, input_ids, *, max_length: int, eos_token_ids=(), do_sample=True, temperature=1.0,
+                 kv_len0: int = 0, kv_lo=None, uncond_input_ids=None, stop_fn=None, has_eos_criteria=None,
+                 collect_trace=False):
+        """input_ids: list[int] tokens not yet in the cache (whole prompt, or LlamaGen's first image token with the
+        condition already cached at slots [0, kv_len0)).  uncond_input_ids: tokens fed to the CFG-uncond row on
+        the first trip (same length; default = input_ids).  Returns the full token list (prompt + generated)."""
+        p, rows, V, dev = self.p, self.rows, self.V, self.dev
+        ids = [int(t) for t in input_ids]
+        cur_len = len(ids)
+        do_cfg = bool(p.do_cfg) and (p.guidance_scale != 1) and rows == 2
+        if rows == 2 and not do_cfg:
+            raise ValueError("stack was built with 2 CFG rows but CFG is disabled")
+        kv_lo = list(kv_lo) if kv_lo is not None else [0] * rows
+        scheme = {"speculative_jacobi": 0, "jacobi": 1}.get(p.prefix_token_sampler_scheme)
+        if scheme is None:
+            raise ValueError(f"prefix_token_sampler_scheme: {p.prefix_token_sampler_scheme}")
+        if p.seed is not None:
+            set_seed(p.seed)   # python / numpy / torch global RNGs: the CPU one drives the fresh-draft randint
+        noise = self.noise_factory(p.seed, dev)
+        lr = (cur_len + p.jacobi_loop_interval_l, cur_len + p.jacobi_loop_interval_r)
+        grammar = self.grammar
+        grammar.reset()
+        grammar.observe(ids)
+        eos = set(int(e) for e in eos_token_ids)
+        stats = SJDStats()
+        self.stats = stats
+
+        out_W = 1                 # output_token_num
+        carried: list[int] = []   # unmatched next tokens (drafts for the next trip)
+        carried_row0 = 0          # row of pbuf[prev] holding carried[0]'s distribution
+        cur = 0                   # pbuf index written by the current trip
+        kv_len = kv_len0
+        first_trip = True
+        finished = False
+        torch.cuda.synchronize(dev)
+        t0 = _time.perf_counter()
+        while not finished:
+            # ---- window -------------------------------------------------------------------------------
+            if first_trip:
+                window = list(ids)
+                q_row = [-1] * len(window)
+            else:
+                n_fill = out_W - 1
+                keep = carried[:n_fill] if len(carried) > n_fill else carried
+                n_rand = max(n_fill - len(carried), 0)
+                fresh = []
+                if n_rand > 0:
+                    r = torch.randint(0, len(self.img_vocab), (1, n_rand))   # CPU global RNG, like :505-509
+                    fresh = self.img_vocab[r[0]].tolist()
+                window = [ids[-1]] + keep + fresh
+                q_row = [-1] + [carried_row0 + j for j in range(len(keep))] + [-1] * n_rand
+            W = len(window)
+            if kv_len + W > self.stack.max_len:
+                raise RuntimeError(f"KV cache too small: need {kv_len + W}, have {self.stack.max_len}")
+            no_cfg = bool(grammar.no_cfg)
+            # ---- forward (prefill may be chunked; only the last `n_out` positions need logits) ----------
+            n_out = out_W
+            if first_trip:
+                un = [int(t) for t in uncond_input_ids] if uncond_input_ids is not None else window
+                chunk = max(1, _lib.SJD_MAX_TOKENS // rows)
+                s = 0
+                while s < W:
+                    e = min(W, s + chunk)
+                    rt = [window[s:e]] + ([un[s:e]] if rows == 2 else [])
+                    logits = self._forward(rt, kv_len + s, kv_lo, n_out if e == W else 1)
+                    s = e
+            else:
+                rt = [window] * rows
+                logits = self._forward(rt, kv_len, kv_lo, n_out)
+            # ---- verify ---------------------------------------------------------------------------------
+            Wv = n_out
+            desc = grammar.describe(Wv)
+            hs, ds = self.h_stage, self.d_stage
+            base = 3 * _lib.SJD_MAX_TOKENS
+            wv_ids = window[-Wv:]
+            hs[base:base + Wv] = torch.tensor(wv_ids, dtype=torch.int32)
+            hs[base + self.Wmax: base + self.Wmax + Wv] = torch.tensor(q_row[-Wv:], dtype=torch.int32)
+            hs[base + 2 * self.Wmax: base + 2 * self.Wmax + Wv] = torch.tensor(desc["forced"], dtype=torch.int32)
+            ds[base: base + 3 * self.Wmax].copy_(hs[base: base + 3 * self.Wmax], non_blocking=True)
+            stats.h2d_bytes += 12 * self.Wmax
+            d_draft = ds[base: base + Wv]
+            a = _lib.VerifyArgs()
+            a.logits = logits.data_ptr()
+            a.W, a.V = Wv, V
+            a.has_uncond, a.apply_cfg = int(rows == 2), int(do_cfg and not no_cfg)
+            a.guidance, a.temperature = float(p.guidance_scale), float(temperature)
+            a.allow_lo, a.allow_hi = desc["allow"] if desc["allow"] else (0, 0)
+            a.forced = ds[base + 2 * self.Wmax:].data_ptr()
+            a.top_k, a.do_sample, a.scheme = int(desc["top_k"]), int(do_sample), scheme
+            a.draft = d_draft.data_ptr()
+            a.q_row = ds[base + self.Wmax:].data_ptr()
+            a.p_prev, a.p_cur = self.pbuf[1 - cur].data_ptr(), self.pbuf[cur].data_ptr()
+            keep_alive = []
+            undo = None
+            if do_sample:
+                e1 = noise.multinomial_noise(Wv, V)
+                keep_alive.append(e1)
+                a.noise_e1 = e1.data_ptr()
+            if scheme == 0 and Wv > 1:
+                u = noise.accept_noise(Wv, V, d_draft)
+                e2, undo = noise.residual_noise_speculative(V)
+                keep_alive += [u, e2]
+                a.noise_u, a.noise_e2 = u.data_ptr(), e2.data_ptr()
+            a.eoi_token, a.text_top_k = int(grammar.eoi_token), int(grammar.text_top_k)
+            a.resid, a.next_tokens = self.resid.data_ptr(), self.d_nxt.data_ptr()
+            a.out_info, a.out_tokens = self.d_out.data_ptr(), self.d_out[4:].data_ptr()
+            stream = torch.cuda.current_stream(dev)
+            _lib.check(self.lib.sjd_verify(C.byref(a), C.c_void_p(stream.cuda_stream)), "sjd_verify")
+            self.h_out[:4 + Wv].copy_(self.d_out[:4 + Wv], non_blocking=True)
+            stats.d2h_bytes += 4 * (4 + Wv)
+            stream.synchronize()
+            res = self.h_out[:4 + Wv].tolist()
+            matched, rejected = res[0], bool(res[1])
+            toks = res[4:4 + Wv]
+            if undo is not None and not rejected:
+                noise.undo(undo)
+            # ---- bookkeeping ----------------------------------------------------------------------------
+            if first_trip or out_W <= 1:
+                n_cached = W            # every fed token is now a valid cache entry
+                new = [toks[-1]]
+                carried, carried_row0 = [], 0
+            else:
+                n_cached = matched
+                new = toks[:matched]
+                carried = toks[matched:]
+                carried_row0 = matched
+            next_W = (min(p.max_num_new_tokens, lr[1] - cur_len)
+                      if (cur_len >= lr[0] and cur_len < lr[1]) else 1)
+            ids += new
+            grammar.observe(new)
+            kv_len += n_cached
+            stats.nfe += 1
+            if collect_trace:
+                stats.trace.append((W, len(new), int(rejected)))
+            out_W = next_W
+            cur = 1 - cur
+            cur_len = len(ids)
+            first_trip = False
+            if (ids[-1] in eos) or cur_len >= max_length or (stop_fn is not None and stop_fn(ids)):
+                finished = True
+        torch.cuda.synchronize(dev)
+        stats.t_inner = _time.perf_counter() - t0
+        stats.new_tokens = len(ids) - len(input_ids)
+        return ids

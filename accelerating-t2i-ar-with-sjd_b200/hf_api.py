@@ -1,0 +1,348 @@
+"""Host-side mirror of the reference's plugin interface for the SJD path — same names, same keyword
+arguments, same error behaviour — backed by the sm_100a engine instead of PyTorch-eager code.
+
+reference                                                       here
+---------------------------------------------------------------------------------------------------------
+scheduler/jacobi_iteration_lumina_mgpt.py:1340 renew_pipeline_sampler   renew_pipeline_sampler
+                                          :598  renew_sampler            renew_sampler  (JacobiSampler._sample)
+                                          :1253 renew_backbone           renew_backbone (mask is index math in-kernel)
+                                          :432  renew_pipeline           renew_pipeline (create_logits_processor)
+scheduler/logit_processor_3dim.py:45,158,355   3-D processors           descriptor classes, evaluated by sjd_verify
+llamagen/llamagen_solver.py:196,349            renew_llamagen, LlamaGenSolver   same names
+
+`_sample(input_ids, logits_processor, stopping_criteria, generation_config, synced_gpus, streamer,
+logits_warper=None, **model_kwargs) -> LongTensor [1, P+N]` keeps the HF-facing contract, so
+`model.generate()` / `solver.generate()` callers (test_lumina_mgpt.py:130, test_llamagen.py:163) are unchanged.
+The transformer weights are packed once (first call) into the engine's layout; models are mutated in place by
+class swapping exactly like the reference.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from . import engine as _engine
+from .model import DeviceStack, StackShape
+
+try:  # HF is plumbing for the boundary only
+    from transformers.generation.logits_process import LogitsProcessor, LogitsProcessorList, TopKLogitsWarper
+except Exception:  # pragma: no cover
+    LogitsProcessor = object
+    LogitsProcessorList = list
+    TopKLogitsWarper = None
+
+
+# --------------------------------------------------------------------------------------------------------
+# processors: parameter holders with the reference's constructor signatures.  Their arithmetic runs inside
+# sjd_verify; calling them on tensors is not part of the product path.
+# --------------------------------------------------------------------------------------------------------
+class _DeviceEvaluated(LogitsProcessor):
+    def __call__(self, input_ids, scores):
+        raise RuntimeError(f"{type(self).__name__} is evaluated on the GPU by sjd_verify; there is no host fallback")
+
+
+class MultiTokensVLLogitsProcessor(_DeviceEvaluated):
+    """scheduler/logit_processor_3dim.py:45-155"""
+
+    def __init__(self, image_start_token_id=None, image_end_token_id=None, image_next_line_token_id=None,
+                 patch_size=None, voc_size=None, device="cpu"):
+        self.image_start_token_id = image_start_token_id
+        self.image_end_token_id = image_end_token_id
+        self.image_next_line_token_id = image_next_line_token_id
+        self.patch_size, self.voc_size = patch_size, voc_size
+        self.h_latent_dim = self.w_latent_dim = None
+
+
+class MultiTokensInterleavedTopKLogitsWarper(_DeviceEvaluated):
+    """scheduler/logit_processor_3dim.py:158-204"""
+
+    def __init__(self, image_top_k, text_top_k, image_start_token_id=None, image_end_token_id=None,
+                 filter_value=-float("Inf"), min_tokens_to_keep=1):
+        if not isinstance(text_top_k, int) or text_top_k <= 0:
+            raise ValueError(f"`text_top_k` has to be a strictly positive integer, but is {text_top_k}")
+        if not isinstance(image_top_k, int) or text_top_k <= 0:
+            raise ValueError(f"`image_top_k` has to be a strictly positive integer, but is {image_top_k}")
+        self.image_top_k = max(image_top_k, min_tokens_to_keep)
+        self.text_top_k = max(text_top_k, min_tokens_to_keep)
+        self.image_start_token_id, self.image_end_token_id = image_start_token_id, image_end_token_id
+
+
+class TopPLogitsWarper3d(_DeviceEvaluated):
+    """scheduler/logit_processor_3dim.py:355-419.  top_p = 1.0 (every shipped driver) leaves the probabilities
+    unchanged; other values are not implemented on device yet and are rejected loudly."""
+
+    def __init__(self, top_p, filter_value=-float("Inf"), min_tokens_to_keep=1):
+        top_p = float(top_p)
+        if top_p < 0 or top_p > 1.0:
+            raise ValueError(f"`top_p` has to be a float > 0 and < 1, but is {top_p}")
+        if not isinstance(min_tokens_to_keep, int) or (min_tokens_to_keep < 1):
+            raise ValueError(f"`min_tokens_to_keep` has to be a positive integer, but is {min_tokens_to_keep}")
+        self.top_p = top_p
+
+
+def grammar_from_processors(processors):
+    """Translate the reference's processor list into the engine's grammar state."""
+    vl = topk = None
+    plain_k = 0
+    for pr in processors or []:
+        if isinstance(pr, MultiTokensVLLogitsProcessor):
+            vl = pr
+        elif isinstance(pr, MultiTokensInterleavedTopKLogitsWarper):
+            topk = pr
+        elif isinstance(pr, TopPLogitsWarper3d):
+            if pr.top_p != 1.0:
+                raise NotImplementedError("top_p < 1 is not implemented in sjd_verify")
+        elif TopKLogitsWarper is not None and isinstance(pr, TopKLogitsWarper):
+            plain_k = int(pr.top_k)
+        else:
+            raise NotImplementedError(f"logits processor {type(pr).__name__} has no device implementation")
+    if vl is not None:
+        return _engine.LuminaGrammarState(
+            image_start=vl.image_start_token_id, image_end=vl.image_end_token_id, eol=vl.image_next_line_token_id,
+            image_top_k=topk.image_top_k if topk else 0, text_top_k=topk.text_top_k if topk else 0)
+    return _engine.PlainTopKState(top_k=plain_k)
+
+
+# --------------------------------------------------------------------------------------------------------
+# weight packing: HF Chameleon / Llama-like (Emu3) and LlamaGen module trees -> engine layout
+# --------------------------------------------------------------------------------------------------------
+def _rope_half(head_dim, n_pos, theta, round_bf16=True):
+    from .families import rope_rotate_half
+    return rope_rotate_half(head_dim, n_pos, theta, round_bf16)
+
+
+def pack_hf_decoder(model, max_len: int, rows: int, device) -> DeviceStack:
+    """ChameleonForConditionalGeneration / Emu3ForCausalLM-style trees: model.model.layers[i].self_attn.{q,k,v,o}_proj,
+    (.q_norm/.k_norm), .mlp.{gate,up,down}_proj, .input_layernorm, .post_attention_layernorm; model.model.norm;
+    model.lm_head (modeling_chameleon.py:235-369, :593-666)."""
+    cfg = model.config
+    core = model.model
+    layers = core.layers
+    H = cfg.num_attention_heads
+    Hkv = getattr(cfg, "num_key_value_heads", H) or H
+    d = cfg.hidden_size
+    Dh = d // H
+    qk_norm = hasattr(layers[0].self_attn, "q_norm")
+
+    def norm_param(p, heads):  # Lumina keeps [model_parallel_size, Dh] and repeat-interleaves (:206-219)
+        p = p.detach()
+        if p.dim() == 1:
+            p = p[None]
+        return p.repeat_interleave(heads // p.shape[0], dim=0) if p.shape[0] != heads else p
+
+    w = {"embed": core.embed_tokens.weight, "final_norm": core.norm.weight, "lm_head": model.lm_head.weight, "layers": []}
+    for L in layers:
+        a, m = L.self_attn, L.mlp
+        e = {"attn_norm": L.input_layernorm.weight,
+             "wqkv": torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0),
+             "wo": a.o_proj.weight, "ffn_norm": L.post_attention_layernorm.weight,
+             "w_gate_up": torch.cat([m.gate_proj.weight, m.up_proj.weight], 0), "w_down": m.down_proj.weight}
+        if qk_norm:
+            e.update(q_norm_w=norm_param(a.q_norm.weight, H), q_norm_b=norm_param(a.q_norm.bias, H),
+                     k_norm_w=norm_param(a.k_norm.weight, Hkv), k_norm_b=norm_param(a.k_norm.bias, Hkv))
+        w["layers"].append(e)
+    shape = StackShape(len(layers), d, H, Hkv, Dh, cfg.intermediate_size, cfg.vocab_size,
+                       float(getattr(cfg, "rms_norm_eps", 1e-5)), qk_norm, False)
+    theta = float(getattr(cfg, "rope_theta", 10000.0) or 10000.0)
+    cos, sin = _rope_half(Dh, max_len, theta)
+    return DeviceStack(shape, w, cos, sin, rows, max_len, device)
+
+
+def pack_llamagen(model, max_len: int, rows: int, device) -> DeviceStack:
+    """gpt-fast style tree of llamagen/llamagen.py:297-335 (fused wqkv, w1/w3/w2)."""
+    from .families import rope_llamagen_2d
+    c = model.config
+    H = c.n_head
+    Dh = c.dim // H
+    w = {"embed": model.tok_embeddings.weight, "final_norm": model.norm.weight, "lm_head": model.output.weight,
+         "layers": []}
+    for L in model.layers:
+        w["layers"].append({"attn_norm": L.attention_norm.weight, "wqkv": L.attention.wqkv.weight,
+                            "wo": L.attention.wo.weight, "ffn_norm": L.ffn_norm.weight,
+                            "w_gate_up": torch.cat([L.feed_forward.w1.weight, L.feed_forward.w3.weight], 0),
+                            "w_down": L.feed_forward.w2.weight})
+    d_ff = model.layers[0].feed_forward.w1.weight.shape[0]
+    shape = StackShape(len(model.layers), c.dim, H, c.n_kv_head or H, Dh, d_ff, c.vocab_size, c.norm_eps, False, True)
+    grid = int(math.isqrt(c.block_size))
+    cos, sin = rope_llamagen_2d(grid, Dh, c.rope_base, c.cls_token_num)
+    return DeviceStack(shape, w, cos, sin, rows, max(max_len, cos.shape[0]), device)
+
+
+# --------------------------------------------------------------------------------------------------------
+# renew_* : class swapping like the reference
+# --------------------------------------------------------------------------------------------------------
+def _criteria_limits(stopping_criteria, generation_config):
+    eos, max_length, extra = [], None, []
+    for c in stopping_criteria or []:
+        if hasattr(c, "eos_token_id"):
+            e = c.eos_token_id
+            eos += [int(x) for x in (e.tolist() if hasattr(e, "tolist") else (e if isinstance(e, (list, tuple)) else [e]))]
+        elif hasattr(c, "max_length"):
+            max_length = int(c.max_length)
+        else:
+            extra.append(c)
+    if max_length is None and generation_config is not None and getattr(generation_config, "max_length", None):
+        max_length = int(generation_config.max_length)
+    return eos, max_length, extra
+
+
+def renew_sampler(model_class):
+    class JacobiSampler(model_class, nn.Module):
+        def __init__(self, *args, **kwargs):
+            super().__init__(*args, **kwargs)
+            self._init_new_params()
+
+        def _init_new_params(self, jacobi_loop_interval_l=1, jacobi_loop_interval_r=(768 // 16) ** 2 + 768 // 16,
+                             max_num_new_tokens=16, guidance_scale=3.0, seed=42, multi_token_init_scheme="random",
+                             do_cfg=True, prefix_token_sampler_scheme="speculative_jacobi",
+                             use_chameleon_tokenizer=True, _init_doubled_attn_mask_cfg=False, **kwargs):
+            """Same keywords/defaults as jacobi_iteration_lumina_mgpt.py:865-910.  The image-token vocabulary used
+            for random drafts is ids 4..8195 (what VocabInfo.image_tokens yields for the Chameleon tokenizer, :879-886)
+            unless `self.img_vocab` is set by the caller."""
+            if use_chameleon_tokenizer:
+                self.img_vocab = torch.arange(4, 8196, dtype=torch.long)
+            elif not hasattr(self, "img_vocab"):
+                self.img_vocab = None
+            self.jacobi_loop_interval_l = jacobi_loop_interval_l
+            self.jacobi_loop_interval_r = jacobi_loop_interval_r
+            self.max_num_new_tokens = max_num_new_tokens
+            self.max_jacobi_iter_num = min(200, self.max_num_new_tokens + 1)
+            self.guidance_scale = guidance_scale
+            self.seed = seed
+            self.generator = None
+            self.multi_token_init_scheme = multi_token_init_scheme
+            self.do_cfg = do_cfg
+            self.prefix_token_sampler_scheme = prefix_token_sampler_scheme
+            self._init_doubled_attn_mask_cfg = _init_doubled_attn_mask_cfg
+
+        # -- engine plumbing ----------------------------------------------------------------------------------
+        def _sjd_params(self):
+            return _engine.SJDParams(self.jacobi_loop_interval_l, self.jacobi_loop_interval_r, self.max_num_new_tokens,
+                                     self.guidance_scale, self.seed, self.multi_token_init_scheme, self.do_cfg,
+                                     self.prefix_token_sampler_scheme)
+
+        def _sjd_stack(self, rows, max_len, device):
+            key = (rows, max_len)
+            st = getattr(self, "_sjd_stack_cache", None)
+            if st is None or st[0] != key:
+                if st is not None:
+                    st[1].close()
+                packer = pack_llamagen if hasattr(self, "tok_embeddings") else pack_hf_decoder
+                st = (key, packer(self, max_len, rows, device))
+                object.__setattr__(self, "_sjd_stack_cache", st)
+            return st[1]
+
+        @torch.no_grad()
+        def _sample(self, input_ids, logits_processor, stopping_criteria, generation_config, synced_gpus, streamer,
+                    logits_warper=None, **model_kwargs):
+            assert not getattr(generation_config, "return_dict_in_generate", False)
+            if input_ids.shape[0] != 1:
+                raise ValueError("the SJD sampler decodes one prompt per call (the reference's B>1 path is broken too)")
+            if self.prefix_token_sampler_scheme not in ("speculative_jacobi", "jacobi"):
+                raise ValueError(f"prefix_token_sampler_scheme: {self.prefix_token_sampler_scheme}")
+            device = input_ids.device
+            do_cfg = bool(self.do_cfg) and self.guidance_scale != 1
+            rows = 2 if do_cfg else 1
+            eos, max_length, extra = _criteria_limits(stopping_criteria, generation_config)
+            prompt = input_ids[0].tolist()
+            kv_len0 = int(getattr(self, "_sjd_kv_len0", 0))   # tokens already cached by a solver-side prefill
+            cap = (max_length or (len(prompt) + 4096)) + self.max_num_new_tokens + kv_len0 + 8
+            stack = self._sjd_stack(rows, int(-(-cap // 64) * 64), device)
+            grammar = grammar_from_processors(list(logits_processor or []) + list(logits_warper or []))
+            eng = _engine.SJDEngine(stack, self._sjd_params(), grammar,
+                                    self.img_vocab if self.img_vocab is not None else torch.arange(stack.shape.vocab))
+            attn = model_kwargs.get("attention_mask")
+            prefill_num = (attn.shape[1] - 1) if attn is not None else len(prompt) - 1
+            kv_lo = [0, prefill_num] if (rows == 2 and not self._init_doubled_attn_mask_cfg
+                                         and not hasattr(self, "tok_embeddings")) else [0] * rows
+            stop_fn = None
+            if extra:
+                def stop_fn(ids):
+                    t = torch.tensor([ids])
+                    return any(bool(torch.as_tensor(c(t, None)).any()) for c in extra)
+            t1 = torch.cuda.Event(enable_timing=True)
+            t2 = torch.cuda.Event(enable_timing=True)
+            t1.record()
+            ids = eng.generate(prompt, max_length=max_length or (len(prompt) + 4096), eos_token_ids=eos,
+                               do_sample=bool(generation_config.do_sample), kv_len0=kv_len0, kv_lo=kv_lo,
+                               temperature=float(getattr(generation_config, "temperature", 1.0) or 1.0),
+                               stop_fn=stop_fn)
+            t2.record()
+            torch.cuda.synchronize()
+            self.sjd_stats = eng.stats
+            # the three lines drivers/logs rely on (jacobi_iteration_lumina_mgpt.py:1217-1220)
+            print("Time elapsed inner: ", t1.elapsed_time(t2) / 1000)
+            print("gen loop num (NFE): ", eng.stats.nfe)
+            print("tokens length: ", len(ids))
+            if streamer is not None:
+                streamer.put(torch.tensor(ids[len(prompt):]))
+                streamer.end()
+            return torch.tensor([ids], dtype=input_ids.dtype, device=device)
+
+    return JacobiSampler
+
+
+def renew_backbone(model_class):
+    """The reference overrides _update_causal_mask to understand 3-D window masks (:1253-1338); here the mask is
+    `kv_lo <= j <= kv_len + i` evaluated inside the attention kernel, so the backbone class needs no change."""
+    class JacobiBackbone(model_class):
+        pass
+    return JacobiBackbone
+
+
+def renew_pipeline(model_class):
+    class JacobiPipeline(model_class):
+        def _init_new_params(self, guidance_scale=3.0, image_top_k=2000, text_top_k=10, **kwargs):
+            self.cfg, self.image_top_k, self.text_top_k = guidance_scale, image_top_k, text_top_k
+
+        def create_logits_processor(self, cfg=3.0, image_top_k=2000, text_top_k=10):
+            image_top_k = getattr(self, "image_top_k", image_top_k)
+            text_top_k = getattr(self, "text_top_k", text_top_k)
+            ip = self.item_processor
+            start = ip.token2id(ip.image_start_token)
+            end = ip.token2id(ip.image_end_token)
+            return LogitsProcessorList([
+                MultiTokensVLLogitsProcessor(image_start_token_id=start, image_end_token_id=end,
+                                             image_next_line_token_id=ip.token2id(ip.new_line_token), patch_size=32,
+                                             voc_size=self.model.config.vocab_size, device=self.device),
+                MultiTokensInterleavedTopKLogitsWarper(image_top_k=image_top_k, text_top_k=text_top_k,
+                                                       image_start_token_id=start, image_end_token_id=end)])
+    return JacobiPipeline
+
+
+def renew_pipeline_sampler(pipe_line, **kwargs):
+    """scheduler/jacobi_iteration_lumina_mgpt.py:1340-1346"""
+    pipe_line.__class__ = renew_pipeline(pipe_line.__class__)
+    pipe_line._init_new_params(**kwargs)
+    pipe_line.model.__class__ = renew_sampler(pipe_line.model.__class__)
+    pipe_line.model._init_new_params(**kwargs)
+    pipe_line.model.model.__class__ = renew_backbone(pipe_line.model.model.__class__)
+    return pipe_line
+
+
+# --------------------------------------------------------------------------------------------------------
+# synthetic-prompt solver used by bench.py / tests: the public call with host buffers on both sides
+# --------------------------------------------------------------------------------------------------------
+class SyntheticLuminaSolver:
+    """generate(prompt_ids: pinned host LongTensor [1, P]) -> host LongTensor [1, P + N].  Mirrors the part of
+    FlexARInferenceSolver.generate (lumina_mgpt/inference_solver.py:298-354) between tokenisation and VQ decode."""
+
+    def __init__(self, eng: _engine.SJDEngine, max_length: int, eos_token_ids=(8710,)):
+        self.engine, self.max_length, self.eos = eng, max_length, list(eos_token_ids)
+
+    @torch.no_grad()
+    def generate(self, prompt_ids: torch.Tensor, seed: int | None = None, do_sample=True, temperature=1.0):
+        dev = self.engine.dev
+        d_prompt = prompt_ids.to(dev, non_blocking=True)          # host -> device, like inference_solver.py:326
+        prompt = d_prompt[0].tolist()
+        P = len(prompt)
+        if seed is not None:
+            self.engine.p.seed = seed
+        ids = self.engine.generate(prompt, max_length=self.max_length, eos_token_ids=self.eos, do_sample=do_sample,
+                                   temperature=temperature, kv_lo=[0, P - 1])
+        self.engine.stats.h2d_bytes += prompt_ids.numel() * 8
+        out = torch.tensor([ids], dtype=torch.int64, device=dev).cpu()  # device -> host result (:350)
+        self.engine.stats.d2h_bytes += out.numel() * 8
+        return out

@@ -143,6 +143,9 @@ typedef struct sjd_forward_args {
 } sjd_forward_args;
 
 int sjd_ctx_forward(sjd_ctx* ctx, const sjd_forward_args* a, void* stream);
+/* Launches only the GEMMs of one window forward (same weights/buffers/order): lets bench.py time the dominant
+ * kernel (gemm_streamk_kernel) in isolation with CUDA events. */
+int sjd_ctx_gemm_only(sjd_ctx* ctx, int W, void* stream);
 /* counts kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t sjd_launch_count(void);
 

@@ -1,0 +1,238 @@
+"""ORACLE tooling (runs only in the build container, where /root/reference exists): drive the UNMODIFIED
+reference scheduler (scheduler/jacobi_iteration_lumina_mgpt.py, scheduler/logit_processor_3dim.py) on CPU and
+record what it does, as golden fixtures under tests/golden/.
+
+  python oracle/mint_golden.py            # writes tests/golden/sjd_loop_*.json, forward_*.npz
+
+The reference pins transformers 4.47.1; this image has 5.5.0, so the eight small compatibility shims of
+SURVEY.md Appendix C are applied before importing it (aliases for removed names — no reference logic changes).
+The transformer is replaced by oracle/fake_lm.py (exactly reproducible logits), so a fixture is just
+{config, prompt, seed} -> {token sequence, per-iteration trace}.  Forward fixtures run the reference's own
+model code (llamagen/llamagen.py, lumina_mgpt/model/chameleon/modeling_chameleon.py) in fp32 on seeded random
+weights and store a few logit rows for oracle/ref_forward.py to be checked against.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+REF = Path(os.environ.get("SJD_REFERENCE", "/root/reference"))
+sys.path.insert(0, str(REPO))
+sys.dont_write_bytecode = True
+
+from oracle.fake_lm import fake_logits  # noqa: E402
+
+
+def apply_shims():
+    import transformers
+    import transformers.generation.logits_process as LP
+    from transformers.generation.utils import GenerationMixin
+    LP.LogitsWarper = LP.LogitsProcessor
+    _hus = GenerationMixin._has_unfinished_sequences
+    GenerationMixin._has_unfinished_sequences = (
+        lambda self, fin, synced, device, cur_len=None, max_length=None: _hus(self, fin, synced, device))
+    GenerationMixin._extract_past_from_model_output = lambda self, outputs: ("past_key_values", outputs.past_key_values)
+
+    class LegacyDynamicCache(transformers.cache_utils.Cache):
+        def __init__(self):
+            self.key_cache, self.value_cache = [], []
+
+        def __len__(self):
+            return len(self.key_cache)
+
+        def get_seq_length(self, layer_idx=0):
+            return 0 if len(self.key_cache) <= layer_idx else self.key_cache[layer_idx].shape[-2]
+
+        def update(self, k, v, layer_idx, cache_kwargs=None):
+            if len(self.key_cache) <= layer_idx:
+                self.key_cache.append(k)
+                self.value_cache.append(v)
+            else:
+                self.key_cache[layer_idx] = torch.cat([self.key_cache[layer_idx], k], -2)
+                self.value_cache[layer_idx] = torch.cat([self.value_cache[layer_idx], v], -2)
+            return self.key_cache[layer_idx], self.value_cache[layer_idx]
+
+    transformers.DynamicCache = LegacyDynamicCache
+    if not torch.cuda.is_available():
+        import time
+
+        class _Ev:
+            def __init__(self, *a, **k):
+                self.t = 0.0
+
+            def record(self):
+                self.t = time.time()
+
+            def elapsed_time(self, other):
+                return (other.t - self.t) * 1e3
+
+        torch.cuda.Event = _Ev
+        torch.cuda.synchronize = lambda *a, **k: None
+        torch.cuda.manual_seed_all = lambda *a, **k: None
+    return LegacyDynamicCache
+
+
+def make_fake_lm(V: int, sharp: float):
+    from transformers.generation.utils import GenerationMixin
+    from types import SimpleNamespace as Out
+
+    class Cfg:
+        vocab_size = V
+        is_encoder_decoder = False
+        pad_token_id = 0
+
+    class FakeLM(torch.nn.Module, GenerationMixin):
+        def __init__(self):
+            super().__init__()
+            self.config = Cfg()
+
+        def forward(self, input_ids=None, position_ids=None, cache_position=None, past_key_values=None,
+                    use_cache=True, attention_mask=None, **kw):
+            rows, W = input_ids.shape
+            kv_len = int(cache_position[0])
+            lg = fake_logits(input_ids.tolist(), kv_len, W, V, sharp).reshape(rows, W, V)
+            dummy = torch.zeros(rows, 1, W, 1)
+            past_key_values.update(dummy, dummy, 0)
+            return Out(logits=torch.from_numpy(lg), past_key_values=past_key_values)
+
+    return FakeLM()
+
+
+def run_reference_loop(case: dict, Cache) -> dict:
+    sys.path.insert(0, str(REF))
+    import scheduler.jacobi_iteration_lumina_mgpt as J
+    from scheduler.logit_processor_3dim import (MultiTokensInterleavedTopKLogitsWarper,
+                                                MultiTokensVLLogitsProcessor, TopPLogitsWarper3d)
+    from transformers import GenerationConfig
+    from transformers.generation.logits_process import LogitsProcessorList, TopKLogitsWarper
+    from transformers.generation.stopping_criteria import (EosTokenCriteria, MaxLengthCriteria,
+                                                           StoppingCriteriaList)
+
+    V = case["V"]
+    m = make_fake_lm(V, case["sharp"])
+    m.__class__ = J.renew_sampler(m.__class__)
+    m._init_new_params(use_chameleon_tokenizer=False, **case["jacobi"])
+    lo, hi = case["img_vocab"]
+    m.img_vocab = torch.arange(lo, hi)
+    if case["grammar"] == "lumina":
+        procs = LogitsProcessorList([
+            MultiTokensVLLogitsProcessor(8197, 8196, 8803, 32, V),
+            MultiTokensInterleavedTopKLogitsWarper(case["image_top_k"], case["text_top_k"], 8197, 8196)])
+    else:
+        procs = LogitsProcessorList([TopKLogitsWarper(top_k=case["image_top_k"]), TopPLogitsWarper3d(top_p=1.0)])
+    gc = GenerationConfig(max_new_tokens=case["max_length"], max_length=case["max_length"], temperature=1.0,
+                          top_k=None, do_sample=case["do_sample"], eos_token_id=case["eos"] or None)
+    gc._pad_token_tensor = torch.tensor(0) if case["eos"] else None
+    crit = [MaxLengthCriteria(case["max_length"])]
+    if case["eos"]:
+        crit.append(EosTokenCriteria(eos_token_id=case["eos"]))
+    trace = []
+    orig = J.prefix_matching_next_tokens
+
+    def spy(*a, **k):
+        r = orig(*a, **k)
+        trace.append({"W": int(k["model_input_ids"].shape[1]), "n_new": int(r[1].shape[1]),
+                      "tokens": [int(t) for t in r[1][0]]})
+        return r
+
+    J.prefix_matching_next_tokens = spy
+    try:
+        prompt = torch.tensor([case["prompt"]])
+        import contextlib
+        import io
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            out = m._sample(prompt, logits_processor=procs, stopping_criteria=StoppingCriteriaList(crit),
+                            generation_config=gc, synced_gpus=False, streamer=None,
+                            attention_mask=torch.ones_like(prompt), past_key_values=Cache(), use_cache=True)
+    finally:
+        J.prefix_matching_next_tokens = orig
+    return {"ids": [int(t) for t in out[0]], "trace": trace}
+
+
+LOOP_CASES = {
+    "lumina_spec_w8": dict(V=9216, sharp=16.0, grammar="lumina", image_top_k=2000, text_top_k=10,
+                           prompt=[1, 100, 200, 8197, 8808, 8808], img_vocab=[4, 8196], do_sample=True, eos=[8710],
+                           max_length=6 + 8 * 9 + 3,
+                           jacobi=dict(jacobi_loop_interval_l=3, jacobi_loop_interval_r=8 * 8 + 8 - 10,
+                                       max_num_new_tokens=8, guidance_scale=3.0, seed=0,
+                                       multi_token_init_scheme="random", do_cfg=True,
+                                       prefix_token_sampler_scheme="speculative_jacobi")),
+    "lumina_spec_w16_cross_eoi": dict(V=9216, sharp=12.0, grammar="lumina", image_top_k=500, text_top_k=10,
+                                      prompt=[7, 8197, 8807, 8809], img_vocab=[4, 8196], do_sample=True, eos=[8710],
+                                      max_length=4 + 6 * 11 + 12,
+                                      jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=200,
+                                                  max_num_new_tokens=16, guidance_scale=3.0, seed=3,
+                                                  multi_token_init_scheme="random", do_cfg=True,
+                                                  prefix_token_sampler_scheme="speculative_jacobi")),
+    "lumina_jacobi_greedy_w8": dict(V=9216, sharp=16.0, grammar="lumina", image_top_k=2000, text_top_k=10,
+                                    prompt=[1, 100, 200, 8197, 8808, 8808], img_vocab=[4, 8196], do_sample=False,
+                                    eos=[8710], max_length=6 + 8 * 9 + 3,
+                                    jacobi=dict(jacobi_loop_interval_l=3, jacobi_loop_interval_r=8 * 8 + 8 - 10,
+                                                max_num_new_tokens=8, guidance_scale=3.0, seed=0,
+                                                multi_token_init_scheme="random", do_cfg=True,
+                                                prefix_token_sampler_scheme="jacobi")),
+    "lumina_jacobi_greedy_w1": dict(V=9216, sharp=16.0, grammar="lumina", image_top_k=2000, text_top_k=10,
+                                    prompt=[1, 100, 200, 8197, 8808, 8808], img_vocab=[4, 8196], do_sample=False,
+                                    eos=[8710], max_length=6 + 8 * 9 + 3,
+                                    jacobi=dict(jacobi_loop_interval_l=3, jacobi_loop_interval_r=8 * 8 + 8 - 10,
+                                                max_num_new_tokens=1, guidance_scale=3.0, seed=0,
+                                                multi_token_init_scheme="random", do_cfg=True,
+                                                prefix_token_sampler_scheme="jacobi")),
+    "lumina_jacobi_sample_w8": dict(V=9216, sharp=16.0, grammar="lumina", image_top_k=2000, text_top_k=10,
+                                    prompt=[1, 100, 200, 8197, 8808, 8808], img_vocab=[4, 8196], do_sample=True,
+                                    eos=[8710], max_length=6 + 8 * 9 + 3,
+                                    jacobi=dict(jacobi_loop_interval_l=3, jacobi_loop_interval_r=8 * 8 + 8 - 10,
+                                                max_num_new_tokens=8, guidance_scale=3.0, seed=1,
+                                                multi_token_init_scheme="random", do_cfg=True,
+                                                prefix_token_sampler_scheme="jacobi")),
+    "lumina_spec_greedy_w8": dict(V=9216, sharp=16.0, grammar="lumina", image_top_k=2000, text_top_k=10,
+                                  prompt=[1, 100, 200, 8197, 8808, 8808], img_vocab=[4, 8196], do_sample=False,
+                                  eos=[8710], max_length=6 + 8 * 9 + 3,
+                                  jacobi=dict(jacobi_loop_interval_l=3, jacobi_loop_interval_r=8 * 8 + 8 - 10,
+                                              max_num_new_tokens=8, guidance_scale=3.0, seed=2,
+                                              multi_token_init_scheme="random", do_cfg=True,
+                                              prefix_token_sampler_scheme="speculative_jacobi")),
+    "lumina_spec_nocfg_w4": dict(V=9216, sharp=16.0, grammar="lumina", image_top_k=50, text_top_k=10,
+                                 prompt=[1, 8197, 8806, 8806], img_vocab=[4, 8196], do_sample=True, eos=[8710],
+                                 max_length=4 + 4 * 5 + 3,
+                                 jacobi=dict(jacobi_loop_interval_l=2, jacobi_loop_interval_r=4 * 4 + 4 - 3,
+                                             max_num_new_tokens=4, guidance_scale=1.0, seed=5,
+                                             multi_token_init_scheme="random", do_cfg=True,
+                                             prefix_token_sampler_scheme="speculative_jacobi")),
+    "plain_topk_spec_w16": dict(V=1024, sharp=12.0, grammar="plain", image_top_k=100, text_top_k=10,
+                                prompt=[207], img_vocab=[0, 1024], do_sample=True, eos=[], max_length=120,
+                                jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=100,
+                                            max_num_new_tokens=16, guidance_scale=4.0, seed=0,
+                                            multi_token_init_scheme="repeat_horizon", do_cfg=True,
+                                            prefix_token_sampler_scheme="speculative_jacobi")),
+}
+
+
+def mint_loops(out_dir: Path):
+    Cache = apply_shims()
+    for name, case in LOOP_CASES.items():
+        res = run_reference_loop(case, Cache)
+        nfe = len(res["trace"])
+        n_new = len(res["ids"]) - len(case["prompt"])
+        print(f"{name}: {n_new} new tokens in {nfe} NFE ({n_new / nfe:.2f} tok/iter)")
+        with open(out_dir / f"sjd_loop_{name}.json", "w") as f:
+            json.dump({"case": case, "result": res,
+                       "minted_with": {"torch": torch.__version__, "reference": "tyshiwo1/Accelerating-T2I-AR-with-SJD@b389cfb"}},
+                      f, separators=(",", ":"))
+
+
+if __name__ == "__main__":
+    out = REPO / "tests" / "golden"
+    out.mkdir(parents=True, exist_ok=True)
+    which = sys.argv[1:] or ["loops", "forward"]
+    if "loops" in which:
+        mint_loops(out)
+    if "forward" in which:
+        from oracle.mint_forward import mint_forward
+        mint_forward(out)

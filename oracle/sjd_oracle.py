@@ -213,6 +213,127 @@ def verify(logits: np.ndarray, W: int, desc: dict, draft: np.ndarray, q_rows: li
             rs = (rs / F32(temperature)).astype(F32)
         rs = topk_filter(rs, rdesc["top_k"])
         rp = softmax(rs)
-        tokens[i - 1] = int(multinomial1(rp, noise_e2[None, :])[0])
+        e2 = noise_e2() if callable(noise_e2) else noise_e2   # callable: drawn only now, like the reference
+        tokens[i - 1] = int(multinomial1(rp, np.asarray(e2, F32).reshape(1, -1))[0])
         break
     return VerifyResult(first, rejected, tokens, nxt, p, text_mode)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the decode loop: JacobiSampler._sample (jacobi_iteration_lumina_mgpt.py:912-1249) restated
+# ---------------------------------------------------------------------------------------------------
+@dataclass
+class OracleParams:
+    """_init_new_params (:865-910)"""
+    jacobi_loop_interval_l: int = 1
+    jacobi_loop_interval_r: int = (768 // 16) ** 2 + 768 // 16
+    max_num_new_tokens: int = 16
+    guidance_scale: float = 3.0
+    seed: int | None = 42
+    multi_token_init_scheme: str = "random"
+    do_cfg: bool = True
+    prefix_token_sampler_scheme: str = "speculative_jacobi"
+
+
+class TorchNoise:
+    """Draws noise with torch exactly where the reference does:
+    CPU-global randint for fresh drafts (:505-509); generator exponential_ inside torch.multinomial (:118);
+    generator rand([B,W,V]) (:260); generator exponential_ for the residual multinomial only on rejection (:237)."""
+
+    def __init__(self, seed, device="cpu"):
+        import random
+        import torch
+        self.torch = torch
+        self.g = None
+        if seed is not None:  # set_seed (:36-45) + per-call generator (:1021-1023)
+            random.seed(seed)
+            np.random.seed(seed)
+            torch.manual_seed(seed)
+            self.g = torch.Generator(device).manual_seed(seed)
+        self.device = device
+
+    def randint(self, high, n):
+        return self.torch.randint(0, high, (1, n))[0].numpy()
+
+    def exponential(self, W, V):
+        return self.torch.empty((W, V), dtype=self.torch.float32, device=self.device).exponential_(
+            1.0, generator=self.g).cpu().numpy()
+
+    def uniform(self, W, V):
+        return self.torch.rand((1, W, V), dtype=self.torch.float32, device=self.device,
+                               generator=self.g)[0].cpu().numpy()
+
+
+def decode(logits_fn, input_ids, *, params: OracleParams, grammar, img_vocab, max_length, eos_ids=(), rows=2,
+           do_sample=True, temperature=1.0, noise=None, max_trips=None, trace=None, stop_fn=None):
+    """Run the SJD loop.  logits_fn(row_tokens: list[list[int]], kv_len: int, n_logit: int) -> float32
+    [rows * n_logit, V] is the model forward for one window (tokens at cache slots kv_len..); the loop handles
+    window construction (:606-740), draft bookkeeping (:378-430), the window-size rule (:1142-1144) and stopping
+    (:1200-1203).  Returns (ids, nfe)."""
+    p = params
+    ids = [int(t) for t in input_ids]
+    cur_len = len(ids)
+    do_cfg = bool(p.do_cfg) and p.guidance_scale != 1 and rows == 2
+    noise = noise or TorchNoise(p.seed)
+    lr = (cur_len + p.jacobi_loop_interval_l, cur_len + p.jacobi_loop_interval_r)
+    out_W = 1
+    carried_tokens: list[int] = []
+    carried_q: list = []          # distributions the carried drafts were sampled from
+    kv_len = 0
+    nfe = 0
+    first = True
+    img_vocab = np.asarray(img_vocab)
+    while True:
+        if first:
+            window, q_rows = list(ids), [None] * len(ids)
+        else:
+            n_fill = out_W - 1
+            keep_t, keep_q = carried_tokens[:n_fill], carried_q[:n_fill]
+            n_rand = max(n_fill - len(carried_tokens), 0)
+            fresh = [int(img_vocab[j]) for j in noise.randint(len(img_vocab), n_rand)] if n_rand > 0 else []
+            window = [ids[-1]] + keep_t + fresh
+            q_rows = [None] + keep_q + [None] * n_rand
+        W = len(window)
+        desc = grammar.describe(ids, out_W)
+        logits = logits_fn([window] * rows, kv_len, out_W)
+        V = logits.shape[-1]
+        wv, qv = window[-out_W:], q_rows[-out_W:]
+        e1 = noise.exponential(out_W, V) if do_sample else None
+        u = e2 = None
+        if out_W > 1 and p.prefix_token_sampler_scheme == "speculative_jacobi":
+            rs = noise.uniform(out_W, V)
+            u = rs[np.arange(out_W), np.asarray(wv)]
+
+        def lazy_e2():  # the residual noise is drawn only if a rejection happens (:237-240)
+            return noise.exponential(1, V)[0]
+
+        def resid_desc(accepted):
+            d = grammar.describe(ids + accepted, 1)
+            d["text_mode"] = not d["in_image"]
+            return d
+        res = verify(logits, out_W, desc, np.asarray(wv), qv, has_uncond=(rows == 2),
+                     apply_cfg=do_cfg and not desc["no_cfg"], guidance=p.guidance_scale, temperature=temperature,
+                     do_sample=do_sample, scheme=p.prefix_token_sampler_scheme, noise_e1=e1, noise_u=u,
+                     noise_e2=lazy_e2, residual_desc_fn=resid_desc)
+        if first or out_W <= 1:
+            new, n_cached = [int(res.tokens[-1])], W
+            carried_tokens, carried_q = [], []
+        else:
+            m = res.matched
+            new, n_cached = [int(t) for t in res.tokens[:m]], m
+            carried_tokens = [int(t) for t in res.tokens[m:]]
+            carried_q = [res.p[j] for j in range(m, out_W)]
+        next_W = min(p.max_num_new_tokens, lr[1] - cur_len) if (lr[0] <= cur_len < lr[1]) else 1
+        if trace is not None:
+            trace.append({"W": W, "n_new": len(new), "rejected": int(res.rejected), "tokens": list(new)})
+        ids += new
+        kv_len += n_cached
+        out_W = next_W
+        cur_len = len(ids)
+        nfe += 1
+        first = False
+        if ids[-1] in set(eos_ids) or cur_len >= max_length or (stop_fn and stop_fn(ids)):
+            break
+        if max_trips is not None and nfe >= max_trips:
+            break
+    return ids, nfe

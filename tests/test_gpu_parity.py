@@ -1,0 +1,302 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libsjd_b200.so; the oracle (oracle/) is only the checker.
+
+  * GEMM (tcgen05 stream-K)            vs torch fp32 matmul of the same bf16 operands      (tolerance: fp32 sum order)
+  * verify kernels                      vs oracle.sjd_oracle.verify                         (tokens / counts bit-exact)
+  * SJD loop (engine + verify kernels)  vs fixtures minted from the UNMODIFIED reference    (token-exact, trace-exact)
+  * window forward                      vs oracle.ref_forward.RefStack (bf16-emulating)     (<= 2 bf16 ulp of logits)
+  * full engine on a tiny real stack    vs oracle loop replaying the engine's own logits    (token-exact)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_loop_goldens
+
+pytestmark = pytest.mark.gpu
+
+GOLD = load_loop_goldens()
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import sjd_b200  # noqa: F401
+    from sjd_b200 import _lib, engine, families, model
+    from oracle import fake_lm, ref_forward, sjd_oracle
+    return dict(lib=_lib.lib(), _lib=_lib, engine=engine, model=model, families=families, O=sjd_oracle,
+                RF=ref_forward, fake=fake_lm, dev=torch.device("cuda:0"))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("N,K,M", [(128, 64, 16), (256, 128, 1), (384, 256, 32), (1000, 256, 48), (2304, 768, 32),
+                                   (4096, 4096, 64), (4096, 4096, 256), (12288, 4096, 64), (22016, 4096, 64),
+                                   (4096, 11008, 64), (16384, 768, 32), (5000, 512, 80)])
+def test_gemm_matches_fp32_reference(env, N, K, M):
+    L, _lib, dev = env["lib"], env["_lib"], env["dev"]
+    torch.manual_seed(N * 7 + K + M)
+    m_tile = (M + 15) // 16 * 16
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    x = torch.zeros(m_tile, K, device=dev, dtype=torch.bfloat16)
+    x[:M] = torch.randn(M, K, device=dev).bfloat16()
+    ws = torch.empty(L.sjd_gemm_workspace_bytes(N, K, m_tile, 0) // 4, device=dev, dtype=torch.float32)
+    out = torch.empty(M, N, device=dev, dtype=torch.float32)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), m_tile, m_tile, ws.data_ptr(), 0, st), "gemm")
+    _lib.check(L.sjd_gemm_reduce_f32(ws.data_ptr(), N, K, m_tile, 0, out.data_ptr(), M, 0, st), "reduce")
+    torch.cuda.synchronize()
+    ref = x[:M].double() @ w.double().T
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 2e-5 * max(1.0, ref.abs().max().item()) * (K / 64) ** 0.5, f"max abs err {err}"
+
+
+def test_gemm_stream_k_grid_independence(env):
+    """The stream-K split must not change results beyond fp32 summation order, for any CTA count."""
+    L, _lib, dev = env["lib"], env["_lib"], env["dev"]
+    N, K, M, m_tile = 1536, 1024, 40, 48
+    torch.manual_seed(3)
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    x = torch.zeros(m_tile, K, device=dev, dtype=torch.bfloat16)
+    x[:M] = torch.randn(M, K, device=dev).bfloat16()
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for grid in (1, 7, 37, 148, 0):
+        ws = torch.empty(L.sjd_gemm_workspace_bytes(N, K, m_tile, grid) // 4, device=dev, dtype=torch.float32)
+        out = torch.empty(M, N, device=dev, dtype=torch.float32)
+        _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), m_tile, m_tile, ws.data_ptr(), grid, st), "gemm")
+        _lib.check(L.sjd_gemm_reduce_f32(ws.data_ptr(), N, K, m_tile, grid, out.data_ptr(), M, 0, st), "reduce")
+        outs.append(out)
+    torch.cuda.synchronize()
+    ref = x[:M].float() @ w.float().T
+    for o in outs:
+        assert (o - ref).abs().max().item() < 1e-4
+    # same grid twice -> bit identical (deterministic reduction order)
+    ws = torch.empty(L.sjd_gemm_workspace_bytes(N, K, m_tile, 0) // 4, device=dev, dtype=torch.float32)
+    out2 = torch.empty(M, N, device=dev, dtype=torch.float32)
+    _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), m_tile, m_tile, ws.data_ptr(), 0, st), "gemm")
+    _lib.check(L.sjd_gemm_reduce_f32(ws.data_ptr(), N, K, m_tile, 0, out2.data_ptr(), M, 0, st), "reduce")
+    torch.cuda.synchronize()
+    assert torch.equal(outs[-1], out2)
+
+
+# ---------------------------------------------------------------------------------------------- verify
+def _verify_case(env, seed, *, W=8, V=9216, scheme="speculative_jacobi", do_sample=True, guidance=3.0,
+                 has_uncond=True, apply_cfg=True, temperature=1.0, top_k=2000, grammar=True, u_scale=1.0):
+    O, dev, engine = env["O"], env["dev"], env["engine"]
+    rng = np.random.default_rng(seed)
+    logits = (rng.standard_normal(((2 if has_uncond else 1) * W, V)) * 1.5).astype(np.float32)
+    if grammar:
+        g = O.LuminaGrammar(image_top_k=top_k)
+        ids = [1, 100, 8197, 8808, 8808] + [int(x) for x in rng.integers(4, 8196, size=seed % 11)]
+        desc = g.describe(ids, W)
+    else:
+        desc = {"allow": None, "forced": [-1] * W, "top_k": top_k, "in_image": True, "no_cfg": False}
+    # distributions of this trip, to build plausible drafts: draft[i] ~ p[i-1], q = a perturbed p[i-1]
+    s = O.logits_to_probs(logits, W, desc, has_uncond=has_uncond, apply_cfg=apply_cfg, guidance=guidance,
+                          temperature=temperature)
+    p = O.softmax(s)
+    draft = rng.integers(4, 8196, size=W).astype(np.int64)
+    p_prev = np.zeros((W, V), np.float32)
+    q_rows, q_idx = [None] * W, [-1] * W
+    for i in range(1, W):
+        if rng.random() < 0.75:
+            pert = s[i - 1] + (rng.standard_normal(V) * 0.7).astype(np.float32)
+            p_prev[i] = O.softmax(pert[None])[0]
+            draft[i] = int(np.argmax(p_prev[i] / rng.exponential(size=V)))
+            q_rows[i], q_idx[i] = p_prev[i], i
+    e1 = rng.exponential(size=(W, V)).astype(np.float32)
+    u = (rng.random(W) * u_scale).astype(np.float32)
+    e2 = rng.exponential(size=V).astype(np.float32)
+    ref = O.verify(logits, W, desc, draft, q_rows, has_uncond=has_uncond, apply_cfg=apply_cfg, guidance=guidance,
+                   temperature=temperature, do_sample=do_sample, scheme=scheme, noise_e1=e1, noise_u=u, noise_e2=e2)
+    t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev) if dt is None else \
+        torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
+    out = engine.verify_call(t(logits), W, V, desc, t(draft, torch.int32), torch.tensor(q_idx, dtype=torch.int32, device=dev),
+                             t(p_prev), has_uncond=has_uncond, apply_cfg=apply_cfg, guidance=guidance,
+                             temperature=temperature, do_sample=do_sample, scheme=0 if scheme == "speculative_jacobi" else 1,
+                             noise_e1=t(e1), noise_u=t(u), noise_e2=t(e2), eoi_token=8196, text_top_k=10)
+    torch.cuda.synchronize()
+    return ref, out
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_verify_speculative_matches_oracle(env, seed):
+    ref, out = _verify_case(env, seed, u_scale=0.6 if seed % 3 else 1.0)
+    assert out["matched"] == ref.matched
+    assert out["rejected"] == ref.rejected
+    assert out["tokens"].cpu().numpy().tolist() == ref.tokens.tolist()
+    assert out["next_tokens"].cpu().numpy().tolist() == ref.next_tokens.tolist()
+    p = out["p"].cpu().numpy()
+    assert np.array_equal(p > 0, ref.p > 0), "top-k / grammar support differs"
+    assert np.abs(p - ref.p).max() <= 1e-6
+
+
+def test_verify_covers_accepts_and_rejects(env):
+    """The seeded cases above must exercise both outcomes, else the parity claim is hollow."""
+    ms = [_verify_case(env, s, u_scale=0.6 if s % 3 else 1.0)[0].matched for s in range(12)]
+    assert max(ms) >= 3 and min(ms) == 1, ms
+
+
+@pytest.mark.parametrize("kw", [
+    dict(scheme="jacobi", do_sample=False), dict(scheme="jacobi", do_sample=True),
+    dict(do_sample=False), dict(apply_cfg=False), dict(has_uncond=False, apply_cfg=False),
+    dict(temperature=0.7), dict(top_k=0), dict(top_k=1), dict(top_k=50, grammar=False, V=1024),
+    dict(W=1), dict(W=32, V=16384, grammar=False, top_k=1000), dict(W=16, V=65536), dict(u_scale=0.05),
+])
+def test_verify_variants_match_oracle(env, kw):
+    for seed in (1, 2, 3):
+        ref, out = _verify_case(env, 100 + seed, **kw)
+        assert out["matched"] == ref.matched, kw
+        assert out["tokens"].cpu().numpy().tolist() == ref.tokens.tolist(), kw
+        assert np.abs(out["p"].cpu().numpy() - ref.p).max() <= 1e-6
+
+
+def test_verify_topk_ties_and_small_support(env):
+    """Ties with the k-th largest score are kept; k beyond the finite support removes nothing."""
+    O, dev, engine = env["O"], env["dev"], env["engine"]
+    W, V = 2, 512
+    logits = np.full((W, V), -3.0, np.float32)
+    logits[0, [5, 9, 17, 33]] = [2.0, 1.0, 1.0, 1.0]      # k = 2 -> the three tied 1.0 stay
+    logits[1, :] = -np.inf
+    logits[1, [7, 8]] = [0.5, 0.25]                        # two finite entries, k = 2
+    desc = {"allow": None, "forced": [-1, -1], "top_k": 2}
+    e1 = np.ones((W, V), np.float32)
+    ref = O.verify(logits, W, desc, np.array([0, 5]), [None, None], has_uncond=False, apply_cfg=False, guidance=1.0,
+                   do_sample=True, scheme="jacobi", noise_e1=e1)
+    out = engine.verify_call(torch.from_numpy(logits).to(dev), W, V, desc, torch.tensor([0, 5], dtype=torch.int32, device=dev),
+                             None, None, has_uncond=False, apply_cfg=False, guidance=1.0, temperature=1.0,
+                             do_sample=True, scheme=1, noise_e1=torch.from_numpy(e1).to(dev))
+    p = out["p"].cpu().numpy()
+    assert (p[0] > 0).sum() == 4 and (p[1] > 0).sum() == 2
+    assert np.abs(p - ref.p).max() <= 1e-6
+    assert out["tokens"].cpu().numpy().tolist() == ref.tokens.tolist()
+
+
+# ---------------------------------------------------------------------------- SJD loop vs the reference
+class _FakeStack:
+    def __init__(self, V, rows, dev, max_len=4096):
+        from types import SimpleNamespace
+        self.shape = SimpleNamespace(vocab=V)
+        self.rows, self.device, self.max_len = rows, dev, max_len
+
+
+def _engine_for_case(env, case, noise_dev="cpu"):
+    engine, fake, dev = env["engine"], env["fake"], env["dev"]
+    j = case["jacobi"]
+    do_cfg = j["do_cfg"] and j["guidance_scale"] != 1
+    rows = 2 if do_cfg else 1
+    if case["grammar"] == "lumina":
+        grammar = engine.LuminaGrammarState(image_top_k=case["image_top_k"], text_top_k=case["text_top_k"])
+    else:
+        grammar = engine.PlainTopKState(top_k=case["image_top_k"])
+
+    class Eng(engine.SJDEngine):
+        def _forward(self, row_tokens, kv_len, kv_lo, n_logit, embeds=None):
+            lg = fake.fake_logits(row_tokens, kv_len, n_logit, case["V"], case["sharp"])
+            return torch.from_numpy(lg).to(dev).view(len(row_tokens), n_logit, case["V"])
+
+    params = engine.SJDParams(**j)
+    return Eng(_FakeStack(case["V"], rows, dev), params, grammar, torch.arange(*case["img_vocab"]),
+               noise_factory=lambda seed, d: engine.NoiseSource(seed, d, gen_device=noise_dev))
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_engine_loop_reproduces_reference_tokens(env, name):
+    """Host loop + CUDA verify kernels, fed the reference's logits and the reference's CPU noise stream, must emit
+    the reference's exact token sequence and accepted-count trace."""
+    g = GOLD[name]
+    case, ref = g["case"], g["result"]
+    eng = _engine_for_case(env, case)
+    ids = eng.generate(case["prompt"], max_length=case["max_length"], eos_token_ids=case["eos"],
+                       do_sample=case["do_sample"], collect_trace=True)
+    assert [t[1] for t in eng.stats.trace] == [t["n_new"] for t in ref["trace"]]
+    assert [t[0] for t in eng.stats.trace] == [t["W"] for t in ref["trace"]]
+    assert ids == ref["ids"]
+    assert eng.stats.nfe == len(ref["trace"])
+
+
+# ------------------------------------------------------------------------------------------ forward
+def _family(env, name):
+    RF = env["RF"]
+    if name == "chameleon":
+        return RF.StackConfig(2, 256, 2, 2, 128, 512, 9216, 1e-5, qk_norm=True), \
+            RF.rope_tables_rotate_half(128, 512, 10000.0, True), [0, 36]
+    if name == "llamagen":
+        return RF.StackConfig(3, 256, 4, 4, 64, 768, 1024, 1e-5, rope_interleaved=True, family="llamagen"), \
+            RF.rope_tables_llamagen_2d(24, 64, 10000, 1), [0, 0]
+    return RF.StackConfig(2, 512, 4, 1, 128, 1024, 5000, 1e-5, family="emu3", rope_theta=1e6), \
+        RF.rope_tables_rotate_half(128, 512, 1e6, True), [0, 5]
+
+
+@pytest.mark.parametrize("family", ["chameleon", "llamagen", "emu3"])
+def test_window_forward_matches_reference_stack(env, family):
+    """Prefill, an AR step, two Jacobi windows with a 9-token roll-back in between, and a short window —
+    logits within 2 bf16 ulp of the bf16-emulating fp32 reference, mean error well below one ulp."""
+    RF, model, dev = env["RF"], env["model"], env["dev"]
+    cfg, (cos, sin), kv_lo = _family(env, family)
+    w = RF.random_weights(cfg, seed=1, device=dev)
+    rows, max_len = 2, 320
+    shape = model.StackShape(cfg.n_layers, cfg.d_model, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cfg.d_ff,
+                             cfg.vocab, cfg.rms_eps, cfg.qk_norm, cfg.rope_interleaved)
+    ds = model.DeviceStack(shape, w, cos, sin, rows, max_len, dev)
+    ref = RF.RefStack(cfg, w, cos.to(dev), sin.to(dev), rows, max_len, emulate_bf16=True)
+    g = torch.Generator().manual_seed(5)
+    kv_len = 0
+    for step, W in enumerate([37, 1, 16, 16, 5, 128]):
+        if step == 3:
+            kv_len -= 9
+        ids = torch.randint(0, cfg.vocab, (rows, W), generator=g).to(dev)
+        pos = torch.arange(kv_len, kv_len + W, device=dev)[None].repeat(rows, 1)
+        rope_pos = torch.stack([(pos[b] - kv_lo[b]).clamp(min=0) for b in range(rows)])
+        n = 1 if step == 0 else W
+        lg = ds.forward(W, rope_pos.int().flatten().contiguous(), pos.int().flatten().contiguous(), kv_len, kv_lo,
+                        ids=ids.int().flatten().contiguous(), n_logit_tokens=n).clone()
+        lr = ref.forward(ids=ids, rope_pos=rope_pos, kv_len=kv_len, kv_lo=kv_lo, cache_pos=pos, n_logit_tokens=n)
+        torch.cuda.synchronize()
+        ulp = 2.0 ** (torch.floor(torch.log2(lr.abs().clamp(min=1e-3))) - 7)
+        assert ((lg - lr).abs() <= 2.0 * ulp + 1e-6).all(), f"{family} step {step}: max {(lg - lr).abs().max().item()}"
+        assert (lg - lr).abs().mean().item() < 2e-3
+        kv_len += W
+    ds.close()
+
+
+def test_engine_on_real_stack_matches_oracle_replay(env):
+    """Tiny Chameleon-shaped stack, real kernels end to end.  The oracle loop is replayed on the logits the
+    engine's forward produced (captured per trip) with the same CPU noise stream: tokens must be identical."""
+    RF, model, engine, O, dev = env["RF"], env["model"], env["engine"], env["O"], env["dev"]
+    cfg, (cos, sin), _ = _family(env, "chameleon")
+    w = RF.random_weights(cfg, seed=4, std=0.08, device=dev)
+    shape = model.StackShape(cfg.n_layers, cfg.d_model, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cfg.d_ff,
+                             cfg.vocab, cfg.rms_eps, cfg.qk_norm, cfg.rope_interleaved)
+    ds = model.DeviceStack(shape, w, cos, sin, 2, 256, dev)
+    captured = []
+
+    class Eng(engine.SJDEngine):
+        def _forward(self, row_tokens, kv_len, kv_lo, n_logit, embeds=None):
+            lg = super()._forward(row_tokens, kv_len, kv_lo, n_logit, embeds)
+            captured.append((len(row_tokens[0]), kv_len, n_logit, lg.detach().cpu().numpy().reshape(-1, cfg.vocab).copy()))
+            return lg
+
+    prompt = [1, 100, 200, 300, 8197, 8808, 8808]
+    kw = dict(jacobi_loop_interval_l=3, jacobi_loop_interval_r=8 * 8 + 8 - 10, max_num_new_tokens=8, guidance_scale=3.0,
+              seed=0, multi_token_init_scheme="random", do_cfg=True, prefix_token_sampler_scheme="speculative_jacobi")
+    eng = Eng(ds, engine.SJDParams(**kw), engine.LuminaGrammarState(), torch.arange(4, 8196),
+              noise_factory=lambda seed, d: engine.NoiseSource(seed, d, gen_device="cpu"))
+    max_len = len(prompt) + 8 * 9 + 2
+    ids = eng.generate(prompt, max_length=max_len, eos_token_ids=[8710], kv_lo=[0, len(prompt) - 1], collect_trace=True)
+    it = iter(captured)
+
+    def replay(rows_tokens, kv_len, n):
+        W, kv, nn, lg = next(it)
+        assert (W, kv, nn) == (len(rows_tokens[0]), kv_len, n), "oracle and engine disagree on the window schedule"
+        return lg
+
+    ids_o, nfe_o = O.decode(replay, prompt, params=O.OracleParams(**kw), grammar=O.LuminaGrammar(),
+                            img_vocab=np.arange(4, 8196), max_length=max_len, eos_ids=[8710], rows=2)
+    assert ids == ids_o and eng.stats.nfe == nfe_o
+    # grammar sanity on real kernels: EOL every 9th image token, EOI after 8 rows
+    img = ids[len(prompt):]
+    assert all(img[i] == 8803 for i in range(8, 72, 9)) and img[72] == 8196
+    assert eng.stats.nfe < len(img), "Jacobi decoding must need fewer forwards than tokens"
+    ds.close()
