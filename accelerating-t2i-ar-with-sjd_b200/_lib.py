@@ -111,17 +111,13 @@ def lib() -> C.CDLL:
     L.sjd_last_error.restype = C.c_char_p
     L.sjd_device_sm_count.restype = C.c_int
     L.sjd_launch_count.restype = C.c_uint64
+    L.sjd_debug_gemm_stamps.restype = None
+    L.sjd_debug_gemm_stamps.argtypes = [C.c_void_p, C.c_int]
     L.sjd_gemm_workspace_bytes.restype = C.c_size_t
     L.sjd_gemm_workspace_bytes.argtypes = [C.c_int] * 4
     L.sjd_gemm_bf16.restype = C.c_int
     L.sjd_gemm_bf16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
-                                C.c_void_p]
-    L.sjd_gemm_reduce_bf16.restype = C.c_int
-    L.sjd_gemm_reduce_bf16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
-                                       C.c_void_p]
-    L.sjd_gemm_reduce_f32.restype = C.c_int
-    L.sjd_gemm_reduce_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
-                                      C.c_void_p]
+                                C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     L.sjd_verify.restype = C.c_int
     L.sjd_verify.argtypes = [C.POINTER(VerifyArgs), C.c_void_p]
     L.sjd_ctx_create.restype = C.c_int

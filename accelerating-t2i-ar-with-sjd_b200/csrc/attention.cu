@@ -61,6 +61,8 @@ template <int DH>
 __global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
   constexpr int ROWB = DH * 2 + 16;  // padded smem row (bytes): conflict-free ldmatrix
   extern __shared__ __align__(16) uint8_t smem[];
+  pdl_wait();
+  pdl_launch_dependents();
   uint8_t* sK = smem;
   uint8_t* sV = smem + kAttnChunk * ROWB;
 
@@ -212,6 +214,8 @@ __global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
 // One warp per (row b, head, query i): merge chunk partials, normalise, write bf16.
 template <int DH>
 __global__ void __launch_bounds__(256) attn_combine_kernel(AttnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int widx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int total = p.rows * p.H * p.W;
@@ -250,20 +254,21 @@ int attn_launch(const AttnParams& p, int head_dim, cudaStream_t stream) {
   dim3 grid(p.n_chunks, p.Hkv, p.rows);
   const int total = p.rows * p.H * p.W;
   dim3 cgrid((total + 7) / 8);
+  int rc = 0;
   if (head_dim == 128) {
     constexpr int smem = 2 * kAttnChunk * (128 * 2 + 16);
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(attn_window_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
-    attn_window_kernel<128><<<grid, nwarps * 32, smem, stream>>>(p);
-    attn_combine_kernel<128><<<cgrid, 256, 0, stream>>>(p);
+    rc |= launch_pdl(attn_window_kernel<128>, grid, dim3(nwarps * 32), smem, stream, p);
+    rc |= launch_pdl(attn_combine_kernel<128>, cgrid, dim3(256), 0, stream, p);
   } else if (head_dim == 64) {
     constexpr int smem = 2 * kAttnChunk * (64 * 2 + 16);
-    attn_window_kernel<64><<<grid, nwarps * 32, smem, stream>>>(p);
-    attn_combine_kernel<64><<<cgrid, 256, 0, stream>>>(p);
+    rc |= launch_pdl(attn_window_kernel<64>, grid, dim3(nwarps * 32), smem, stream, p);
+    rc |= launch_pdl(attn_combine_kernel<64>, cgrid, dim3(256), 0, stream, p);
   } else {
     return -3;
   }
-  return cudaGetLastError() == cudaSuccess ? 0 : -6;
+  return rc;
 }
 
 }  // namespace sjd

@@ -159,6 +159,20 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(uint32_t M, uint32_t 
 }
 
 // ----------------------------------------------------------------------------------------
+// programmatic dependent launch + cross-CTA flags
+// ----------------------------------------------------------------------------------------
+// Blocks until the kernel this one depends on has completed and its memory is visible (no-op without PDL).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the dependent kernel start being scheduled; it still synchronises with pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ----------------------------------------------------------------------------------------
 // small math helpers
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -172,6 +186,25 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ----------------------------------------------------------------------------------------
+// host: launch with the programmatic-stream-serialization attribute (kernels call pdl_wait() themselves)
+// ----------------------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+static inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...) == cudaSuccess ? 0 : -6;
 }
 
 }  // namespace sjd

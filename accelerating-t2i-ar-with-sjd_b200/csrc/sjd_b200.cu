@@ -4,13 +4,14 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <vector>
 
 #include "../../include/sjd_b200.h"
 #include "attention.cu"
 #include "block_ops.cu"
-#include "gemm_tcgen05.cu"
+#include "gemm_fused.cu"
 #include "verify.cu"
 
 namespace sjd {
@@ -26,43 +27,34 @@ static int fail(int code, const char* what) {
 
 static inline int round16(int m) { return (m + 15) & ~15; }
 
-__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int W,
-                                   int n, int d) {
-  // dst row r = b*n + t  <-  src row b*W + (W-n+t)
-  const int r = blockIdx.x, b = r / n, t = r - b * n;
-  const uint4* s = reinterpret_cast<const uint4*>(src + size_t(b * W + (W - n + t)) * d);
-  uint4* o = reinterpret_cast<uint4*>(dst + size_t(r) * d);
-  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) o[i] = s[i];
-}
-
 struct WeightMap {
   CUtensorMap map;
-  int N = 0, K = 0;
+  int N = 0, K = 0;   // per-layer rows / reduction length
   bool ok = false;
-};
-
-struct Layer {
-  sjd_layer_weights w;
-  WeightMap qkv, o, gate_up, down;
-  bool set = false;
 };
 
 }  // namespace sjd
 
 struct sjd_ctx {
   sjd_model_cfg cfg;
-  std::vector<sjd::Layer> layers;
-  const __nv_bfloat16* embed = nullptr;
-  const __nv_bfloat16* final_norm = nullptr;
-  const float* rope_cos = nullptr;
-  const float* rope_sin = nullptr;
-  sjd::WeightMap lm_head;
-  // device buffers
+  std::vector<char> layer_set;
+  bool globals_set = false, have_embed = false;
+  // ---- context-owned, re-laid-out weights (one buffer per projection type, layers stacked along rows) ----
+  __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr;   // [L*N, K]
+  __nv_bfloat16 *attn_norm = nullptr, *ffn_norm = nullptr;                          // [L, d]
+  __nv_bfloat16 *qn_w = nullptr, *qn_b = nullptr, *kn_w = nullptr, *kn_b = nullptr; // [L, H|Hkv, Dh]
+  __nv_bfloat16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
+  float *rope_cos = nullptr, *rope_sin = nullptr;
+  sjd::WeightMap m_qkv, m_o, m_gu, m_down, m_head;
+  // ---- activations / caches / workspace ----
   __nv_bfloat16 *h = nullptr, *xn = nullptr, *q = nullptr, *attn = nullptr, *act = nullptr, *xl = nullptr;
   __nv_bfloat16 *kcache = nullptr, *vcache = nullptr;
-  float *ws = nullptr, *part_o = nullptr, *part_ml = nullptr;
-  size_t ws_floats = 0, bytes = 0;
-  int max_chunks = 0;
+  uint8_t* ws = nullptr;
+  float *part_o = nullptr, *part_ml = nullptr;
+  int32_t *pos_zero = nullptr, *pos_last = nullptr;   // [SJD_MAX_TOKENS] dummies for sjd_ctx_gemm_only
+  size_t ws_bytes = 0, bytes = 0;
+  int max_chunks = 0, arrive_cap = 0;
+  std::vector<void*> allocs;
   // activation tensor maps per m_tile (index m_tile/16), built lazily
   CUtensorMap xmap_xn[17], xmap_attn[17], xmap_act[17], xmap_xl[17];
   bool xmap_ok[17] = {false};
@@ -70,10 +62,14 @@ struct sjd_ctx {
 
 namespace sjd {
 
-static int dmalloc(sjd_ctx* c, void** p, size_t bytes) {
-  if (cudaMalloc(p, bytes) != cudaSuccess) return SJD_E_ALLOC;
-  cudaMemset(*p, 0, bytes);
+template <typename T>
+static int dmalloc(sjd_ctx* c, T** p, size_t bytes) {
+  void* v = nullptr;
+  if (cudaMalloc(&v, bytes ? bytes : 16) != cudaSuccess) return SJD_E_ALLOC;
+  cudaMemset(v, 0, bytes ? bytes : 16);
   c->bytes += bytes;
+  c->allocs.push_back(v);
+  *p = static_cast<T*>(v);
   return 0;
 }
 
@@ -90,44 +86,38 @@ static int ensure_xmaps(sjd_ctx* c, int m_tile) {
   return 0;
 }
 
-static int set_wmap(WeightMap* wm, const void* ptr, int N, int K) {
+static int set_wmap(WeightMap* wm, const void* ptr, int layers, int N, int K) {
   if (!ptr || K % kBlockK) return SJD_E_ARG;
-  if (make_tmap_bf16_2d(&wm->map, ptr, uint64_t(N), uint64_t(K), kBlockN)) return SJD_E_TMAP;
+  if (make_tmap_bf16_2d(&wm->map, ptr, uint64_t(layers) * uint64_t(N), uint64_t(K), kBlockN)) return SJD_E_TMAP;
   wm->N = N;
   wm->K = K;
   wm->ok = true;
   return 0;
 }
 
-// one GEMM of the stack: weights map x activation map -> stream-K partials in c->ws
-static int run_gemm(sjd_ctx* c, const WeightMap& wm, const CUtensorMap& xmap, int m_tile, StreamK* sk_out,
+// workspace pointers of one GEMM launch inside the context's workspace
+static void bind_ws(sjd_ctx* c, const StreamK& sk, GemmEpi* ep) {
+  const GemmWorkspace w = gemm_workspace(sk, c->arrive_cap);
+  ep->ws = reinterpret_cast<float*>(c->ws + w.slots_off);
+  ep->ssq = reinterpret_cast<float*>(c->ws + w.ssq_off);
+  ep->tile_arrive = reinterpret_cast<uint32_t*>(c->ws + w.arrive_off);
+  ep->ctr = reinterpret_cast<uint32_t*>(c->ws + w.ctr_off);
+}
+
+// one GEMM of the stack: stacked weights (layer `layer`) x activation map, fused epilogue `ep`
+static int run_gemm(sjd_ctx* c, const WeightMap& wm, int layer, const CUtensorMap& xmap, int m_tile, GemmEpi ep,
                     cudaStream_t s) {
   GemmLaunch g;
   g.tmap_w = wm.map;
   g.tmap_x = xmap;
+  g.w_row0 = layer * wm.N;
   g.sk = gemm_partition(wm.N, wm.K, m_tile, 0);
-  if (g.sk.ws_floats() > c->ws_floats) return SJD_E_ARG;
-  const uint32_t stage_bytes = kATileBytes + uint32_t(m_tile) * kBlockK * 2;
-  int stages = int((200u * 1024u) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  g.num_stages = stages;
-  uint32_t cols = 32;
-  while (cols < uint32_t(2 * m_tile)) cols <<= 1;
-  g.tmem_cols = cols;
-  g.smem_bytes = uint32_t(stages) * stage_bytes + 1024;
-  *sk_out = g.sk;
+  if (gemm_shape(&g, m_tile)) return SJD_E_SMEM;
+  if (gemm_workspace(g.sk, c->arrive_cap).bytes > c->ws_bytes) return SJD_E_ARG;
+  ep.N = wm.N;
+  bind_ws(c, g.sk, &ep);
   g_launches++;
-  return gemm_launch(&g, c->ws, s);
-}
-
-static int gemm_attr_once() {
-  static int rc = 1;
-  if (rc == 1)
-    rc = cudaFuncSetAttribute(gemm_streamk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) ==
-                 cudaSuccess
-             ? 0
-             : SJD_E_ATTR;
-  return rc;
+  return gemm_launch(&g, ep, s);
 }
 
 }  // namespace sjd
@@ -136,40 +126,51 @@ using namespace sjd;
 
 extern "C" {
 
-int sjd_version(void) { return 100; }
+int sjd_version(void) { return 200; }
 const char* sjd_last_error(void) { return g_err; }
 int sjd_device_sm_count(void) { return device_num_sms(); }
 uint64_t sjd_launch_count(void) { return g_launches.load(); }
 
-size_t sjd_gemm_workspace_bytes(int N, int K, int m_tile, int grid_limit) {
-  return gemm_partition(N, K, m_tile, grid_limit).ws_floats() * sizeof(float);
+void sjd_debug_gemm_stamps(void* device_buf, int n_launches) {
+  g_dbg_buf = static_cast<long long*>(device_buf);
+  g_dbg_cap = n_launches;
+  g_dbg_idx = 0;
 }
 
-int sjd_gemm_bf16(const void* w, int N, int K, const void* x, int x_rows, int m_tile, void* ws, int grid_limit,
-                  void* stream) {
+size_t sjd_gemm_workspace_bytes(int N, int K, int m_tile, int grid_limit) {
+  return gemm_workspace(gemm_partition(N, K, m_tile, grid_limit)).bytes;
+}
+
+int sjd_gemm_bf16(const void* w, int N, int K, const void* x, int x_rows, int M, void* out, int out_f32,
+                  int round_bf16, void* ws, int grid_limit, void* stream) {
+  if (!w || !x || !out || !ws || M < 1 || M > SJD_MAX_TOKENS) return fail(SJD_E_ARG, "sjd_gemm_bf16: bad argument");
+  const int m_tile = round16(M);
+  if (K % kBlockK != 0 || x_rows < m_tile) return fail(SJD_E_ARG, "sjd_gemm_bf16: K % 64 != 0 or x has < m_tile rows");
   if (gemm_attr_once()) return fail(SJD_E_ATTR, "cudaFuncSetAttribute(gemm)");
   GemmLaunch g;
-  int rc = gemm_prepare(&g, w, N, K, x, x_rows, m_tile, grid_limit);
-  if (rc) return fail(rc, "gemm_prepare");
+  g.w_row0 = 0;
+  g.sk = gemm_partition(N, K, m_tile, grid_limit);
+  if (gemm_shape(&g, m_tile)) return fail(SJD_E_SMEM, "sjd_gemm_bf16: shared memory");
+  if (make_tmap_bf16_2d(&g.tmap_w, w, uint64_t(N), uint64_t(K), kBlockN)) return fail(SJD_E_TMAP, "weight tensor map");
+  if (make_tmap_bf16_2d(&g.tmap_x, x, uint64_t(x_rows), uint64_t(K), uint32_t(m_tile)))
+    return fail(SJD_E_TMAP, "activation tensor map");
+  GemmEpi ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = out_f32 ? EPI_F32 : EPI_BF16;
+  ep.M = M;
+  ep.N = N;
+  ep.out = out;
+  ep.ld_out = N;
+  ep.round_bf16 = round_bf16;
+  const GemmWorkspace wl = gemm_workspace(g.sk);
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  ep.ws = reinterpret_cast<float*>(b + wl.slots_off);
+  ep.ssq = reinterpret_cast<float*>(b + wl.ssq_off);
+  ep.tile_arrive = reinterpret_cast<uint32_t*>(b + wl.arrive_off);
+  ep.ctr = reinterpret_cast<uint32_t*>(b + wl.ctr_off);
   g_launches++;
-  rc = gemm_launch(&g, static_cast<float*>(ws), static_cast<cudaStream_t>(stream));
+  const int rc = gemm_launch(&g, ep, static_cast<cudaStream_t>(stream));
   return rc ? fail(rc, "gemm_launch") : 0;
-}
-
-int sjd_gemm_reduce_bf16(const void* ws, int N, int K, int m_tile, int grid_limit, void* out, int M, void* stream) {
-  StreamK sk = gemm_partition(N, K, m_tile, grid_limit);
-  g_launches++;
-  int rc = reduce_bf16(static_cast<const float*>(ws), sk, static_cast<__nv_bfloat16*>(out), M, N,
-                       static_cast<cudaStream_t>(stream));
-  return rc ? fail(rc, "reduce_bf16") : 0;
-}
-
-int sjd_gemm_reduce_f32(const void* ws, int N, int K, int m_tile, int grid_limit, float* out, int M, int round_bf16,
-                        void* stream) {
-  StreamK sk = gemm_partition(N, K, m_tile, grid_limit);
-  g_launches++;
-  int rc = logits_reduce(static_cast<const float*>(ws), sk, out, M, N, round_bf16, static_cast<cudaStream_t>(stream));
-  return rc ? fail(rc, "logits_reduce") : 0;
 }
 
 int sjd_verify(const sjd_verify_args* a, void* stream) {
@@ -194,41 +195,76 @@ int sjd_verify(const sjd_verify_args* a, void* stream) {
 int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
   if (!cfg || !out) return fail(SJD_E_ARG, "sjd_ctx_create: null");
   const sjd_model_cfg& g = *cfg;
-  if (g.rows < 1 || g.rows > SJD_MAX_ROWS || (g.head_dim != 64 && g.head_dim != 128) || g.d_model % 64 ||
-      g.d_ff % 64 || (g.n_heads * g.head_dim) % 64 || g.n_heads % g.n_kv_heads || g.max_len < 1)
+  const int hd = g.n_heads * g.head_dim;
+  const int nqkv = (g.n_heads + 2 * g.n_kv_heads) * g.head_dim;
+  if (g.rows < 1 || g.rows > SJD_MAX_ROWS || (g.head_dim != 64 && g.head_dim != 128) || g.d_model % 128 ||
+      g.d_ff % 64 || hd % 64 || nqkv % 128 || g.n_heads % g.n_kv_heads || g.max_len < 1 || g.n_layers < 1 ||
+      g.n_rope_pos < 1)
     return fail(SJD_E_ARG, "sjd_ctx_create: unsupported shape");
+  if (!g.rope_interleaved && g.head_dim != 128)
+    return fail(SJD_E_ARG, "sjd_ctx_create: rotate-half RoPE needs head_dim 128");
+  if (g.qk_norm && (g.rope_interleaved || g.head_dim != 128))
+    return fail(SJD_E_ARG, "sjd_ctx_create: qk_norm needs head_dim 128 with rotate-half RoPE");
   if (gemm_attr_once()) return fail(SJD_E_ATTR, "cudaFuncSetAttribute(gemm)");
   sjd_ctx* c = new sjd_ctx();
   c->cfg = g;
-  c->layers.resize(g.n_layers);
-  const int hd = g.n_heads * g.head_dim;
-  const size_t T = SJD_MAX_TOKENS;
+  c->layer_set.assign(g.n_layers, 0);
+  const size_t T = SJD_MAX_TOKENS, L = g.n_layers, d = g.d_model;
   int rc = 0;
-  rc |= dmalloc(c, (void**)&c->h, T * g.d_model * 2);
-  rc |= dmalloc(c, (void**)&c->xn, T * g.d_model * 2);
-  rc |= dmalloc(c, (void**)&c->xl, T * g.d_model * 2);
-  rc |= dmalloc(c, (void**)&c->q, T * hd * 2);
-  rc |= dmalloc(c, (void**)&c->attn, T * hd * 2);
-  rc |= dmalloc(c, (void**)&c->act, T * size_t(g.d_ff) * 2);
-  const size_t cache_elems = size_t(g.n_layers) * g.rows * g.n_kv_heads * size_t(g.max_len) * g.head_dim;
-  rc |= dmalloc(c, (void**)&c->kcache, cache_elems * 2);
-  rc |= dmalloc(c, (void**)&c->vcache, cache_elems * 2);
-  // workspace: largest stream-K footprint over the GEMMs of the stack at the largest m_tile
-  size_t wsf = 0;
-  const int Ns[5] = {(g.n_heads + 2 * g.n_kv_heads) * g.head_dim, g.d_model, 2 * g.d_ff, g.d_model, g.vocab};
-  const int Ks[5] = {g.d_model, hd, g.d_model, g.d_ff, g.d_model};
-  for (int i = 0; i < 5; ++i) {
-    size_t f = gemm_partition(Ns[i], Ks[i], SJD_MAX_TOKENS, 0).ws_floats();
-    if (f > wsf) wsf = f;
+  rc |= dmalloc(c, &c->wqkv, L * nqkv * d * 2);
+  rc |= dmalloc(c, &c->wo, L * d * hd * 2);
+  rc |= dmalloc(c, &c->wgu, L * 2 * size_t(g.d_ff) * d * 2);
+  rc |= dmalloc(c, &c->wdown, L * d * size_t(g.d_ff) * 2);
+  rc |= dmalloc(c, &c->attn_norm, L * d * 2);
+  rc |= dmalloc(c, &c->ffn_norm, L * d * 2);
+  if (g.qk_norm) {
+    rc |= dmalloc(c, &c->qn_w, L * hd * 2);
+    rc |= dmalloc(c, &c->qn_b, L * hd * 2);
+    rc |= dmalloc(c, &c->kn_w, L * size_t(g.n_kv_heads) * g.head_dim * 2);
+    rc |= dmalloc(c, &c->kn_b, L * size_t(g.n_kv_heads) * g.head_dim * 2);
   }
-  c->ws_floats = wsf;
-  rc |= dmalloc(c, (void**)&c->ws, wsf * sizeof(float));
+  rc |= dmalloc(c, &c->embed, size_t(g.vocab) * d * 2);
+  rc |= dmalloc(c, &c->lm_head, size_t(g.vocab) * d * 2);
+  rc |= dmalloc(c, &c->final_norm, d * 2);
+  rc |= dmalloc(c, &c->rope_cos, size_t(g.n_rope_pos) * (g.head_dim / 2) * 4);
+  rc |= dmalloc(c, &c->rope_sin, size_t(g.n_rope_pos) * (g.head_dim / 2) * 4);
+  rc |= dmalloc(c, &c->h, T * d * 2);
+  rc |= dmalloc(c, &c->xn, T * d * 2);
+  rc |= dmalloc(c, &c->xl, T * d * 2);
+  rc |= dmalloc(c, &c->q, T * hd * 2);
+  rc |= dmalloc(c, &c->attn, T * hd * 2);
+  rc |= dmalloc(c, &c->act, T * size_t(g.d_ff) * 2);
+  const size_t cache_elems = L * g.rows * g.n_kv_heads * size_t(g.max_len) * g.head_dim;
+  rc |= dmalloc(c, &c->kcache, cache_elems * 2);
+  rc |= dmalloc(c, &c->vcache, cache_elems * 2);
+  // workspace: largest footprint over the GEMMs of the stack at the largest m_tile (counters start at zero)
+  size_t wsb = 0;
+  const int Ns[5] = {nqkv, g.d_model, 2 * g.d_ff, g.d_model, g.vocab};
+  const int Ks[5] = {g.d_model, hd, g.d_model, g.d_ff, g.d_model};
+  for (int i = 0; i < 5; ++i) c->arrive_cap = std::max(c->arrive_cap, (Ns[i] + kBlockN - 1) / kBlockN);
+  for (int i = 0; i < 5; ++i) {
+    const size_t b = gemm_workspace(gemm_partition(Ns[i], Ks[i], SJD_MAX_TOKENS, 0), c->arrive_cap).bytes;
+    if (b > wsb) wsb = b;
+  }
+  c->ws_bytes = wsb;
+  rc |= dmalloc(c, &c->ws, wsb);
   c->max_chunks = (g.max_len + kAttnChunk - 1) / kAttnChunk;
-  rc |= dmalloc(c, (void**)&c->part_o, size_t(c->max_chunks) * T * hd * sizeof(float));
-  rc |= dmalloc(c, (void**)&c->part_ml, size_t(c->max_chunks) * T * g.n_heads * 2 * sizeof(float));
+  rc |= dmalloc(c, &c->part_o, size_t(c->max_chunks) * T * hd * sizeof(float));
+  rc |= dmalloc(c, &c->part_ml, size_t(c->max_chunks) * T * g.n_heads * 2 * sizeof(float));
+  rc |= dmalloc(c, &c->pos_zero, T * 4);
+  rc |= dmalloc(c, &c->pos_last, T * 4);
+  if (!rc) {
+    std::vector<int32_t> last(T, g.max_len - 1);
+    cudaMemcpy(c->pos_last, last.data(), T * 4, cudaMemcpyHostToDevice);
+    rc |= set_wmap(&c->m_qkv, c->wqkv, g.n_layers, nqkv, g.d_model);
+    rc |= set_wmap(&c->m_o, c->wo, g.n_layers, g.d_model, hd);
+    rc |= set_wmap(&c->m_gu, c->wgu, g.n_layers, 2 * g.d_ff, g.d_model);
+    rc |= set_wmap(&c->m_down, c->wdown, g.n_layers, g.d_model, g.d_ff);
+    rc |= set_wmap(&c->m_head, c->lm_head, 1, g.vocab, g.d_model);
+  }
   if (rc) {
     sjd_ctx_destroy(c);
-    return fail(SJD_E_ALLOC, "sjd_ctx_create: cudaMalloc");
+    return fail(SJD_E_ALLOC, "sjd_ctx_create: cudaMalloc / tensor maps");
   }
   *out = c;
   return 0;
@@ -236,8 +272,7 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
 
 void sjd_ctx_destroy(sjd_ctx* c) {
   if (!c) return;
-  void* ptrs[] = {c->h, c->xn, c->xl, c->q, c->attn, c->act, c->kcache, c->vcache, c->ws, c->part_o, c->part_ml};
-  for (void* p : ptrs)
+  for (void* p : c->allocs)
     if (p) cudaFree(p);
   delete c;
 }
@@ -247,30 +282,114 @@ size_t sjd_ctx_device_bytes(const sjd_ctx* c) { return c ? c->bytes : 0; }
 int sjd_ctx_set_layer(sjd_ctx* c, int layer, const sjd_layer_weights* w) {
   if (!c || !w || layer < 0 || layer >= c->cfg.n_layers) return fail(SJD_E_ARG, "sjd_ctx_set_layer: bad args");
   const sjd_model_cfg& g = c->cfg;
-  Layer& L = c->layers[layer];
-  L.w = *w;
-  const int hd = g.n_heads * g.head_dim;
-  int rc = 0;
-  rc |= set_wmap(&L.qkv, w->wqkv, (g.n_heads + 2 * g.n_kv_heads) * g.head_dim, g.d_model);
-  rc |= set_wmap(&L.o, w->wo, g.d_model, hd);
-  rc |= set_wmap(&L.gate_up, w->w_gate_up, 2 * g.d_ff, g.d_model);
-  rc |= set_wmap(&L.down, w->w_down, g.d_model, g.d_ff);
-  if (rc || !w->attn_norm || !w->ffn_norm) return fail(SJD_E_TMAP, "sjd_ctx_set_layer: tensor map / null weight");
+  if (!w->attn_norm || !w->ffn_norm || !w->wqkv || !w->wo || !w->w_gate_up || !w->w_down)
+    return fail(SJD_E_ARG, "sjd_ctx_set_layer: null weight");
   if (g.qk_norm && (!w->q_norm_w || !w->q_norm_b || !w->k_norm_w || !w->k_norm_b))
     return fail(SJD_E_ARG, "sjd_ctx_set_layer: qk_norm weights missing");
-  L.set = true;
+  const size_t d = g.d_model, hd = size_t(g.n_heads) * g.head_dim, kvd = size_t(g.n_kv_heads) * g.head_dim;
+  const size_t nqkv = hd + 2 * kvd, ff = g.d_ff, l = layer;
+  cudaError_t e = cudaSuccess;
+  auto cp = [&](void* dst, const void* src, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, 0);
+  };
+  cp(c->wqkv + l * nqkv * d, w->wqkv, nqkv * d * 2);
+  cp(c->wo + l * d * hd, w->wo, d * hd * 2);
+  cp(c->wdown + l * d * ff, w->w_down, d * ff * 2);
+  cp(c->attn_norm + l * d, w->attn_norm, d * 2);
+  cp(c->ffn_norm + l * d, w->ffn_norm, d * 2);
+  if (g.qk_norm) {
+    cp(c->qn_w + l * hd, w->q_norm_w, hd * 2);
+    cp(c->qn_b + l * hd, w->q_norm_b, hd * 2);
+    cp(c->kn_w + l * kvd, w->k_norm_w, kvd * 2);
+    cp(c->kn_b + l * kvd, w->k_norm_b, kvd * 2);
+  }
+  if (e != cudaSuccess) return fail(SJD_E_LAUNCH, "sjd_ctx_set_layer: copy");
+  if (pack_gate_up(static_cast<const __nv_bfloat16*>(w->w_gate_up), c->wgu + l * 2 * ff * d, g.d_ff, g.d_model, 0))
+    return fail(SJD_E_LAUNCH, "sjd_ctx_set_layer: pack_gate_up");
+  if (cudaStreamSynchronize(0) != cudaSuccess) return fail(SJD_E_LAUNCH, "sjd_ctx_set_layer: sync");
+  c->layer_set[layer] = 1;
   return 0;
 }
 
 int sjd_ctx_set_globals(sjd_ctx* c, const void* embed, const void* final_norm, const void* lm_head,
                         const float* rope_cos, const float* rope_sin) {
   if (!c || !final_norm || !lm_head || !rope_cos || !rope_sin) return fail(SJD_E_ARG, "sjd_ctx_set_globals: null");
-  c->embed = static_cast<const __nv_bfloat16*>(embed);
-  c->final_norm = static_cast<const __nv_bfloat16*>(final_norm);
-  c->rope_cos = rope_cos;
-  c->rope_sin = rope_sin;
-  if (set_wmap(&c->lm_head, lm_head, c->cfg.vocab, c->cfg.d_model)) return fail(SJD_E_TMAP, "lm_head tensor map");
+  const sjd_model_cfg& g = c->cfg;
+  const size_t vd = size_t(g.vocab) * g.d_model * 2, rb = size_t(g.n_rope_pos) * (g.head_dim / 2) * 4;
+  cudaError_t e = cudaSuccess;
+  if (embed) e = cudaMemcpy(c->embed, embed, vd, cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(c->lm_head, lm_head, vd, cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(c->final_norm, final_norm, size_t(g.d_model) * 2, cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(c->rope_cos, rope_cos, rb, cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(c->rope_sin, rope_sin, rb, cudaMemcpyDeviceToDevice);
+  if (e != cudaSuccess) return fail(SJD_E_LAUNCH, "sjd_ctx_set_globals: copy");
+  c->have_embed = embed != nullptr;
+  c->globals_set = true;
   return 0;
+}
+
+static int ctx_ready(sjd_ctx* c) {
+  if (!c->globals_set) return fail(SJD_E_STATE, "globals not set");
+  for (char s : c->layer_set)
+    if (!s) return fail(SJD_E_STATE, "layer weights not set");
+  return 0;
+}
+
+// the GEMM + attention chain of one window forward; gemm_only skips attention (bench roofline leg)
+static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm_only, cudaStream_t s) {
+  const sjd_model_cfg& g = c->cfg;
+  const int M = g.rows * W, m_tile = round16(M), mi = m_tile / 16;
+  const int hd = g.n_heads * g.head_dim;
+  int rc = 0;
+  AttnParams ap;
+  memset(&ap, 0, sizeof(ap));
+  if (!gemm_only) {
+    ap.q = c->q; ap.part_o = c->part_o; ap.part_ml = c->part_ml; ap.out = c->attn;
+    ap.rows = g.rows; ap.W = W; ap.H = g.n_heads; ap.Hkv = g.n_kv_heads; ap.Lmax = g.max_len; ap.kv_len = a->kv_len;
+    for (int b = 0; b < kAttnMaxRows; ++b) ap.kv_lo[b] = b < g.rows ? a->kv_lo[b] : 0;
+    ap.n_chunks = (a->kv_len + W + kAttnChunk - 1) / kAttnChunk;
+    ap.scale_log2e = 1.4426950408889634f / sqrtf(float(g.head_dim));
+  }
+  const size_t layer_cache = size_t(g.rows) * g.n_kv_heads * size_t(g.max_len) * g.head_dim;
+  const size_t kvd = size_t(g.n_kv_heads) * g.head_dim;
+  GemmEpi base;
+  memset(&base, 0, sizeof(base));
+  base.M = M;
+  for (int l = 0; l < g.n_layers && !rc; ++l) {
+    GemmEpi e = base;
+    e.mode = EPI_QKV;
+    e.q_out = c->q;
+    e.k_cache = c->kcache + size_t(l) * layer_cache;
+    e.v_cache = c->vcache + size_t(l) * layer_cache;
+    e.rope_pos = a->rope_pos; e.cache_pos = a->cache_pos; e.rope_cos = c->rope_cos; e.rope_sin = c->rope_sin;
+    if (g.qk_norm) {
+      e.q_norm_w = c->qn_w + size_t(l) * hd; e.q_norm_b = c->qn_b + size_t(l) * hd;
+      e.k_norm_w = c->kn_w + size_t(l) * kvd; e.k_norm_b = c->kn_b + size_t(l) * kvd;
+    }
+    e.W = W; e.H = g.n_heads; e.Hkv = g.n_kv_heads; e.Lmax = g.max_len; e.Dh = g.head_dim;
+    e.rope_interleaved = g.rope_interleaved;
+    rc |= run_gemm(c, c->m_qkv, l, c->xmap_xn[mi], m_tile, e, s);
+    if (!gemm_only) {
+      ap.k = e.k_cache; ap.v = e.v_cache;
+      rc |= attn_launch(ap, g.head_dim, s);
+      g_launches += 2;
+    }
+    e = base;
+    e.mode = EPI_RESID_NORM;
+    e.h = c->h; e.xn = c->xn; e.eps = g.rms_eps;
+    e.norm_w = c->ffn_norm + size_t(l) * g.d_model;
+    rc |= run_gemm(c, c->m_o, l, c->xmap_attn[mi], m_tile, e, s);
+    e = base;
+    e.mode = EPI_SILU_MUL;
+    e.out = c->act; e.ld_out = g.d_ff;
+    rc |= run_gemm(c, c->m_gu, l, c->xmap_xn[mi], m_tile, e, s);
+    e = base;
+    e.mode = EPI_RESID_NORM;
+    e.h = c->h; e.xn = c->xn; e.eps = g.rms_eps;
+    e.norm_w = (l + 1 < g.n_layers) ? c->attn_norm + size_t(l + 1) * g.d_model : c->final_norm;
+    rc |= run_gemm(c, c->m_down, l, c->xmap_act[mi], m_tile, e, s);
+  }
+  return rc;
 }
 
 int sjd_ctx_forward(sjd_ctx* c, const sjd_forward_args* a, void* stream) {
@@ -282,97 +401,62 @@ int sjd_ctx_forward(sjd_ctx* c, const sjd_forward_args* a, void* stream) {
   if (a->kv_len < 0 || a->kv_len + W > g.max_len) return fail(SJD_E_ARG, "sjd_ctx_forward: KV cache overflow");
   if (a->n_logit_tokens < 1 || a->n_logit_tokens > W || !a->logits || !a->rope_pos || !a->cache_pos)
     return fail(SJD_E_ARG, "sjd_ctx_forward: bad logits/pos args");
-  if (!c->lm_head.ok) return fail(SJD_E_STATE, "sjd_ctx_forward: globals not set");
-  for (auto& L : c->layers)
-    if (!L.set) return fail(SJD_E_STATE, "sjd_ctx_forward: layer weights not set");
+  if (ctx_ready(c)) return SJD_E_STATE;
   if (!a->ids && !a->embeds) return fail(SJD_E_ARG, "sjd_ctx_forward: ids or embeds required");
-  if (a->ids && !c->embed) return fail(SJD_E_STATE, "sjd_ctx_forward: no embedding table");
+  if (a->ids && !c->have_embed) return fail(SJD_E_STATE, "sjd_ctx_forward: no embedding table");
   const int m_tile = round16(M), mi = m_tile / 16;
   if (ensure_xmaps(c, m_tile)) return fail(SJD_E_TMAP, "activation tensor maps");
-  const int hd = g.n_heads * g.head_dim;
-  int rc = 0;
-  uint64_t launches = 0;
-
-  if (a->ids) { rc |= embed_rows(a->ids, c->embed, c->h, M, g.d_model, s); launches++; }
-  else if (cudaMemcpyAsync(c->h, a->embeds, size_t(M) * g.d_model * 2, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
-    return fail(SJD_E_LAUNCH, "embeds copy");
-  rc |= rmsnorm_rows(c->h, static_cast<const __nv_bfloat16*>(c->layers[0].w.attn_norm), c->xn, M, g.d_model,
-                     g.rms_eps, s);
-  launches++;
-
-  AttnParams ap;
-  ap.q = c->q; ap.part_o = c->part_o; ap.part_ml = c->part_ml; ap.out = c->attn;
-  ap.rows = g.rows; ap.W = W; ap.H = g.n_heads; ap.Hkv = g.n_kv_heads; ap.Lmax = g.max_len; ap.kv_len = a->kv_len;
-  for (int b = 0; b < kAttnMaxRows; ++b) ap.kv_lo[b] = b < g.rows ? a->kv_lo[b] : 0;
-  ap.n_chunks = (a->kv_len + W + kAttnChunk - 1) / kAttnChunk;
-  ap.scale_log2e = 1.4426950408889634f / sqrtf(float(g.head_dim));
-  const size_t layer_cache = size_t(g.rows) * g.n_kv_heads * size_t(g.max_len) * g.head_dim;
-
-  StreamK sk;
-  for (int l = 0; l < g.n_layers && !rc; ++l) {
-    Layer& L = c->layers[l];
-    rc |= run_gemm(c, L.qkv, c->xmap_xn[mi], m_tile, &sk, s);
-    QkvPostParams qp;
-    qp.ws = c->ws; qp.sk = sk; qp.q_out = c->q;
-    qp.k_cache = c->kcache + size_t(l) * layer_cache; qp.v_cache = c->vcache + size_t(l) * layer_cache;
-    qp.rope_pos = a->rope_pos; qp.cache_pos = a->cache_pos; qp.rope_cos = c->rope_cos; qp.rope_sin = c->rope_sin;
-    qp.q_norm_w = g.qk_norm ? static_cast<const __nv_bfloat16*>(L.w.q_norm_w) : nullptr;
-    qp.q_norm_b = g.qk_norm ? static_cast<const __nv_bfloat16*>(L.w.q_norm_b) : nullptr;
-    qp.k_norm_w = g.qk_norm ? static_cast<const __nv_bfloat16*>(L.w.k_norm_w) : nullptr;
-    qp.k_norm_b = g.qk_norm ? static_cast<const __nv_bfloat16*>(L.w.k_norm_b) : nullptr;
-    qp.M = M; qp.W = W; qp.H = g.n_heads; qp.Hkv = g.n_kv_heads; qp.Lmax = g.max_len;
-    qp.rope_interleaved = g.rope_interleaved;
-    rc |= qkv_post(qp, g.head_dim, s);
-    ap.k = qp.k_cache; ap.v = qp.v_cache;
-    rc |= attn_launch(ap, g.head_dim, s);
-    rc |= run_gemm(c, L.o, c->xmap_attn[mi], m_tile, &sk, s);
-    rc |= reduce_residual_rmsnorm(c->ws, sk, c->h, static_cast<const __nv_bfloat16*>(L.w.ffn_norm), c->xn, M,
-                                  g.d_model, g.rms_eps, s);
-    rc |= run_gemm(c, L.gate_up, c->xmap_xn[mi], m_tile, &sk, s);
-    rc |= silu_mul(c->ws, sk, c->act, M, g.d_ff, s);
-    rc |= run_gemm(c, L.down, c->xmap_act[mi], m_tile, &sk, s);
-    const void* next_norm = (l + 1 < g.n_layers) ? c->layers[l + 1].w.attn_norm : c->final_norm;
-    rc |= reduce_residual_rmsnorm(c->ws, sk, c->h, static_cast<const __nv_bfloat16*>(next_norm), c->xn, M,
-                                  g.d_model, g.rms_eps, s);
-    launches += 6;  // 4 GEMMs are counted in run_gemm
-  }
+  int rc = embed_rmsnorm_rows(a->ids, c->embed, static_cast<const __nv_bfloat16*>(a->embeds), c->h, c->attn_norm,
+                              c->xn, M, g.d_model, g.rms_eps, s);
+  g_launches++;
+  rc |= forward_chain(c, W, a, false, s);
   if (rc) return fail(SJD_E_LAUNCH, "sjd_ctx_forward: layer launch");
 
   const int n = a->n_logit_tokens, Ml = g.rows * n;
-  const int ml_tile = round16(Ml), mli = ml_tile / 16;
+  GemmEpi e;
+  memset(&e, 0, sizeof(e));
+  e.mode = EPI_F32;
+  e.M = Ml;
+  e.out = a->logits;
+  e.ld_out = g.vocab;
+  e.round_bf16 = g.logits_round_bf16;
   if (n == W) {
-    rc |= run_gemm(c, c->lm_head, c->xmap_xn[mi], m_tile, &sk, s);
+    rc |= run_gemm(c, c->m_head, 0, c->xmap_xn[mi], m_tile, e, s);
   } else {
+    const int ml_tile = round16(Ml), mli = ml_tile / 16;
     if (ensure_xmaps(c, ml_tile)) return fail(SJD_E_TMAP, "activation tensor maps");
-    gather_rows_kernel<<<Ml, 128, 0, s>>>(c->xn, c->xl, W, n, g.d_model);
-    launches++;
-    rc |= run_gemm(c, c->lm_head, c->xmap_xl[mli], ml_tile, &sk, s);
+    rc |= gather_rows(c->xn, c->xl, g.rows, W, n, g.d_model, s);
+    g_launches++;
+    rc |= run_gemm(c, c->m_head, 0, c->xmap_xl[mli], ml_tile, e, s);
   }
-  rc |= logits_reduce(c->ws, sk, a->logits, Ml, g.vocab, g.logits_round_bf16, s);
-  launches++;
-  g_launches += launches;
   if (rc || cudaGetLastError() != cudaSuccess) return fail(SJD_E_LAUNCH, "sjd_ctx_forward: head launch");
   return 0;
 }
 
-// Launch only the GEMMs of one window forward (same weights, activation buffers and launch order as
-// sjd_ctx_forward) — used by bench.py to time the dominant kernel in isolation for the roofline line.
+// Launches only the fused GEMMs of one window forward (same weights, buffers, epilogues and launch order as
+// sjd_ctx_forward, attention skipped) — used by bench.py to time the dominant kernel in isolation.
 int sjd_ctx_gemm_only(sjd_ctx* c, int W, void* stream) {
   if (!c || W < 1 || c->cfg.rows * W > SJD_MAX_TOKENS) return fail(SJD_E_ARG, "sjd_ctx_gemm_only: bad args");
-  if (!c->lm_head.ok) return fail(SJD_E_STATE, "sjd_ctx_gemm_only: globals not set");
+  if (ctx_ready(c)) return SJD_E_STATE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int m_tile = round16(c->cfg.rows * W), mi = m_tile / 16;
+  const sjd_model_cfg& g = c->cfg;
+  const int M = g.rows * W, m_tile = round16(M), mi = m_tile / 16;
   if (ensure_xmaps(c, m_tile)) return fail(SJD_E_TMAP, "activation tensor maps");
-  StreamK sk;
-  int rc = 0;
-  for (auto& L : c->layers) {
-    if (!L.set) return fail(SJD_E_STATE, "sjd_ctx_gemm_only: layer weights not set");
-    rc |= run_gemm(c, L.qkv, c->xmap_xn[mi], m_tile, &sk, s);
-    rc |= run_gemm(c, L.o, c->xmap_attn[mi], m_tile, &sk, s);
-    rc |= run_gemm(c, L.gate_up, c->xmap_xn[mi], m_tile, &sk, s);
-    rc |= run_gemm(c, L.down, c->xmap_act[mi], m_tile, &sk, s);
-  }
-  rc |= run_gemm(c, c->lm_head, c->xmap_xn[mi], m_tile, &sk, s);
+  // qkv epilogue: rope position 0, k/v land in the last cache slot (never a live key: kv_len + W <= max_len - 1
+  // is not guaranteed, so callers must not interleave this with a decode in flight)
+  sjd_forward_args a;
+  memset(&a, 0, sizeof(a));
+  a.rope_pos = c->pos_zero;
+  a.cache_pos = c->pos_last;
+  int rc = forward_chain(c, W, &a, true, s);
+  GemmEpi e;
+  memset(&e, 0, sizeof(e));
+  e.mode = EPI_F32;
+  e.M = M;
+  e.out = c->part_o;   // scratch: rows*W*vocab floats must fit (checked)
+  e.ld_out = g.vocab;
+  if (size_t(M) * g.vocab > size_t(c->max_chunks) * SJD_MAX_TOKENS * g.n_heads * g.head_dim) e.M = 1;
+  rc |= run_gemm(c, c->m_head, 0, c->xmap_xn[mi], m_tile, e, s);
   return rc ? fail(SJD_E_LAUNCH, "sjd_ctx_gemm_only") : 0;
 }
 

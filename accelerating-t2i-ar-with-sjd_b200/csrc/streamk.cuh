@@ -1,10 +1,10 @@
-// Stream-K work partition shared by the weight-streaming GEMM (producer of partial tiles) and the
-// reduce epilogues (consumers).  A GEMM  Y[M,N] = X[M,K] * W[N,K]^T  is cut into
+// Stream-K work partition of the weight-streaming GEMM (gemm_fused.cu).  A GEMM  Y[M,N] = X[M,K] * W[N,K]^T  is cut into
 //   units u = tile * KB + kb,  tile in [0, n_tiles) (128 weight rows), kb in [0, KB) (64 K columns)
 // and CTA c of G owns the contiguous range [c*U/G, (c+1)*U/G).  Each maximal run of units of one tile
-// inside one CTA is a *segment*; its fp32 partial tile goes to workspace slot (tile + c), which is
-// unique per segment (tiles are non-decreasing in c).  The final value of tile t is the sum, in CTA
-// order, over the CTAs [first_cta(t), last_cta(t)] — a fixed order, so results are deterministic.
+// inside one CTA is a *segment*.  Only the first and the last segment of a CTA can be part of a split tile, so a
+// CTA parks at most two fp32 partial tiles (workspace slots 2c and 2c+1).  The final value of a split tile t is
+// the sum of the partials of first_cta(t) .. last_cta(t) in CTA order — a fixed order, so results are
+// bit-reproducible.
 #pragma once
 #include <stdint.h>
 
@@ -29,18 +29,6 @@ struct StreamK {
     return owner(uint32_t(tile + 1) * kb - 1);
   }
   __host__ __device__ __forceinline__ size_t slot_floats() const { return size_t(m_tile) * 128; }
-  __host__ __device__ __forceinline__ size_t ws_floats() const {
-    return size_t(n_tiles + grid) * slot_floats();
-  }
 };
-
-// Sum of the partial tiles for output element (m, n); ws layout is [slot][m][128].
-__device__ __forceinline__ float streamk_gather(const float* __restrict__ ws, const StreamK& sk, int m, int n) {
-  const int tile = n >> 7, nl = n & 127;
-  const int c0 = sk.first_cta(tile), c1 = sk.last_cta(tile);
-  float acc = 0.f;
-  for (int c = c0; c <= c1; ++c) acc += ws[size_t(tile + c) * sk.slot_floats() + size_t(m) * 128 + nl];
-  return acc;
-}
 
 }  // namespace sjd

@@ -42,12 +42,9 @@ class DeviceStack:
         self.device = torch.device(device)
         dev = self.device
         bf = torch.bfloat16
-        self._keep = []
 
-        def put(t, dtype=bf):
-            t = t.detach().to(device=dev, dtype=dtype).contiguous()
-            self._keep.append(t)
-            return t
+        def put(t, dtype=bf):   # staging only: the context copies / re-lays out everything it is given
+            return t.detach().to(device=dev, dtype=dtype).contiguous()
 
         self.rope_cos = put(rope_cos, torch.float32)
         self.rope_sin = put(rope_sin, torch.float32)
@@ -60,20 +57,23 @@ class DeviceStack:
         with torch.cuda.device(dev):
             _lib.check(self.lib.sjd_ctx_create(C.byref(cfg), C.byref(h)), "sjd_ctx_create")
         self.ctx = h
-        self.embed = put(weights["embed"]) if weights.get("embed") is not None else None
-        self.final_norm = put(weights["final_norm"])
-        self.lm_head = put(weights["lm_head"])
-        for l, L in enumerate(weights["layers"]):
-            lw = _lib.LayerWeights()
-            for name in ("attn_norm", "wqkv", "wo", "ffn_norm", "w_gate_up", "w_down"):
-                setattr(lw, name, put(L[name]).data_ptr())
-            if shape.qk_norm:
-                for name in ("q_norm_w", "q_norm_b", "k_norm_w", "k_norm_b"):
-                    setattr(lw, name, put(L[name]).data_ptr())
-            _lib.check(self.lib.sjd_ctx_set_layer(self.ctx, l, C.byref(lw)), "sjd_ctx_set_layer")
-        _lib.check(self.lib.sjd_ctx_set_globals(
-            self.ctx, self.embed.data_ptr() if self.embed is not None else None, self.final_norm.data_ptr(),
-            self.lm_head.data_ptr(), self.rope_cos.data_ptr(), self.rope_sin.data_ptr()), "sjd_ctx_set_globals")
+        with torch.cuda.device(dev):
+            for l, L in enumerate(weights["layers"]):
+                lw = _lib.LayerWeights()
+                names = ["attn_norm", "wqkv", "wo", "ffn_norm", "w_gate_up", "w_down"]
+                if shape.qk_norm:
+                    names += ["q_norm_w", "q_norm_b", "k_norm_w", "k_norm_b"]
+                staged = {name: put(L[name]) for name in names}
+                for name, t in staged.items():
+                    setattr(lw, name, t.data_ptr())
+                _lib.check(self.lib.sjd_ctx_set_layer(self.ctx, l, C.byref(lw)), "sjd_ctx_set_layer")  # syncs
+                del staged
+            embed = put(weights["embed"]) if weights.get("embed") is not None else None
+            final_norm, lm_head = put(weights["final_norm"]), put(weights["lm_head"])
+            _lib.check(self.lib.sjd_ctx_set_globals(
+                self.ctx, embed.data_ptr() if embed is not None else None, final_norm.data_ptr(),
+                lm_head.data_ptr(), self.rope_cos.data_ptr(), self.rope_sin.data_ptr()), "sjd_ctx_set_globals")
+            torch.cuda.synchronize(dev)
         self.logits_buf = torch.empty(_lib.SJD_MAX_TOKENS, shape.vocab, dtype=torch.float32, device=dev)
 
     def device_bytes(self) -> int:

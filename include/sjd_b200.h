@@ -39,19 +39,17 @@ const char* sjd_last_error(void);
 int sjd_device_sm_count(void);
 
 /* ------------------------------------------------------------------------------------------------
- * Stand-alone weight-streaming GEMM  Y[M,N] = X[M,K] * W[N,K]^T  (bf16 in, fp32 accumulate).
- * Replaces nn.Linear -> cuBLAS in the reference forward (modeling_chameleon.py:527-529,579,193-195,1560;
- * llamagen/llamagen.py:248,277,200,332).  `x` must have at least m_tile rows (m_tile = M rounded up to 16,
- * <= 256).  Partial tiles land in `ws` (sjd_gemm_workspace_bytes); sjd_gemm_reduce_* finish them.
- * grid_limit <= 0 means one CTA per SM.
+ * Stand-alone weight-streaming GEMM  Y[M,N] = X[M,K] * W[N,K]^T  (bf16 in, fp32 accumulate), the kernel every
+ * projection of the window forward runs on.  Replaces nn.Linear -> cuBLAS in the reference forward
+ * (modeling_chameleon.py:527-529,579,193-195,1560; llamagen/llamagen.py:248,277,200,332).
+ * `x` must have at least m_tile = round_up(M,16) rows (<= 256); K % 64 == 0.  `out` is [M,N] fp32 (out_f32=1,
+ * optionally rounded through bf16) or bf16.  `ws` is sjd_gemm_workspace_bytes() of device memory that must be
+ * ZERO before its first use (the kernel leaves its counters zero).  Split tiles are fixed up in-kernel in a fixed
+ * order, so results are bit-reproducible.  grid_limit <= 0 means one CTA per SM.
  * ---------------------------------------------------------------------------------------------- */
 size_t sjd_gemm_workspace_bytes(int N, int K, int m_tile, int grid_limit);
-int sjd_gemm_bf16(const void* w, int N, int K, const void* x, int x_rows, int m_tile, void* ws, int grid_limit,
-                  void* stream);
-int sjd_gemm_reduce_bf16(const void* ws, int N, int K, int m_tile, int grid_limit, void* out_bf16, int M,
-                         void* stream);
-int sjd_gemm_reduce_f32(const void* ws, int N, int K, int m_tile, int grid_limit, float* out_f32, int M,
-                        int round_bf16, void* stream);
+int sjd_gemm_bf16(const void* w, int N, int K, const void* x, int x_rows, int M, void* out, int out_f32,
+                  int round_bf16, void* ws, int grid_limit, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Verify step (one call per Jacobi iteration).  Replaces sampling_logits2tokens
@@ -108,7 +106,7 @@ typedef struct sjd_model_cfg {
   int32_t logits_round_bf16; /* 1: round logits through bf16 like a bf16 lm_head */
 } sjd_model_cfg;
 
-typedef struct sjd_layer_weights {   /* device pointers, bf16, nn.Linear layout [out, in] */
+typedef struct sjd_layer_weights {   /* device pointers, bf16, nn.Linear layout [out, in]; COPIED by set_layer */
   const void* attn_norm;   /* [d] */
   const void* wqkv;        /* [(H + 2*Hkv) * Dh, d]  rows: q heads, k heads, v heads */
   const void* q_norm_w; const void* q_norm_b;  /* [H, Dh] or NULL */
@@ -124,9 +122,11 @@ typedef struct sjd_ctx sjd_ctx;
 int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out);
 void sjd_ctx_destroy(sjd_ctx* ctx);
 size_t sjd_ctx_device_bytes(const sjd_ctx* ctx);
+/* The context re-lays the weights out once into its own memory (layers stacked per projection type, gate/up rows
+ * interleaved 64/64 so SiLU*up fuses into the GEMM epilogue); the caller may free its tensors afterwards. */
 int sjd_ctx_set_layer(sjd_ctx* ctx, int layer, const sjd_layer_weights* w);
 /* embed: [vocab, d] bf16 (may be NULL if every forward passes embeddings); final_norm [d]; lm_head [vocab, d];
- * rope_cos/sin: fp32 [n_rope_pos, head_dim/2]. */
+ * rope_cos/sin: fp32 [n_rope_pos, head_dim/2].  Copied. */
 int sjd_ctx_set_globals(sjd_ctx* ctx, const void* embed, const void* final_norm, const void* lm_head,
                         const float* rope_cos, const float* rope_sin);
 
@@ -143,9 +143,12 @@ typedef struct sjd_forward_args {
 } sjd_forward_args;
 
 int sjd_ctx_forward(sjd_ctx* ctx, const sjd_forward_args* a, void* stream);
-/* Launches only the GEMMs of one window forward (same weights/buffers/order): lets bench.py time the dominant
- * kernel (gemm_streamk_kernel) in isolation with CUDA events. */
+/* Launches only the fused GEMMs of one window forward (same weights/buffers/epilogues/order, attention skipped):
+ * lets bench.py time the dominant kernel (gemm_fused_kernel) in isolation with CUDA events. */
 int sjd_ctx_gemm_only(sjd_ctx* ctx, int W, void* stream);
+/* Developer timing: when device_buf != NULL every following GEMM launch i writes clock64 stamps of its epilogue
+ * stages to device_buf[(i % n_launches)][cta < 256][8] (int64).  NULL switches it off. */
+void sjd_debug_gemm_stamps(void* device_buf, int n_launches);
 /* counts kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t sjd_launch_count(void);
 

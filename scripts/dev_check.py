@@ -28,11 +28,10 @@ def gemm_case(N, K, M, time_it=False, grid=0):
     x = torch.zeros(max(m_tile, 16), K, device=dev, dtype=torch.bfloat16)
     x[:M] = (torch.randn(M, K, device=dev)).bfloat16()
     wsb = L.sjd_gemm_workspace_bytes(N, K, m_tile, grid)
-    ws = torch.empty(wsb // 4, device=dev, dtype=torch.float32)
+    ws = torch.zeros(wsb, device=dev, dtype=torch.uint8)
     out = torch.empty(M, N, device=dev, dtype=torch.float32)
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), x.shape[0], m_tile, ws.data_ptr(), grid, st), "gemm")
-    _lib.check(L.sjd_gemm_reduce_f32(ws.data_ptr(), N, K, m_tile, grid, out.data_ptr(), M, 0, st), "reduce")
+    _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), x.shape[0], M, out.data_ptr(), 1, 0, ws.data_ptr(), grid, st), "gemm")
     torch.cuda.synchronize()
     ref = x[:M].float() @ w.float().T
     err = (out - ref).abs().max().item()
@@ -43,12 +42,12 @@ def gemm_case(N, K, M, time_it=False, grid=0):
         ncopy = max(2, int(400e6 // (N * K * 2)) + 1)
         ws_list = [(torch.randn(N, K, device=dev) * 0.05).bfloat16() for _ in range(ncopy)]
         for i in range(3):
-            L.sjd_gemm_bf16(ws_list[i % ncopy].data_ptr(), N, K, x.data_ptr(), x.shape[0], m_tile, ws.data_ptr(), grid, st)
+            L.sjd_gemm_bf16(ws_list[i % ncopy].data_ptr(), N, K, x.data_ptr(), x.shape[0], M, out.data_ptr(), 1, 0, ws.data_ptr(), grid, st)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         iters = 20
         e0.record()
         for i in range(iters):
-            L.sjd_gemm_bf16(ws_list[i % ncopy].data_ptr(), N, K, x.data_ptr(), x.shape[0], m_tile, ws.data_ptr(), grid, st)
+            L.sjd_gemm_bf16(ws_list[i % ncopy].data_ptr(), N, K, x.data_ptr(), x.shape[0], M, out.data_ptr(), 1, 0, ws.data_ptr(), grid, st)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters

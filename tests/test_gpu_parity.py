@@ -40,11 +40,13 @@ def test_gemm_matches_fp32_reference(env, N, K, M):
     w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     x = torch.zeros(m_tile, K, device=dev, dtype=torch.bfloat16)
     x[:M] = torch.randn(M, K, device=dev).bfloat16()
-    ws = torch.empty(L.sjd_gemm_workspace_bytes(N, K, m_tile, 0) // 4, device=dev, dtype=torch.float32)
+    ws = torch.zeros(L.sjd_gemm_workspace_bytes(N, K, m_tile, 0), device=dev, dtype=torch.uint8)
     out = torch.empty(M, N, device=dev, dtype=torch.float32)
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), m_tile, m_tile, ws.data_ptr(), 0, st), "gemm")
-    _lib.check(L.sjd_gemm_reduce_f32(ws.data_ptr(), N, K, m_tile, 0, out.data_ptr(), M, 0, st), "reduce")
+    for _ in range(2):   # second launch proves the in-kernel counters were left re-armed
+        out.fill_(float("nan"))
+        _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), m_tile, M, out.data_ptr(), 1, 0, ws.data_ptr(), 0, st),
+                   "gemm")
     torch.cuda.synchronize()
     ref = x[:M].double() @ w.double().T
     err = (out.double() - ref).abs().max().item()
@@ -62,22 +64,28 @@ def test_gemm_stream_k_grid_independence(env):
     st = torch.cuda.current_stream().cuda_stream
     outs = []
     for grid in (1, 7, 37, 148, 0):
-        ws = torch.empty(L.sjd_gemm_workspace_bytes(N, K, m_tile, grid) // 4, device=dev, dtype=torch.float32)
+        ws = torch.zeros(L.sjd_gemm_workspace_bytes(N, K, m_tile, grid), device=dev, dtype=torch.uint8)
         out = torch.empty(M, N, device=dev, dtype=torch.float32)
-        _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), m_tile, m_tile, ws.data_ptr(), grid, st), "gemm")
-        _lib.check(L.sjd_gemm_reduce_f32(ws.data_ptr(), N, K, m_tile, grid, out.data_ptr(), M, 0, st), "reduce")
+        _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), m_tile, M, out.data_ptr(), 1, 0, ws.data_ptr(), grid, st),
+                   "gemm")
         outs.append(out)
     torch.cuda.synchronize()
     ref = x[:M].float() @ w.float().T
     for o in outs:
         assert (o - ref).abs().max().item() < 1e-4
     # same grid twice -> bit identical (deterministic reduction order)
-    ws = torch.empty(L.sjd_gemm_workspace_bytes(N, K, m_tile, 0) // 4, device=dev, dtype=torch.float32)
+    ws = torch.zeros(L.sjd_gemm_workspace_bytes(N, K, m_tile, 0), device=dev, dtype=torch.uint8)
     out2 = torch.empty(M, N, device=dev, dtype=torch.float32)
-    _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), m_tile, m_tile, ws.data_ptr(), 0, st), "gemm")
-    _lib.check(L.sjd_gemm_reduce_f32(ws.data_ptr(), N, K, m_tile, 0, out2.data_ptr(), M, 0, st), "reduce")
+    _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), m_tile, M, out2.data_ptr(), 1, 0, ws.data_ptr(), 0, st),
+               "gemm")
     torch.cuda.synchronize()
     assert torch.equal(outs[-1], out2)
+    # bf16 output epilogue
+    out3 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    _lib.check(L.sjd_gemm_bf16(w.data_ptr(), N, K, x.data_ptr(), m_tile, M, out3.data_ptr(), 0, 0, ws.data_ptr(), 0, st),
+               "gemm")
+    torch.cuda.synchronize()
+    assert torch.equal(out3, out2.bfloat16())
 
 
 # ---------------------------------------------------------------------------------------------- verify
@@ -259,11 +267,11 @@ def test_window_forward_matches_reference_stack(env, family):
         l32 = ref32.forward(ids=ids, rope_pos=rope_pos, kv_len=kv_len, kv_lo=kv_lo, cache_pos=pos, n_logit_tokens=n)
         torch.cuda.synchronize()
         # (a) against the bf16-emulating reference: two bf16 pipelines that differ only in fp32 summation order
-        #     disagree by a few bf16 ulp at worst (one rounding flip early in the stack propagates) and by a
-        #     fraction of an ulp on average
-        ulp = 2.0 ** (torch.floor(torch.log2(lr.abs().clamp(min=2.0 ** -6))) - 7)
-        assert ((lg - lr).abs() <= 4.0 * ulp).all(), f"{family} step {step}: max {(lg - lr).abs().max().item()}"
-        assert (lg - lr).abs().mean().item() < 2e-3
+        #     disagree by a few bf16 ulp OF THE LOGIT SCALE at worst (a logit is a sum of O(1) terms, so its error
+        #     does not shrink with its own magnitude) and by a fraction of that ulp on average
+        ulp = 2.0 ** (torch.floor(torch.log2(lr.abs().max())).item() - 7)
+        assert (lg - lr).abs().max().item() <= 2.5 * ulp, f"{family} step {step}: max {(lg - lr).abs().max().item()}"
+        assert (lg - lr).abs().mean().item() < 0.25 * ulp
         # (b) against the exact fp32 forward: our error must not exceed the reference's own bf16 error
         e_ours, e_ref = (lg - l32).abs(), (lr - l32).abs()
         assert e_ours.max().item() <= 1.5 * e_ref.max().item() + 1e-6, (e_ours.max().item(), e_ref.max().item())
