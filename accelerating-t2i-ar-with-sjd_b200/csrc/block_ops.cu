@@ -3,8 +3,7 @@
 //                       stack (modeling_chameleon.py:68-73, llamagen.py:179-181)
 //   gather_rows         keeps the last n tokens of every CFG row for the lm_head (the reference slices logits
 //                       after computing all of them, jacobi_iteration_lumina_mgpt.py:97)
-//   pack_gate_up        one-time weight re-layout: gate/up rows interleaved so one GEMM tile (and one epilogue
-//                       lane) carries both halves of 64 act columns
+//   pack_tiles          one-time weight re-layout into contiguous 16 KB GEMM tiles (+ gate/up row interleave)
 // Every other element-wise / normalisation op of the block is an epilogue of gemm_fused.cu.
 #include "common.cuh"
 
@@ -58,15 +57,28 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_b
   for (int i = threadIdx.x; i < d / 8; i += blockDim.x) o[i] = s[i];
 }
 
-// dst [2*ff, d]: row blk*128 + 4l + e  <-  (e < 2 ? gate[blk*64 + 2l + e] : up[blk*64 + 2l + e - 2]);
-// src = [gate rows; up rows].  Lane l of the GEMM epilogue then holds gate and up of act columns 2l, 2l+1.
-__global__ void pack_gate_up_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int ff,
-                                    int d) {
-  const int r = blockIdx.x, blk = r >> 7, j = r & 127, l = j >> 2, e = j & 3;
-  const int srow = e < 2 ? blk * 64 + 2 * l + e : ff + blk * 64 + 2 * l + (e - 2);
-  const uint4* s = reinterpret_cast<const uint4*>(src + size_t(srow) * d);
-  uint4* o = reinterpret_cast<uint4*>(dst + size_t(r) * d);
-  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) o[i] = s[i];
+// One-time weight re-layout into contiguous GEMM tiles: dst[(tile*KB + kb)][128][64] <- src[row(tile, r)][kb*64 ..],
+// so that every TMA box of the weight stream is one contiguous 16 KB block of HBM.  Rows beyond N are zero.
+// gate_up != 0 additionally interleaves gate/up rows (src = [gate rows; up rows], ff rows each): tile row 4l+e is
+// gate[64*tile + 2l + e] for e < 2 and up[64*tile + 2l + e - 2] otherwise, so that lane l of the GEMM epilogue holds
+// gate and up of act columns 2l, 2l+1.
+__global__ void pack_tiles_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int K,
+                                  int gate_up_ff) {
+  const int KB = K / 64;
+  const int r = blockIdx.x & 127, tile = blockIdx.x >> 7;
+  int srow;
+  if (gate_up_ff) {
+    const int l = r >> 2, e = r & 3;
+    srow = e < 2 ? tile * 64 + 2 * l + e : gate_up_ff + tile * 64 + 2 * l + (e - 2);
+  } else {
+    srow = tile * 128 + r;
+  }
+  for (int i = threadIdx.x; i < K / 8; i += blockDim.x) {   // 16-byte chunks along K
+    const int kb = i >> 3, c = i & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (srow < N) v = *reinterpret_cast<const uint4*>(src + size_t(srow) * K + size_t(i) * 8);
+    *reinterpret_cast<uint4*>(dst + ((size_t(tile) * KB + kb) * 128 + r) * 64 + c * 8) = v;
+  }
 }
 
 // ---- launchers --------------------------------------------------------------------------
@@ -77,8 +89,9 @@ int embed_rmsnorm_rows(const int* ids, const __nv_bfloat16* table, const __nv_bf
 int gather_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int rows, int W, int n, int d, cudaStream_t s) {
   return launch_pdl(gather_rows_kernel, dim3(rows * n), dim3(128), 0, s, src, dst, W, n, d);
 }
-int pack_gate_up(const __nv_bfloat16* src, __nv_bfloat16* dst, int ff, int d, cudaStream_t s) {
-  pack_gate_up_kernel<<<2 * ff, 128, 0, s>>>(src, dst, ff, d);
+int pack_tiles(const __nv_bfloat16* src, __nv_bfloat16* dst, int N, int K, int gate_up_ff, cudaStream_t s) {
+  const int n_tiles = (N + 127) / 128;
+  pack_tiles_kernel<<<n_tiles * 128, 128, 0, s>>>(src, dst, N, K, gate_up_ff);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 

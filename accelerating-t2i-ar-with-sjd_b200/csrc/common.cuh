@@ -86,6 +86,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// L2 prefetch of one 2-D box (fire and forget): keeps HBM streaming while the smem ring is blocked
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------
@@ -165,6 +172,19 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(uint32_t M, uint32_t 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // Lets the dependent kernel start being scheduled; it still synchronises with pdl_wait().
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Polite spin: relaxed polls with back-off (a hot line polled by 148 CTAs otherwise starves the L2 slice that also
+// serves the counters' atomics), one acquire fence once the value is there.
+__device__ __forceinline__ void spin_until_ge(const uint32_t* p, uint32_t target) {
+  uint32_t v, ns = 64;
+  while (true) {
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v >= target) break;
+    __nanosleep(ns);
+    if (ns < 512) ns <<= 1;
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v;

@@ -32,12 +32,17 @@
 
 namespace sjd {
 
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kGemmThreads = 128 + kEpiThreads;  // warp 0 weight TMA, 1 MMA, 2 activation TMA, 3 idle, 4..19 epilogue
 constexpr int kBlockN = 128;  // weight rows per tile (UMMA M)
 constexpr int kBlockK = 64;   // bf16 K elements per stage = one 128-byte swizzle row
 constexpr int kMaxStages = 12;
 constexpr uint32_t kATileBytes = kBlockN * kBlockK * 2;  // 16 KB
-constexpr int kEpiChunk = 32;                             // token columns staged per epilogue pass
+constexpr int kCtrStride = 64;                            // u32 between hot counters: one 256-byte region each
+constexpr int kTileCtrStride = 8;                         // u32 per tile {arrived, done, pad..}: 32 bytes
+constexpr int kLookahead = 32;                            // weight units (16 KB) prefetched into L2 beyond the ring
+constexpr int kEpiChunk = 64;                             // token columns staged per epilogue pass
 constexpr uint32_t kEpiStageBytes = kEpiChunk * kBlockN * 4;  // 16 KB
 
 enum EpiMode { EPI_F32 = 0, EPI_BF16 = 1, EPI_QKV = 2, EPI_RESID_NORM = 3, EPI_SILU_MUL = 4 };
@@ -71,12 +76,13 @@ struct GemmEpi {
   int W, H, Hkv, Lmax, Dh, rope_interleaved;
   // split-K fix-up + grid-wide meeting point
   float* ws;                   // [2*grid][m_tile][128] fp32 partial slots (first / last segment of each CTA)
-  uint32_t* tile_arrive;       // [n_tiles][2] {arrived, done}, zero between launches
-  uint32_t* ctr;               // [2], zero between launches
-  long long* dbg;              // optional [grid][8] clock64 stamps of the epilogue's stages (developer timing)
+  uint32_t* tile_arrive;       // [n_tiles][kTileCtrStride] {arrived, done, pad}, zero between launches
+  uint32_t* ctr;               // [0], [kCtrStride]: row-statistic meeting point {in, done}, zero between launches
+  long long* dbg;              // optional [grid][16] clock64 stamps of the epilogue's stages (developer timing)
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ---- row epilogues ---------------------------------------------------------------------------------------
 // A finished tile is consumed row by row (token row m; this lane holds tile columns 4*lane .. 4*lane+3).  Every
@@ -244,18 +250,44 @@ __device__ __forceinline__ void epi_apply(const GemmEpi& ep, const EpiTileConst&
   }
 }
 
+// ---- a chain of GEMMs executed by one persistent kernel ---------------------------------------------------
+constexpr int kMaxChainOps = 4;
+struct TmapSet {
+  CUtensorMap w[5];   // weights: qkv, o, gate_up, down, lm_head (context) / [0] stand-alone
+  CUtensorMap x[4];   // activations: xn, attn, act, xl (context) / [0] stand-alone
+};
+struct GemmOp {
+  int wmap, xmap;
+  int w_row0;     // plain [N,K] weights: first weight row of this op (layer * N)
+  int w_tiled;    // 1: weights re-laid out as contiguous [unit][128][64] tiles; w_row0 is then the first UNIT
+
+  StreamK sk;
+  GemmEpi ep;
+};
+struct Chain {
+  int n_ops, num_stages;
+  int lookahead;   // weight units prefetched into L2 beyond the ring
+  uint32_t tmem_cols;
+  uint32_t* fin;   // [(kMaxChainOps + 1) * kCtrStride] rows finalised per op (+ exit counter); zero between launches
+  GemmOp ops[kMaxChainOps];
+};
+
+// One persistent CTA per SM runs every GEMM of the chain back to back.  The WEIGHT producer never waits for
+// data — it keeps the smem ring full across op boundaries — while the ACTIVATION producer of op i+1 waits for
+// op i's "rows finalised" counter (op 0: for the previous kernel, griddepcontrol.wait).  So the HBM weight stream
+// of the next projection overlaps the cross-CTA fix-up / normalisation tail of the current one.
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-                  const int w_row0, const StreamK sk, const int num_stages, const uint32_t tmem_cols,
-                  const GemmEpi ep) {
+gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_holder;
   __shared__ int2 s_pos[256];   // EPI_QKV: {rope_pos, cache_pos} per token row
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_stages = ch.num_stages;
+  const int m_tile = ch.ops[0].sk.m_tile;   // common to the chain
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_tile_bytes = uint32_t(sk.m_tile) * kBlockK * 2;
+  const uint32_t b_tile_bytes = uint32_t(m_tile) * kBlockK * 2;
   const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -267,329 +299,376 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                                                size_t(num_stages) * stage_bytes);
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_w);
-    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < ch.n_ops; ++i) {
+      tma_prefetch_desc(&maps.w[ch.ops[i].wmap]);
+      tma_prefetch_desc(&maps.x[ch.ops[i].xmap]);
+    }
     for (int s = 0; s < num_stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), kEpiWarps);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_holder), tmem_cols);
+    tmem_alloc(smem_u32(&tmem_holder), ch.tmem_cols);
     tmem_relinquish();
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_holder;
-  pdl_launch_dependents();  // the next kernel may become resident (and prefetch its weights) as CTAs of this one retire
+  pdl_launch_dependents();  // the next kernel may become resident as CTAs of this one retire
 
   const int cta = blockIdx.x;
-  const uint32_t u0 = sk.begin(cta), u1 = sk.begin(cta + 1);
-  const uint32_t KB = uint32_t(sk.kb);
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== WEIGHT producer: never waits for data, only for ring slots =====
+    // While the ring is blocked (the consumer is waiting for activations at an op boundary) it keeps HBM busy
+    // by prefetching the next weight tiles into L2, up to kLookahead units ahead.
     if (lane == 0) {
-      // (1) weights for the first ring-full of units: independent of the previous kernel
-      const uint32_t n_pre = min(uint32_t(num_stages), u1 - u0);
-      for (uint32_t i = 0; i < n_pre; ++i) {
-        const uint32_t u = u0 + i, tile = u / KB, kb = u - tile * KB;
-        mbar_arrive_expect_tx(full_bar(int(i)), stage_bytes);
-        tma_load_2d(smem_base + i * stage_bytes, &tmap_w, int(kb * kBlockK), w_row0 + int(tile * kBlockN),
-                    full_bar(int(i)), kPolicyEvictFirst);
+      int stage = 0;
+      uint32_t phase = 0;
+      int pf_i = 0;                 // prefetch cursor (op, unit), never behind the issue cursor
+      uint32_t pf_u = ch.ops[0].sk.begin(cta);
+      int pf_ahead = 0;             // units the prefetch cursor is ahead of the issue cursor
+      auto w_coords = [&](const GemmOp& op, uint32_t u, int& c0, int& c1) {
+        if (op.w_tiled) { c0 = 0; c1 = (op.w_row0 + int(u)) * kBlockN; }
+        else { const uint32_t KB = uint32_t(op.sk.kb), tile = u / KB; c0 = int((u - tile * KB) * kBlockK); c1 = op.w_row0 + int(tile * kBlockN); }
+      };
+      auto pf_normalise = [&]() {   // skip exhausted ops
+        while (pf_i < ch.n_ops && pf_u >= ch.ops[pf_i].sk.begin(cta + 1)) {
+          ++pf_i;
+          if (pf_i < ch.n_ops) pf_u = ch.ops[pf_i].sk.begin(cta);
+        }
+      };
+      for (int i = 0; i < ch.n_ops; ++i) {
+        const GemmOp& op = ch.ops[i];
+        const CUtensorMap* tw = &maps.w[op.wmap];
+        const uint32_t u0 = op.sk.begin(cta), u1 = op.sk.begin(cta + 1);
+        for (uint32_t u = u0; u < u1; ++u) {
+          while (!mbar_try_wait(empty_bar(stage), phase ^ 1)) {
+            if (pf_ahead == 0) { pf_i = i; pf_u = u; }
+            pf_normalise();
+            if (pf_ahead < ch.lookahead && pf_i < ch.n_ops) {
+              int c0, c1;
+              w_coords(ch.ops[pf_i], pf_u, c0, c1);
+              tma_prefetch_l2_2d(&maps.w[ch.ops[pf_i].wmap], c0, c1);
+              ++pf_u;
+              ++pf_ahead;
+            } else {
+              __nanosleep(64);
+            }
+          }
+          int c0, c1;
+          w_coords(op, u, c0, c1);
+          mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+          tma_load_2d(smem_base + uint32_t(stage) * stage_bytes, tw, c0, c1, full_bar(stage), kPolicyEvictFirst);
+          if (pf_ahead > 0) --pf_ahead;
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+        }
       }
-      // (2) activations exist only once the previous kernel has completed
-      pdl_wait();
-      for (uint32_t i = 0; i < n_pre; ++i) {
-        const uint32_t u = u0 + i, kb = u % KB;
-        tma_load_2d(smem_base + i * stage_bytes + kATileBytes, &tmap_x, int(kb * kBlockK), 0, full_bar(int(i)),
-                    kPolicyEvictLast);
-      }
-      // (3) steady state
-      int stage = int(n_pre % uint32_t(num_stages));
-      uint32_t phase = (n_pre == uint32_t(num_stages)) ? 1u : 0u;
-      for (uint32_t u = u0 + n_pre; u < u1; ++u) {
-        const uint32_t tile = u / KB, kb = u - tile * KB;
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
-        const uint32_t sa = smem_base + uint32_t(stage) * stage_bytes;
-        tma_load_2d(sa, &tmap_w, int(kb * kBlockK), w_row0 + int(tile * kBlockN), full_bar(stage), kPolicyEvictFirst);
-        tma_load_2d(sa + kATileBytes, &tmap_x, int(kb * kBlockK), 0, full_bar(stage), kPolicyEvictLast);
-        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 2) {
+    // ===== ACTIVATION producer: op i's input exists once op i-1 is finalised everywhere =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < ch.n_ops; ++i) {
+        const GemmOp& op = ch.ops[i];
+        const CUtensorMap* tx = &maps.x[op.xmap];
+        const uint32_t u0 = op.sk.begin(cta), u1 = op.sk.begin(cta + 1), KB = uint32_t(op.sk.kb);
+        if (u0 < u1) {
+          if (i == 0) {
+            pdl_wait();
+          } else {
+            const GemmOp& pr = ch.ops[i - 1];
+            const uint32_t target = uint32_t(pr.sk.n_tiles) * uint32_t(pr.ep.M);
+            spin_until_ge(&ch.fin[(i - 1) * kCtrStride], target);
+            fence_proxy_async_all();  // other CTAs' generic-proxy stores -> this thread's TMA reads
+          }
+        }
+        for (uint32_t u = u0; u < u1; ++u) {
+          const uint32_t kb = u % KB;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          tma_load_2d(smem_base + uint32_t(stage) * stage_bytes + kATileBytes, tx, int(kb * kBlockK), 0,
+                      full_bar(stage), kPolicyEvictLast);
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16_f32(kBlockN, uint32_t(sk.m_tile));
+      const uint32_t idesc = umma_idesc_bf16_f32(kBlockN, uint32_t(m_tile));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      uint32_t u = u0;
-      while (u < u1) {
-        const uint32_t tile = u / KB;
-        const uint32_t seg_end = min(u1, (tile + 1) * KB);
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc) * uint32_t(sk.m_tile);
-        uint32_t accumulate = 0;
-        for (; u < seg_end; ++u) {
-          mbar_wait(full_bar(stage), phase);
+      for (int i = 0; i < ch.n_ops; ++i) {
+        const GemmOp& op = ch.ops[i];
+        const uint32_t u0 = op.sk.begin(cta), u1 = op.sk.begin(cta + 1), KB = uint32_t(op.sk.kb);
+        uint32_t u = u0;
+        while (u < u1) {
+          const uint32_t tile = u / KB;
+          const uint32_t seg_end = min(u1, (tile + 1) * KB);
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
           tcgen05_fence_after();
-          const uint32_t sa = smem_base + uint32_t(stage) * stage_bytes;
-          const uint64_t da = umma_desc_sw128_kmajor(sa);
-          const uint64_t db = umma_desc_sw128_kmajor(sa + kATileBytes);
+          const uint32_t d_tmem = tmem_base + uint32_t(acc) * uint32_t(m_tile);
+          uint32_t accumulate = 0;
+          for (; u < seg_end; ++u) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_base + uint32_t(stage) * stage_bytes;
+            const uint64_t da = umma_desc_sw128_kmajor(sa);
+            const uint64_t db = umma_desc_sw128_kmajor(sa + kATileBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_bf16_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, accumulate);
-            accumulate = 1;
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+              umma_bf16_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(empty_bar(stage));
-          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+          umma_commit(tfull_bar(acc));
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
-        umma_commit(tfull_bar(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {
-    // ===== epilogue warps =====
+  } else if (warp >= 4) {
+    // ===== epilogue warps (16): TMEM lane quarter = warp % 4, column group = (warp - 4) / 4 =====
     //  whole tile inside this CTA's range : TMEM -> smem staging -> fused epilogue, right away
     //  split tile (first / last segment)   : TMEM -> this CTA's fp32 partial slot; after the CTA's last segment the
     //                                        contributors of a tile share its rows (reduce-scatter): contributor j of
     //                                        k sums all k partials, in CTA order, for rows [jM/k, (j+1)M/k) and runs
     //                                        the fused epilogue on them — the fix-up is spread over all CTAs
+    // One scheduler runs one instruction stream at a time, so the epilogue's speed comes from having many warps
+    // (one token row each), not from unrolling.
     pdl_wait();  // everything below touches buffers the previous kernel may still be writing
-    if (ep.mode == EPI_QKV) {
-      for (int m = threadIdx.x - 64; m < ep.M; m += 128) s_pos[m] = make_int2(ep.rope_pos[m], ep.cache_pos[m]);
-      epi_bar();
-    }
-    const int ew = warp - 2;       // 0..3
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int ew = warp - 4;        // 0..15
+    const int quarter = ew & 3;     // TMEM lane quarter this warp may access (== warp % 4)
+    const int cgrp = ew >> 2;       // which 16-column blocks of the accumulator this warp drains
     const int nrow = quarter * 32 + lane;  // weight row of this thread inside the tile
-    const int tid_e = threadIdx.x - 64;    // 0..127
-    const size_t slot_floats = sk.slot_floats();
-    long long* dbg = (ep.dbg && tid_e == 0) ? ep.dbg + size_t(cta) * 8 : nullptr;
-    if (dbg) dbg[0] = clock64();
+    const int tid_e = threadIdx.x - 128;   // 0..511
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t u = u0;
-    int n_whole = 0, first_whole = -1;   // whole tiles finished here (consecutive)
-    int pend_tile[2] = {-1, -1};         // split tiles this CTA contributed to
-    int n_pend = 0;
-    while (u < u1) {
-      const uint32_t tile = u / KB;
-      const uint32_t seg_end = min(u1, (tile + 1) * KB);
-      const bool whole = (tile * KB >= u0) && ((tile + 1) * KB <= u1);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
-      if (dbg) dbg[(seg_end == u1) ? 2 : 1] = clock64();   // accumulator of a (1) non-last / (2) last segment ready
-      const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc) * uint32_t(sk.m_tile);
-      if (!whole) {
-        // slot 2*cta: the CTA's first segment; 2*cta+1: its last segment (when that is a different, split tile)
-        const int slot = 2 * cta + ((u == u0) ? 0 : 1);
-        float* dst = ep.ws + size_t(slot) * slot_floats + nrow;
-        for (int m0 = 0; m0 < sk.m_tile; m0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(t_addr + uint32_t(m0), v);
-          tmem_ld_wait();
-          if (m0 < ep.M) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) __stcg(dst + size_t(m0 + j) * 128, __uint_as_float(v[j]));
-          }
-        }
-        tcgen05_fence_before();
-        mbar_arrive(tempty_bar(acc));
-        __threadfence();
+#pragma unroll 1
+    for (int op_i = 0; op_i < ch.n_ops; ++op_i) {
+      const GemmOp& op = ch.ops[op_i];
+      const GemmEpi& ep = op.ep;
+      const StreamK& sk = op.sk;
+      const uint32_t u0 = sk.begin(cta), u1 = sk.begin(cta + 1), KB = uint32_t(sk.kb);
+      if (ep.mode == EPI_QKV) {
+        // (for op_i > 0 the positions are kernel inputs, not produced by the chain: safe to read right away)
+        for (int m = tid_e; m < ep.M; m += kEpiThreads) s_pos[m] = make_int2(ep.rope_pos[m], ep.cache_pos[m]);
         epi_bar();
-        if (tid_e == 0) atomicAdd(&ep.tile_arrive[2 * tile], 1u);
-        pend_tile[n_pend++] = int(tile);
-      } else {
-        const EpiTileConst tc = epi_tile_const(ep, int(tile), lane);
-        for (int c0m = 0; c0m < sk.m_tile; c0m += kEpiChunk) {
-          const int cw = min(kEpiChunk, sk.m_tile - c0m);
-          for (int j0 = 0; j0 < cw; j0 += 16) {
+      }
+      const size_t slot_floats = sk.slot_floats();
+      long long* dbg = (ep.dbg && tid_e == 0) ? ep.dbg + size_t(cta) * 16 : nullptr;
+      if (dbg) dbg[0] = clock64();
+      uint32_t u = u0;
+      int n_whole = 0, first_whole = -1;   // whole tiles finished here (consecutive)
+      int pend_tile0 = -1, pend_tile1 = -1, n_pend = 0;   // split tiles this CTA contributed to
+#pragma unroll 1
+      while (u < u1) {
+        const uint32_t tile = u / KB;
+        const uint32_t seg_end = min(u1, (tile + 1) * KB);
+        const bool whole = (tile * KB >= u0) && ((tile + 1) * KB <= u1);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        if (dbg) dbg[(seg_end == u1) ? 2 : 1] = clock64();   // accumulator of a (1) non-last / (2) last segment ready
+        const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc) * uint32_t(sk.m_tile);
+        if (!whole) {
+          // slot 2*cta: the CTA's first segment; 2*cta+1: its last segment (when that is a different, split tile)
+          const int slot = 2 * cta + ((u == u0) ? 0 : 1);
+          float* dst = ep.ws + size_t(slot) * slot_floats + nrow;
+#pragma unroll 1
+          for (int m0 = 16 * cgrp; m0 < sk.m_tile; m0 += 64) {
             uint32_t v[16];
-            tmem_ld_32x32b_x16(t_addr + uint32_t(c0m + j0), v);
+            tmem_ld_32x32b_x16(t_addr + uint32_t(m0), v);
             tmem_ld_wait();
+            if (m0 < ep.M) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) stage_tile[(j0 + j) * kBlockN + nrow] = __uint_as_float(v[j]);
-          }
-          if (c0m + kEpiChunk >= sk.m_tile) {  // accumulator fully drained
-            tcgen05_fence_before();
-            mbar_arrive(tempty_bar(acc));
-          }
-          epi_bar();  // staging tile complete
-          {
-            constexpr int R = kEpiChunk / 4;  // rows per warp per chunk, all in flight at once
-            const int ml0 = ew * R, mrow0 = c0m + ml0;
-            const int n_rows = min(min(R, cw - ml0), ep.M - mrow0);  // warp-uniform, may be <= 0
-            EpiAux aux[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-              if (r < n_rows) aux[r] = epi_load_aux(ep, tc, int(tile), mrow0 + r, lane, s_pos);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              if (r < n_rows) {
-                const float4 t = *reinterpret_cast<const float4*>(stage_tile + (ml0 + r) * kBlockN + 4 * lane);
-                float v[4] = {t.x, t.y, t.z, t.w};
-                epi_apply(ep, tc, aux[r], int(tile), mrow0 + r, lane, v, sk.m_tile);
-              }
+              for (int j = 0; j < 16; ++j) __stcg(dst + size_t(m0 + j) * 128, __uint_as_float(v[j]));
             }
           }
-          epi_bar();  // rows done before the next chunk overwrites the staging tile
-        }
-        if (n_whole++ == 0) first_whole = int(tile);
-      }
-      u = seg_end;
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-    if (dbg) dbg[3] = clock64();   // all segments drained / parked
-    // ---- deferred fix-up of the split tiles: this CTA's share of the rows ------------------------------
-    int share_lo[2] = {0, 0}, share_hi[2] = {0, 0};
-    for (int pi = 0; pi < n_pend; ++pi) {
-      const int tile = pend_tile[pi];
-      const int c_first = sk.first_cta(tile), c_last = sk.last_cta(tile);
-      const int k = c_last - c_first + 1, j = cta - c_first;
-      if (tid_e == 0) {
-        while (ld_acquire_u32(&ep.tile_arrive[2 * tile]) < uint32_t(k)) __nanosleep(32);
-      }
-      epi_bar();  // orders thread 0's acquire before everybody's partial reads
-      const int r_lo = (j * ep.M) / k, r_hi = ((j + 1) * ep.M) / k;
-      share_lo[pi] = r_lo;
-      share_hi[pi] = r_hi;
-      const EpiTileConst tc = epi_tile_const(ep, tile, lane);
-      // the slot contributor c used for this tile: its first segment iff the tile holds the start of its range
-      const int t_first_slot_cta = c_first;  // only c_first may have the tile as a non-first segment
-      const bool first_uses_last_slot = (sk.begin(c_first) / KB) != uint32_t(tile);
-      constexpr int R = 2, C = 4;
-      for (int m = r_lo + R * ew; m < r_hi; m += 4 * R) {
-        const int nr = min(R, r_hi - m);
-        EpiAux aux[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (r < nr) aux[r] = epi_load_aux(ep, tc, tile, m + r, lane, s_pos);
-        float v[R][4];
-#pragma unroll
-        for (int r = 0; r < R; ++r) v[r][0] = v[r][1] = v[r][2] = v[r][3] = 0.f;
-        for (int cb = c_first; cb <= c_last; cb += C) {
-          float4 pv[C][R];
-#pragma unroll
-          for (int cc = 0; cc < C; ++cc) {
-            const int c = cb + cc;
-            const int slot = 2 * c + ((c == t_first_slot_cta && first_uses_last_slot) ? 1 : 0);
-            const float* pc = ep.ws + size_t(slot) * slot_floats + size_t(m) * 128 + 4 * lane;
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-              pv[cc][r] = (c <= c_last && r < nr) ? __ldcg(reinterpret_cast<const float4*>(pc + r * 128))
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          epi_bar();   // every warp's partial stores happen-before thread 0's (cumulative) fence + flag
+          if (tid_e == 0) {
+            __threadfence();
+            atomicAdd(&ep.tile_arrive[kTileCtrStride * tile], 1u);
           }
+          if (n_pend++ == 0) pend_tile0 = int(tile); else pend_tile1 = int(tile);
+        } else {
+          const EpiTileConst tc = epi_tile_const(ep, int(tile), lane);
+#pragma unroll 1
+          for (int c0m = 0; c0m < sk.m_tile; c0m += kEpiChunk) {
+            const int cw = min(kEpiChunk, sk.m_tile - c0m);
+#pragma unroll 1
+            for (int j0 = 16 * cgrp; j0 < cw; j0 += 64) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(t_addr + uint32_t(c0m + j0), v);
+              tmem_ld_wait();
 #pragma unroll
-          for (int cc = 0; cc < C; ++cc) {   // CTA order: bit-reproducible
-            if (cb + cc <= c_last) {
+              for (int j = 0; j < 16; ++j) stage_tile[(j0 + j) * kBlockN + nrow] = __uint_as_float(v[j]);
+            }
+            if (c0m + kEpiChunk >= sk.m_tile) {  // accumulator fully drained
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty_bar(acc));
+            }
+            epi_bar();  // staging tile complete
+#pragma unroll 1
+            for (int ml = ew; ml < cw; ml += kEpiWarps) {   // one token row per warp at a time
+              const int m = c0m + ml;
+              if (m >= ep.M) break;
+              const EpiAux aux = epi_load_aux(ep, tc, int(tile), m, lane, s_pos);
+              const float4 t = *reinterpret_cast<const float4*>(stage_tile + ml * kBlockN + 4 * lane);
+              float v[4] = {t.x, t.y, t.z, t.w};
+              epi_apply(ep, tc, aux, int(tile), m, lane, v, sk.m_tile);
+            }
+            epi_bar();  // rows done before the next chunk overwrites the staging tile
+          }
+          if (n_whole++ == 0) first_whole = int(tile);
+        }
+        u = seg_end;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (dbg) dbg[3] = clock64();   // all segments drained / parked
+      // ---- deferred fix-up of the split tiles: this CTA's share of the rows ------------------------------
+      int share_lo0 = 0, share_hi0 = 0, share_lo1 = 0, share_hi1 = 0;
+#pragma unroll 1
+      for (int pq = 0; pq < n_pend; ++pq) {
+        // the LAST segment's tile first: its other contributors parked it at the start of their ranges, so it is
+        // ready now; the first segment's tile is completed by CTAs that are only now finishing
+        const int pi = n_pend - 1 - pq;
+        const int tile = pi == 0 ? pend_tile0 : pend_tile1;
+        const int c_first = sk.first_cta(tile), c_last = sk.last_cta(tile);
+        const int k = c_last - c_first + 1, j = cta - c_first;
+        if (tid_e == 0) spin_until_ge(&ep.tile_arrive[kTileCtrStride * tile], uint32_t(k));
+        epi_bar();  // orders thread 0's acquire before everybody's partial reads
+        if (dbg && pi == 0) dbg[8] = clock64();    // first split tile: all partials arrived
+        const int r_lo = (j * ep.M) / k, r_hi = ((j + 1) * ep.M) / k;
+        if (pi == 0) { share_lo0 = r_lo; share_hi0 = r_hi; } else { share_lo1 = r_lo; share_hi1 = r_hi; }
+        const EpiTileConst tc = epi_tile_const(ep, tile, lane);
+        // the slot contributor c used for this tile: its first segment iff the tile holds the start of its range;
+        // only c_first can have the tile as a non-first segment
+        const bool first_uses_last_slot = (sk.begin(c_first) / KB) != uint32_t(tile);
+        constexpr int C = 4;   // partials in flight per row
+#pragma unroll 1
+        for (int m = r_lo + ew; m < r_hi; m += kEpiWarps) {
+          const EpiAux aux = epi_load_aux(ep, tc, tile, m, lane, s_pos);
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int cb = c_first; cb <= c_last; cb += C) {
+            float4 pv[C];
 #pragma unroll
-              for (int r = 0; r < R; ++r) {
-                v[r][0] += pv[cc][r].x; v[r][1] += pv[cc][r].y; v[r][2] += pv[cc][r].z; v[r][3] += pv[cc][r].w;
-              }
+            for (int cc = 0; cc < C; ++cc) {   // unconditional (clamped) loads so that they batch
+              const int c = min(cb + cc, c_last);
+              const int slot = 2 * c + ((c == c_first && first_uses_last_slot) ? 1 : 0);
+              pv[cc] = __ldcg(reinterpret_cast<const float4*>(ep.ws + size_t(slot) * slot_floats + size_t(m) * 128 + 4 * lane));
+            }
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) {   // CTA order: bit-reproducible
+              if (cb + cc <= c_last) { v[0] += pv[cc].x; v[1] += pv[cc].y; v[2] += pv[cc].z; v[3] += pv[cc].w; }
             }
           }
+          epi_apply(ep, tc, aux, tile, m, lane, v, sk.m_tile);
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (r < nr) epi_apply(ep, tc, aux[r], tile, m + r, lane, v[r], sk.m_tile);
-      }
-      // re-arm the tile's counters once every contributor has read the partials
-      epi_bar();
-      if (tid_e == 0) {
-        const uint32_t done = atomicAdd(&ep.tile_arrive[2 * tile + 1], 1u) + 1u;
-        if (done == uint32_t(k)) {
-          ep.tile_arrive[2 * tile] = 0;
-          ep.tile_arrive[2 * tile + 1] = 0;
-        }
-      }
-    }
-    if (dbg) dbg[4] = clock64();   // fix-up shares done
-    // ---- EPI_RESID_NORM, second half: the row statistic needs every tile ------------------------------
-    if (ep.mode == EPI_RESID_NORM) {
-      const uint32_t my_rows = uint32_t(n_whole) * uint32_t(ep.M) + uint32_t(share_hi[0] - share_lo[0]) +
-                               uint32_t(share_hi[1] - share_lo[1]);
-      const uint32_t all_rows = uint32_t(sk.n_tiles) * uint32_t(ep.M);
-      if (my_rows > 0) {
-        __threadfence();
+        if (dbg && pi == 0) dbg[9] = clock64();    // first split tile: share finalised
+        // re-arm the tile's counters once every contributor has read the partials
         epi_bar();
         if (tid_e == 0) {
+          const uint32_t done = atomicAdd(&ep.tile_arrive[kTileCtrStride * tile + 1], 1u) + 1u;
+          if (done == uint32_t(k)) {
+            ep.tile_arrive[kTileCtrStride * tile] = 0;
+            ep.tile_arrive[kTileCtrStride * tile + 1] = 0;
+          }
+        }
+      }
+      if (dbg) dbg[4] = clock64();   // fix-up shares done
+      const uint32_t my_rows = uint32_t(n_whole) * uint32_t(ep.M) + uint32_t(share_hi0 - share_lo0) +
+                               uint32_t(share_hi1 - share_lo1);
+      // ---- EPI_RESID_NORM, second half: the row statistic needs every tile ------------------------------
+      if (ep.mode == EPI_RESID_NORM && my_rows > 0) {
+        const uint32_t all_rows = uint32_t(sk.n_tiles) * uint32_t(ep.M);
+        epi_bar();
+        if (tid_e == 0) {
+          __threadfence();
           atomicAdd(&ep.ctr[0], my_rows);
-          while (ld_acquire_u32(&ep.ctr[0]) < all_rows) __nanosleep(32);
+          spin_until_ge(&ep.ctr[0], all_rows);
           if (dbg) dbg[5] = clock64();   // every tile's statistic is in
         }
         epi_bar();
         const float inv_d = 1.f / float(ep.N);
         // pieces: [first_whole, first_whole + n_whole) x rows [0, M), then the two shares
+#pragma unroll 1
         for (int piece = 0; piece < 3; ++piece) {
           int t_lo, t_n, r_lo, r_hi;
           if (piece == 0) { t_lo = first_whole; t_n = n_whole; r_lo = 0; r_hi = ep.M; }
-          else { t_lo = pend_tile[piece - 1]; t_n = (piece - 1 < n_pend) ? 1 : 0; r_lo = share_lo[piece - 1]; r_hi = share_hi[piece - 1]; }
+          else if (piece == 1) { t_lo = pend_tile0; t_n = n_pend > 0 ? 1 : 0; r_lo = share_lo0; r_hi = share_hi0; }
+          else { t_lo = pend_tile1; t_n = n_pend > 1 ? 1 : 0; r_lo = share_lo1; r_hi = share_hi1; }
           if (t_n <= 0 || r_hi <= r_lo) continue;
-          constexpr int R2 = 4;   // rows per warp in flight
-          for (int mb = r_lo + ew * R2; mb < r_hi; mb += 4 * R2) {
-            float rinv[R2];
-#pragma unroll
-            for (int r = 0; r < R2; ++r) {
-              float sacc = 0.f;
-              if (mb + r < r_hi)
-                for (int t = lane; t < sk.n_tiles; t += 32) sacc += __ldcg(ep.ssq + size_t(t) * sk.m_tile + mb + r);
-              rinv[r] = sacc;
-            }
-#pragma unroll
-            for (int r = 0; r < R2; ++r) rinv[r] = rsqrtf(warp_sum(rinv[r]) * inv_d + ep.eps);
+#pragma unroll 1
+          for (int m = r_lo + ew; m < r_hi; m += kEpiWarps) {
+            float sacc = 0.f;
+            for (int t = lane; t < sk.n_tiles; t += 32) sacc += __ldcg(ep.ssq + size_t(t) * sk.m_tile + m);
+            const float rinv = rsqrtf(warp_sum(sacc) * inv_d + ep.eps);
+#pragma unroll 1
             for (int t = t_lo; t < t_lo + t_n; ++t) {
-              float wv[4];
+              const size_t off = size_t(m) * ep.N + size_t(t) * kBlockN + 4 * lane;
+              float wv[4], hv[4], o[4];
               unpack4(*reinterpret_cast<const uint2*>(ep.norm_w + t * kBlockN + 4 * lane), wv);
-              uint2 hraw[R2];
+              unpack4(*reinterpret_cast<const uint2*>(ep.h + off), hv);
 #pragma unroll
-              for (int r = 0; r < R2; ++r)
-                if (mb + r < r_hi)
-                  hraw[r] = *reinterpret_cast<const uint2*>(ep.h + size_t(mb + r) * ep.N + size_t(t) * kBlockN + 4 * lane);
-#pragma unroll
-              for (int r = 0; r < R2; ++r) {
-                if (mb + r < r_hi) {
-                  float hv[4], o[4];
-                  unpack4(hraw[r], hv);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) o[e] = wv[e] * bf16_round(hv[e] * rinv[r]);
-                  *reinterpret_cast<uint2*>(ep.xn + size_t(mb + r) * ep.N + size_t(t) * kBlockN + 4 * lane) = pack4(o);
-                }
-              }
+              for (int e = 0; e < 4; ++e) o[e] = wv[e] * bf16_round(hv[e] * rinv);
+              *reinterpret_cast<uint2*>(ep.xn + off) = pack4(o);
             }
           }
         }
+        if (dbg) dbg[10] = clock64();   // xn rows written
         epi_bar();
         if (tid_e == 0) {
-          const uint32_t done = atomicAdd(&ep.ctr[1], my_rows) + my_rows;
+          const uint32_t done = atomicAdd(&ep.ctr[kCtrStride], my_rows) + my_rows;
           if (done == all_rows) {  // everybody is past the meeting point: re-arm for the next launch
             ep.ctr[0] = 0;
-            ep.ctr[1] = 0;
+            ep.ctr[kCtrStride] = 0;
           }
         }
       }
+      // ---- publish: this CTA's rows of op_i are final (the next op's activation producer waits for all) ----
+      if (my_rows > 0) {
+        epi_bar();
+        if (tid_e == 0) {
+          __threadfence();
+          atomicAdd(&ch.fin[op_i * kCtrStride], my_rows);
+        }
+      }
+      if (dbg) dbg[6] = clock64();   // epilogue warps done with this op
+    }  // op loop
+    // ---- last CTA out re-arms the chain counters for the next launch ----
+    if (tid_e == 0) {
+      __threadfence();
+      const uint32_t out = atomicAdd(&ch.fin[kMaxChainOps * kCtrStride], 1u) + 1u;
+      if (out == gridDim.x) {
+        for (int i = 0; i <= kMaxChainOps; ++i) ch.fin[i * kCtrStride] = 0;
+      }
     }
-    if (dbg) dbg[6] = clock64();   // epilogue warps done
   }
 
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    tmem_dealloc(tmem_base, ch.tmem_cols);
   }
 }
 
@@ -627,6 +706,11 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// tiled weights: [units * 128 rows, 64 cols] bf16, one box = one contiguous 16 KB tile
+int make_tmap_tiled(CUtensorMap* out, const void* ptr, uint64_t units) {
+  return make_tmap_bf16_2d(out, ptr, units * kBlockN, kBlockK, kBlockN);
+}
+
 static int g_num_sms = 0;
 int device_num_sms() {
   if (!g_num_sms) {
@@ -645,11 +729,12 @@ StreamK gemm_partition(int N, int K, int m_tile, int grid_limit) {
   int g = grid_limit > 0 ? grid_limit : device_num_sms();
   uint32_t U = uint32_t(sk.n_tiles) * uint32_t(sk.kb);
   sk.grid = int(U < uint32_t(g) ? U : uint32_t(g));
+  if (uint64_t(U) * uint64_t(sk.grid) >= (1ull << 31)) sk.grid = 0;   // 32-bit partition math would overflow: rejected by the caller
   return sk;
 }
 
 // workspace layout (counters FIRST, so their place does not move with m_tile / grid and they stay zero):
-//   [ctr: 4 u32][tile {arrive, done}: 2*cap u32, padded to 16 B][ssq: n_tiles * m_tile floats][2*grid partial slots]
+//   [2 KB of counters, one per 256 B: stats {in, done}, stand-alone chain counters][tile {arrive, done}: 32 B each][ssq: n_tiles * m_tile floats][2*grid partial slots]
 struct GemmWorkspace {
   size_t ctr_off, arrive_off, ssq_off, slots_off, bytes;
 };
@@ -659,17 +744,14 @@ GemmWorkspace gemm_workspace(const StreamK& sk, int arrive_cap = 0) {
   GemmWorkspace w;
   const int cap = arrive_cap > sk.n_tiles ? arrive_cap : sk.n_tiles;
   w.ctr_off = 0;
-  w.arrive_off = 16;
-  w.ssq_off = w.arrive_off + ((size_t(cap) * 8 + 15) & ~size_t(15));
+  w.arrive_off = 2048;
+  w.ssq_off = w.arrive_off + size_t(cap) * kTileCtrStride * 4;
   w.slots_off = w.ssq_off + size_t(sk.n_tiles) * sk.m_tile * 4;
   w.bytes = w.slots_off + 2 * size_t(sk.grid) * sk.slot_floats() * 4;
   return w;
 }
 
-struct GemmLaunch {
-  CUtensorMap tmap_w, tmap_x;
-  int w_row0;
-  StreamK sk;
+struct ChainShape {
   int num_stages;
   uint32_t tmem_cols;
   uint32_t smem_bytes;
@@ -688,7 +770,7 @@ int gemm_smem_budget() {
 }
 
 // ring depth / TMEM columns / dynamic smem for a given m_tile
-int gemm_shape(GemmLaunch* g, int m_tile) {
+int gemm_shape(ChainShape* g, int m_tile) {
   if (m_tile % 16 != 0 || m_tile < 16 || m_tile > 256) return -3;
   const uint32_t stage_bytes = kATileBytes + uint32_t(m_tile) * kBlockK * 2;
   const uint32_t budget = uint32_t(gemm_smem_budget()) - 1024 - kEpiStageBytes;
@@ -706,34 +788,47 @@ int gemm_shape(GemmLaunch* g, int m_tile) {
 int gemm_attr_once() {
   static int rc = 1;
   if (rc == 1)
-    rc = cudaFuncSetAttribute(gemm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024) ==
+    rc = cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024) ==
                  cudaSuccess
              ? 0
              : -5;
   return rc;
 }
 
-long long* g_dbg_buf = nullptr;   // [g_dbg_cap launches][grid <= 256][8]
+long long* g_dbg_buf = nullptr;   // [g_dbg_cap ops][256 CTAs][8]
 int g_dbg_cap = 0;
 unsigned long long g_dbg_idx = 0;
 
-int gemm_launch(const GemmLaunch* g, const GemmEpi& ep_in, cudaStream_t stream) {
-  GemmEpi ep = ep_in;
-  ep.dbg = g_dbg_buf ? g_dbg_buf + size_t(g_dbg_idx++ % uint64_t(g_dbg_cap)) * 256 * 8 : nullptr;
+// ops of one chain must share m_tile; the grid is the largest per-op grid (CTAs beyond an op's grid idle in it)
+int chain_launch(const TmapSet& maps, Chain ch, cudaStream_t stream) {
+  if (ch.n_ops < 1 || ch.n_ops > kMaxChainOps) return -3;
+  ChainShape shp;
+  if (gemm_shape(&shp, ch.ops[0].sk.m_tile)) return -4;
+  ch.num_stages = shp.num_stages;
+  ch.tmem_cols = shp.tmem_cols;
+  static int lookahead = -1;
+  if (lookahead < 0) {
+    const char* e = getenv("SJD_GEMM_LOOKAHEAD");
+    lookahead = e ? atoi(e) : kLookahead;
+  }
+  ch.lookahead = lookahead;
+  int grid = 0;
+  for (int i = 0; i < ch.n_ops; ++i) {
+    if (ch.ops[i].sk.m_tile != ch.ops[0].sk.m_tile || ch.ops[i].sk.grid < 1) return -3;
+    grid = ch.ops[i].sk.grid > grid ? ch.ops[i].sk.grid : grid;
+    ch.ops[i].ep.dbg = g_dbg_buf ? g_dbg_buf + size_t(g_dbg_idx++ % uint64_t(g_dbg_cap)) * 256 * 16 : nullptr;
+  }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(g->sk.grid);
+  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = g->smem_bytes;
+  cfg.dynamicSmemBytes = shp.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_fused_kernel, g->tmap_w, g->tmap_x, g->w_row0, g->sk, g->num_stages,
-                            g->tmem_cols, ep) == cudaSuccess
-             ? 0
-             : -6;
+  return cudaLaunchKernelEx(&cfg, gemm_chain_kernel, maps, ch) == cudaSuccess ? 0 : -6;
 }
 
 }  // namespace sjd

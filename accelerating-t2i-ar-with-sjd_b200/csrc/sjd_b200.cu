@@ -45,7 +45,8 @@ struct sjd_ctx {
   __nv_bfloat16 *qn_w = nullptr, *qn_b = nullptr, *kn_w = nullptr, *kn_b = nullptr; // [L, H|Hkv, Dh]
   __nv_bfloat16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
   float *rope_cos = nullptr, *rope_sin = nullptr;
-  sjd::WeightMap m_qkv, m_o, m_gu, m_down, m_head;
+  sjd::WeightMap m_qkv, m_o, m_gu, m_down, m_head;   // .map copies live in maps[mi].w[0..4]
+  uint32_t* fin = nullptr;                             // chain counters [kMaxChainOps + 1]
   // ---- activations / caches / workspace ----
   __nv_bfloat16 *h = nullptr, *xn = nullptr, *q = nullptr, *attn = nullptr, *act = nullptr, *xl = nullptr;
   __nv_bfloat16 *kcache = nullptr, *vcache = nullptr;
@@ -56,7 +57,7 @@ struct sjd_ctx {
   int max_chunks = 0, arrive_cap = 0;
   std::vector<void*> allocs;
   // activation tensor maps per m_tile (index m_tile/16), built lazily
-  CUtensorMap xmap_xn[17], xmap_attn[17], xmap_act[17], xmap_xl[17];
+  sjd::TmapSet maps[17];   // w[]: qkv, o, gate_up, down, lm_head ; x[]: xn, attn, act, xl (box rows = m_tile)
   bool xmap_ok[17] = {false};
 };
 
@@ -78,17 +79,22 @@ static int ensure_xmaps(sjd_ctx* c, int m_tile) {
   if (c->xmap_ok[idx]) return 0;
   const sjd_model_cfg& g = c->cfg;
   const int hd = g.n_heads * g.head_dim;
-  if (make_tmap_bf16_2d(&c->xmap_xn[idx], c->xn, SJD_MAX_TOKENS, g.d_model, m_tile)) return SJD_E_TMAP;
-  if (make_tmap_bf16_2d(&c->xmap_attn[idx], c->attn, SJD_MAX_TOKENS, hd, m_tile)) return SJD_E_TMAP;
-  if (make_tmap_bf16_2d(&c->xmap_act[idx], c->act, SJD_MAX_TOKENS, g.d_ff, m_tile)) return SJD_E_TMAP;
-  if (make_tmap_bf16_2d(&c->xmap_xl[idx], c->xl, SJD_MAX_TOKENS, g.d_model, m_tile)) return SJD_E_TMAP;
+  TmapSet& t = c->maps[idx];
+  t.w[0] = c->m_qkv.map; t.w[1] = c->m_o.map; t.w[2] = c->m_gu.map; t.w[3] = c->m_down.map; t.w[4] = c->m_head.map;
+  if (make_tmap_bf16_2d(&t.x[0], c->xn, SJD_MAX_TOKENS, g.d_model, m_tile)) return SJD_E_TMAP;
+  if (make_tmap_bf16_2d(&t.x[1], c->attn, SJD_MAX_TOKENS, hd, m_tile)) return SJD_E_TMAP;
+  if (make_tmap_bf16_2d(&t.x[2], c->act, SJD_MAX_TOKENS, g.d_ff, m_tile)) return SJD_E_TMAP;
+  if (make_tmap_bf16_2d(&t.x[3], c->xl, SJD_MAX_TOKENS, g.d_model, m_tile)) return SJD_E_TMAP;
   c->xmap_ok[idx] = true;
   return 0;
 }
 
+// weights are stored tile-packed: [layers][n_tiles][K/64][128][64] (pack_tiles_kernel)
+static size_t packed_elems(int N, int K) { return size_t((N + kBlockN - 1) / kBlockN) * kBlockN * size_t(K); }
 static int set_wmap(WeightMap* wm, const void* ptr, int layers, int N, int K) {
   if (!ptr || K % kBlockK) return SJD_E_ARG;
-  if (make_tmap_bf16_2d(&wm->map, ptr, uint64_t(layers) * uint64_t(N), uint64_t(K), kBlockN)) return SJD_E_TMAP;
+  const uint64_t units = uint64_t(layers) * uint64_t((N + kBlockN - 1) / kBlockN) * uint64_t(K / kBlockK);
+  if (make_tmap_tiled(&wm->map, ptr, units)) return SJD_E_TMAP;
   wm->N = N;
   wm->K = K;
   wm->ok = true;
@@ -104,21 +110,40 @@ static void bind_ws(sjd_ctx* c, const StreamK& sk, GemmEpi* ep) {
   ep->ctr = reinterpret_cast<uint32_t*>(c->ws + w.ctr_off);
 }
 
-// one GEMM of the stack: stacked weights (layer `layer`) x activation map, fused epilogue `ep`
-static int run_gemm(sjd_ctx* c, const WeightMap& wm, int layer, const CUtensorMap& xmap, int m_tile, GemmEpi ep,
-                    cudaStream_t s) {
-  GemmLaunch g;
-  g.tmap_w = wm.map;
-  g.tmap_x = xmap;
-  g.w_row0 = layer * wm.N;
-  g.sk = gemm_partition(wm.N, wm.K, m_tile, 0);
-  if (gemm_shape(&g, m_tile)) return SJD_E_SMEM;
-  if (gemm_workspace(g.sk, c->arrive_cap).bytes > c->ws_bytes) return SJD_E_ARG;
-  ep.N = wm.N;
-  bind_ws(c, g.sk, &ep);
-  g_launches++;
-  return gemm_launch(&g, ep, s);
-}
+// A chain under construction: GEMMs are appended and flushed as ONE persistent kernel (gemm_chain_kernel)
+// whenever something else (attention, the lm_head row gather) has to run in between.
+struct ChainBuilder {
+  sjd_ctx* c;
+  int m_tile;
+  cudaStream_t s;
+  Chain ch;
+  int rc = 0;
+  ChainBuilder(sjd_ctx* c_, int m_tile_, cudaStream_t s_) : c(c_), m_tile(m_tile_), s(s_) { reset(); }
+  void reset() {
+    memset(&ch, 0, sizeof(ch));
+    ch.fin = c->fin;
+  }
+  enum { W_QKV = 0, W_O = 1, W_GU = 2, W_DOWN = 3, W_HEAD = 4, X_XN = 0, X_ATTN = 1, X_ACT = 2, X_XL = 3 };
+  void add(const WeightMap& wm, int wmap, int layer, int xmap, GemmEpi ep) {
+    if (ch.n_ops == kMaxChainOps) flush();
+    GemmOp& op = ch.ops[ch.n_ops++];
+    op.wmap = wmap;
+    op.xmap = xmap;
+    op.sk = gemm_partition(wm.N, wm.K, m_tile, 0);
+    op.w_tiled = 1;
+    op.w_row0 = layer * op.sk.n_tiles * op.sk.kb;   // first unit of this layer's weights
+    if (gemm_workspace(op.sk, c->arrive_cap).bytes > c->ws_bytes) rc |= SJD_E_ARG;
+    ep.N = wm.N;
+    bind_ws(c, op.sk, &ep);
+    op.ep = ep;
+  }
+  void flush() {
+    if (ch.n_ops == 0) return;
+    g_launches++;
+    if (!rc) rc |= chain_launch(c->maps[m_tile / 16], ch, s);
+    reset();
+  }
+};
 
 }  // namespace sjd
 
@@ -147,30 +172,33 @@ int sjd_gemm_bf16(const void* w, int N, int K, const void* x, int x_rows, int M,
   const int m_tile = round16(M);
   if (K % kBlockK != 0 || x_rows < m_tile) return fail(SJD_E_ARG, "sjd_gemm_bf16: K % 64 != 0 or x has < m_tile rows");
   if (gemm_attr_once()) return fail(SJD_E_ATTR, "cudaFuncSetAttribute(gemm)");
-  GemmLaunch g;
-  g.w_row0 = 0;
-  g.sk = gemm_partition(N, K, m_tile, grid_limit);
-  if (gemm_shape(&g, m_tile)) return fail(SJD_E_SMEM, "sjd_gemm_bf16: shared memory");
-  if (make_tmap_bf16_2d(&g.tmap_w, w, uint64_t(N), uint64_t(K), kBlockN)) return fail(SJD_E_TMAP, "weight tensor map");
-  if (make_tmap_bf16_2d(&g.tmap_x, x, uint64_t(x_rows), uint64_t(K), uint32_t(m_tile)))
+  const StreamK sk = gemm_partition(N, K, m_tile, grid_limit);
+  TmapSet maps;
+  memset(&maps, 0, sizeof(maps));
+  if (make_tmap_bf16_2d(&maps.w[0], w, uint64_t(N), uint64_t(K), kBlockN)) return fail(SJD_E_TMAP, "weight tensor map");
+  if (make_tmap_bf16_2d(&maps.x[0], x, uint64_t(x_rows), uint64_t(K), uint32_t(m_tile)))
     return fail(SJD_E_TMAP, "activation tensor map");
-  GemmEpi ep;
-  memset(&ep, 0, sizeof(ep));
+  Chain ch;
+  memset(&ch, 0, sizeof(ch));
+  GemmEpi& ep = ch.ops[0].ep;
   ep.mode = out_f32 ? EPI_F32 : EPI_BF16;
   ep.M = M;
   ep.N = N;
   ep.out = out;
   ep.ld_out = N;
   ep.round_bf16 = round_bf16;
-  const GemmWorkspace wl = gemm_workspace(g.sk);
+  const GemmWorkspace wl = gemm_workspace(sk);
   uint8_t* b = static_cast<uint8_t*>(ws);
   ep.ws = reinterpret_cast<float*>(b + wl.slots_off);
   ep.ssq = reinterpret_cast<float*>(b + wl.ssq_off);
   ep.tile_arrive = reinterpret_cast<uint32_t*>(b + wl.arrive_off);
   ep.ctr = reinterpret_cast<uint32_t*>(b + wl.ctr_off);
+  ch.fin = reinterpret_cast<uint32_t*>(b + wl.ctr_off) + 2 * kCtrStride;   // ctr region: 2 KB = 8 counters of 256 B
+  ch.n_ops = 1;
+  ch.ops[0].sk = sk;
   g_launches++;
-  const int rc = gemm_launch(&g, ep, static_cast<cudaStream_t>(stream));
-  return rc ? fail(rc, "gemm_launch") : 0;
+  const int rc = chain_launch(maps, ch, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "chain_launch") : 0;
 }
 
 int sjd_verify(const sjd_verify_args* a, void* stream) {
@@ -211,10 +239,10 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
   c->layer_set.assign(g.n_layers, 0);
   const size_t T = SJD_MAX_TOKENS, L = g.n_layers, d = g.d_model;
   int rc = 0;
-  rc |= dmalloc(c, &c->wqkv, L * nqkv * d * 2);
-  rc |= dmalloc(c, &c->wo, L * d * hd * 2);
-  rc |= dmalloc(c, &c->wgu, L * 2 * size_t(g.d_ff) * d * 2);
-  rc |= dmalloc(c, &c->wdown, L * d * size_t(g.d_ff) * 2);
+  rc |= dmalloc(c, &c->wqkv, L * packed_elems(nqkv, g.d_model) * 2);
+  rc |= dmalloc(c, &c->wo, L * packed_elems(g.d_model, hd) * 2);
+  rc |= dmalloc(c, &c->wgu, L * packed_elems(2 * g.d_ff, g.d_model) * 2);
+  rc |= dmalloc(c, &c->wdown, L * packed_elems(g.d_model, g.d_ff) * 2);
   rc |= dmalloc(c, &c->attn_norm, L * d * 2);
   rc |= dmalloc(c, &c->ffn_norm, L * d * 2);
   if (g.qk_norm) {
@@ -224,7 +252,7 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
     rc |= dmalloc(c, &c->kn_b, L * size_t(g.n_kv_heads) * g.head_dim * 2);
   }
   rc |= dmalloc(c, &c->embed, size_t(g.vocab) * d * 2);
-  rc |= dmalloc(c, &c->lm_head, size_t(g.vocab) * d * 2);
+  rc |= dmalloc(c, &c->lm_head, packed_elems(g.vocab, g.d_model) * 2);
   rc |= dmalloc(c, &c->final_norm, d * 2);
   rc |= dmalloc(c, &c->rope_cos, size_t(g.n_rope_pos) * (g.head_dim / 2) * 4);
   rc |= dmalloc(c, &c->rope_sin, size_t(g.n_rope_pos) * (g.head_dim / 2) * 4);
@@ -251,6 +279,7 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
   c->max_chunks = (g.max_len + kAttnChunk - 1) / kAttnChunk;
   rc |= dmalloc(c, &c->part_o, size_t(c->max_chunks) * T * hd * sizeof(float));
   rc |= dmalloc(c, &c->part_ml, size_t(c->max_chunks) * T * g.n_heads * 2 * sizeof(float));
+  rc |= dmalloc(c, &c->fin, (kMaxChainOps + 1) * kCtrStride * 4);
   rc |= dmalloc(c, &c->pos_zero, T * 4);
   rc |= dmalloc(c, &c->pos_last, T * 4);
   if (!rc) {
@@ -287,14 +316,18 @@ int sjd_ctx_set_layer(sjd_ctx* c, int layer, const sjd_layer_weights* w) {
   if (g.qk_norm && (!w->q_norm_w || !w->q_norm_b || !w->k_norm_w || !w->k_norm_b))
     return fail(SJD_E_ARG, "sjd_ctx_set_layer: qk_norm weights missing");
   const size_t d = g.d_model, hd = size_t(g.n_heads) * g.head_dim, kvd = size_t(g.n_kv_heads) * g.head_dim;
-  const size_t nqkv = hd + 2 * kvd, ff = g.d_ff, l = layer;
+  const size_t nqkv = hd + 2 * kvd, l = layer;
   cudaError_t e = cudaSuccess;
   auto cp = [&](void* dst, const void* src, size_t bytes) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, 0);
   };
-  cp(c->wqkv + l * nqkv * d, w->wqkv, nqkv * d * 2);
-  cp(c->wo + l * d * hd, w->wo, d * hd * 2);
-  cp(c->wdown + l * d * ff, w->w_down, d * ff * 2);
+  int prc = 0;
+  auto bfp = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
+  prc |= pack_tiles(bfp(w->wqkv), c->wqkv + l * packed_elems(int(nqkv), g.d_model), int(nqkv), g.d_model, 0, 0);
+  prc |= pack_tiles(bfp(w->wo), c->wo + l * packed_elems(g.d_model, int(hd)), g.d_model, int(hd), 0, 0);
+  prc |= pack_tiles(bfp(w->w_down), c->wdown + l * packed_elems(g.d_model, g.d_ff), g.d_model, g.d_ff, 0, 0);
+  prc |= pack_tiles(bfp(w->w_gate_up), c->wgu + l * packed_elems(2 * g.d_ff, g.d_model), 2 * g.d_ff, g.d_model, g.d_ff, 0);
+  if (prc) return fail(SJD_E_LAUNCH, "sjd_ctx_set_layer: pack_tiles");
   cp(c->attn_norm + l * d, w->attn_norm, d * 2);
   cp(c->ffn_norm + l * d, w->ffn_norm, d * 2);
   if (g.qk_norm) {
@@ -304,8 +337,6 @@ int sjd_ctx_set_layer(sjd_ctx* c, int layer, const sjd_layer_weights* w) {
     cp(c->kn_b + l * kvd, w->k_norm_b, kvd * 2);
   }
   if (e != cudaSuccess) return fail(SJD_E_LAUNCH, "sjd_ctx_set_layer: copy");
-  if (pack_gate_up(static_cast<const __nv_bfloat16*>(w->w_gate_up), c->wgu + l * 2 * ff * d, g.d_ff, g.d_model, 0))
-    return fail(SJD_E_LAUNCH, "sjd_ctx_set_layer: pack_gate_up");
   if (cudaStreamSynchronize(0) != cudaSuccess) return fail(SJD_E_LAUNCH, "sjd_ctx_set_layer: sync");
   c->layer_set[layer] = 1;
   return 0;
@@ -318,7 +349,9 @@ int sjd_ctx_set_globals(sjd_ctx* c, const void* embed, const void* final_norm, c
   const size_t vd = size_t(g.vocab) * g.d_model * 2, rb = size_t(g.n_rope_pos) * (g.head_dim / 2) * 4;
   cudaError_t e = cudaSuccess;
   if (embed) e = cudaMemcpy(c->embed, embed, vd, cudaMemcpyDeviceToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(c->lm_head, lm_head, vd, cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess && pack_tiles(static_cast<const __nv_bfloat16*>(lm_head), c->lm_head, g.vocab, g.d_model, 0, 0))
+    e = cudaErrorUnknown;
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(c->final_norm, final_norm, size_t(g.d_model) * 2, cudaMemcpyDeviceToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(c->rope_cos, rope_cos, rb, cudaMemcpyDeviceToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(c->rope_sin, rope_sin, rb, cudaMemcpyDeviceToDevice);
@@ -335,10 +368,13 @@ static int ctx_ready(sjd_ctx* c) {
   return 0;
 }
 
-// the GEMM + attention chain of one window forward; gemm_only skips attention (bench roofline leg)
-static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm_only, cudaStream_t s) {
+// The layer stack of one window forward.  Per layer: [QKV] -> attention -> [O, GATE_UP, DOWN, next layer's QKV];
+// the bracketed groups run as one persistent chain kernel each.  `head` (lm_head epilogue) joins the last chain
+// when it can consume xn directly.  gemm_only skips attention (bench roofline leg).
+static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm_only, const GemmEpi* head,
+                         cudaStream_t s) {
   const sjd_model_cfg& g = c->cfg;
-  const int M = g.rows * W, m_tile = round16(M), mi = m_tile / 16;
+  const int M = g.rows * W, m_tile = round16(M);
   const int hd = g.n_heads * g.head_dim;
   int rc = 0;
   AttnParams ap;
@@ -355,7 +391,8 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
   GemmEpi base;
   memset(&base, 0, sizeof(base));
   base.M = M;
-  for (int l = 0; l < g.n_layers && !rc; ++l) {
+  ChainBuilder cb(c, m_tile, s);
+  auto qkv_epi = [&](int l) {
     GemmEpi e = base;
     e.mode = EPI_QKV;
     e.q_out = c->q;
@@ -368,28 +405,36 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
     }
     e.W = W; e.H = g.n_heads; e.Hkv = g.n_kv_heads; e.Lmax = g.max_len; e.Dh = g.head_dim;
     e.rope_interleaved = g.rope_interleaved;
-    rc |= run_gemm(c, c->m_qkv, l, c->xmap_xn[mi], m_tile, e, s);
+    return e;
+  };
+  cb.add(c->m_qkv, ChainBuilder::W_QKV, 0, ChainBuilder::X_XN, qkv_epi(0));
+  for (int l = 0; l < g.n_layers && !rc; ++l) {
     if (!gemm_only) {
-      ap.k = e.k_cache; ap.v = e.v_cache;
+      cb.flush();
+      ap.k = c->kcache + size_t(l) * layer_cache;
+      ap.v = c->vcache + size_t(l) * layer_cache;
       rc |= attn_launch(ap, g.head_dim, s);
       g_launches += 2;
     }
-    e = base;
+    GemmEpi e = base;
     e.mode = EPI_RESID_NORM;
     e.h = c->h; e.xn = c->xn; e.eps = g.rms_eps;
     e.norm_w = c->ffn_norm + size_t(l) * g.d_model;
-    rc |= run_gemm(c, c->m_o, l, c->xmap_attn[mi], m_tile, e, s);
+    cb.add(c->m_o, ChainBuilder::W_O, l, ChainBuilder::X_ATTN, e);
     e = base;
     e.mode = EPI_SILU_MUL;
     e.out = c->act; e.ld_out = g.d_ff;
-    rc |= run_gemm(c, c->m_gu, l, c->xmap_xn[mi], m_tile, e, s);
+    cb.add(c->m_gu, ChainBuilder::W_GU, l, ChainBuilder::X_XN, e);
     e = base;
     e.mode = EPI_RESID_NORM;
     e.h = c->h; e.xn = c->xn; e.eps = g.rms_eps;
     e.norm_w = (l + 1 < g.n_layers) ? c->attn_norm + size_t(l + 1) * g.d_model : c->final_norm;
-    rc |= run_gemm(c, c->m_down, l, c->xmap_act[mi], m_tile, e, s);
+    cb.add(c->m_down, ChainBuilder::W_DOWN, l, ChainBuilder::X_ACT, e);
+    if (l + 1 < g.n_layers) cb.add(c->m_qkv, ChainBuilder::W_QKV, l + 1, ChainBuilder::X_XN, qkv_epi(l + 1));
+    else if (head) cb.add(c->m_head, ChainBuilder::W_HEAD, 0, ChainBuilder::X_XN, *head);
   }
-  return rc;
+  cb.flush();
+  return rc | cb.rc;
 }
 
 int sjd_ctx_forward(sjd_ctx* c, const sjd_forward_args* a, void* stream) {
@@ -404,14 +449,11 @@ int sjd_ctx_forward(sjd_ctx* c, const sjd_forward_args* a, void* stream) {
   if (ctx_ready(c)) return SJD_E_STATE;
   if (!a->ids && !a->embeds) return fail(SJD_E_ARG, "sjd_ctx_forward: ids or embeds required");
   if (a->ids && !c->have_embed) return fail(SJD_E_STATE, "sjd_ctx_forward: no embedding table");
-  const int m_tile = round16(M), mi = m_tile / 16;
+  const int m_tile = round16(M);
   if (ensure_xmaps(c, m_tile)) return fail(SJD_E_TMAP, "activation tensor maps");
   int rc = embed_rmsnorm_rows(a->ids, c->embed, static_cast<const __nv_bfloat16*>(a->embeds), c->h, c->attn_norm,
                               c->xn, M, g.d_model, g.rms_eps, s);
   g_launches++;
-  rc |= forward_chain(c, W, a, false, s);
-  if (rc) return fail(SJD_E_LAUNCH, "sjd_ctx_forward: layer launch");
-
   const int n = a->n_logit_tokens, Ml = g.rows * n;
   GemmEpi e;
   memset(&e, 0, sizeof(e));
@@ -421,15 +463,19 @@ int sjd_ctx_forward(sjd_ctx* c, const sjd_forward_args* a, void* stream) {
   e.ld_out = g.vocab;
   e.round_bf16 = g.logits_round_bf16;
   if (n == W) {
-    rc |= run_gemm(c, c->m_head, 0, c->xmap_xn[mi], m_tile, e, s);
+    rc |= forward_chain(c, W, a, false, &e, s);   // lm_head rides in the last chain
   } else {
-    const int ml_tile = round16(Ml), mli = ml_tile / 16;
+    rc |= forward_chain(c, W, a, false, nullptr, s);
+    const int ml_tile = round16(Ml);
     if (ensure_xmaps(c, ml_tile)) return fail(SJD_E_TMAP, "activation tensor maps");
     rc |= gather_rows(c->xn, c->xl, g.rows, W, n, g.d_model, s);
     g_launches++;
-    rc |= run_gemm(c, c->m_head, 0, c->xmap_xl[mli], ml_tile, e, s);
+    ChainBuilder cb(c, ml_tile, s);
+    cb.add(c->m_head, ChainBuilder::W_HEAD, 0, ChainBuilder::X_XL, e);
+    cb.flush();
+    rc |= cb.rc;
   }
-  if (rc || cudaGetLastError() != cudaSuccess) return fail(SJD_E_LAUNCH, "sjd_ctx_forward: head launch");
+  if (rc || cudaGetLastError() != cudaSuccess) return fail(SJD_E_LAUNCH, "sjd_ctx_forward: launch");
   return 0;
 }
 
@@ -440,7 +486,7 @@ int sjd_ctx_gemm_only(sjd_ctx* c, int W, void* stream) {
   if (ctx_ready(c)) return SJD_E_STATE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const sjd_model_cfg& g = c->cfg;
-  const int M = g.rows * W, m_tile = round16(M), mi = m_tile / 16;
+  const int M = g.rows * W, m_tile = round16(M);
   if (ensure_xmaps(c, m_tile)) return fail(SJD_E_TMAP, "activation tensor maps");
   // qkv epilogue: rope position 0, k/v land in the last cache slot (never a live key: kv_len + W <= max_len - 1
   // is not guaranteed, so callers must not interleave this with a decode in flight)
@@ -448,15 +494,14 @@ int sjd_ctx_gemm_only(sjd_ctx* c, int W, void* stream) {
   memset(&a, 0, sizeof(a));
   a.rope_pos = c->pos_zero;
   a.cache_pos = c->pos_last;
-  int rc = forward_chain(c, W, &a, true, s);
   GemmEpi e;
   memset(&e, 0, sizeof(e));
   e.mode = EPI_F32;
   e.M = M;
-  e.out = c->part_o;   // scratch: rows*W*vocab floats must fit (checked)
+  e.out = c->part_o;   // scratch: rows*W*vocab floats must fit, else only one row is written
   e.ld_out = g.vocab;
   if (size_t(M) * g.vocab > size_t(c->max_chunks) * SJD_MAX_TOKENS * g.n_heads * g.head_dim) e.M = 1;
-  rc |= run_gemm(c, c->m_head, 0, c->xmap_xn[mi], m_tile, e, s);
+  const int rc = forward_chain(c, W, &a, true, &e, s);
   return rc ? fail(SJD_E_LAUNCH, "sjd_ctx_gemm_only") : 0;
 }
 

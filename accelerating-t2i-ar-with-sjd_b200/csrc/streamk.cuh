@@ -17,12 +17,14 @@ struct StreamK {
   int grid;      // G
 
   __host__ __device__ __forceinline__ uint32_t units() const { return uint32_t(n_tiles) * uint32_t(kb); }
+  // CTAs beyond `grid` (a chain kernel may be launched wider than this op) get an empty range.
   __host__ __device__ __forceinline__ uint32_t begin(int c) const {
-    return uint32_t((uint64_t(c) * units()) / uint64_t(grid));
+    const uint32_t cc = uint32_t(c < grid ? c : grid);
+    return (cc * units()) / uint32_t(grid);   // 32-bit: the host checks units() * grid < 2^31
   }
   // CTA that owns unit u: the largest c with begin(c) <= u.
   __host__ __device__ __forceinline__ int owner(uint32_t u) const {
-    return int((uint64_t(u + 1) * uint64_t(grid) - 1) / uint64_t(units()));
+    return int(((u + 1) * uint32_t(grid) - 1) / units());
   }
   __host__ __device__ __forceinline__ int first_cta(int tile) const { return owner(uint32_t(tile) * kb); }
   __host__ __device__ __forceinline__ int last_cta(int tile) const {

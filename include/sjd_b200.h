@@ -147,7 +147,7 @@ int sjd_ctx_forward(sjd_ctx* ctx, const sjd_forward_args* a, void* stream);
  * lets bench.py time the dominant kernel (gemm_fused_kernel) in isolation with CUDA events. */
 int sjd_ctx_gemm_only(sjd_ctx* ctx, int W, void* stream);
 /* Developer timing: when device_buf != NULL every following GEMM launch i writes clock64 stamps of its epilogue
- * stages to device_buf[(i % n_launches)][cta < 256][8] (int64).  NULL switches it off. */
+ * stages to device_buf[(i % n_launches)][cta < 256][16] (int64).  NULL switches it off. */
 void sjd_debug_gemm_stamps(void* device_buf, int n_launches);
 /* counts kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t sjd_launch_count(void);

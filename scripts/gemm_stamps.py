@@ -13,7 +13,7 @@ lib = _lib.lib(); s = torch.cuda.current_stream().cuda_stream
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 for _ in range(3): lib.sjd_ctx_gemm_only(st.ctx, W, s)
 n = 4 * shape.n_layers + 1
-buf = torch.zeros(n, 256, 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(n, 256, 16, dtype=torch.int64, device=dev)
 lib.sjd_debug_gemm_stamps(buf.data_ptr(), n)
 lib.sjd_ctx_gemm_only(st.ctx, W, s)
 torch.cuda.synchronize()
@@ -28,4 +28,4 @@ for i in range(n):
         v = v[t[:, j] > 0]
         return (f"{v.mean():6.1f}/{v.max():6.1f}" if len(v) else "   -  /   -  ")
     nm = names[i % 4] if i < n - 1 else "lm_head"
-    print(f"{nm:8s} mean/max us since epilogue start: last-acc-ready {col(2)}  parked {col(3)}  fixup-done {col(4)}  stats-in {col(5)}  end {col(6)}")
+    print(f"{nm:8s} mean/max us: last-acc {col(2)} parked {col(3)} | t0-arrived {col(8)} t0-share-done {col(9)} | fixup-done {col(4)} stats-in {col(5)} xn-written {col(10)} end {col(6)} | share: setup {col(7)} loads-done {col(14)} apply-done {col(15)} | probe L2 load cycles mean/max {b[i,:148,13].mean()*1.965e3:.0f}/{b[i,:148,13].max()*1.965e3:.0f}")

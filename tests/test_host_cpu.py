@@ -43,9 +43,9 @@ def test_library_is_built_for_sm100a_with_tcgen05_and_tma(lib):
 
 def test_stream_k_workspace_is_host_computable(lib):
     L = lib.lib()
-    # counters (16 B + two u32 per tile, padded to 16 B) + per-tile row statistics + two fp32 partial slots per CTA
-    assert L.sjd_gemm_workspace_bytes(4096, 4096, 64, 148) == 16 + 32 * 8 + 32 * 64 * 4 + 2 * 148 * 64 * 128 * 4
-    assert L.sjd_gemm_workspace_bytes(184622, 4096, 128, 148) == 16 + 1443 * 8 + 8 + 1443 * 128 * 4 + 2 * 148 * 128 * 128 * 4
+    # 2 KB of counters + 32 B of {arrived, done} per tile + per-tile row statistics + two fp32 partial slots per CTA
+    assert L.sjd_gemm_workspace_bytes(4096, 4096, 64, 148) == 2048 + 32 * 32 + 32 * 64 * 4 + 2 * 148 * 64 * 128 * 4
+    assert L.sjd_gemm_workspace_bytes(184622, 4096, 128, 148) == 2048 + 1443 * 32 + 1443 * 128 * 4 + 2 * 148 * 128 * 128 * 4
 
 
 def test_no_compute_without_gpu_fails_loudly(lib):
