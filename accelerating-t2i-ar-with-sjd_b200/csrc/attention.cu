@@ -1,7 +1,7 @@
 // Jacobi draft-window attention over the static KV cache (decode-shaped, split-KV).
-// For every CFG row b, kv head and 128-key chunk one CTA streams the K/V chunk once into shared memory
-// (cp.async, zero-filled past the end) and every warp runs flash-style online softmax for one 16-query
-// tile of one query head (mma.sync m16n8k16 bf16, fp32 accumulate).  The Jacobi window mask of the
+// For every CFG row b, kv head and key split one CTA streams its span of the K/V cache through shared memory in
+// 64-key sub-chunks (cp.async double buffering, zero-filled past the end) while every warp runs flash-style online
+// softmax for one 16-query tile of one query head (mma.sync m16n8k16 bf16, fp32 accumulate).  The Jacobi window mask of the
 // reference — key j visible to window query i iff  kv_lo[b] <= j <= kv_len + i — is evaluated from
 // indices; no mask tensor exists (reference builds [2B,1,W,T+W] additive masks:
 // scheduler/jacobi_iteration_lumina_mgpt.py:1256-1336, consumed by SDPA at
@@ -11,7 +11,6 @@
 
 namespace sjd {
 
-constexpr int kAttnChunk = 128;   // keys per CTA
 constexpr int kAttnSub = 64;      // keys per online-softmax step
 constexpr int kAttnMaxRows = 8;   // CFG rows supported by the descriptor
 
@@ -25,7 +24,8 @@ struct AttnParams {
   int rows, W, H, Hkv, Lmax;
   int kv_len;               // keys cached before this window
   int kv_lo[kAttnMaxRows];  // first visible key per row
-  int n_chunks;
+  int n_chunks;             // key splits (one partial each)
+  int span;                 // keys per split (multiple of kAttnSub)
   float scale_log2e;        // softmax scale * log2(e)
 };
 
@@ -57,157 +57,178 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// grid: (key splits, Hkv * tile groups, rows); block: one warp per 16-query tile (<= 8 warps).
+// Each CTA walks its span of keys in 64-key sub-chunks, double buffered with cp.async so that the K/V stream of
+// sub-chunk s+1 is in flight while sub-chunk s is being multiplied.
 template <int DH>
 __global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
   constexpr int ROWB = DH * 2 + 16;  // padded smem row (bytes): conflict-free ldmatrix
+  constexpr int STAGE = kAttnSub * ROWB;
   extern __shared__ __align__(16) uint8_t smem[];
   pdl_wait();
   pdl_launch_dependents();
-  uint8_t* sK = smem;
-  uint8_t* sV = smem + kAttnChunk * ROWB;
+  uint8_t* sKb = smem;               // [2][kAttnSub][ROWB]
+  uint8_t* sVb = smem + 2 * STAGE;   // [2][kAttnSub][ROWB]
 
-  const int chunk = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
+  const int split = blockIdx.x, hkv = blockIdx.y % p.Hkv, tgroup = blockIdx.y / p.Hkv, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int T = p.kv_len + p.W;
-  const int key0 = chunk * kAttnChunk;
-  const int nkeys = min(kAttnChunk, T - key0);
   const int G = p.H / p.Hkv;
   const int tiles_per_head = (p.W + 15) >> 4;
   const int n_tiles = G * tiles_per_head;
   const int lo = p.kv_lo[b];
-
-  const bool chunk_live = (key0 + nkeys > lo);  // some key of the chunk may be visible
-  if (chunk_live) {
-    const __nv_bfloat16* kg = p.k + (size_t(b) * p.Hkv + hkv) * size_t(p.Lmax) * DH + size_t(key0) * DH;
-    const __nv_bfloat16* vg = p.v + (size_t(b) * p.Hkv + hkv) * size_t(p.Lmax) * DH + size_t(key0) * DH;
-    constexpr int VEC_PER_ROW = DH / 8;
-    for (int idx = threadIdx.x; idx < kAttnChunk * VEC_PER_ROW; idx += blockDim.x) {
-      const int r = idx / VEC_PER_ROW, c = idx - r * VEC_PER_ROW;
-      const int nb = r < nkeys ? 16 : 0;
-      const size_t goff = size_t(r < nkeys ? r : 0) * DH + c * 8;
-      cp_async_16(smem_u32(sK + r * ROWB + c * 16), kg + goff, nb);
-      cp_async_16(smem_u32(sV + r * ROWB + c * 16), vg + goff, nb);
-    }
-    cp_async_wait_all();
-  }
-  __syncthreads();
-
+  const int tile = tgroup * nwarps + warp;
+  const bool has_tile = tile < n_tiles;
+  const int hq = hkv * G + (has_tile ? tile / tiles_per_head : 0);
+  const int i0 = has_tile ? (tile % tiles_per_head) * 16 : 0;
   const int g = lane >> 2, t = lane & 3;
-  for (int tile = warp; tile < n_tiles; tile += nwarps) {
-    const int hq = hkv * G + tile / tiles_per_head;
-    const int i0 = (tile % tiles_per_head) * 16;
-    const int r0 = i0 + g, r1 = i0 + g + 8;  // query indices of this thread's two rows
-    float o[DH / 8][4];
-#pragma unroll
-    for (int n = 0; n < DH / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int r0 = i0 + g, r1 = i0 + g + 8;  // query indices of this thread's two rows
 
-    if (chunk_live) {
-      // Q fragments straight from global memory
-      uint32_t qf[DH / 16][4];
-      const __nv_bfloat16* q0 = p.q + (size_t(b * p.W + r0) * p.H + hq) * DH;
-      const __nv_bfloat16* q1 = p.q + (size_t(b * p.W + r1) * p.H + hq) * DH;
+  // span of this split, trimmed to what any query of the window can see: keys [lo, T)
+  int k_begin = split * p.span, k_end = min(T, k_begin + p.span);
+  k_begin = max(k_begin, (lo / kAttnSub) * kAttnSub);
+  const int n_sub = k_end > k_begin ? (k_end - k_begin + kAttnSub - 1) / kAttnSub : 0;
+  const __nv_bfloat16* kg = p.k + (size_t(b) * p.Hkv + hkv) * size_t(p.Lmax) * DH;
+  const __nv_bfloat16* vg = p.v + (size_t(b) * p.Hkv + hkv) * size_t(p.Lmax) * DH;
+  auto load_sub = [&](int s) {
+    constexpr int VEC_PER_ROW = DH / 8;
+    const int key0 = k_begin + s * kAttnSub, nkeys = min(kAttnSub, k_end - key0);
+    uint8_t* dK = sKb + (s & 1) * STAGE;
+    uint8_t* dV = sVb + (s & 1) * STAGE;
+    for (int idx = threadIdx.x; idx < kAttnSub * VEC_PER_ROW; idx += blockDim.x) {
+      const int r = idx / VEC_PER_ROW, c = idx - r * VEC_PER_ROW;
+      const int nb = r < nkeys ? 16 : 0;   // rows past the end are zero-filled
+      const size_t goff = size_t(key0 + (r < nkeys ? r : 0)) * DH + c * 8;
+      cp_async_16(smem_u32(dK + r * ROWB + c * 16), kg + goff, nb);
+      cp_async_16(smem_u32(dV + r * ROWB + c * 16), vg + goff, nb);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float o[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  uint32_t qf[DH / 16][4];
+  if (n_sub > 0) {
+    load_sub(0);
+    // Q fragments straight from global memory
+    const __nv_bfloat16* q0 = p.q + (size_t(b * p.W + min(r0, p.W - 1)) * p.H + hq) * DH;
+    const __nv_bfloat16* q1 = p.q + (size_t(b * p.W + min(r1, p.W - 1)) * p.H + hq) * DH;
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+      const int c = kk * 16 + t * 2;
+      qf[kk][0] = (has_tile && r0 < p.W) ? *reinterpret_cast<const uint32_t*>(q0 + c) : 0u;
+      qf[kk][1] = (has_tile && r1 < p.W) ? *reinterpret_cast<const uint32_t*>(q1 + c) : 0u;
+      qf[kk][2] = (has_tile && r0 < p.W) ? *reinterpret_cast<const uint32_t*>(q0 + c + 8) : 0u;
+      qf[kk][3] = (has_tile && r1 < p.W) ? *reinterpret_cast<const uint32_t*>(q1 + c + 8) : 0u;
+    }
+  }
+#pragma unroll 1
+  for (int s = 0; s < n_sub; ++s) {
+    if (s + 1 < n_sub) {
+      load_sub(s + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int key0 = k_begin + s * kAttnSub;
+    // causal skip: every key of this sub-chunk is beyond the last query of the tile
+    if (has_tile && key0 <= p.kv_len + min(i0 + 15, p.W - 1)) {
+      const uint8_t* sK = sKb + (s & 1) * STAGE;
+      const uint8_t* sV = sVb + (s & 1) * STAGE;
+      float sc[kAttnSub / 8][4];
+#pragma unroll
+      for (int n = 0; n < kAttnSub / 8; ++n) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
-        const int c = kk * 16 + t * 2;
-        qf[kk][0] = r0 < p.W ? *reinterpret_cast<const uint32_t*>(q0 + c) : 0u;
-        qf[kk][1] = r1 < p.W ? *reinterpret_cast<const uint32_t*>(q1 + c) : 0u;
-        qf[kk][2] = r0 < p.W ? *reinterpret_cast<const uint32_t*>(q0 + c + 8) : 0u;
-        qf[kk][3] = r1 < p.W ? *reinterpret_cast<const uint32_t*>(q1 + c + 8) : 0u;
-      }
-      for (int sub = 0; sub < nkeys; sub += kAttnSub) {
-        // causal skip: every key of this sub-block is beyond the last query of the tile
-        if (key0 + sub > p.kv_len + min(i0 + 15, p.W - 1)) break;
-        float s[kAttnSub / 8][4];
 #pragma unroll
-        for (int n = 0; n < kAttnSub / 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) {
-#pragma unroll
-          for (int np = 0; np < kAttnSub / 16; ++np) {
-            // matrices: (keys 0-7,d 0-7) (keys 0-7,d 8-15) (keys 8-15,d 0-7) (keys 8-15,d 8-15)
-            const int key = sub + np * 16 + (lane & 7) + ((lane >> 4) << 3);
-            const int dof = kk * 16 + (((lane >> 3) & 1) << 3);
-            uint32_t b0, b1, b2, b3;
-            ldmatrix_x4(smem_u32(sK + key * ROWB + dof * 2), b0, b1, b2, b3);
-            mma_bf16_16816(s[np * 2], qf[kk], b0, b1);
-            mma_bf16_16816(s[np * 2 + 1], qf[kk], b2, b3);
-          }
-        }
-        // mask + online softmax (scores scaled into log2 domain)
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int n = 0; n < kAttnSub / 8; ++n) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = key0 + sub + n * 8 + t * 2 + (e & 1);
-            const int qi = (e < 2) ? r0 : r1;
-            const bool ok = (j >= lo) && (j <= p.kv_len + qi) && (j < T) && (qi < p.W);
-            const float val = ok ? s[n][e] * p.scale_log2e : -INFINITY;
-            s[n][e] = val;
-            if (e < 2) mx0 = fmaxf(mx0, val); else mx1 = fmaxf(mx1, val);
-          }
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-        const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0, ms1 = (mn1 == -INFINITY) ? 0.f : mn1;
-        const float a0 = exp2f(m0 - ms0), a1 = exp2f(m1 - ms1);  // m == -inf -> 0
-        m0 = mn0; m1 = mn1;
-        l0 *= a0; l1 *= a1;
-#pragma unroll
-        for (int n = 0; n < DH / 8; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
-        float ps0 = 0.f, ps1 = 0.f;
-        uint32_t pf[kAttnSub / 16][4];
-#pragma unroll
-        for (int n = 0; n < kAttnSub / 8; ++n) {
-          const float e0 = exp2f(s[n][0] - ms0), e1 = exp2f(s[n][1] - ms0);
-          const float e2 = exp2f(s[n][2] - ms1), e3 = exp2f(s[n][3] - ms1);
-          // probabilities enter P*V as bf16, like the reference's bf16 SDPA
-          const uint32_t p01 = pack_bf16(e0, e1), p23 = pack_bf16(e2, e3);
-          const __nv_bfloat162 v01 = *reinterpret_cast<const __nv_bfloat162*>(&p01);
-          const __nv_bfloat162 v23 = *reinterpret_cast<const __nv_bfloat162*>(&p23);
-          ps0 += __low2float(v01) + __high2float(v01);
-          ps1 += __low2float(v23) + __high2float(v23);
-          pf[n >> 1][(n & 1) * 2 + 0] = p01;
-          pf[n >> 1][(n & 1) * 2 + 1] = p23;
-        }
-        l0 += ps0; l1 += ps1;
-#pragma unroll
-        for (int kk = 0; kk < kAttnSub / 16; ++kk) {
-#pragma unroll
-          for (int dp = 0; dp < DH / 16; ++dp) {
-            // trans matrices: (keys 0-7,d 0-7) (keys 8-15,d 0-7) (keys 0-7,d 8-15) (keys 8-15,d 8-15)
-            const int key = sub + kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-            const int dof = dp * 16 + ((lane >> 4) << 3);
-            uint32_t b0, b1, b2, b3;
-            ldmatrix_x4_trans(smem_u32(sV + key * ROWB + dof * 2), b0, b1, b2, b3);
-            mma_bf16_16816(o[dp * 2], pf[kk], b0, b1);
-            mma_bf16_16816(o[dp * 2 + 1], pf[kk], b2, b3);
-          }
+        for (int np = 0; np < kAttnSub / 16; ++np) {
+          // matrices: (keys 0-7,d 0-7) (keys 0-7,d 8-15) (keys 8-15,d 0-7) (keys 8-15,d 8-15)
+          const int key = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+          const int dof = kk * 16 + (((lane >> 3) & 1) << 3);
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(smem_u32(sK + key * ROWB + dof * 2), b0, b1, b2, b3);
+          mma_bf16_16816(sc[np * 2], qf[kk], b0, b1);
+          mma_bf16_16816(sc[np * 2 + 1], qf[kk], b2, b3);
         }
       }
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    }
-    // write partials
-    const size_t base = ((size_t(chunk) * p.rows + b) * p.H + hq) * size_t(p.W);
-    if (r0 < p.W) {
-      float* po = p.part_o + (base + r0) * DH;
+      // mask + online softmax (scores scaled into log2 domain)
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int n = 0; n < DH / 8; ++n) *reinterpret_cast<float2*>(po + n * 8 + t * 2) = make_float2(o[n][0], o[n][1]);
-      if (t == 0) { p.part_ml[(base + r0) * 2] = m0; p.part_ml[(base + r0) * 2 + 1] = l0; }
-    }
-    if (r1 < p.W) {
-      float* po = p.part_o + (base + r1) * DH;
+      for (int n = 0; n < kAttnSub / 8; ++n) {
 #pragma unroll
-      for (int n = 0; n < DH / 8; ++n) *reinterpret_cast<float2*>(po + n * 8 + t * 2) = make_float2(o[n][2], o[n][3]);
-      if (t == 0) { p.part_ml[(base + r1) * 2] = m1; p.part_ml[(base + r1) * 2 + 1] = l1; }
+        for (int e = 0; e < 4; ++e) {
+          const int j = key0 + n * 8 + t * 2 + (e & 1);
+          const int qi = (e < 2) ? r0 : r1;
+          const bool ok = (j >= lo) && (j <= p.kv_len + qi) && (j < k_end) && (qi < p.W);
+          const float val = ok ? sc[n][e] * p.scale_log2e : -INFINITY;
+          sc[n][e] = val;
+          if (e < 2) mx0 = fmaxf(mx0, val); else mx1 = fmaxf(mx1, val);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+      const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0, ms1 = (mn1 == -INFINITY) ? 0.f : mn1;
+      const float a0 = exp2f(m0 - ms0), a1 = exp2f(m1 - ms1);  // m == -inf -> 0
+      m0 = mn0; m1 = mn1;
+      l0 *= a0; l1 *= a1;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
+      float ps0 = 0.f, ps1 = 0.f;
+      uint32_t pf[kAttnSub / 16][4];
+#pragma unroll
+      for (int n = 0; n < kAttnSub / 8; ++n) {
+        const float e0 = exp2f(sc[n][0] - ms0), e1 = exp2f(sc[n][1] - ms0);
+        const float e2 = exp2f(sc[n][2] - ms1), e3 = exp2f(sc[n][3] - ms1);
+        // probabilities enter P*V as bf16, like the reference's bf16 SDPA
+        const uint32_t p01 = pack_bf16(e0, e1), p23 = pack_bf16(e2, e3);
+        const __nv_bfloat162 v01 = *reinterpret_cast<const __nv_bfloat162*>(&p01);
+        const __nv_bfloat162 v23 = *reinterpret_cast<const __nv_bfloat162*>(&p23);
+        ps0 += __low2float(v01) + __high2float(v01);
+        ps1 += __low2float(v23) + __high2float(v23);
+        pf[n >> 1][(n & 1) * 2 + 0] = p01;
+        pf[n >> 1][(n & 1) * 2 + 1] = p23;
+      }
+      l0 += ps0; l1 += ps1;
+#pragma unroll
+      for (int kk = 0; kk < kAttnSub / 16; ++kk) {
+#pragma unroll
+        for (int dp = 0; dp < DH / 16; ++dp) {
+          // trans matrices: (keys 0-7,d 0-7) (keys 8-15,d 0-7) (keys 0-7,d 8-15) (keys 8-15,d 8-15)
+          const int key = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+          const int dof = dp * 16 + ((lane >> 4) << 3);
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4_trans(smem_u32(sV + key * ROWB + dof * 2), b0, b1, b2, b3);
+          mma_bf16_16816(o[dp * 2], pf[kk], b0, b1);
+          mma_bf16_16816(o[dp * 2 + 1], pf[kk], b2, b3);
+        }
+      }
     }
+    __syncthreads();   // everybody is done with this stage before sub-chunk s+2 lands in it
+  }
+  if (!has_tile) return;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // write partials
+  const size_t base = ((size_t(split) * p.rows + b) * p.H + hq) * size_t(p.W);
+  if (r0 < p.W) {
+    float* po = p.part_o + (base + r0) * DH;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) *reinterpret_cast<float2*>(po + n * 8 + t * 2) = make_float2(o[n][0], o[n][1]);
+    if (t == 0) { p.part_ml[(base + r0) * 2] = m0; p.part_ml[(base + r0) * 2 + 1] = l0; }
+  }
+  if (r1 < p.W) {
+    float* po = p.part_o + (base + r1) * DH;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) *reinterpret_cast<float2*>(po + n * 8 + t * 2) = make_float2(o[n][2], o[n][3]);
+    if (t == 0) { p.part_ml[(base + r1) * 2] = m1; p.part_ml[(base + r1) * 2 + 1] = l1; }
   }
 }
 
@@ -247,22 +268,39 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(AttnParams p) {
   for (int e = 0; e < PER; ++e) dst[lane + 32 * e] = __float2bfloat16_rn(acc[e] * inv);
 }
 
+// Chooses the key split: enough CTAs to fill the machine about three deep, spans in whole 64-key sub-chunks.
+void attn_plan(AttnParams* p, int sm_count) {
+  const int T = p->kv_len + p->W;
+  const int G = p->H / p->Hkv;
+  const int n_tiles = G * ((p->W + 15) / 16);
+  const int tgroups = (n_tiles + 7) / 8;
+  const int base_ctas = p->rows * p->Hkv * tgroups;
+  int want = (3 * sm_count + base_ctas - 1) / base_ctas;   // splits wanted
+  const int n_sub = (T + kAttnSub - 1) / kAttnSub;
+  if (want > n_sub) want = n_sub;
+  if (want < 1) want = 1;
+  const int sub_per_split = (n_sub + want - 1) / want;
+  p->span = sub_per_split * kAttnSub;
+  p->n_chunks = (T + p->span - 1) / p->span;
+}
+
 int attn_launch(const AttnParams& p, int head_dim, cudaStream_t stream) {
   const int G = p.H / p.Hkv;
   const int n_tiles = G * ((p.W + 15) / 16);
-  int nwarps = n_tiles < 8 ? n_tiles : 8;
-  dim3 grid(p.n_chunks, p.Hkv, p.rows);
+  const int nwarps = n_tiles < 8 ? n_tiles : 8;
+  const int tgroups = (n_tiles + nwarps - 1) / nwarps;
+  dim3 grid(p.n_chunks, p.Hkv * tgroups, p.rows);
   const int total = p.rows * p.H * p.W;
   dim3 cgrid((total + 7) / 8);
   int rc = 0;
   if (head_dim == 128) {
-    constexpr int smem = 2 * kAttnChunk * (128 * 2 + 16);
+    constexpr int smem = 4 * kAttnSub * (128 * 2 + 16);
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(attn_window_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
     rc |= launch_pdl(attn_window_kernel<128>, grid, dim3(nwarps * 32), smem, stream, p);
     rc |= launch_pdl(attn_combine_kernel<128>, cgrid, dim3(256), 0, stream, p);
   } else if (head_dim == 64) {
-    constexpr int smem = 2 * kAttnChunk * (64 * 2 + 16);
+    constexpr int smem = 4 * kAttnSub * (64 * 2 + 16);
     rc |= launch_pdl(attn_window_kernel<64>, grid, dim3(nwarps * 32), smem, stream, p);
     rc |= launch_pdl(attn_combine_kernel<64>, cgrid, dim3(256), 0, stream, p);
   } else {

@@ -276,7 +276,7 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
   }
   c->ws_bytes = wsb;
   rc |= dmalloc(c, &c->ws, wsb);
-  c->max_chunks = (g.max_len + kAttnChunk - 1) / kAttnChunk;
+  c->max_chunks = (g.max_len + kAttnSub - 1) / kAttnSub;   // upper bound on key splits
   rc |= dmalloc(c, &c->part_o, size_t(c->max_chunks) * T * hd * sizeof(float));
   rc |= dmalloc(c, &c->part_ml, size_t(c->max_chunks) * T * g.n_heads * 2 * sizeof(float));
   rc |= dmalloc(c, &c->fin, (kMaxChainOps + 1) * kCtrStride * 4);
@@ -383,7 +383,7 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
     ap.q = c->q; ap.part_o = c->part_o; ap.part_ml = c->part_ml; ap.out = c->attn;
     ap.rows = g.rows; ap.W = W; ap.H = g.n_heads; ap.Hkv = g.n_kv_heads; ap.Lmax = g.max_len; ap.kv_len = a->kv_len;
     for (int b = 0; b < kAttnMaxRows; ++b) ap.kv_lo[b] = b < g.rows ? a->kv_lo[b] : 0;
-    ap.n_chunks = (a->kv_len + W + kAttnChunk - 1) / kAttnChunk;
+    attn_plan(&ap, device_num_sms());
     ap.scale_log2e = 1.4426950408889634f / sqrtf(float(g.head_dim));
   }
   const size_t layer_cache = size_t(g.rows) * g.n_kv_heads * size_t(g.max_len) * g.head_dim;
