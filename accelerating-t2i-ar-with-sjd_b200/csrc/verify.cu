@@ -204,6 +204,118 @@ __device__ int block_topk_softmax_sample(float* __restrict__ row, int V, int top
   return block_argmax(best, besti, sc);
 }
 
+// ---- register-resident variant --------------------------------------------------------------------------
+// When the grammar (or the vocabulary) leaves at most kVerifyThreads * VPT candidate ids [lo, lo + n), each thread
+// keeps its VPT processed scores in registers and every pass (max, radix select, sum, sample) runs on them: the
+// logits are read once and the probabilities written once.  Element j of thread t is id v0 + j*blockDim + t with v0
+// = lo rounded down to a multiple of blockDim, i.e. exactly the ids (in the same ascending order) the strided
+// global-memory variant gives that thread, so the block reductions — and therefore every result — are bit-identical.
+template <int VPT>
+__device__ uint32_t block_kth_key_regs(const float (&s)[VPT], int k, BlockScratch& sc) {
+  uint32_t prefix = 0, mask = 0;
+  uint32_t remaining = uint32_t(k);
+  const int shifts[3] = {21, 10, 0};
+  const int nbits[3] = {11, 11, 10};
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = shifts[pass];
+    const uint32_t nb = 1u << nbits[pass];
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) sc.hist[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const float f = s[j];
+      if (f != -INFINITY) {
+        const uint32_t key = f2key(f);
+        if ((key & mask) == prefix) atomicAdd(&sc.hist[(key >> shift) & (nb - 1)], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const uint32_t lane = threadIdx.x;
+      const uint32_t per = nb / 32;
+      const uint32_t hi = nb - lane * per;  // exclusive top of this lane's chunk (lane 0 = largest keys)
+      uint32_t csum = 0;
+      for (uint32_t j = 0; j < per; ++j) csum += sc.hist[hi - 1 - j];
+      uint32_t incl = csum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= uint32_t(o)) incl += t;
+      }
+      const uint32_t excl = incl - csum;
+      const bool mine = (excl < remaining) && (incl >= remaining);
+      if (mine) {
+        uint32_t run = excl;
+        for (uint32_t j = 0; j < per; ++j) {
+          const uint32_t c = sc.hist[hi - 1 - j];
+          if (run + c >= remaining) {
+            sc.sel_bin = hi - 1 - j;
+            sc.sel_above = run;
+            break;
+          }
+          run += c;
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= sc.sel_bin << shift;
+    mask |= (nb - 1) << shift;
+    remaining -= sc.sel_above;
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// s[j]: processed score of id v0 + j*blockDim + tid (-inf when removed or outside [lo, hi)).  Writes the
+// probabilities of ids [lo, hi) to p_out (the caller zeroes the rest of the row) and returns the token.
+template <int VPT>
+__device__ int block_topk_softmax_sample_regs(float (&s)[VPT], int v0, int lo, int hi, int top_k, int do_sample,
+                                              const float* __restrict__ noise_e, float* __restrict__ p_out,
+                                              int V, BlockScratch& sc) {
+  float mx = -INFINITY;
+  int nfin = 0;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    mx = fmaxf(mx, s[j]);
+    nfin += (s[j] != -INFINITY);
+  }
+  mx = block_max(mx, sc);
+  nfin = block_sumi(nfin, sc);
+  float thr = -INFINITY;  // scores < thr are removed
+  if (top_k > 0 && top_k < V && nfin > top_k) {
+    const uint32_t key = block_kth_key_regs<VPT>(s, top_k, sc);
+    const uint32_t u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+    thr = __uint_as_float(u);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j)
+    if (s[j] >= thr && s[j] != -INFINITY) sum += expf(s[j] - mx);
+  sum = block_sumf(sum, sc);
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int v = v0 + j * blockDim.x + threadIdx.x;
+    if (v >= lo && v < hi) {
+      const float f = s[j];
+      const bool keep = (f >= thr && f != -INFINITY);
+      const float pr = keep ? expf(f - mx) / sum : 0.f;
+      if (p_out) p_out[v] = pr;
+      float val;
+      if (do_sample) val = pr / noise_e[v];
+      else val = keep ? f : -INFINITY;
+      if (val > best) { best = val; besti = v; }  // ascending v per thread keeps the lowest index on ties
+    }
+  }
+  // ids outside the candidate range have probability 0: in sampling mode 0 / noise = 0 can still win the argmax
+  // when every candidate probability is 0 too — impossible here (the kept maximum has probability > 0)
+  return block_argmax(best, besti, sc);
+}
+
+constexpr int kRegVPT = 16;   // ids per thread held in registers: candidate ranges spanning up to 16 384 ids
+
 // One CTA per window position.
 __global__ void __launch_bounds__(kVerifyThreads) verify_rows_kernel(VerifyParams p) {
   __shared__ BlockScratch sc;
@@ -215,14 +327,45 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_rows_kernel(VerifyParam
   const int forced = p.forced ? p.forced[i] : -1;
   const bool ranged = p.allow_hi > p.allow_lo;
   const bool mix = p.has_uncond && p.apply_cfg;
+  if (forced >= 0) {
+    // forced position: the distribution is one-hot whatever the logits are (0 -> exp(0)/1 = 1)
+    for (int v = threadIdx.x; v < V; v += blockDim.x) row[v] = (v == forced) ? 1.f : 0.f;
+    if (threadIdx.x == 0) p.next_tokens[i] = forced;
+    return;
+  }
+  const int lo = ranged ? max(p.allow_lo, 0) : 0, hi = ranged ? min(p.allow_hi, V) : V;
+  const int v0 = (lo / int(blockDim.x)) * int(blockDim.x);
+  if (hi - v0 <= int(blockDim.x) * kRegVPT) {
+    float s[kRegVPT];
+#pragma unroll
+    for (int j = 0; j < kRegVPT; ++j) {
+      const int v = v0 + j * blockDim.x + threadIdx.x;
+      float sv = -INFINITY;
+      if (v >= lo && v < hi) {
+        sv = c[v];
+        if (mix) {
+          const float uu = u[v];
+          sv = __fadd_rn(__fmul_rn(p.guidance, __fsub_rn(sv, uu)), uu);
+        }
+        if (p.temperature != 1.f) sv = sv / p.temperature;
+      }
+      s[j] = sv;
+    }
+    // everything outside the candidate range has probability zero
+    for (int v = threadIdx.x; v < lo; v += blockDim.x) row[v] = 0.f;
+    for (int v = hi + threadIdx.x; v < V; v += blockDim.x) row[v] = 0.f;
+    const int tok = block_topk_softmax_sample_regs<kRegVPT>(s, v0, lo, hi, p.top_k, p.do_sample,
+                                                            p.noise_e1 + size_t(i) * V, row, V, sc);
+    if (threadIdx.x == 0) p.next_tokens[i] = tok;
+    return;
+  }
   for (int v = threadIdx.x; v < V; v += blockDim.x) {
     float s = c[v];
     if (mix) {
       const float uu = u[v];
       s = __fadd_rn(__fmul_rn(p.guidance, __fsub_rn(s, uu)), uu);
     }
-    if (forced >= 0) s = (v == forced) ? 0.f : -INFINITY;
-    else if (ranged && (v < p.allow_lo || v >= p.allow_hi)) s = -INFINITY;
+    if (ranged && (v < p.allow_lo || v >= p.allow_hi)) s = -INFINITY;
     if (p.temperature != 1.f) s = s / p.temperature;
     row[v] = s;
   }
@@ -277,16 +420,37 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyPar
     const bool text = s_text_mode != 0;
     const int forced = (!text && p.forced) ? p.forced[j] : -1;
     const bool ranged = !text && (p.allow_hi > p.allow_lo);
-    for (int v = threadIdx.x; v < V; v += blockDim.x) {
-      const float q = b ? b[v] : (v == xd ? 1.f : 0.f);
-      float s = logf(fmaxf(__fsub_rn(a[v], q), 0.f));
-      if (forced >= 0) s = (v == forced) ? 0.f : -INFINITY;
-      else if (ranged && (v < p.allow_lo || v >= p.allow_hi)) s = -INFINITY;
-      if (p.temperature != 1.f) s = s / p.temperature;
-      p.resid[v] = s;
+    const int lo = ranged ? max(p.allow_lo, 0) : 0, hi = ranged ? min(p.allow_hi, V) : V;
+    const int v0 = (lo / int(blockDim.x)) * int(blockDim.x);
+    const int top_k = text ? p.text_top_k : p.top_k;
+    int tok;
+    if (forced >= 0) {
+      tok = forced;   // one-hot residual support after the grammar: the multinomial can only return it
+    } else if (hi - v0 <= int(blockDim.x) * kRegVPT) {
+      float s[kRegVPT];
+#pragma unroll
+      for (int jj = 0; jj < kRegVPT; ++jj) {
+        const int v = v0 + jj * blockDim.x + threadIdx.x;
+        float sv = -INFINITY;
+        if (v >= lo && v < hi) {
+          const float q = b ? b[v] : (v == xd ? 1.f : 0.f);
+          sv = logf(fmaxf(__fsub_rn(a[v], q), 0.f));
+          if (p.temperature != 1.f) sv = sv / p.temperature;
+        }
+        s[jj] = sv;
+      }
+      tok = block_topk_softmax_sample_regs<kRegVPT>(s, v0, lo, hi, top_k, 1, p.noise_e2, nullptr, V, sc);
+    } else {
+      for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        const float q = b ? b[v] : (v == xd ? 1.f : 0.f);
+        float s = logf(fmaxf(__fsub_rn(a[v], q), 0.f));
+        if (ranged && (v < p.allow_lo || v >= p.allow_hi)) s = -INFINITY;
+        if (p.temperature != 1.f) s = s / p.temperature;
+        p.resid[v] = s;
+      }
+      __syncthreads();
+      tok = block_topk_softmax_sample(p.resid, V, top_k, 1, p.noise_e2, sc);
     }
-    __syncthreads();
-    const int tok = block_topk_softmax_sample(p.resid, V, text ? p.text_top_k : p.top_k, 1, p.noise_e2, sc);
     if (threadIdx.x == 0) p.out_tokens[j] = tok;
   }
   if (threadIdx.x == 0) {
