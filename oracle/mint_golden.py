@@ -104,11 +104,34 @@ def make_fake_lm(V: int, sharp: float):
     return FakeLM()
 
 
+def load_reference_scheduler():
+    """Import the REFERENCE's scheduler modules by file path.  (`import scheduler` would resolve to this repo's
+    drop-in package of the same name: a regular package beats the reference's namespace package on sys.path.)"""
+    import importlib.util
+    import types
+    if "scheduler" in sys.modules and not str(getattr(sys.modules["scheduler"], "__path__", [""])[0]).startswith(str(REF)):
+        for k in [k for k in sys.modules if k == "scheduler" or k.startswith("scheduler.")]:
+            del sys.modules[k]
+    pkg = types.ModuleType("scheduler")
+    pkg.__path__ = [str(REF / "scheduler")]
+    sys.modules["scheduler"] = pkg
+    mods = {}
+    for name in ("logit_processor_3dim", "jacobi_iteration_lumina_mgpt"):
+        spec = importlib.util.spec_from_file_location(f"scheduler.{name}", REF / "scheduler" / f"{name}.py")
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[f"scheduler.{name}"] = mod
+        spec.loader.exec_module(mod)
+        assert str(REF) in mod.__file__
+        mods[name] = mod
+    return mods["jacobi_iteration_lumina_mgpt"], mods["logit_processor_3dim"]
+
+
 def run_reference_loop(case: dict, Cache) -> dict:
     sys.path.insert(0, str(REF))
-    import scheduler.jacobi_iteration_lumina_mgpt as J
-    from scheduler.logit_processor_3dim import (MultiTokensInterleavedTopKLogitsWarper,
-                                                MultiTokensVLLogitsProcessor, TopPLogitsWarper3d)
+    J, LP3 = load_reference_scheduler()
+    MultiTokensInterleavedTopKLogitsWarper = LP3.MultiTokensInterleavedTopKLogitsWarper
+    MultiTokensVLLogitsProcessor = LP3.MultiTokensVLLogitsProcessor
+    TopPLogitsWarper3d = LP3.TopPLogitsWarper3d
     from transformers import GenerationConfig
     from transformers.generation.logits_process import LogitsProcessorList, TopKLogitsWarper
     from transformers.generation.stopping_criteria import (EosTokenCriteria, MaxLengthCriteria,
@@ -228,11 +251,12 @@ def mint_loops(out_dir: Path):
 
 
 if __name__ == "__main__":
-    out = REPO / "tests" / "golden"
+    out = Path(os.environ.get("SJD_GOLDEN_OUT", REPO / "tests" / "golden"))
     out.mkdir(parents=True, exist_ok=True)
     which = sys.argv[1:] or ["loops", "forward"]
     if "loops" in which:
         mint_loops(out)
     if "forward" in which:
-        from oracle.mint_forward import mint_forward
-        mint_forward(out)
+        from oracle import mint_forward_golden as F
+        F.mint_llamagen()
+        F.mint_chameleon()

@@ -68,3 +68,68 @@ def test_topk_keeps_ties():
     # k larger than the number of finite entries: threshold is -inf, nothing more is removed
     out = O.topk_filter(s, 6)
     assert np.isfinite(out[0]).tolist() == [True, True, True, True, False, True]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# forward oracle (oracle/ref_forward.RefStack) vs the reference's own model code (fixtures minted by
+# oracle/mint_forward_golden.py from llamagen/llamagen.py and lumina_mgpt/model/chameleon/modeling_chameleon.py, fp32 CPU)
+# ------------------------------------------------------------------------------------------------------------
+def _load_forward(name):
+    from conftest import GOLDEN
+    return np.load(GOLDEN / f"forward_{name}.npz")
+
+
+def test_forward_oracle_matches_reference_llamagen():
+    import torch
+    from oracle import ref_forward as RF
+    z = _load_forward("llamagen")
+    L, d, H, Hkv, Dh, ff, V = (int(x) for x in z["cfg"])
+    cfg = RF.StackConfig(L, d, H, Hkv, Dh, ff, V, float(z["eps"][0]), rope_interleaved=True, family="llamagen")
+    w = RF.random_weights(cfg, seed=int(z["seed"][0]), std=0.05)   # what the minting script copied into the reference
+    cos, sin = RF.rope_tables_llamagen_2d(int(z["grid"][0]), Dh, float(z["rope_base"][0]), 1)
+    ref = RF.RefStack(cfg, w, cos, sin, rows=2, max_len=40, emulate_bf16=False)
+    ids_i = 0
+    for ci, (kind, kv_len, W) in enumerate(z["calls"]):
+        pos = torch.arange(kv_len, kv_len + W)[None].repeat(2, 1)
+        if kind == 0:   # condition-token prefill: the class embedding comes in as `embeds`
+            lg = ref.forward(embeds=torch.from_numpy(z["cond_embeds"]), rope_pos=pos, kv_len=int(kv_len), kv_lo=[0, 0],
+                             cache_pos=pos)
+        else:
+            lg = ref.forward(ids=torch.from_numpy(z[f"ids{ids_i}"]), rope_pos=pos, kv_len=int(kv_len), kv_lo=[0, 0],
+                             cache_pos=pos)
+            ids_i += 1
+        want = z[f"logits{ci}"]
+        assert lg.shape == want.shape
+        assert np.abs(lg.numpy() - want).max() <= 2e-4, f"call {ci}: {np.abs(lg.numpy() - want).max()}"
+
+
+def test_forward_oracle_matches_reference_chameleon():
+    """Lumina-mGPT backbone incl. per-head QK-LayerNorm, rotate-half RoPE, the renewed 3-D-mask-aware
+    _update_causal_mask, a KV roll-back and the CFG-uncond row whose prompt prefix is hidden."""
+    import torch
+    from oracle import ref_forward as RF
+    z = _load_forward("chameleon")
+    L, d, H, Hkv, Dh, ff, V = (int(x) for x in z["cfg"])
+    P = int(z["P"][0])
+    cfg = RF.StackConfig(L, d, H, Hkv, Dh, ff, V, float(z["eps"][0]), qk_norm=True, rope_theta=float(z["theta"][0]))
+    w = RF.random_weights(cfg, seed=int(z["seed"][0]), std=0.05)   # what the minting script copied into the reference
+    r = int(z["qk_norm_rows"][0])
+    if r != H:   # the vendored ChameleonLayerNorm shares rows across heads (repeat_interleave, :206-219)
+        for Lw in w["layers"]:
+            for k in ("q_norm_w", "q_norm_b", "k_norm_w", "k_norm_b"):
+                Lw[k] = Lw[k][:r].repeat_interleave(H // r, dim=0)
+    cos, sin = RF.rope_tables_rotate_half(Dh, 128, float(z["theta"][0]), False)
+    ref = RF.RefStack(cfg, w, cos, sin, rows=2, max_len=64, emulate_bf16=False)
+    kv_lo = [0, P - 1]
+    for ci, (kv_len, W) in enumerate(z["calls"]):
+        pos = torch.arange(kv_len, kv_len + W)[None].repeat(2, 1)
+        rope = torch.stack([(pos[b] - kv_lo[b]).clamp(min=0) for b in range(2)])
+        lg = ref.forward(ids=torch.from_numpy(z[f"ids{ci}"]), rope_pos=rope, kv_len=int(kv_len), kv_lo=kv_lo, cache_pos=pos)
+        want = z[f"logits{ci}"]
+        got = lg.numpy()
+        if ci == 0:
+            # uncond row, prompt prefix positions: every key is hidden for them -> the reference attends uniformly
+            # (min_dtype masks), the engine outputs zeros; those rows are never consumed (only the last token's
+            # logits are, sampling_logits2tokens :97).  Compare what is consumed.
+            got, want = got[:, -1], want[:, -1]
+        assert np.abs(got - want).max() <= 2e-4, f"call {ci}: {np.abs(got - want).max()}"
