@@ -57,11 +57,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// grid: (key splits, Hkv * tile groups, rows); block: one warp per 16-query tile (<= 8 warps).
+// grid: (key splits, Hkv * tile groups, rows); block: TWO warps per 16-query tile (<= 4 tiles per CTA).
 // Each CTA walks its span of keys in 64-key sub-chunks, double buffered with cp.async so that the K/V stream of
-// sub-chunk s+1 is in flight while sub-chunk s is being multiplied.
-template <int DH>
-__global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
+// sub-chunk s+1 is in flight while sub-chunk s is being multiplied.  The two warps of a tile take one 32-key half of
+// every sub-chunk each (twice the warps in flight for the same shared memory) and merge their online-softmax states
+// through shared memory at the end.  Only sub-chunks that touch the hidden prefix or the causal window are masked
+// element by element; interior ones skip the mask arithmetic.
+constexpr int kAttnHalf = kAttnSub / 2;   // keys per warp per sub-chunk
+constexpr int kAttnMaxTiles = 4;          // query tiles per CTA (8 warps)
+
+template <int DH, int NTHREADS, int MINB>
+__global__ void __launch_bounds__(NTHREADS, MINB) attn_window_kernel(AttnParams p) {
   constexpr int ROWB = DH * 2 + 16;  // padded smem row (bytes): conflict-free ldmatrix
   constexpr int STAGE = kAttnSub * ROWB;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -71,13 +77,14 @@ __global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
   uint8_t* sVb = smem + 2 * STAGE;   // [2][kAttnSub][ROWB]
 
   const int split = blockIdx.x, hkv = blockIdx.y % p.Hkv, tgroup = blockIdx.y / p.Hkv, b = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tiles_here = blockDim.x >> 6;
   const int T = p.kv_len + p.W;
   const int G = p.H / p.Hkv;
   const int tiles_per_head = (p.W + 15) >> 4;
   const int n_tiles = G * tiles_per_head;
   const int lo = p.kv_lo[b];
-  const int tile = tgroup * nwarps + warp;
+  const int tl = warp >> 1, kh = warp & 1;   // tile slot in this CTA, key half
+  const int tile = tgroup * tiles_here + tl;
   const bool has_tile = tile < n_tiles;
   const int hq = hkv * G + (has_tile ? tile / tiles_per_head : 0);
   const int i0 = has_tile ? (tile % tiles_per_head) * 16 : 0;
@@ -133,18 +140,18 @@ __global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    const int key0 = k_begin + s * kAttnSub;
-    // causal skip: every key of this sub-chunk is beyond the last query of the tile
-    if (has_tile && key0 <= p.kv_len + min(i0 + 15, p.W - 1)) {
-      const uint8_t* sK = sKb + (s & 1) * STAGE;
-      const uint8_t* sV = sVb + (s & 1) * STAGE;
-      float sc[kAttnSub / 8][4];
+    const int key0 = k_begin + s * kAttnSub + kh * kAttnHalf;   // first key of this warp's half
+    // causal skip: every key of this half is beyond the last query of the tile, or past the end of the span
+    if (has_tile && key0 < k_end && key0 <= p.kv_len + min(i0 + 15, p.W - 1)) {
+      const uint8_t* sK = sKb + (s & 1) * STAGE + kh * kAttnHalf * ROWB;
+      const uint8_t* sV = sVb + (s & 1) * STAGE + kh * kAttnHalf * ROWB;
+      float sc[kAttnHalf / 8][4];
 #pragma unroll
-      for (int n = 0; n < kAttnSub / 8; ++n) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+      for (int n = 0; n < kAttnHalf / 8; ++n) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
 #pragma unroll
-        for (int np = 0; np < kAttnSub / 16; ++np) {
+        for (int np = 0; np < kAttnHalf / 16; ++np) {
           // matrices: (keys 0-7,d 0-7) (keys 0-7,d 8-15) (keys 8-15,d 0-7) (keys 8-15,d 8-15)
           const int key = np * 16 + (lane & 7) + ((lane >> 4) << 3);
           const int dof = kk * 16 + (((lane >> 3) & 1) << 3);
@@ -154,18 +161,30 @@ __global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
           mma_bf16_16816(sc[np * 2 + 1], qf[kk], b2, b3);
         }
       }
-      // mask + online softmax (scores scaled into log2 domain)
+      // scale into the log2 domain; mask only where the half touches the hidden prefix, the causal window or the end
+      const bool interior = (key0 >= lo) && (key0 + kAttnHalf - 1 <= p.kv_len + i0) && (key0 + kAttnHalf <= k_end) &&
+                            (i0 + 15 < p.W);
       float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (interior) {
 #pragma unroll
-      for (int n = 0; n < kAttnSub / 8; ++n) {
+        for (int n = 0; n < kAttnHalf / 8; ++n) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = key0 + n * 8 + t * 2 + (e & 1);
-          const int qi = (e < 2) ? r0 : r1;
-          const bool ok = (j >= lo) && (j <= p.kv_len + qi) && (j < k_end) && (qi < p.W);
-          const float val = ok ? sc[n][e] * p.scale_log2e : -INFINITY;
-          sc[n][e] = val;
-          if (e < 2) mx0 = fmaxf(mx0, val); else mx1 = fmaxf(mx1, val);
+          for (int e = 0; e < 4; ++e) sc[n][e] *= p.scale_log2e;
+          mx0 = fmaxf(mx0, fmaxf(sc[n][0], sc[n][1]));
+          mx1 = fmaxf(mx1, fmaxf(sc[n][2], sc[n][3]));
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < kAttnHalf / 8; ++n) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = key0 + n * 8 + t * 2 + (e & 1);
+            const int qi = (e < 2) ? r0 : r1;
+            const bool ok = (j >= lo) && (j <= p.kv_len + qi) && (j < k_end) && (qi < p.W);
+            const float val = ok ? sc[n][e] * p.scale_log2e : -INFINITY;
+            sc[n][e] = val;
+            if (e < 2) mx0 = fmaxf(mx0, val); else mx1 = fmaxf(mx1, val);
+          }
         }
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
@@ -180,9 +199,9 @@ __global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
 #pragma unroll
       for (int n = 0; n < DH / 8; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
       float ps0 = 0.f, ps1 = 0.f;
-      uint32_t pf[kAttnSub / 16][4];
+      uint32_t pf[kAttnHalf / 16][4];
 #pragma unroll
-      for (int n = 0; n < kAttnSub / 8; ++n) {
+      for (int n = 0; n < kAttnHalf / 8; ++n) {
         const float e0 = exp2f(sc[n][0] - ms0), e1 = exp2f(sc[n][1] - ms0);
         const float e2 = exp2f(sc[n][2] - ms1), e3 = exp2f(sc[n][3] - ms1);
         // probabilities enter P*V as bf16, like the reference's bf16 SDPA
@@ -196,7 +215,7 @@ __global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
       }
       l0 += ps0; l1 += ps1;
 #pragma unroll
-      for (int kk = 0; kk < kAttnSub / 16; ++kk) {
+      for (int kk = 0; kk < kAttnHalf / 16; ++kk) {
 #pragma unroll
         for (int dp = 0; dp < DH / 16; ++dp) {
           // trans matrices: (keys 0-7,d 0-7) (keys 8-15,d 0-7) (keys 0-7,d 8-15) (keys 8-15,d 8-15)
@@ -211,11 +230,42 @@ __global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
     }
     __syncthreads();   // everybody is done with this stage before sub-chunk s+2 lands in it
   }
-  if (!has_tile) return;
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // ---- merge the two key halves of each tile through shared memory (the K/V stages are free now) ----
+  float* xch = reinterpret_cast<float*>(smem) + size_t(tl) * (16 * (DH + 2));   // [16 rows][DH + 2]
+  if (kh == 1) {
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      *reinterpret_cast<float2*>(xch + g * (DH + 2) + n * 8 + t * 2) = make_float2(o[n][0], o[n][1]);
+      *reinterpret_cast<float2*>(xch + (g + 8) * (DH + 2) + n * 8 + t * 2) = make_float2(o[n][2], o[n][3]);
+    }
+    if (t == 0) {
+      xch[g * (DH + 2) + DH] = m0; xch[g * (DH + 2) + DH + 1] = l0;
+      xch[(g + 8) * (DH + 2) + DH] = m1; xch[(g + 8) * (DH + 2) + DH + 1] = l1;
+    }
+  }
+  __syncthreads();
+  if (kh == 1 || !has_tile) return;
+  {
+    const float om0 = xch[g * (DH + 2) + DH], ol0 = xch[g * (DH + 2) + DH + 1];
+    const float om1 = xch[(g + 8) * (DH + 2) + DH], ol1 = xch[(g + 8) * (DH + 2) + DH + 1];
+    const float nm0 = fmaxf(m0, om0), nm1 = fmaxf(m1, om1);
+    const float s0 = (nm0 == -INFINITY) ? 0.f : nm0, s1 = (nm1 == -INFINITY) ? 0.f : nm1;
+    const float wa0 = exp2f(m0 - s0), wb0 = exp2f(om0 - s0), wa1 = exp2f(m1 - s1), wb1 = exp2f(om1 - s1);
+    l0 = l0 * wa0 + ol0 * wb0;
+    l1 = l1 * wa1 + ol1 * wb1;
+    m0 = nm0; m1 = nm1;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      const float2 x0 = *reinterpret_cast<const float2*>(xch + g * (DH + 2) + n * 8 + t * 2);
+      const float2 x1 = *reinterpret_cast<const float2*>(xch + (g + 8) * (DH + 2) + n * 8 + t * 2);
+      o[n][0] = o[n][0] * wa0 + x0.x * wb0; o[n][1] = o[n][1] * wa0 + x0.y * wb0;
+      o[n][2] = o[n][2] * wa1 + x1.x * wb1; o[n][3] = o[n][3] * wa1 + x1.y * wb1;
+    }
+  }
   // write partials
   const size_t base = ((size_t(split) * p.rows + b) * p.H + hq) * size_t(p.W);
   if (r0 < p.W) {
@@ -232,7 +282,9 @@ __global__ void __launch_bounds__(256) attn_window_kernel(AttnParams p) {
   }
 }
 
-// One warp per (row b, head, query i): merge chunk partials, normalise, write bf16.
+// One warp per (row b, head, query i): merge chunk partials, normalise, write bf16.  Loads are issued in batches of
+// kCombBatch chunks (clamped indices, surplus weights zero) so the L2 round trips overlap.
+constexpr int kCombBatch = 8;
 template <int DH>
 __global__ void __launch_bounds__(256) attn_combine_kernel(AttnParams p) {
   pdl_wait();
@@ -244,22 +296,39 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(AttnParams p) {
   const int i = widx % p.W, h = (widx / p.W) % p.H, b = widx / (p.W * p.H);
   const size_t stride = size_t(p.rows) * p.H * p.W;  // per chunk
   const size_t idx = (size_t(b) * p.H + h) * p.W + i;
-  float mmax = -INFINITY;
-  for (int c = 0; c < p.n_chunks; ++c) mmax = fmaxf(mmax, p.part_ml[(c * stride + idx) * 2]);
   constexpr int PER = DH / 32;
   float acc[PER];
 #pragma unroll
   for (int e = 0; e < PER; ++e) acc[e] = 0.f;
-  float lsum = 0.f;
-  if (mmax != -INFINITY) {
-    for (int c = 0; c < p.n_chunks; ++c) {
-      const float m = p.part_ml[(c * stride + idx) * 2];
-      if (m == -INFINITY) continue;
-      const float w = exp2f(m - mmax);
-      lsum += w * p.part_ml[(c * stride + idx) * 2 + 1];
-      const float* po = p.part_o + (c * stride + idx) * DH;
+  float mrun = -INFINITY, lsum = 0.f;
+  for (int c0 = 0; c0 < p.n_chunks; c0 += kCombBatch) {
+    float2 ml[kCombBatch];
+    float po[kCombBatch][PER];
 #pragma unroll
-      for (int e = 0; e < PER; ++e) acc[e] += w * po[lane + 32 * e];
+    for (int k = 0; k < kCombBatch; ++k) {
+      const int c = min(c0 + k, p.n_chunks - 1);
+      ml[k] = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (c * stride + idx) * 2));
+#pragma unroll
+      for (int e = 0; e < PER; ++e) po[k][e] = __ldcg(p.part_o + (c * stride + idx) * DH + lane + 32 * e);
+    }
+    float mb = mrun;
+#pragma unroll
+    for (int k = 0; k < kCombBatch; ++k)
+      if (c0 + k < p.n_chunks) mb = fmaxf(mb, ml[k].x);
+    if (mb == -INFINITY) continue;
+    const float rescale = exp2f(mrun - mb);   // mrun == -inf -> 0
+    lsum *= rescale;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) acc[e] *= rescale;
+    mrun = mb;
+#pragma unroll
+    for (int k = 0; k < kCombBatch; ++k) {
+      if (c0 + k < p.n_chunks && ml[k].x != -INFINITY) {
+        const float w = exp2f(ml[k].x - mb);
+        lsum += w * ml[k].y;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) acc[e] += w * po[k][e];
+      }
     }
   }
   const float inv = lsum > 0.f ? 1.f / lsum : 0.f;  // fully masked query (CFG hidden prefix) -> 0
@@ -268,14 +337,14 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(AttnParams p) {
   for (int e = 0; e < PER; ++e) dst[lane + 32 * e] = __float2bfloat16_rn(acc[e] * inv);
 }
 
-// Chooses the key split: enough CTAs to fill the machine about three deep, spans in whole 64-key sub-chunks.
+// Chooses the key split: as many CTAs as fit in ONE wave of three per SM, spans in whole 64-key sub-chunks.
 void attn_plan(AttnParams* p, int sm_count) {
   const int T = p->kv_len + p->W;
   const int G = p->H / p->Hkv;
   const int n_tiles = G * ((p->W + 15) / 16);
-  const int tgroups = (n_tiles + 7) / 8;
+  const int tgroups = (n_tiles + kAttnMaxTiles - 1) / kAttnMaxTiles;
   const int base_ctas = p->rows * p->Hkv * tgroups;
-  int want = (3 * sm_count + base_ctas - 1) / base_ctas;   // splits wanted
+  int want = (3 * sm_count) / base_ctas;   // splits wanted: never more CTAs than the 3-per-SM slots (no second wave)
   const int n_sub = (T + kAttnSub - 1) / kAttnSub;
   if (want > n_sub) want = n_sub;
   if (want < 1) want = 1;
@@ -287,25 +356,41 @@ void attn_plan(AttnParams* p, int sm_count) {
 int attn_launch(const AttnParams& p, int head_dim, cudaStream_t stream) {
   const int G = p.H / p.Hkv;
   const int n_tiles = G * ((p.W + 15) / 16);
-  const int nwarps = n_tiles < 8 ? n_tiles : 8;
-  const int tgroups = (n_tiles + nwarps - 1) / nwarps;
+  const int tiles_here = n_tiles < kAttnMaxTiles ? n_tiles : kAttnMaxTiles;
+  const int nwarps = 2 * tiles_here;
+  const int tgroups = (n_tiles + tiles_here - 1) / tiles_here;
   dim3 grid(p.n_chunks, p.Hkv * tgroups, p.rows);
   const int total = p.rows * p.H * p.W;
   dim3 cgrid((total + 7) / 8);
   int rc = 0;
+  // thread count = 64 * tiles per CTA; the register cap is chosen so that three 64/128-thread CTAs share an SM
+#define SJD_ATTN_LAUNCH(DH_, NT_, MINB_)                                                                          \
+  do {                                                                                                            \
+    constexpr int smem = 4 * kAttnSub * (DH_ * 2 + 16);                                                           \
+    static bool set = false;                                                                                      \
+    if (!set) {                                                                                                   \
+      cudaFuncSetAttribute(attn_window_kernel<DH_, NT_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+      set = true;                                                                                                 \
+    }                                                                                                             \
+    rc |= launch_pdl(attn_window_kernel<DH_, NT_, MINB_>, grid, dim3(NT_), smem, stream, p);                      \
+  } while (0)
+  const int nt = nwarps * 32;
   if (head_dim == 128) {
-    constexpr int smem = 4 * kAttnSub * (128 * 2 + 16);
-    static bool set = false;
-    if (!set) { cudaFuncSetAttribute(attn_window_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
-    rc |= launch_pdl(attn_window_kernel<128>, grid, dim3(nwarps * 32), smem, stream, p);
+    if (nt == 64) SJD_ATTN_LAUNCH(128, 64, 3);
+    else if (nt == 128) SJD_ATTN_LAUNCH(128, 128, 3);
+    else if (nt == 192) SJD_ATTN_LAUNCH(128, 192, 1);
+    else SJD_ATTN_LAUNCH(128, 256, 1);
     rc |= launch_pdl(attn_combine_kernel<128>, cgrid, dim3(256), 0, stream, p);
   } else if (head_dim == 64) {
-    constexpr int smem = 4 * kAttnSub * (64 * 2 + 16);
-    rc |= launch_pdl(attn_window_kernel<64>, grid, dim3(nwarps * 32), smem, stream, p);
+    if (nt == 64) SJD_ATTN_LAUNCH(64, 64, 3);
+    else if (nt == 128) SJD_ATTN_LAUNCH(64, 128, 3);
+    else if (nt == 192) SJD_ATTN_LAUNCH(64, 192, 1);
+    else SJD_ATTN_LAUNCH(64, 256, 1);
     rc |= launch_pdl(attn_combine_kernel<64>, cgrid, dim3(256), 0, stream, p);
   } else {
     return -3;
   }
+#undef SJD_ATTN_LAUNCH
   return rc;
 }
 
