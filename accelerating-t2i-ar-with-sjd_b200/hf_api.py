@@ -224,15 +224,17 @@ def renew_sampler(model_class):
                                      self.prefix_token_sampler_scheme)
 
         def _sjd_stack(self, rows, max_len, device):
-            key = (rows, max_len)
+            """Weights are packed once per (rows, capacity); a larger cached context is reused as is, so a solver-side
+            prefill and the following _sample share one KV cache."""
             st = getattr(self, "_sjd_stack_cache", None)
-            if st is None or st[0] != key:
-                if st is not None:
-                    st[1].close()
-                packer = pack_llamagen if hasattr(self, "tok_embeddings") else pack_hf_decoder
-                st = (key, packer(self, max_len, rows, device))
-                object.__setattr__(self, "_sjd_stack_cache", st)
-            return st[1]
+            if st is not None and st.rows == rows and st.max_len >= max_len and st.ctx is not None:
+                return st
+            if st is not None:
+                st.close()
+            packer = pack_llamagen if hasattr(self, "tok_embeddings") else pack_hf_decoder
+            st = packer(self, max_len, rows, device)
+            object.__setattr__(self, "_sjd_stack_cache", st)
+            return st
 
         @torch.no_grad()
         def _sample(self, input_ids, logits_processor, stopping_criteria, generation_config, synced_gpus, streamer,

@@ -265,7 +265,7 @@ class TorchNoise:
 
 
 def decode(logits_fn, input_ids, *, params: OracleParams, grammar, img_vocab, max_length, eos_ids=(), rows=2,
-           do_sample=True, temperature=1.0, noise=None, max_trips=None, trace=None, stop_fn=None):
+           do_sample=True, temperature=1.0, noise=None, max_trips=None, trace=None, stop_fn=None, kv_len0=0):
     """Run the SJD loop.  logits_fn(row_tokens: list[list[int]], kv_len: int, n_logit: int) -> float32
     [rows * n_logit, V] is the model forward for one window (tokens at cache slots kv_len..); the loop handles
     window construction (:606-740), draft bookkeeping (:378-430), the window-size rule (:1142-1144) and stopping
@@ -279,7 +279,7 @@ def decode(logits_fn, input_ids, *, params: OracleParams, grammar, img_vocab, ma
     out_W = 1
     carried_tokens: list[int] = []
     carried_q: list = []          # distributions the carried drafts were sampled from
-    kv_len = 0
+    kv_len = kv_len0   # keys cached before the loop (LlamaGen: the condition tokens, llamagen_solver.py:417)
     nfe = 0
     first = True
     img_vocab = np.asarray(img_vocab)

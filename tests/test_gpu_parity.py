@@ -319,3 +319,74 @@ def test_engine_on_real_stack_matches_oracle_replay(env):
     assert all(img[i] == 8803 for i in range(8, 72, 9)) and img[72] == 8196
     assert eng.stats.nfe < len(img), "Jacobi decoding must need fewer forwards than tokens"
     ds.close()
+
+
+# ------------------------------------------------------------------------------- LlamaGen boundary (config 1)
+def test_llamagen_solver_flow_on_gpu(env):
+    """The reference's test_llamagen.py call sequence against this repo's drop-in modules, on the GPU:
+    llamagen.llamagen.Transformer -> renew_llamagen -> renew_sampler -> LlamaGenSolver.generate.  Every forward's
+    logits are captured and the oracle flow (pinned to the reference by tests/golden/llamagen_flow.json) is replayed on
+    them with the same generators: identical image tokens."""
+    import json
+    from conftest import GOLDEN
+    from llamagen.llamagen import ModelArgs, Transformer
+    from llamagen.llamagen_solver import LlamaGenSolver, renew_llamagen
+    from scheduler.jacobi_iteration_lumina_mgpt import renew_sampler
+    from oracle import llamagen_flow
+    RF, O, model_mod, dev = env["RF"], env["O"], env["model"], env["dev"]
+    g = json.loads((GOLDEN / "llamagen_flow.json").read_text())
+    case, ref = g["case"], g["result"]
+    args = ModelArgs(dim=case["dim"], n_layer=case["n_layer"], n_head=case["n_head"], vocab_size=case["vocab"],
+                     block_size=case["grid"] ** 2, cls_token_num=case["cls_token_num"], num_classes=case["num_classes"],
+                     model_type="c2i", class_dropout_prob=0.1)
+    m = Transformer(args)
+    cfg, w, cls_table, _, _ = llamagen_flow.build_stack(case, ref["ff"], ref["norm_eps"], ref["rope_base"])
+    ff = ref["ff"]
+    with torch.no_grad():
+        m.tok_embeddings.weight.copy_(w["embed"]); m.norm.weight.copy_(w["final_norm"]); m.output.weight.copy_(w["lm_head"])
+        m.cls_embedding.embedding_table.weight.copy_(cls_table)
+        for L, wl in zip(m.layers, w["layers"]):
+            L.attention_norm.weight.copy_(wl["attn_norm"]); L.attention.wqkv.weight.copy_(wl["wqkv"])
+            L.attention.wo.weight.copy_(wl["wo"]); L.ffn_norm.weight.copy_(wl["ffn_norm"])
+            L.feed_forward.w1.weight.copy_(wl["w_gate_up"][:ff]); L.feed_forward.w3.weight.copy_(wl["w_gate_up"][ff:])
+            L.feed_forward.w2.weight.copy_(wl["w_down"])
+    m = m.to(dev, torch.bfloat16).eval()
+    m.__class__ = renew_llamagen(m.__class__)
+    m._init_new_params(**case["jacobi"])
+    m.__class__ = renew_sampler(m.__class__)
+    m._init_new_params(use_chameleon_tokenizer=False, **case["jacobi"])
+    m.img_vocab = torch.arange(case["vocab"])
+    captured = []
+    orig_forward = model_mod.DeviceStack.forward
+
+    def spy(self, *a, **k):
+        lg = orig_forward(self, *a, **k)
+        captured.append(lg.detach().float().cpu().numpy().reshape(-1, case["vocab"]).copy())
+        return lg
+
+    model_mod.DeviceStack.forward = spy
+    try:
+        solver = LlamaGenSolver(m, case["top_k"], case["top_p"])
+        torch.manual_seed(case["global_seed"])
+        # the engine's default noise generator lives on the GPU; the oracle replay below uses the same device generator
+        out = solver.generate(torch.tensor([case["class_id"]], device=dev), case["grid"] ** 2, None,
+                              cfg_scale=case["cfg_scale"], temperature=case["temperature"], top_k=case["top_k"],
+                              top_p=case["top_p"], sample_logits=True)
+    finally:
+        model_mod.DeviceStack.forward = orig_forward
+    tokens = out[0].tolist()
+    assert len(tokens) == case["grid"] ** 2 and all(0 <= t < case["vocab"] for t in tokens)
+    assert m.sjd_stats.nfe < len(tokens), "Jacobi decoding must need fewer forwards than tokens"
+    # ---- oracle replay on the captured logits (first token: global generator on the device, like the solver) ----
+    it = iter(captured)
+    torch.manual_seed(case["global_seed"])
+    lg0 = torch.from_numpy(next(it)).to(dev)
+    from llamagen.llamagen_solver import _first_token
+    tok0 = int(_first_token(lg0, case["cfg_scale"], temperature=case["temperature"], top_k=case["top_k"],
+                            top_p=case["top_p"])[0, 0])
+    assert tok0 == tokens[0]
+    ids_o, nfe_o = O.decode(lambda r, k, n: next(it), [tok0], params=O.OracleParams(**case["jacobi"]),
+                            grammar=O.PlainTopK(top_k=case["top_k"]), img_vocab=np.arange(case["vocab"]),
+                            max_length=case["grid"] ** 2, eos_ids=[], rows=2, do_sample=True, temperature=1.0,
+                            kv_len0=case["cls_token_num"], noise=O.TorchNoise(case["jacobi"]["seed"], device=str(dev)))
+    assert ids_o[-len(tokens):] == tokens and nfe_o == m.sjd_stats.nfe

@@ -133,3 +133,17 @@ def test_forward_oracle_matches_reference_chameleon():
             # logits are, sampling_logits2tokens :97).  Compare what is consumed.
             got, want = got[:, -1], want[:, -1]
         assert np.abs(got - want).max() <= 2e-4, f"call {ci}: {np.abs(got - want).max()}"
+
+
+def test_llamagen_flow_oracle_matches_reference():
+    """BASELINE config 1 in miniature: the reference's complete test_llamagen.py call sequence (GPT -> renew_llamagen ->
+    renew_sampler -> LlamaGenSolver.generate, fp32 on CPU) vs the oracle restatement of that flow driving the forward
+    oracle: identical image-token sequence."""
+    import json
+    from conftest import GOLDEN
+    from oracle import llamagen_flow
+    g = json.loads((GOLDEN / "llamagen_flow.json").read_text())
+    case, ref = g["case"], g["result"]
+    tokens, nfe = llamagen_flow.generate(case, ref["ff"], ref["norm_eps"], ref["rope_base"])
+    assert tokens == ref["tokens"]
+    assert nfe < len(tokens)
