@@ -443,12 +443,17 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
   } else if (warp >= 4) {
     // ===== epilogue warps (16): TMEM lane quarter = warp % 4, column group = (warp - 4) / 4 =====
     //  whole tile inside this CTA's range : TMEM -> smem staging -> fused epilogue, right away
-    //  split tile (first / last segment)   : TMEM -> this CTA's fp32 partial slot; after the CTA's last segment the
-    //                                        contributors of a tile share its rows (reduce-scatter): contributor j of
-    //                                        k sums all k partials, in CTA order, for rows [jM/k, (j+1)M/k) and runs
-    //                                        the fused epilogue on them — the fix-up is spread over all CTAs
+    //  split tile, ordinary epilogues       : the CTA that owns the tile's head segment (which it computes LAST) is the
+    //                                         tile's finisher; every other contributor has the tile as the FIRST segment
+    //                                         of its range and parks its fp32 partial early.  The finisher adds the
+    //                                         partials in CTA order (bit-reproducible) and runs the epilogue: nobody
+    //                                         waits for a neighbour that is still streaming.
+    //  EPI_RESID_NORM                       : the row statistic needs every tile of a row, so ALL segments are parked,
+    //                                         one grid-wide counter tells when, and one CTA per token row then sums the
+    //                                         row's tiles, adds the residual, computes the RMS statistic locally and
+    //                                         writes h and xn — one exchange and one pass instead of two of each.
     // One scheduler runs one instruction stream at a time, so the epilogue's speed comes from having many warps
-    // (one token row each), not from unrolling.
+    // (one token row / one tile each), not from unrolling.
     pdl_wait();  // everything below touches buffers the previous kernel may still be writing
     const int ew = warp - 4;        // 0..15
     const int quarter = ew & 3;     // TMEM lane quarter this warp may access (== warp % 4)
@@ -463,6 +468,7 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
       const GemmEpi& ep = op.ep;
       const StreamK& sk = op.sk;
       const uint32_t u0 = sk.begin(cta), u1 = sk.begin(cta + 1), KB = uint32_t(sk.kb);
+      const bool row_mode = (ep.mode == EPI_RESID_NORM);
       if (ep.mode == EPI_QKV) {
         // (for op_i > 0 the positions are kernel inputs, not produced by the chain: safe to read right away)
         for (int m = tid_e; m < ep.M; m += kEpiThreads) s_pos[m] = make_int2(ep.rope_pos[m], ep.cache_pos[m]);
@@ -472,19 +478,19 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
       long long* dbg = (ep.dbg && tid_e == 0) ? ep.dbg + size_t(cta) * 16 : nullptr;
       if (dbg) dbg[0] = clock64();
       uint32_t u = u0;
-      int n_whole = 0, first_whole = -1;   // whole tiles finished here (consecutive)
-      int pend_tile0 = -1, pend_tile1 = -1, n_pend = 0;   // split tiles this CTA contributed to
+      uint32_t my_rows = 0;   // (tile, token row) pairs this CTA made final
 #pragma unroll 1
       while (u < u1) {
         const uint32_t tile = u / KB;
         const uint32_t seg_end = min(u1, (tile + 1) * KB);
-        const bool whole = (tile * KB >= u0) && ((tile + 1) * KB <= u1);
+        const bool head = (tile * KB >= u0);                    // this CTA owns the tile's first k-block
+        const bool whole = head && ((tile + 1) * KB <= u1);
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
         if (dbg) dbg[(seg_end == u1) ? 2 : 1] = clock64();   // accumulator of a (1) non-last / (2) last segment ready
         const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc) * uint32_t(sk.m_tile);
-        if (!whole) {
-          // slot 2*cta: the CTA's first segment; 2*cta+1: its last segment (when that is a different, split tile)
+        if (row_mode || !head) {
+          // park the partial.  slot 2*cta: the CTA's first segment; 2*cta+1: its last (row mode only, <= 2 segments)
           const int slot = 2 * cta + ((u == u0) ? 0 : 1);
           float* dst = ep.ws + size_t(slot) * slot_floats + nrow;
 #pragma unroll 1
@@ -500,13 +506,20 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
-          epi_bar();   // every warp's partial stores happen-before thread 0's (cumulative) fence + flag
-          if (tid_e == 0) {
-            __threadfence();
-            atomicAdd(&ep.tile_arrive[kTileCtrStride * tile], 1u);
+          if (!row_mode) {
+            epi_bar();   // every warp's partial stores happen-before thread 0's (cumulative) fence + flag
+            if (tid_e == 0) {
+              __threadfence();
+              atomicAdd(&ep.tile_arrive[kTileCtrStride * tile], 1u);
+            }
           }
-          if (n_pend++ == 0) pend_tile0 = int(tile); else pend_tile1 = int(tile);
         } else {
+          // head segment (whole tile, or the finisher's part of a split tile): stage, add the parked partials, finish
+          const int c_last = whole ? cta : sk.last_cta(int(tile));
+          if (c_last > cta && tid_e == 0) {
+            spin_until_ge(&ep.tile_arrive[kTileCtrStride * tile], uint32_t(c_last - cta));
+            ep.tile_arrive[kTileCtrStride * tile] = 0;   // leave it zero for the next launch
+          }
           const EpiTileConst tc = epi_tile_const(ep, int(tile), lane);
 #pragma unroll 1
           for (int c0m = 0; c0m < sk.m_tile; c0m += kEpiChunk) {
@@ -524,7 +537,7 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
               __syncwarp();
               if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
-            epi_bar();  // staging tile complete
+            epi_bar();  // staging tile complete; also orders thread 0's acquire before everybody's partial reads
 #pragma unroll 1
             for (int ml = ew; ml < cw; ml += kEpiWarps) {   // one token row per warp at a time
               const int m = c0m + ml;
@@ -532,118 +545,121 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
               const EpiAux aux = epi_load_aux(ep, tc, int(tile), m, lane, s_pos);
               const float4 t = *reinterpret_cast<const float4*>(stage_tile + ml * kBlockN + 4 * lane);
               float v[4] = {t.x, t.y, t.z, t.w};
+              constexpr int C = 4;   // partials in flight
+#pragma unroll 1
+              for (int cb = cta + 1; cb <= c_last; cb += C) {
+                float4 pv[C];
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) {   // unconditional (clamped) loads so that they batch
+                  const int c = min(cb + cc, c_last);
+                  pv[cc] = __ldcg(reinterpret_cast<const float4*>(ep.ws + size_t(2 * c) * slot_floats + size_t(m) * 128 + 4 * lane));
+                }
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc)   // CTA order: bit-reproducible
+                  if (cb + cc <= c_last) { v[0] += pv[cc].x; v[1] += pv[cc].y; v[2] += pv[cc].z; v[3] += pv[cc].w; }
+              }
               epi_apply(ep, tc, aux, int(tile), m, lane, v, sk.m_tile);
             }
             epi_bar();  // rows done before the next chunk overwrites the staging tile
           }
-          if (n_whole++ == 0) first_whole = int(tile);
+          my_rows += uint32_t(ep.M);
         }
         u = seg_end;
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
       if (dbg) dbg[3] = clock64();   // all segments drained / parked
-      // ---- deferred fix-up of the split tiles: this CTA's share of the rows ------------------------------
-      int share_lo0 = 0, share_hi0 = 0, share_lo1 = 0, share_hi1 = 0;
-#pragma unroll 1
-      for (int pq = 0; pq < n_pend; ++pq) {
-        // the LAST segment's tile first: its other contributors parked it at the start of their ranges, so it is
-        // ready now; the first segment's tile is completed by CTAs that are only now finishing
-        const int pi = n_pend - 1 - pq;
-        const int tile = pi == 0 ? pend_tile0 : pend_tile1;
-        const int c_first = sk.first_cta(tile), c_last = sk.last_cta(tile);
-        const int k = c_last - c_first + 1, j = cta - c_first;
-        if (tid_e == 0) spin_until_ge(&ep.tile_arrive[kTileCtrStride * tile], uint32_t(k));
-        epi_bar();  // orders thread 0's acquire before everybody's partial reads
-        if (dbg && pi == 0) dbg[8] = clock64();    // first split tile: all partials arrived
-        const int r_lo = (j * ep.M) / k, r_hi = ((j + 1) * ep.M) / k;
-        if (pi == 0) { share_lo0 = r_lo; share_hi0 = r_hi; } else { share_lo1 = r_lo; share_hi1 = r_hi; }
-        const EpiTileConst tc = epi_tile_const(ep, tile, lane);
-        // the slot contributor c used for this tile: its first segment iff the tile holds the start of its range;
-        // only c_first can have the tile as a non-first segment
-        const bool first_uses_last_slot = (sk.begin(c_first) / KB) != uint32_t(tile);
-        constexpr int C = 4;   // partials in flight per row
-#pragma unroll 1
-        for (int m = r_lo + ew; m < r_hi; m += kEpiWarps) {
-          const EpiAux aux = epi_load_aux(ep, tc, tile, m, lane, s_pos);
-          float v[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int cb = c_first; cb <= c_last; cb += C) {
-            float4 pv[C];
-#pragma unroll
-            for (int cc = 0; cc < C; ++cc) {   // unconditional (clamped) loads so that they batch
-              const int c = min(cb + cc, c_last);
-              const int slot = 2 * c + ((c == c_first && first_uses_last_slot) ? 1 : 0);
-              pv[cc] = __ldcg(reinterpret_cast<const float4*>(ep.ws + size_t(slot) * slot_floats + size_t(m) * 128 + 4 * lane));
-            }
-#pragma unroll
-            for (int cc = 0; cc < C; ++cc) {   // CTA order: bit-reproducible
-              if (cb + cc <= c_last) { v[0] += pv[cc].x; v[1] += pv[cc].y; v[2] += pv[cc].z; v[3] += pv[cc].w; }
-            }
+      // ---- EPI_RESID_NORM: one CTA per token row finishes the row across all tiles -----------------------------
+      if (row_mode) {
+        float* red = stage_tile;   // [kEpiWarps] partial sums of squares
+        const uint32_t G = uint32_t(sk.grid);
+        if (u1 > u0) {             // this CTA parked something: tell the row owners
+          epi_bar();
+          if (tid_e == 0) {
+            __threadfence();
+            atomicAdd(&ep.ctr[0], 1u);
           }
-          epi_apply(ep, tc, aux, tile, m, lane, v, sk.m_tile);
         }
-        if (dbg && pi == 0) dbg[9] = clock64();    // first split tile: share finalised
-        // re-arm the tile's counters once every contributor has read the partials
-        epi_bar();
-        if (tid_e == 0) {
-          const uint32_t done = atomicAdd(&ep.tile_arrive[kTileCtrStride * tile + 1], 1u) + 1u;
-          if (done == uint32_t(k)) {
-            ep.tile_arrive[kTileCtrStride * tile] = 0;
-            ep.tile_arrive[kTileCtrStride * tile + 1] = 0;
+        // rows m with (m * G) / M == cta
+        const int m_lo = int((uint32_t(cta) * uint32_t(ep.M) + G - 1) / G);
+        const int m_hi = uint32_t(cta) < G ? int((uint32_t(cta + 1) * uint32_t(ep.M) + G - 1) / G) : m_lo;
+        if (m_hi > m_lo) {
+          if (tid_e == 0) spin_until_ge(&ep.ctr[0], G);
+          epi_bar();
+          if (dbg) dbg[5] = clock64();   // every partial of the op is parked
+          const float inv_d = 1.f / float(ep.N);
+          constexpr int TPW = 4;         // tiles per warp: n_tiles <= 64 (checked on the host)
+#pragma unroll 1
+          for (int m = m_lo; m < m_hi; ++m) {
+            float x[TPW][4];
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < TPW; ++i) {
+              const int t = ew + kEpiWarps * i;
+              if (t < sk.n_tiles) {
+                const int c_first = sk.first_cta(t), c_last = sk.last_cta(t);
+                const bool first_uses_last_slot = (sk.begin(c_first) / KB) != uint32_t(t);
+                const size_t off = size_t(m) * ep.N + size_t(t) * kBlockN + 4 * lane;
+                const uint2 hraw = *reinterpret_cast<const uint2*>(ep.h + off);
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                constexpr int C = 4;
+#pragma unroll 1
+                for (int cb = c_first; cb <= c_last; cb += C) {
+                  float4 pv[C];
+#pragma unroll
+                  for (int cc = 0; cc < C; ++cc) {
+                    const int c = min(cb + cc, c_last);
+                    const int slot = 2 * c + ((c == c_first && first_uses_last_slot) ? 1 : 0);
+                    pv[cc] = __ldcg(reinterpret_cast<const float4*>(ep.ws + size_t(slot) * slot_floats + size_t(m) * 128 + 4 * lane));
+                  }
+#pragma unroll
+                  for (int cc = 0; cc < C; ++cc)   // CTA order: bit-reproducible
+                    if (cb + cc <= c_last) { v[0] += pv[cc].x; v[1] += pv[cc].y; v[2] += pv[cc].z; v[3] += pv[cc].w; }
+                }
+                float hv[4];
+                unpack4(hraw, hv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  x[i][e] = bf16_round(hv[e] + bf16_round(v[e]));
+                  ss += x[i][e] * x[i][e];
+                }
+              }
+            }
+            ss = warp_sum(ss);
+            if (lane == 0) red[ew] = ss;
+            epi_bar();
+            float tot = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < kEpiWarps; ++w2) tot += red[w2];   // fixed order
+            const float rinv = rsqrtf(tot * inv_d + ep.eps);
+#pragma unroll
+            for (int i = 0; i < TPW; ++i) {
+              const int t = ew + kEpiWarps * i;
+              if (t < sk.n_tiles) {
+                const size_t off = size_t(m) * ep.N + size_t(t) * kBlockN + 4 * lane;
+                float wv[4], o[4];
+                unpack4(*reinterpret_cast<const uint2*>(ep.norm_w + t * kBlockN + 4 * lane), wv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = wv[e] * bf16_round(x[i][e] * rinv);
+                *reinterpret_cast<uint2*>(ep.h + off) = pack4(x[i]);
+                *reinterpret_cast<uint2*>(ep.xn + off) = pack4(o);
+              }
+            }
+            epi_bar();   // red[] is reused by the next row
+          }
+          my_rows += uint32_t(m_hi - m_lo) * uint32_t(sk.n_tiles);
+          if (dbg) dbg[10] = clock64();   // rows written
+          if (tid_e == 0) {
+            // re-arm once every row owner has read the partials (M rows in total)
+            const uint32_t done = atomicAdd(&ep.ctr[kCtrStride], uint32_t(m_hi - m_lo)) + uint32_t(m_hi - m_lo);
+            if (done == uint32_t(ep.M)) {
+              ep.ctr[0] = 0;
+              ep.ctr[kCtrStride] = 0;
+            }
           }
         }
       }
-      if (dbg) dbg[4] = clock64();   // fix-up shares done
-      const uint32_t my_rows = uint32_t(n_whole) * uint32_t(ep.M) + uint32_t(share_hi0 - share_lo0) +
-                               uint32_t(share_hi1 - share_lo1);
-      // ---- EPI_RESID_NORM, second half: the row statistic needs every tile ------------------------------
-      if (ep.mode == EPI_RESID_NORM && my_rows > 0) {
-        const uint32_t all_rows = uint32_t(sk.n_tiles) * uint32_t(ep.M);
-        epi_bar();
-        if (tid_e == 0) {
-          __threadfence();
-          atomicAdd(&ep.ctr[0], my_rows);
-          spin_until_ge(&ep.ctr[0], all_rows);
-          if (dbg) dbg[5] = clock64();   // every tile's statistic is in
-        }
-        epi_bar();
-        const float inv_d = 1.f / float(ep.N);
-        // pieces: [first_whole, first_whole + n_whole) x rows [0, M), then the two shares
-#pragma unroll 1
-        for (int piece = 0; piece < 3; ++piece) {
-          int t_lo, t_n, r_lo, r_hi;
-          if (piece == 0) { t_lo = first_whole; t_n = n_whole; r_lo = 0; r_hi = ep.M; }
-          else if (piece == 1) { t_lo = pend_tile0; t_n = n_pend > 0 ? 1 : 0; r_lo = share_lo0; r_hi = share_hi0; }
-          else { t_lo = pend_tile1; t_n = n_pend > 1 ? 1 : 0; r_lo = share_lo1; r_hi = share_hi1; }
-          if (t_n <= 0 || r_hi <= r_lo) continue;
-#pragma unroll 1
-          for (int m = r_lo + ew; m < r_hi; m += kEpiWarps) {
-            float sacc = 0.f;
-            for (int t = lane; t < sk.n_tiles; t += 32) sacc += __ldcg(ep.ssq + size_t(t) * sk.m_tile + m);
-            const float rinv = rsqrtf(warp_sum(sacc) * inv_d + ep.eps);
-#pragma unroll 1
-            for (int t = t_lo; t < t_lo + t_n; ++t) {
-              const size_t off = size_t(m) * ep.N + size_t(t) * kBlockN + 4 * lane;
-              float wv[4], hv[4], o[4];
-              unpack4(*reinterpret_cast<const uint2*>(ep.norm_w + t * kBlockN + 4 * lane), wv);
-              unpack4(*reinterpret_cast<const uint2*>(ep.h + off), hv);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = wv[e] * bf16_round(hv[e] * rinv);
-              *reinterpret_cast<uint2*>(ep.xn + off) = pack4(o);
-            }
-          }
-        }
-        if (dbg) dbg[10] = clock64();   // xn rows written
-        epi_bar();
-        if (tid_e == 0) {
-          const uint32_t done = atomicAdd(&ep.ctr[kCtrStride], my_rows) + my_rows;
-          if (done == all_rows) {  // everybody is past the meeting point: re-arm for the next launch
-            ep.ctr[0] = 0;
-            ep.ctr[kCtrStride] = 0;
-          }
-        }
-      }
+      if (dbg) dbg[4] = clock64();
       // ---- publish: this CTA's rows of op_i are final (the next op's activation producer waits for all) ----
       if (my_rows > 0) {
         epi_bar();
@@ -815,6 +831,10 @@ int chain_launch(const TmapSet& maps, Chain ch, cudaStream_t stream) {
   int grid = 0;
   for (int i = 0; i < ch.n_ops; ++i) {
     if (ch.ops[i].sk.m_tile != ch.ops[0].sk.m_tile || ch.ops[i].sk.grid < 1) return -3;
+    if (ch.ops[i].ep.mode == EPI_RESID_NORM) {   // row-owner scheme: <= 2 segments per CTA, <= 64 tiles per row
+      const StreamK& k = ch.ops[i].sk;
+      if (k.n_tiles > 64 || (k.units() + uint32_t(k.grid) - 1) / uint32_t(k.grid) > uint32_t(k.kb)) return -3;
+    }
     grid = ch.ops[i].sk.grid > grid ? ch.ops[i].sk.grid : grid;
     ch.ops[i].ep.dbg = g_dbg_buf ? g_dbg_buf + size_t(g_dbg_idx++ % uint64_t(g_dbg_cap)) * 256 * 16 : nullptr;
   }
