@@ -211,7 +211,7 @@ int sjd_verify(const sjd_verify_args* a, void* stream) {
   VerifyParams p;
   p.logits = a->logits; p.W = a->W; p.V = a->V; p.has_uncond = a->has_uncond; p.apply_cfg = a->apply_cfg;
   p.guidance = a->guidance; p.temperature = a->temperature; p.allow_lo = a->allow_lo; p.allow_hi = a->allow_hi;
-  p.forced = a->forced; p.top_k = a->top_k; p.do_sample = a->do_sample; p.scheme = a->scheme; p.draft = a->draft;
+  p.forced = a->forced; p.forced_resid = a->forced_resid; p.top_k = a->top_k; p.do_sample = a->do_sample; p.scheme = a->scheme; p.draft = a->draft;
   p.q_row = a->q_row; p.p_prev = a->p_prev; p.p_cur = a->p_cur; p.noise_e1 = a->noise_e1; p.noise_u = a->noise_u;
   p.noise_e2 = a->noise_e2; p.eoi_token = a->eoi_token; p.text_top_k = a->text_top_k; p.resid = a->resid;
   p.next_tokens = a->next_tokens; p.out_tokens = a->out_tokens; p.out_info = a->out_info;

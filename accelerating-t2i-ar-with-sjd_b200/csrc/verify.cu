@@ -28,6 +28,7 @@ struct VerifyParams {
   float temperature;     // scores / temperature when != 1
   int allow_lo, allow_hi;  // ids outside [lo,hi) -> -inf; disabled when hi <= lo
   const int* forced;     // [W] forced token id per window position, or -1
+  const int* forced_resid;  // [W] forced id of the residual distribution at reject position j; null = forced
   int top_k;             // 0 = off
   int do_sample;         // 0 = argmax
   int scheme;            // 0 = speculative_jacobi, 1 = jacobi
@@ -418,7 +419,8 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyPar
     const float* b = qr < 0 ? nullptr : p.p_prev + size_t(qr) * V;
     const int xd = p.draft[first];
     const bool text = s_text_mode != 0;
-    const int forced = (!text && p.forced) ? p.forced[j] : -1;
+    const int* fr = p.forced_resid ? p.forced_resid : p.forced;
+    const int forced = (!text && fr) ? fr[j] : -1;
     const bool ranged = !text && (p.allow_hi > p.allow_lo);
     const int lo = ranged ? max(p.allow_lo, 0) : 0, hi = ranged ? min(p.allow_hi, V) : V;
     const int v0 = (lo / int(blockDim.x)) * int(blockDim.x);

@@ -135,6 +135,64 @@ class LuminaGrammarState:
         return d
 
 
+class Emu3GrammarState:
+    """Host-side state of the Emu3 image grammar (reference: EOLLogitProcessor3d, scheduler/jacobi_iteration_emu3.py:44-128,
+    built on Emu3PrefixConstrainedLogitsHelper, emu3/mllm/utils_emu3.py:19-62): only visual ids are allowed; positions
+    after the image token are forced to EOL every width+1 tokens, to EOF / EOI / EOS at (width+1)*height + 1 / 2 / 3 and —
+    once a window reaches past that — its LAST rows to PAD (the reference slices `batch_scores[start:, :]` with a start
+    that goes negative, :120-125; reproduced as is).  CFG is never switched off for Emu3 (the processor has no
+    image_start_token_id, jacobi_iteration_lumina_mgpt.py:1086-1096).  HF appends TopKLogitsWarper(top_k)."""
+    eoi_token = -1      # no text-mode switch: the grammar is purely positional
+    text_top_k = 0
+    no_cfg = False
+
+    def __init__(self, height, width, img_token, eol, eof, eoi, eos, pad, visual_lo, visual_hi, top_k=2048):
+        self.height, self.width, self.img_token = height, width, img_token
+        self.eol, self.eof, self.eoi, self.eos, self.pad = eol, eof, eoi, eos, pad
+        self.allow, self.top_k = (visual_lo, visual_hi), top_k
+        self.reset()
+
+    def reset(self):
+        self.tokenlen = None   # tokens after the first image token; None until it has been seen
+
+    def observe(self, tokens):
+        for t in tokens:
+            if self.tokenlen is None:
+                if t == self.img_token:
+                    self.tokenlen = 0
+            else:
+                self.tokenlen += 1
+
+    def describe(self, n: int) -> dict:
+        if self.tokenlen is None:
+            raise ValueError("Emu3 grammar: the prompt does not contain the image token")
+        d = {"allow": self.allow, "forced": [-1] * n, "top_k": self.top_k}
+        line = self.width + 1
+        for line_len, tok in ((line, self.eol), (line * self.height + 1, self.eof), (line * self.height + 2, self.eoi),
+                              (line * self.height + 3, self.eos)):
+            lo_, hi_ = self.tokenlen + 1, self.tokenlen + n
+            for mult in range(-(-lo_ // line_len), hi_ // line_len + 1):
+                pos = line_len * mult - (self.tokenlen + 1)
+                if 0 <= pos < n:
+                    d["forced"][pos] = tok
+        limit = line * self.height + 3
+        if self.tokenlen + n > limit:
+            for pos in list(range(n))[limit - self.tokenlen:]:
+                d["forced"][pos] = self.pad
+        return d
+
+    def describe_residual(self, n: int) -> list:
+        """Forced id of the residual distribution at each reject position j: the reference re-runs the processor on a
+        ONE-token window after the j accepted tokens (reject_sampling_single_token,
+        jacobi_iteration_lumina_mgpt.py:209-241), and this grammar depends on the window length in its PAD tail."""
+        out, keep = [], self.tokenlen
+        for j in range(n):
+            self.tokenlen = keep + j
+            out.append(self.describe(1)["forced"][0])
+        self.tokenlen = keep
+        return out
+
+
 class PlainTopKState:
     """No grammar: HF TopKLogitsWarper(k) [+ TopPLogitsWarper3d(1.0), a no-op] — LlamaGen
     (llamagen/llamagen_solver.py:458-470)."""
@@ -237,7 +295,7 @@ class SJDEngine:
         Wmax = _lib.SJD_MAX_TOKENS // self.rows
         self.Wmax = Wmax
         self.pbuf = [torch.zeros(Wmax, self.V, dtype=torch.float32, device=self.dev) for _ in range(2)]
-        n_i32 = 3 * _lib.SJD_MAX_TOKENS + 3 * Wmax + 16
+        n_i32 = 3 * _lib.SJD_MAX_TOKENS + 4 * Wmax + 16
         self.h_stage = torch.empty(n_i32, dtype=torch.int32).pin_memory()
         self.d_stage = torch.empty(n_i32, dtype=torch.int32, device=self.dev)
         self.d_out = torch.empty(4 + Wmax, dtype=torch.int32, device=self.dev)
@@ -346,8 +404,11 @@ class SJDEngine:
             hs[base:base + Wv] = torch.tensor(wv_ids, dtype=torch.int32)
             hs[base + self.Wmax: base + self.Wmax + Wv] = torch.tensor(q_row[-Wv:], dtype=torch.int32)
             hs[base + 2 * self.Wmax: base + 2 * self.Wmax + Wv] = torch.tensor(desc["forced"], dtype=torch.int32)
-            ds[base: base + 3 * self.Wmax].copy_(hs[base: base + 3 * self.Wmax], non_blocking=True)
-            stats.h2d_bytes += 12 * self.Wmax
+            resid_forced = grammar.describe_residual(Wv) if hasattr(grammar, "describe_residual") else None
+            if resid_forced is not None:
+                hs[base + 3 * self.Wmax: base + 3 * self.Wmax + Wv] = torch.tensor(resid_forced, dtype=torch.int32)
+            ds[base: base + 4 * self.Wmax].copy_(hs[base: base + 4 * self.Wmax], non_blocking=True)
+            stats.h2d_bytes += 16 * self.Wmax
             d_draft = ds[base: base + Wv]
             a = _lib.VerifyArgs()
             a.logits = logits.data_ptr()
@@ -356,6 +417,7 @@ class SJDEngine:
             a.guidance, a.temperature = float(p.guidance_scale), float(temperature)
             a.allow_lo, a.allow_hi = desc["allow"] if desc["allow"] else (0, 0)
             a.forced = ds[base + 2 * self.Wmax:].data_ptr()
+            a.forced_resid = ds[base + 3 * self.Wmax:].data_ptr() if resid_forced is not None else None
             a.top_k, a.do_sample, a.scheme = int(desc["top_k"]), int(do_sample), scheme
             a.draft = d_draft.data_ptr()
             a.q_row = ds[base + self.Wmax:].data_ptr()

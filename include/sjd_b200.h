@@ -67,6 +67,9 @@ typedef struct sjd_verify_args {
   float temperature;
   int32_t allow_lo, allow_hi; /* grammar: ids outside [lo,hi) suppressed; off when hi <= lo */
   const int32_t* forced;  /* [W] forced id per window position (EOL/EOI/...), -1 = free; may be NULL */
+  const int32_t* forced_resid; /* [W] forced id of the RESIDUAL distribution when the draft after position j is rejected
+                           * (the reference re-runs its processors on a 1-token window there, which a position-
+                           * and window-length-dependent grammar such as Emu3's answers differently); NULL = `forced` */
   int32_t top_k;          /* 0 = off; ties with the k-th largest are kept (scores < kth removed) */
   int32_t do_sample;      /* 0: argmax */
   int32_t scheme;         /* 0: 'speculative_jacobi', 1: 'jacobi' (:1032-1048) */

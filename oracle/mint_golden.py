@@ -147,6 +147,23 @@ def run_reference_loop(case: dict, Cache) -> dict:
         procs = LogitsProcessorList([
             MultiTokensVLLogitsProcessor(8197, 8196, 8803, 32, V),
             MultiTokensInterleavedTopKLogitsWarper(case["image_top_k"], case["text_top_k"], 8197, 8196)])
+    elif case["grammar"] == "emu3":
+        # Emu3PrefixConstrainedLogitsHelper (emu3/mllm/utils_emu3.py:19-62) class-swapped to the 3-D processor exactly
+        # like renew_solver does (scheduler/jacobi_iteration_emu3.py:379-380); HF appends TopKLogitsWarper for
+        # GenerationConfig(top_k=...) (test_emu3.py:83-90)
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_utils_emu3", REF / "emu3" / "mllm" / "utils_emu3.py")
+        U = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(U)
+        spec = importlib.util.spec_from_file_location("scheduler.jacobi_iteration_emu3", REF / "scheduler" / "jacobi_iteration_emu3.py")
+        E = importlib.util.module_from_spec(spec)
+        sys.modules["scheduler.jacobi_iteration_emu3"] = E
+        spec.loader.exec_module(E)
+        e = case["emu3"]
+        fn = U.Emu3PrefixConstrainedLogitsHelper(e["height"], e["width"], e["img_token"], e["eoi"], e["eos"], e["eol"],
+                                                 e["eof"], e["pad"], torch.arange(e["visual"][0], e["visual"][1]))
+        fn.__class__ = E.renew_end_of_line_logit_processor_3d(fn.__class__)
+        procs = LogitsProcessorList([fn, TopKLogitsWarper(top_k=case["image_top_k"])])
     else:
         procs = LogitsProcessorList([TopKLogitsWarper(top_k=case["image_top_k"]), TopPLogitsWarper3d(top_p=1.0)])
     gc = GenerationConfig(max_new_tokens=case["max_length"], max_length=case["max_length"], temperature=1.0,
@@ -178,7 +195,23 @@ def run_reference_loop(case: dict, Cache) -> dict:
     return {"ids": [int(t) for t in out[0]], "trace": trace}
 
 
+_EMU3 = dict(height=4, width=6, img_token=900, eol=901, eof=902, eoi=903, eos=904, pad=905, visual=[1000, 3048])
 LOOP_CASES = {
+    # Emu3 grammar (a11): 4 x 6 grid -> EOL after every 6 visual tokens, then EOF, EOI, EOS (stops the run)
+    "emu3_spec_w8": dict(V=4096, sharp=14.0, grammar="emu3", emu3=_EMU3, image_top_k=512, text_top_k=10,
+                         prompt=[5, 17, 23, 900], img_vocab=[1000, 3048], do_sample=True, eos=[904],
+                         max_length=4 + 7 * 4 + 3 + 4,
+                         jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=200, max_num_new_tokens=8,
+                                     guidance_scale=3.0, seed=2, multi_token_init_scheme="random", do_cfg=True,
+                                     prefix_token_sampler_scheme="speculative_jacobi")),
+    # ... and past EOS into the forced-PAD region (no EOS criterion), window crossing EOF/EOI/EOS
+    "emu3_spec_w16_pad_tail": dict(V=4096, sharp=10.0, grammar="emu3", emu3=_EMU3, image_top_k=300, text_top_k=10,
+                                   prompt=[900], img_vocab=[1000, 3048], do_sample=True, eos=[],
+                                   max_length=1 + 7 * 4 + 3 + 6,
+                                   jacobi=dict(jacobi_loop_interval_l=2, jacobi_loop_interval_r=200,
+                                               max_num_new_tokens=16, guidance_scale=2.0, seed=9,
+                                               multi_token_init_scheme="random", do_cfg=True,
+                                               prefix_token_sampler_scheme="speculative_jacobi")),
     "lumina_spec_w8": dict(V=9216, sharp=16.0, grammar="lumina", image_top_k=2000, text_top_k=10,
                            prompt=[1, 100, 200, 8197, 8808, 8808], img_vocab=[4, 8196], do_sample=True, eos=[8710],
                            max_length=6 + 8 * 9 + 3,

@@ -82,6 +82,43 @@ class LuminaGrammar:
 
 
 @dataclass
+class Emu3Grammar:
+    """EOLLogitProcessor3d (scheduler/jacobi_iteration_emu3.py:44-128) as index arithmetic: only visual ids
+    [visual_lo, visual_hi) are allowed; window positions are forced to EOL every width+1 tokens after the image token,
+    to EOF / EOI / EOS at (width+1)*height + 1 / 2 / 3, and — once the window reaches past that — the LAST rows of the
+    window (python slice semantics of `batch_scores[start:, :]` with a possibly negative start, :120-125) to PAD.
+    Non-visual ids get finfo.min there, which softmax / top-k treat like -inf.  HF appends TopKLogitsWarper(top_k)."""
+    height: int = 90
+    width: int = 90
+    img_token: int = 0
+    eol: int = 0
+    eof: int = 0
+    eoi: int = 0
+    eos: int = 0
+    pad: int = 0
+    visual_lo: int = 0
+    visual_hi: int = 0
+    top_k: int = 2048
+
+    def describe(self, ids: list[int], n: int) -> dict:
+        offset = ids.index(self.img_token)            # first occurrence (offset_cache, :52-54)
+        tokenlen = len(ids) - (offset + 1)
+        d = {"in_image": True, "allow": (self.visual_lo, self.visual_hi), "forced": [-1] * n, "top_k": self.top_k,
+             "no_cfg": False}
+        line = self.width + 1
+        for line_len, tok in ((line, self.eol), (line * self.height + 1, self.eof), (line * self.height + 2, self.eoi),
+                              (line * self.height + 3, self.eos)):
+            for pos in eol_positions(tokenlen, n, line_len):
+                if 0 <= pos < n:
+                    d["forced"][pos] = tok
+        limit = line * self.height + 3
+        if tokenlen + n > limit:
+            for pos in list(range(n))[limit - tokenlen:]:
+                d["forced"][pos] = self.pad
+        return d
+
+
+@dataclass
 class PlainTopK:
     """LlamaGen / Emu3-style processors without grammar: HF TopKLogitsWarper (+ TopPLogitsWarper3d with p = 1,
     a no-op on probabilities; llamagen/llamagen_solver.py:458-470)."""

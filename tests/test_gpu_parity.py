@@ -196,6 +196,10 @@ def _engine_for_case(env, case, noise_dev="cpu"):
     rows = 2 if do_cfg else 1
     if case["grammar"] == "lumina":
         grammar = engine.LuminaGrammarState(image_top_k=case["image_top_k"], text_top_k=case["text_top_k"])
+    elif case["grammar"] == "emu3":
+        e = case["emu3"]
+        grammar = engine.Emu3GrammarState(e["height"], e["width"], e["img_token"], e["eol"], e["eof"], e["eoi"], e["eos"],
+                                          e["pad"], e["visual"][0], e["visual"][1], top_k=case["image_top_k"])
     else:
         grammar = engine.PlainTopKState(top_k=case["image_top_k"])
 

@@ -90,6 +90,32 @@ def test_grammar_state_matches_oracle_grammar(lib):
             produced += m
 
 
+def test_emu3_grammar_state_matches_oracle_grammar(lib):
+    """Emu3 grammar: incremental product-side state == oracle restatement (itself pinned to the reference's
+    EOLLogitProcessor3d by tests/golden/sjd_loop_emu3_*.json), through EOL / EOF / EOI / EOS and into the PAD tail."""
+    from oracle import sjd_oracle as O
+    from sjd_b200.engine import Emu3GrammarState
+    rnd = random.Random(1)
+    for trial in range(30):
+        h, w = rnd.randint(1, 4), rnd.randint(1, 6)
+        args = (h, w, 900, 901, 902, 903, 904, 905, 1000, 3048)
+        og, pg = O.Emu3Grammar(*args, top_k=64), Emu3GrammarState(*args, top_k=64)
+        ids = [rnd.randint(1, 800) for _ in range(rnd.randint(0, 4))] + [900]
+        pg.reset()
+        pg.observe(ids)
+        produced, total = 0, (w + 1) * h + 3
+        while produced < total + 12:
+            n = rnd.randint(1, 11)
+            d_o, d_p = og.describe(ids, n), pg.describe(n)
+            assert d_o["forced"] == d_p["forced"], (trial, ids, n)
+            assert tuple(d_o["allow"]) == tuple(d_p["allow"]) and d_o["top_k"] == d_p["top_k"]
+            m = rnd.randint(1, n)
+            new = [d_o["forced"][j] if d_o["forced"][j] >= 0 else rnd.randint(1000, 3047) for j in range(m)]
+            ids = ids + new
+            pg.observe(new)
+            produced += m
+
+
 def test_prompt_sharding_covers_all_prompts(lib):
     from sjd_b200.replicas import shard_prompts
     for world in (1, 2, 4, 8):

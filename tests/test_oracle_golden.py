@@ -20,6 +20,10 @@ def run_oracle(case, max_trips=None):
     params = O.OracleParams(**j)
     if case["grammar"] == "lumina":
         grammar = O.LuminaGrammar(image_top_k=case["image_top_k"], text_top_k=case["text_top_k"])
+    elif case["grammar"] == "emu3":
+        e = case["emu3"]
+        grammar = O.Emu3Grammar(e["height"], e["width"], e["img_token"], e["eol"], e["eof"], e["eoi"], e["eos"], e["pad"],
+                                e["visual"][0], e["visual"][1], top_k=case["image_top_k"])
     else:
         grammar = O.PlainTopK(top_k=case["image_top_k"])
     trace = []
