@@ -82,12 +82,31 @@ class TopPLogitsWarper3d(_DeviceEvaluated):
         self.top_p = top_p
 
 
+def renew_end_of_line_logit_processor_3d(model_class):
+    """scheduler/jacobi_iteration_emu3.py:41-151: class-swaps Emu3PrefixConstrainedLogitsHelper (emu3/mllm/utils_emu3.py:
+    19-62: height, width, img_token, eoi/eos/eol/eof/pad tokens, visual_tokens) into the 3-D processor.  Here it stays
+    a parameter holder; its arithmetic runs in sjd_verify (engine.Emu3GrammarState)."""
+    class EOLLogitProcessor3d(model_class, _DeviceEvaluated):
+        _sjd_emu3_grammar = True
+    return EOLLogitProcessor3d
+
+
+def _visual_range(visual_tokens):
+    v = torch.as_tensor(visual_tokens).flatten().tolist()
+    lo, hi = min(v), max(v) + 1
+    if hi - lo != len(set(v)):
+        raise NotImplementedError("visual token ids must form one contiguous range for the device grammar")
+    return lo, hi
+
+
 def grammar_from_processors(processors):
     """Translate the reference's processor list into the engine's grammar state."""
-    vl = topk = None
+    vl = topk = emu = None
     plain_k = 0
     for pr in processors or []:
-        if isinstance(pr, MultiTokensVLLogitsProcessor):
+        if getattr(pr, "_sjd_emu3_grammar", False):
+            emu = pr
+        elif isinstance(pr, MultiTokensVLLogitsProcessor):
             vl = pr
         elif isinstance(pr, MultiTokensInterleavedTopKLogitsWarper):
             topk = pr
@@ -98,6 +117,11 @@ def grammar_from_processors(processors):
             plain_k = int(pr.top_k)
         else:
             raise NotImplementedError(f"logits processor {type(pr).__name__} has no device implementation")
+    if emu is not None:
+        lo, hi = _visual_range(emu.visual_tokens)
+        return _engine.Emu3GrammarState(int(emu.height), int(emu.width), int(emu.img_token), int(emu.eol_token),
+                                        int(emu.eof_token), int(emu.eoi_token), int(emu.eos_token), int(emu.pad_token),
+                                        lo, hi, top_k=plain_k)
     if vl is not None:
         return _engine.LuminaGrammarState(
             image_start=vl.image_start_token_id, image_end=vl.image_end_token_id, eol=vl.image_next_line_token_id,
@@ -145,7 +169,11 @@ def pack_hf_decoder(model, max_len: int, rows: int, device) -> DeviceStack:
         w["layers"].append(e)
     shape = StackShape(len(layers), d, H, Hkv, Dh, cfg.intermediate_size, cfg.vocab_size,
                        float(getattr(cfg, "rms_norm_eps", 1e-5)), qk_norm, False)
-    theta = float(getattr(cfg, "rope_theta", 10000.0) or 10000.0)
+    theta = getattr(cfg, "rope_theta", None)
+    if theta is None:   # HF >= 5 keeps it in config.rope_parameters
+        rp = getattr(cfg, "rope_parameters", None) or {}
+        theta = rp.get("rope_theta", 10000.0) if isinstance(rp, dict) else 10000.0
+    theta = float(theta)
     cos, sin = _rope_half(Dh, max_len, theta)
     return DeviceStack(shape, w, cos, sin, rows, max_len, device)
 
@@ -259,6 +287,20 @@ def renew_sampler(model_class):
             prefill_num = (attn.shape[1] - 1) if attn is not None else len(prompt) - 1
             kv_lo = [0, prefill_num] if (rows == 2 and not self._init_doubled_attn_mask_cfg
                                          and not hasattr(self, "tok_embeddings")) else [0] * rows
+            uncond = None
+            neg = model_kwargs.get("neg_input_ids")
+            if neg is not None:
+                # Emu3: the CFG-uncond row is a real negative prompt; both rows are left-padded to one length
+                # (get_double_cfg_input_ids, logit_processor_3dim.py:422-440) and the padding is hidden by the mask
+                if rows != 2:
+                    raise ValueError("neg_input_ids given but CFG is disabled")
+                pad = int(self.config.pad_token_id)
+                P = max(len(prompt), neg.shape[1])
+                uncond = [pad] * (P - neg.shape[1]) + neg[0].tolist()
+                prompt = [pad] * (P - len(prompt)) + prompt
+                kv_lo = [next((i for i, t in enumerate(r) if t != pad), len(r) - 1) for r in (prompt, uncond)]
+                if attn is not None and attn.dim() == 2 and attn.shape[0] == 2:
+                    kv_lo = [int((attn[b] == 0).long().cumprod(0).sum()) for b in range(2)]
             stop_fn = None
             if extra:
                 def stop_fn(ids):
@@ -270,7 +312,7 @@ def renew_sampler(model_class):
             ids = eng.generate(prompt, max_length=max_length or (len(prompt) + 4096), eos_token_ids=eos,
                                do_sample=bool(generation_config.do_sample), kv_len0=kv_len0, kv_lo=kv_lo,
                                temperature=float(getattr(generation_config, "temperature", 1.0) or 1.0),
-                               stop_fn=stop_fn)
+                               stop_fn=stop_fn, uncond_input_ids=uncond)
             t2.record()
             torch.cuda.synchronize()
             self.sjd_stats = eng.stats
@@ -284,6 +326,60 @@ def renew_sampler(model_class):
             return torch.tensor([ids], dtype=input_ids.dtype, device=device)
 
     return JacobiSampler
+
+
+def renew_sampler_forward(model_class):
+    """scheduler/jacobi_iteration_emu3.py:153-368.  The reference wraps forward() to build the 4-D mask itself; here the
+    mask is index math in the attention kernel, so only the CFG input preparation and the parameter defaults remain."""
+    class JacobiModel(model_class):
+        def _init_new_params(self, *args, use_chameleon_tokenizer=False, _init_doubled_attn_mask_cfg=True,
+                             visual_tokens=None, **kwargs):
+            keep = getattr(self, "img_vocab", None)
+            super()._init_new_params(*args, use_chameleon_tokenizer=use_chameleon_tokenizer,
+                                     _init_doubled_attn_mask_cfg=_init_doubled_attn_mask_cfg, **kwargs)
+            if keep is not None:   # renew_sampler ran first with its Chameleon default (reference quirk, SURVEY §3.4)
+                self.img_vocab = keep
+            if getattr(self, "img_vocab", None) is None:
+                self.img_vocab = torch.as_tensor(visual_tokens) if visual_tokens is not None else None
+
+        def prepare_batch_cfg_model_inputs(self, input_ids, neg_input_ids=None, attention_mask=None):
+            """:234-278 — left-pads positive and negative prompt to one length and builds the [2B, P] keep-mask."""
+            B, P = input_ids.shape
+            pad = self.config.pad_token_id
+            out = {"input_ids": input_ids, "attention_mask": attention_mask}
+            rows = 2 * B if self.do_cfg else B
+            maxP = max(P, neg_input_ids.shape[1] if neg_input_ids is not None else P)
+            keep = torch.zeros((rows, maxP), dtype=torch.bool, device=input_ids.device)
+            keep[:B, -P:] = input_ids != pad
+            if neg_input_ids is not None:
+                both = torch.full((2 * B, maxP), pad, dtype=input_ids.dtype, device=input_ids.device)
+                both[:B, -P:] = input_ids
+                both[B:, -neg_input_ids.shape[1]:] = neg_input_ids
+                out["input_ids"] = both
+                out["pos_input_ids"] = both[:B]
+                keep = both != pad
+            if attention_mask is None:
+                out["attention_mask"] = keep.to(torch.float32)
+            elif attention_mask.shape[0] == B:
+                raise NotImplementedError
+            return out
+
+    return JacobiModel
+
+
+def renew_solver(model, processor, **jacobi_param_dict):
+    """scheduler/jacobi_iteration_emu3.py:370-412: returns (model, LogitsProcessorList([constrained_fn]))."""
+    h = jacobi_param_dict.pop("h", None)
+    w = jacobi_param_dict.pop("w", None)
+    jacobi_param_dict.pop("neg_inputs", None)
+    jacobi_param_dict.pop("classifier_free_guidance", None)
+    constrained_fn = processor.build_prefix_constrained_fn(h, w)
+    constrained_fn.__class__ = renew_end_of_line_logit_processor_3d(constrained_fn.__class__)
+    model.__class__ = renew_sampler(model.__class__)
+    model._init_new_params(**jacobi_param_dict)
+    model.__class__ = renew_sampler_forward(model.__class__)
+    model._init_new_params(visual_tokens=constrained_fn.visual_tokens, **jacobi_param_dict)
+    return model, LogitsProcessorList([constrained_fn])
 
 
 def renew_backbone(model_class):

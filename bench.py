@@ -234,6 +234,10 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     stack.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ================================================================= reference arm / cpu baseline (oracle port)

@@ -394,3 +394,78 @@ def test_llamagen_solver_flow_on_gpu(env):
                             max_length=case["grid"] ** 2, eos_ids=[], rows=2, do_sample=True, temperature=1.0,
                             kv_len0=case["cls_token_num"], noise=O.TorchNoise(case["jacobi"]["seed"], device=str(dev)))
     assert ids_o[-len(tokens):] == tokens and nfe_o == m.sjd_stats.nfe
+
+
+# ------------------------------------------------------------------------------- Emu3 boundary (config 4 family)
+def test_emu3_adaptor_flow_on_gpu(env):
+    """The Emu3 entry points of the plugin API (scheduler.jacobi_iteration_emu3: renew_end_of_line_logit_processor_3d,
+    renew_sampler_forward, prepare_batch_cfg_model_inputs, `_sample(..., neg_input_ids=...)`) on a tiny Llama-style GQA
+    model (what Emu3's LM is): left-padded negative prompt as the CFG-uncond row, positional EOL/EOF/EOI/EOS grammar,
+    HF TopKLogitsWarper.  Engine output == oracle replay on the captured logits; grammar positions checked."""
+    from transformers import GenerationConfig, LlamaConfig, LlamaForCausalLM
+    from transformers.generation.logits_process import LogitsProcessorList, TopKLogitsWarper
+    from transformers.generation.stopping_criteria import EosTokenCriteria, MaxLengthCriteria, StoppingCriteriaList
+    from scheduler.jacobi_iteration_emu3 import renew_end_of_line_logit_processor_3d, renew_sampler_forward
+    from scheduler.jacobi_iteration_lumina_mgpt import renew_sampler
+    O, model_mod, dev = env["O"], env["model"], env["dev"]
+    torch.manual_seed(0)
+    cfg = LlamaConfig(vocab_size=4096, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=1, rms_norm_eps=1e-5, max_position_embeddings=256,
+                      pad_token_id=0, tie_word_embeddings=False)
+    m = LlamaForCausalLM(cfg)
+    with torch.no_grad():
+        for p_ in m.parameters():
+            if p_.dim() >= 2:
+                p_.normal_(0.0, 0.08)
+    m = m.to(dev, torch.bfloat16).eval()
+
+    class Helper:   # stand-in for Emu3PrefixConstrainedLogitsHelper (emu3/mllm/utils_emu3.py:19-41): attributes only
+        def __init__(self):
+            self.height, self.width, self.img_token = 4, 6, 900
+            self.eol_token, self.eof_token, self.eoi_token, self.eos_token, self.pad_token = 901, 902, 903, 904, 905
+            self.visual_tokens = torch.arange(1000, 3048)
+            self.offset_cache = {}
+
+    fn = Helper()
+    fn.__class__ = renew_end_of_line_logit_processor_3d(fn.__class__)
+    jac = dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=200, max_num_new_tokens=8, guidance_scale=3.0, seed=4,
+               multi_token_init_scheme="random", do_cfg=True, prefix_token_sampler_scheme="speculative_jacobi")
+    m.__class__ = renew_sampler(m.__class__)
+    m._init_new_params(use_chameleon_tokenizer=False, **jac)
+    m.__class__ = renew_sampler_forward(m.__class__)
+    m._init_new_params(visual_tokens=fn.visual_tokens, **jac)
+    assert m.img_vocab is not None and int(m.img_vocab[0]) == 1000
+    pos = torch.tensor([[5, 17, 23, 11, 900]], device=dev)
+    neg = torch.tensor([[7, 9, 900]], device=dev)
+    mi = m.prepare_batch_cfg_model_inputs(pos, neg)
+    assert mi["input_ids"].tolist() == [[5, 17, 23, 11, 900], [0, 0, 7, 9, 900]]
+    assert mi["attention_mask"].tolist() == [[1, 1, 1, 1, 1], [0, 0, 1, 1, 1]]
+    P, n_img = 5, 7 * 4 + 3
+    crit = StoppingCriteriaList([MaxLengthCriteria(P + n_img + 4), EosTokenCriteria(eos_token_id=[904])])
+    gc = GenerationConfig(max_length=P + n_img + 4, do_sample=True, temperature=1.0, top_k=None)
+    captured = []
+    orig_forward = model_mod.DeviceStack.forward
+
+    def spy(self, *a, **k):
+        lg = orig_forward(self, *a, **k)
+        captured.append(lg.detach().float().cpu().numpy().reshape(-1, cfg.vocab_size).copy())
+        return lg
+
+    model_mod.DeviceStack.forward = spy
+    try:
+        out = m._sample(mi["pos_input_ids"], logits_processor=LogitsProcessorList([fn, TopKLogitsWarper(top_k=512)]),
+                        stopping_criteria=crit, generation_config=gc, synced_gpus=False, streamer=None,
+                        attention_mask=mi["attention_mask"], neg_input_ids=neg)
+    finally:
+        model_mod.DeviceStack.forward = orig_forward
+    ids = out[0].tolist()
+    img = ids[P:]
+    assert all(img[i] == 901 for i in range(6, 28, 7)), img          # EOL closes every row of 6 visual tokens
+    assert img[28:31] == [902, 903, 904], img                          # EOF, EOI, EOS
+    assert all(1000 <= t < 3048 for i, t in enumerate(img[:28]) if i % 7 != 6)
+    it = iter(captured)
+    g = O.Emu3Grammar(4, 6, 900, 901, 902, 903, 904, 905, 1000, 3048, top_k=512)
+    ids_o, nfe_o = O.decode(lambda r, k, n: next(it), [5, 17, 23, 11, 900], params=O.OracleParams(**jac), grammar=g,
+                            img_vocab=np.arange(1000, 3048), max_length=P + n_img + 4, eos_ids=[904], rows=2,
+                            do_sample=True, noise=O.TorchNoise(jac["seed"], device=str(dev)))
+    assert ids_o == ids and nfe_o == m.sjd_stats.nfe
