@@ -142,6 +142,8 @@ def pack_hf_decoder(model, max_len: int, rows: int, device) -> DeviceStack:
     (.q_norm/.k_norm), .mlp.{gate,up,down}_proj, .input_layernorm, .post_attention_layernorm; model.model.norm;
     model.lm_head (modeling_chameleon.py:235-369, :593-666)."""
     cfg = model.config
+    if getattr(cfg, "swin_norm", False):
+        raise NotImplementedError("swin_norm decoder layers (Chameleon-34B, modeling_chameleon.py:669-741) are not supported")
     core = model.model
     layers = core.layers
     H = cfg.num_attention_heads

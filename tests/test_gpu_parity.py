@@ -469,3 +469,58 @@ def test_emu3_adaptor_flow_on_gpu(env):
                             img_vocab=np.arange(1000, 3048), max_length=P + n_img + 4, eos_ids=[904], rows=2,
                             do_sample=True, noise=O.TorchNoise(jac["seed"], device=str(dev)))
     assert ids_o == ids and nfe_o == m.sjd_stats.nfe
+
+
+# ------------------------------------------------------- independent check: HF's own Chameleon forward (Anole's model)
+def test_forward_matches_hf_chameleon_bf16(env):
+    """The module tree Anole runs (transformers.ChameleonForConditionalGeneration, model_wrappers/model_loader.py:12-13)
+    packed by hf_api.pack_hf_decoder and run by the engine vs that model's OWN PyTorch bf16 forward on the GPU:
+    prefill and window logits within 3 bf16 ulp of the logit scale, mean within half an ulp (both pipelines round every linear / norm output to bf16)."""
+    from transformers import ChameleonConfig, ChameleonForConditionalGeneration
+    from sjd_b200 import hf_api
+    dev = env["dev"]
+    torch.manual_seed(1)
+    cfg = ChameleonConfig(vocab_size=2048, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                          num_attention_heads=2, num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-5,
+                          vocabulary_map={"<image>": 3, "IMGIMGA": 4, "IMGIMGB": 5},
+                          vq_config={"embed_dim": 8, "num_embeddings": 16, "resolution": 32, "channel_multiplier": [1, 1],
+                                     "base_channels": 32, "num_res_blocks": 1, "latent_channels": 8})
+    m = ChameleonForConditionalGeneration(cfg)
+    with torch.no_grad():
+        for n_, p_ in m.named_parameters():
+            if "vqmodel" in n_:
+                continue
+            if p_.dim() >= 2 and "norm" not in n_:
+                p_.normal_(0.0, 0.02)
+            elif "norm" in n_ and n_.endswith("weight"):
+                p_.normal_(1.0, 0.1)
+            elif "norm" in n_ and n_.endswith("bias"):
+                p_.normal_(0.0, 0.1)
+    m = m.to(dev, torch.bfloat16).eval()
+    P = 23
+    ids = torch.randint(6, cfg.vocab_size, (1, P), device=dev)
+    with torch.no_grad():
+        ref = m(input_ids=ids, use_cache=False).logits.float()[0]          # [P, V]
+    stack = hf_api.pack_hf_decoder(m, max_len=128, rows=1, device=dev)
+    pos = torch.arange(P, dtype=torch.int32, device=dev)
+    ours = stack.forward(P, pos, pos, 0, [0], ids=ids[0].int().contiguous(), n_logit_tokens=P)[0].clone()
+    torch.cuda.synchronize()
+    keep = (ref > -1e30).all(0)     # HF blanks the image-token columns of the logits (finfo.min); compare the others
+    assert int(keep.sum()) >= cfg.vocab_size - 8
+    ref, ours = ref[:, keep], ours[:, keep]
+    ulp = 2.0 ** (torch.floor(torch.log2(ref.abs().max())).item() - 7)
+    err = (ours - ref).abs()
+    print('hf-chameleon prefill: max err', err.max().item(), 'mean', err.mean().item(), 'ulp', ulp, 'absmax', ref.abs().max().item())
+    assert err.max().item() <= 3.0 * ulp, (err.max().item(), ulp)
+    assert err.mean().item() <= 0.5 * ulp
+    # a window step over the cache as well: tokens P..P+7 with the first P cached by the call above
+    W = 8
+    ids2 = torch.randint(6, cfg.vocab_size, (1, W), device=dev)
+    with torch.no_grad():
+        ref2 = m(input_ids=torch.cat([ids, ids2], 1), use_cache=False).logits.float()[0, P:]
+    pos2 = torch.arange(P, P + W, dtype=torch.int32, device=dev)
+    ours2 = stack.forward(W, pos2, pos2, P, [0], ids=ids2[0].int().contiguous(), n_logit_tokens=W)[0].clone()
+    torch.cuda.synchronize()
+    err2 = (ours2[:, keep] - ref2[:, keep]).abs()
+    assert err2.max().item() <= 3.0 * ulp, (err2.max().item(), ulp)
+    stack.close()
