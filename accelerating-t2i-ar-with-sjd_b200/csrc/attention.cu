@@ -6,8 +6,7 @@
 // indices; no mask tensor exists (reference builds [2B,1,W,T+W] additive masks:
 // scheduler/jacobi_iteration_lumina_mgpt.py:1256-1336, consumed by SDPA at
 // lumina_mgpt/model/chameleon/modeling_chameleon.py:567-574; llamagen/llamagen.py:269-273).
-// The CTA that delivers the last key split merges the split partials (log-sum-exp combine) into the bf16 attention
-// output — there is no second kernel.
+// A second kernel merges the per-chunk partials (log-sum-exp combine) into the bf16 attention output.
 #include "common.cuh"
 
 namespace sjd {
@@ -22,7 +21,6 @@ struct AttnParams {
   float* part_o;            // [chunks][rows][H][W][Dh]
   float* part_ml;           // [chunks][rows][H][W][2]
   __nv_bfloat16* out;       // [rows*W][H*Dh]
-  unsigned int* counters;   // [rows][Hkv * tile groups] split arrivals, zero between launches
   int rows, W, H, Hkv, Lmax;
   int kv_len;               // keys cached before this window
   int kv_lo[kAttnMaxRows];  // first visible key per row
@@ -57,55 +55,6 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// One warp per (row b, head, query i): merge the key-split partials, normalise, write bf16 (called by the CTA that
-// delivers the last split).  Loads are issued in batches of
-// kCombBatch chunks (clamped indices, surplus weights zero) so the L2 round trips overlap.
-constexpr int kCombBatch = 8;
-template <int DH>
-__device__ __forceinline__ void attn_combine_row(const AttnParams& p, int b, int h, int i, int lane) {
-  const size_t stride = size_t(p.rows) * p.H * p.W;  // per chunk
-  const size_t idx = (size_t(b) * p.H + h) * p.W + i;
-  constexpr int PER = DH / 32;
-  float acc[PER];
-#pragma unroll
-  for (int e = 0; e < PER; ++e) acc[e] = 0.f;
-  float mrun = -INFINITY, lsum = 0.f;
-  for (int c0 = 0; c0 < p.n_chunks; c0 += kCombBatch) {
-    float2 ml[kCombBatch];
-    float po[kCombBatch][PER];
-#pragma unroll
-    for (int k = 0; k < kCombBatch; ++k) {
-      const int c = min(c0 + k, p.n_chunks - 1);
-      ml[k] = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (c * stride + idx) * 2));
-#pragma unroll
-      for (int e = 0; e < PER; ++e) po[k][e] = __ldcg(p.part_o + (c * stride + idx) * DH + lane + 32 * e);
-    }
-    float mb = mrun;
-#pragma unroll
-    for (int k = 0; k < kCombBatch; ++k)
-      if (c0 + k < p.n_chunks) mb = fmaxf(mb, ml[k].x);
-    if (mb == -INFINITY) continue;
-    const float rescale = exp2f(mrun - mb);   // mrun == -inf -> 0
-    lsum *= rescale;
-#pragma unroll
-    for (int e = 0; e < PER; ++e) acc[e] *= rescale;
-    mrun = mb;
-#pragma unroll
-    for (int k = 0; k < kCombBatch; ++k) {
-      if (c0 + k < p.n_chunks && ml[k].x != -INFINITY) {
-        const float w = exp2f(ml[k].x - mb);
-        lsum += w * ml[k].y;
-#pragma unroll
-        for (int e = 0; e < PER; ++e) acc[e] += w * po[k][e];
-      }
-    }
-  }
-  const float inv = lsum > 0.f ? 1.f / lsum : 0.f;  // fully masked query (CFG hidden prefix) -> 0
-  __nv_bfloat16* dst = p.out + (size_t(b * p.W + i) * p.H + h) * DH;
-#pragma unroll
-  for (int e = 0; e < PER; ++e) dst[lane + 32 * e] = __float2bfloat16_rn(acc[e] * inv);
 }
 
 // grid: (key splits, Hkv * tile groups, rows); block: TWO warps per 16-query tile (<= 4 tiles per CTA).
@@ -299,7 +248,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB) attn_window_kernel(AttnParams 
     }
   }
   __syncthreads();
-  if (kh == 0 && has_tile) {
+  if (kh == 1 || !has_tile) return;
+  {
     const float om0 = xch[g * (DH + 2) + DH], ol0 = xch[g * (DH + 2) + DH + 1];
     const float om1 = xch[(g + 8) * (DH + 2) + DH], ol1 = xch[(g + 8) * (DH + 2) + DH + 1];
     const float nm0 = fmaxf(m0, om0), nm1 = fmaxf(m1, om1);
@@ -315,41 +265,76 @@ __global__ void __launch_bounds__(NTHREADS, MINB) attn_window_kernel(AttnParams 
       o[n][0] = o[n][0] * wa0 + x0.x * wb0; o[n][1] = o[n][1] * wa0 + x0.y * wb0;
       o[n][2] = o[n][2] * wa1 + x1.x * wb1; o[n][3] = o[n][3] * wa1 + x1.y * wb1;
     }
-    // write partials
-    const size_t base = ((size_t(split) * p.rows + b) * p.H + hq) * size_t(p.W);
-    if (r0 < p.W) {
-      float* po = p.part_o + (base + r0) * DH;
+  }
+  // write partials
+  const size_t base = ((size_t(split) * p.rows + b) * p.H + hq) * size_t(p.W);
+  if (r0 < p.W) {
+    float* po = p.part_o + (base + r0) * DH;
 #pragma unroll
-      for (int n = 0; n < DH / 8; ++n) __stcg(reinterpret_cast<float2*>(po + n * 8 + t * 2), make_float2(o[n][0], o[n][1]));
-      if (t == 0) __stcg(reinterpret_cast<float2*>(p.part_ml + (base + r0) * 2), make_float2(m0, l0));
-    }
-    if (r1 < p.W) {
-      float* po = p.part_o + (base + r1) * DH;
+    for (int n = 0; n < DH / 8; ++n) *reinterpret_cast<float2*>(po + n * 8 + t * 2) = make_float2(o[n][0], o[n][1]);
+    if (t == 0) { p.part_ml[(base + r0) * 2] = m0; p.part_ml[(base + r0) * 2 + 1] = l0; }
+  }
+  if (r1 < p.W) {
+    float* po = p.part_o + (base + r1) * DH;
 #pragma unroll
-      for (int n = 0; n < DH / 8; ++n) __stcg(reinterpret_cast<float2*>(po + n * 8 + t * 2), make_float2(o[n][2], o[n][3]));
-      if (t == 0) __stcg(reinterpret_cast<float2*>(p.part_ml + (base + r1) * 2), make_float2(m1, l1));
+    for (int n = 0; n < DH / 8; ++n) *reinterpret_cast<float2*>(po + n * 8 + t * 2) = make_float2(o[n][2], o[n][3]);
+    if (t == 0) { p.part_ml[(base + r1) * 2] = m1; p.part_ml[(base + r1) * 2 + 1] = l1; }
+  }
+}
+
+// One warp per (row b, head, query i): merge chunk partials, normalise, write bf16.  Loads are issued in batches of
+// kCombBatch chunks (clamped indices, surplus weights zero) so the L2 round trips overlap.
+constexpr int kCombBatch = 8;
+template <int DH>
+__global__ void __launch_bounds__(256) attn_combine_kernel(AttnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int widx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int total = p.rows * p.H * p.W;
+  if (widx >= total) return;
+  const int i = widx % p.W, h = (widx / p.W) % p.H, b = widx / (p.W * p.H);
+  const size_t stride = size_t(p.rows) * p.H * p.W;  // per chunk
+  const size_t idx = (size_t(b) * p.H + h) * p.W + i;
+  constexpr int PER = DH / 32;
+  float acc[PER];
+#pragma unroll
+  for (int e = 0; e < PER; ++e) acc[e] = 0.f;
+  float mrun = -INFINITY, lsum = 0.f;
+  for (int c0 = 0; c0 < p.n_chunks; c0 += kCombBatch) {
+    float2 ml[kCombBatch];
+    float po[kCombBatch][PER];
+#pragma unroll
+    for (int k = 0; k < kCombBatch; ++k) {
+      const int c = min(c0 + k, p.n_chunks - 1);
+      ml[k] = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (c * stride + idx) * 2));
+#pragma unroll
+      for (int e = 0; e < PER; ++e) po[k][e] = __ldcg(p.part_o + (c * stride + idx) * DH + lane + 32 * e);
+    }
+    float mb = mrun;
+#pragma unroll
+    for (int k = 0; k < kCombBatch; ++k)
+      if (c0 + k < p.n_chunks) mb = fmaxf(mb, ml[k].x);
+    if (mb == -INFINITY) continue;
+    const float rescale = exp2f(mrun - mb);   // mrun == -inf -> 0
+    lsum *= rescale;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) acc[e] *= rescale;
+    mrun = mb;
+#pragma unroll
+    for (int k = 0; k < kCombBatch; ++k) {
+      if (c0 + k < p.n_chunks && ml[k].x != -INFINITY) {
+        const float w = exp2f(ml[k].x - mb);
+        lsum += w * ml[k].y;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) acc[e] += w * po[k][e];
+      }
     }
   }
-  // ---- the CTA that delivers the last key split of this (row, kv head, tile group) merges all splits ----
-  __shared__ int s_last;
-  __syncthreads();   // every warp's partial stores happen-before thread 0's (cumulative) fence + counter bump
-  if (threadIdx.x == 0) {
-    __threadfence();
-    unsigned int* ctr = p.counters + (size_t(b) * gridDim.y + blockIdx.y);
-    const unsigned int prev = atomicAdd(ctr, 1u);
-    s_last = (prev == unsigned(p.n_chunks - 1));
-    if (s_last) { *ctr = 0; __threadfence(); }
-  }
-  __syncthreads();
-  if (s_last) {
-    const int nwarps = blockDim.x >> 5;
-    const int rows_here = min(tiles_here, n_tiles - tgroup * tiles_here) * 16;
-    for (int r = warp; r < rows_here; r += nwarps) {
-      const int tt = tgroup * tiles_here + r / 16;
-      const int i = (tt % tiles_per_head) * 16 + (r % 16);
-      if (i < p.W) attn_combine_row<DH>(p, b, hkv * G + tt / tiles_per_head, i, lane);
-    }
-  }
+  const float inv = lsum > 0.f ? 1.f / lsum : 0.f;  // fully masked query (CFG hidden prefix) -> 0
+  __nv_bfloat16* dst = p.out + (size_t(b * p.W + i) * p.H + h) * DH;
+#pragma unroll
+  for (int e = 0; e < PER; ++e) dst[lane + 32 * e] = __float2bfloat16_rn(acc[e] * inv);
 }
 
 // Chooses the key split: as many CTAs as fit in ONE wave of three per SM, spans in whole 64-key sub-chunks.
@@ -375,6 +360,8 @@ int attn_launch(const AttnParams& p, int head_dim, cudaStream_t stream) {
   const int nwarps = 2 * tiles_here;
   const int tgroups = (n_tiles + tiles_here - 1) / tiles_here;
   dim3 grid(p.n_chunks, p.Hkv * tgroups, p.rows);
+  const int total = p.rows * p.H * p.W;
+  dim3 cgrid((total + 7) / 8);
   int rc = 0;
   // thread count = 64 * tiles per CTA; the register cap is chosen so that three 64/128-thread CTAs share an SM
 #define SJD_ATTN_LAUNCH(DH_, NT_, MINB_)                                                                          \
@@ -393,11 +380,13 @@ int attn_launch(const AttnParams& p, int head_dim, cudaStream_t stream) {
     else if (nt == 128) SJD_ATTN_LAUNCH(128, 128, 3);
     else if (nt == 192) SJD_ATTN_LAUNCH(128, 192, 1);
     else SJD_ATTN_LAUNCH(128, 256, 1);
+    rc |= launch_pdl(attn_combine_kernel<128>, cgrid, dim3(256), 0, stream, p);
   } else if (head_dim == 64) {
     if (nt == 64) SJD_ATTN_LAUNCH(64, 64, 3);
     else if (nt == 128) SJD_ATTN_LAUNCH(64, 128, 3);
     else if (nt == 192) SJD_ATTN_LAUNCH(64, 192, 1);
     else SJD_ATTN_LAUNCH(64, 256, 1);
+    rc |= launch_pdl(attn_combine_kernel<64>, cgrid, dim3(256), 0, stream, p);
   } else {
     return -3;
   }

@@ -52,7 +52,6 @@ struct sjd_ctx {
   __nv_bfloat16 *kcache = nullptr, *vcache = nullptr;
   uint8_t* ws = nullptr;
   float *part_o = nullptr, *part_ml = nullptr;
-  unsigned int* attn_ctr = nullptr;   // split-arrival counters of the attention kernel
   int32_t *pos_zero = nullptr, *pos_last = nullptr;   // [SJD_MAX_TOKENS] dummies for sjd_ctx_gemm_only
   size_t ws_bytes = 0, bytes = 0;
   int max_chunks = 0, arrive_cap = 0;
@@ -281,7 +280,6 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
   rc |= dmalloc(c, &c->part_o, size_t(c->max_chunks) * T * hd * sizeof(float));
   rc |= dmalloc(c, &c->part_ml, size_t(c->max_chunks) * T * g.n_heads * 2 * sizeof(float));
   rc |= dmalloc(c, &c->fin, (kMaxChainOps + 1) * kCtrStride * 4);
-  rc |= dmalloc(c, &c->attn_ctr, size_t(g.rows) * g.n_kv_heads * size_t((g.n_heads / g.n_kv_heads) * ((SJD_MAX_TOKENS / g.rows + 15) / 16)) * 4);
   rc |= dmalloc(c, &c->pos_zero, T * 4);
   rc |= dmalloc(c, &c->pos_last, T * 4);
   if (!rc) {
@@ -382,7 +380,7 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
   AttnParams ap;
   memset(&ap, 0, sizeof(ap));
   if (!gemm_only) {
-    ap.q = c->q; ap.part_o = c->part_o; ap.part_ml = c->part_ml; ap.out = c->attn; ap.counters = c->attn_ctr;
+    ap.q = c->q; ap.part_o = c->part_o; ap.part_ml = c->part_ml; ap.out = c->attn;
     ap.rows = g.rows; ap.W = W; ap.H = g.n_heads; ap.Hkv = g.n_kv_heads; ap.Lmax = g.max_len; ap.kv_len = a->kv_len;
     for (int b = 0; b < kAttnMaxRows; ++b) ap.kv_lo[b] = b < g.rows ? a->kv_lo[b] : 0;
     attn_plan(&ap, device_num_sms());
@@ -416,7 +414,7 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
       ap.k = c->kcache + size_t(l) * layer_cache;
       ap.v = c->vcache + size_t(l) * layer_cache;
       rc |= attn_launch(ap, g.head_dim, s);
-      g_launches += 1;
+      g_launches += 2;
     }
     GemmEpi e = base;
     e.mode = EPI_RESID_NORM;
