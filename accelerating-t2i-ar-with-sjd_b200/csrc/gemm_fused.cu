@@ -9,22 +9,26 @@
 //   * persistent grid of one CTA per SM; stream-K split of the flattened (tile, k-block) space so every SM
 //     streams the same number of weight bytes whatever N is (streamk.cuh);
 //   * warp 0 = TMA producer (SWIZZLE_128B, deep mbarrier ring), warp 1 = single-thread tcgen05.mma issuer,
-//     warps 2..5 = epilogue;
-//   * programmatic dependent launch: the producer fills the whole ring with WEIGHT tiles before
-//     griddepcontrol.wait — weights never depend on the previous kernel, only the activation tiles do — so the
-//     HBM stream of GEMM n+1 starts while GEMM n (or the attention kernel) is still draining;
-//   * split tiles are fixed up in-kernel, reduce-scatter style: every contributor parks its fp32 partial, bumps a
-//     per-tile counter, and — after its own last segment — sums ALL partials of the tile in CTA order
-//     (bit-reproducible) for its share of the token rows and runs the epilogue on them.  The fix-up is spread
-//     over all CTAs; no reduce kernels, no atomics on data.
+//     warp 2 = activation TMA, warps 4..19 = epilogue;
+//   * a launch runs a CHAIN of up to 4 GEMMs ([o_proj, gate_up, down, next qkv] | lm_head): the weight producer never
+//     waits for data — it keeps the ring full across op boundaries and prefetches the next tiles into L2 while the
+//     ring is blocked — and a separate activation producer waits for the previous op's "rows finalised" counter
+//     (op 0: griddepcontrol.wait, the kernel is launched with programmatic dependent launch);
+//   * split tiles are fixed up in-kernel, deterministically (partials are always added in CTA order):
+//       ordinary epilogues — the CTA that owns a tile's head segment (which it computes last) is the finisher; the
+//         other contributors have the tile as their FIRST segment and park fp32 partials early, so the finisher
+//         never waits for a neighbour that is still streaming;
+//       residual + RMSNorm — the statistic spans all tiles of a row, so every segment is parked, one grid-wide
+//         counter tells when, and one CTA per token row sums the row's tiles, adds the residual, computes the
+//         statistic locally and writes h and xn (one exchange, one pass);
+//   * 16 epilogue warps: a scheduler issues one warp at a time, so the once-per-tile epilogue needs many warps.
 // Epilogues (what the reference does in separate eager kernels after each nn.Linear):
 //   EPI_F32        fp32 out (lm_head logits, modeling_chameleon.py:1560-1561), optional bf16 rounding
 //   EPI_BF16       bf16 out (generic projection)
 //   EPI_QKV        per-head QK-LayerNorm (:216-219) + RoPE (:153-177 rotate-half | llamagen.py:457-467 pairs)
 //                  + KV-cache append (replaces DynamicCache.update's torch.cat, :547) + q store
-//   EPI_RESID_NORM h += y ; xn = RMSNorm(h) * w  (residual + next norm, :643-659, :68-73) — the row statistic
-//                  spans all tiles, so finishers meet at a grid-wide counter before writing xn
-//   EPI_SILU_MUL   act = silu(gate) * up on gate/up rows interleaved 64/64 per tile (:193-195)
+//   EPI_RESID_NORM h += y ; xn = RMSNorm(h) * w  (residual + next norm, :643-659, :68-73), row-owner scheme above
+//   EPI_SILU_MUL   act = silu(gate) * up on gate/up rows interleaved inside each tile (:193-195)
 // Rounding points follow the bf16 reference: every nn.Linear output, norm output and residual sum is rounded to
 // bf16 before the next op; reductions and norms are computed in fp32.
 #include "common.cuh"
