@@ -285,14 +285,18 @@ __global__ void __launch_bounds__(NTHREADS, MINB) attn_window_kernel(AttnParams 
 // One warp per (row b, head, query i): merge chunk partials, normalise, write bf16.  Loads are issued in batches of
 // kCombBatch chunks (clamped indices, surplus weights zero) so the L2 round trips overlap.
 constexpr int kCombBatch = 8;
+
+// what the combine needs, small enough to ride in the GEMM chain kernel's parameters
+struct AttnCombine {
+  const float* part_o;    // [splits][rows][H][W][Dh]
+  const float* part_ml;   // [splits][rows][H][W][2]
+  __nv_bfloat16* out;     // [rows*W][H*Dh]
+  int rows, W, H, n_chunks, head_dim;
+};
+
+// one warp: merge the split partials of row `widx` = ((b * H + h) * W + i), normalise, write bf16
 template <int DH>
-__global__ void __launch_bounds__(256) attn_combine_kernel(AttnParams p) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const int widx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const int total = p.rows * p.H * p.W;
-  if (widx >= total) return;
+__device__ __forceinline__ void attn_combine_row(const AttnCombine& p, int widx, int lane) {
   const int i = widx % p.W, h = (widx / p.W) % p.H, b = widx / (p.W * p.H);
   const size_t stride = size_t(p.rows) * p.H * p.W;  // per chunk
   const size_t idx = (size_t(b) * p.H + h) * p.W + i;
@@ -337,6 +341,16 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(AttnParams p) {
   for (int e = 0; e < PER; ++e) dst[lane + 32 * e] = __float2bfloat16_rn(acc[e] * inv);
 }
 
+// stand-alone combine kernel (used when no GEMM chain follows the attention)
+template <int DH>
+__global__ void __launch_bounds__(256) attn_combine_kernel(AttnCombine c) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int widx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (widx >= c.rows * c.H * c.W) return;
+  attn_combine_row<DH>(c, widx, threadIdx.x & 31);
+}
+
 // Chooses the key split: as many CTAs as fit in ONE wave of three per SM, spans in whole 64-key sub-chunks.
 void attn_plan(AttnParams* p, int sm_count) {
   const int T = p->kv_len + p->W;
@@ -353,7 +367,16 @@ void attn_plan(AttnParams* p, int sm_count) {
   p->n_chunks = (T + p->span - 1) / p->span;
 }
 
-int attn_launch(const AttnParams& p, int head_dim, cudaStream_t stream) {
+AttnCombine attn_combine_desc(const AttnParams& p, int head_dim) {
+  AttnCombine c;
+  c.part_o = p.part_o; c.part_ml = p.part_ml; c.out = p.out;
+  c.rows = p.rows; c.W = p.W; c.H = p.H; c.n_chunks = p.n_chunks; c.head_dim = head_dim;
+  return c;
+}
+
+// with_combine = false: the caller folds the split merge into the GEMM chain kernel that follows (its epilogue
+// warps are idle at that point) instead of paying a kernel for it
+int attn_launch(const AttnParams& p, int head_dim, bool with_combine, cudaStream_t stream) {
   const int G = p.H / p.Hkv;
   const int n_tiles = G * ((p.W + 15) / 16);
   const int tiles_here = n_tiles < kAttnMaxTiles ? n_tiles : kAttnMaxTiles;
@@ -380,13 +403,13 @@ int attn_launch(const AttnParams& p, int head_dim, cudaStream_t stream) {
     else if (nt == 128) SJD_ATTN_LAUNCH(128, 128, 3);
     else if (nt == 192) SJD_ATTN_LAUNCH(128, 192, 1);
     else SJD_ATTN_LAUNCH(128, 256, 1);
-    rc |= launch_pdl(attn_combine_kernel<128>, cgrid, dim3(256), 0, stream, p);
+    if (with_combine) rc |= launch_pdl(attn_combine_kernel<128>, cgrid, dim3(256), 0, stream, attn_combine_desc(p, 128));
   } else if (head_dim == 64) {
     if (nt == 64) SJD_ATTN_LAUNCH(64, 64, 3);
     else if (nt == 128) SJD_ATTN_LAUNCH(64, 128, 3);
     else if (nt == 192) SJD_ATTN_LAUNCH(64, 192, 1);
     else SJD_ATTN_LAUNCH(64, 256, 1);
-    rc |= launch_pdl(attn_combine_kernel<64>, cgrid, dim3(256), 0, stream, p);
+    if (with_combine) rc |= launch_pdl(attn_combine_kernel<64>, cgrid, dim3(256), 0, stream, attn_combine_desc(p, 64));
   } else {
     return -3;
   }

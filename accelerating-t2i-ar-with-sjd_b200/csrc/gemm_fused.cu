@@ -33,6 +33,7 @@
 // bf16 before the next op; reductions and norms are computed in fp32.
 #include "common.cuh"
 #include "streamk.cuh"
+// (attention.cu is included before this file in the translation unit: AttnCombine, attn_combine_row)
 
 namespace sjd {
 
@@ -272,7 +273,10 @@ struct Chain {
   int n_ops, num_stages;
   int lookahead;   // weight units prefetched into L2 beyond the ring
   uint32_t tmem_cols;
-  uint32_t* fin;   // [(kMaxChainOps + 1) * kCtrStride] rows finalised per op (+ exit counter); zero between launches
+  uint32_t* fin;   // [(kMaxChainOps + 2) * kCtrStride] rows finalised per op, exit counter, pre-op counter; zero between launches
+  // optional pre-op run by the (otherwise idle) epilogue warps before op 0: merge the attention's key-split partials
+  // into the bf16 rows that op 0 (o_proj) reads; pre.n_chunks == 0 switches it off
+  AttnCombine pre;
   GemmOp ops[kMaxChainOps];
 };
 
@@ -388,6 +392,10 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
         if (u0 < u1) {
           if (i == 0) {
             pdl_wait();
+            if (ch.pre.n_chunks > 0) {   // op 0 reads what the pre-op writes
+              spin_until_ge(&ch.fin[(kMaxChainOps + 1) * kCtrStride], uint32_t(ch.pre.rows * ch.pre.H * ch.pre.W));
+              fence_proxy_async_all();
+            }
           } else {
             const GemmOp& pr = ch.ops[i - 1];
             const uint32_t target = uint32_t(pr.sk.n_tiles) * uint32_t(pr.ep.M);
@@ -464,6 +472,28 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
     const int cgrp = ew >> 2;       // which 16-column blocks of the accumulator this warp drains
     const int nrow = quarter * 32 + lane;  // weight row of this thread inside the tile
     const int tid_e = threadIdx.x - 128;   // 0..511
+    if (ch.pre.n_chunks > 0) {
+      // ---- pre-op: split-KV combine of the attention that ran before this kernel, one (row, head, query) per warp ----
+      const int total = ch.pre.rows * ch.pre.H * ch.pre.W;
+      uint32_t mine = 0;
+#pragma unroll 1
+      for (int r = cta * kEpiWarps + ew; r < total; r += int(gridDim.x) * kEpiWarps) {
+        if (ch.pre.head_dim == 128) attn_combine_row<128>(ch.pre, r, lane);
+        else attn_combine_row<64>(ch.pre, r, lane);
+        ++mine;
+      }
+      // rows per CTA: every warp counted its own; publish the CTA's total
+      mine = __shfl_sync(0xffffffffu, mine, 0);
+      __shared__ uint32_t s_pre_rows;
+      if (tid_e == 0) s_pre_rows = 0;
+      epi_bar();
+      if (lane == 0 && mine) atomicAdd(&s_pre_rows, mine);
+      epi_bar();
+      if (tid_e == 0 && s_pre_rows) {
+        __threadfence();
+        atomicAdd(&ch.fin[(kMaxChainOps + 1) * kCtrStride], s_pre_rows);
+      }
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
 #pragma unroll 1
@@ -679,7 +709,7 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
       __threadfence();
       const uint32_t out = atomicAdd(&ch.fin[kMaxChainOps * kCtrStride], 1u) + 1u;
       if (out == gridDim.x) {
-        for (int i = 0; i <= kMaxChainOps; ++i) ch.fin[i * kCtrStride] = 0;
+        for (int i = 0; i <= kMaxChainOps + 1; ++i) ch.fin[i * kCtrStride] = 0;
       }
     }
   }

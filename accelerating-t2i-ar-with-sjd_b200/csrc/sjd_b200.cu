@@ -193,7 +193,7 @@ int sjd_gemm_bf16(const void* w, int N, int K, const void* x, int x_rows, int M,
   ep.ssq = reinterpret_cast<float*>(b + wl.ssq_off);
   ep.tile_arrive = reinterpret_cast<uint32_t*>(b + wl.arrive_off);
   ep.ctr = reinterpret_cast<uint32_t*>(b + wl.ctr_off);
-  ch.fin = reinterpret_cast<uint32_t*>(b + wl.ctr_off) + 2 * kCtrStride;   // ctr region: 2 KB = 8 counters of 256 B
+  ch.fin = reinterpret_cast<uint32_t*>(b + wl.ctr_off) + 2 * kCtrStride;   // ctr region: 2 KB = 8 counters of 256 B (2 + 6 used)
   ch.n_ops = 1;
   ch.ops[0].sk = sk;
   g_launches++;
@@ -279,7 +279,7 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
   c->max_chunks = (g.max_len + kAttnSub - 1) / kAttnSub;   // upper bound on key splits
   rc |= dmalloc(c, &c->part_o, size_t(c->max_chunks) * T * hd * sizeof(float));
   rc |= dmalloc(c, &c->part_ml, size_t(c->max_chunks) * T * g.n_heads * 2 * sizeof(float));
-  rc |= dmalloc(c, &c->fin, (kMaxChainOps + 1) * kCtrStride * 4);
+  rc |= dmalloc(c, &c->fin, (kMaxChainOps + 2) * kCtrStride * 4);
   rc |= dmalloc(c, &c->pos_zero, T * 4);
   rc |= dmalloc(c, &c->pos_last, T * 4);
   if (!rc) {
@@ -413,8 +413,9 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
       cb.flush();
       ap.k = c->kcache + size_t(l) * layer_cache;
       ap.v = c->vcache + size_t(l) * layer_cache;
-      rc |= attn_launch(ap, g.head_dim, s);
-      g_launches += 2;
+      rc |= attn_launch(ap, g.head_dim, false, s);   // the split merge rides in the next chain kernel (pre-op)
+      cb.ch.pre = attn_combine_desc(ap, g.head_dim);
+      g_launches += 1;
     }
     GemmEpi e = base;
     e.mode = EPI_RESID_NORM;
