@@ -60,7 +60,7 @@ class VerifyArgs(C.Structure):
         ("has_uncond", C.c_int32), ("apply_cfg", C.c_int32),
         ("guidance", C.c_float), ("temperature", C.c_float),
         ("allow_lo", C.c_int32), ("allow_hi", C.c_int32),
-        ("forced", C.c_void_p), ("forced_resid", C.c_void_p), ("top_k", C.c_int32), ("do_sample", C.c_int32), ("scheme", C.c_int32),
+        ("forced", C.c_void_p), ("forced_resid", C.c_void_p), ("top_k", C.c_int32), ("top_p_thresh", C.c_float), ("do_sample", C.c_int32), ("scheme", C.c_int32),
         ("draft", C.c_void_p), ("q_row", C.c_void_p), ("p_prev", C.c_void_p), ("p_cur", C.c_void_p),
         ("noise_e1", C.c_void_p), ("noise_u", C.c_void_p), ("noise_e2", C.c_void_p),
         ("eoi_token", C.c_int32), ("text_top_k", C.c_int32),

@@ -205,13 +205,14 @@ int sjd_verify(const sjd_verify_args* a, void* stream) {
   if (!a || !a->logits || !a->p_cur || !a->draft || !a->out_tokens || !a->out_info || !a->next_tokens || !a->resid)
     return fail(SJD_E_ARG, "sjd_verify: null argument");
   if (a->W < 1 || a->W > SJD_MAX_TOKENS || a->V < 2) return fail(SJD_E_ARG, "sjd_verify: bad W/V");
+  if (!(a->top_p_thresh >= 0.f && a->top_p_thresh <= 1.f)) return fail(SJD_E_ARG, "sjd_verify: top_p_thresh outside [0, 1]");
   if (a->do_sample && !a->noise_e1) return fail(SJD_E_ARG, "sjd_verify: noise_e1 required when sampling");
   if (a->scheme == 0 && a->W > 1 && (!a->noise_u || !a->noise_e2 || !a->q_row))
     return fail(SJD_E_ARG, "sjd_verify: speculative scheme needs noise_u, noise_e2, q_row");
   VerifyParams p;
   p.logits = a->logits; p.W = a->W; p.V = a->V; p.has_uncond = a->has_uncond; p.apply_cfg = a->apply_cfg;
   p.guidance = a->guidance; p.temperature = a->temperature; p.allow_lo = a->allow_lo; p.allow_hi = a->allow_hi;
-  p.forced = a->forced; p.forced_resid = a->forced_resid; p.top_k = a->top_k; p.do_sample = a->do_sample; p.scheme = a->scheme; p.draft = a->draft;
+  p.forced = a->forced; p.forced_resid = a->forced_resid; p.top_k = a->top_k; p.top_p_thresh = a->top_p_thresh; p.do_sample = a->do_sample; p.scheme = a->scheme; p.draft = a->draft;
   p.q_row = a->q_row; p.p_prev = a->p_prev; p.p_cur = a->p_cur; p.noise_e1 = a->noise_e1; p.noise_u = a->noise_u;
   p.noise_e2 = a->noise_e2; p.eoi_token = a->eoi_token; p.text_top_k = a->text_top_k; p.resid = a->resid;
   p.next_tokens = a->next_tokens; p.out_tokens = a->out_tokens; p.out_info = a->out_info;
@@ -413,9 +414,14 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
       cb.flush();
       ap.k = c->kcache + size_t(l) * layer_cache;
       ap.v = c->vcache + size_t(l) * layer_cache;
-      rc |= attn_launch(ap, g.head_dim, false, s);   // the split merge rides in the next chain kernel (pre-op)
-      cb.ch.pre = attn_combine_desc(ap, g.head_dim);
-      g_launches += 1;
+      // developer timing (scripts/chain_time.py): SJD_DEBUG_ATTN=1 keeps the chain split here but launches no attention,
+      // which separates the cost of the two kernel boundaries from the cost of the attention kernel itself
+      static const int dbg_attn = getenv("SJD_DEBUG_ATTN") ? atoi(getenv("SJD_DEBUG_ATTN")) : 0;
+      if (dbg_attn != 1) {
+        rc |= attn_launch(ap, g.head_dim, false, s);   // the split merge rides in the next chain kernel (pre-op)
+        cb.ch.pre = attn_combine_desc(ap, g.head_dim);
+        g_launches += 1;
+      }
     }
     GemmEpi e = base;
     e.mode = EPI_RESID_NORM;

@@ -8,6 +8,7 @@
 //   SpeculativeSampler.__call__            scheduler/jacobi_iteration_lumina_mgpt.py:247-315
 //   reject_sampling_single_token           :209-241, get_reject_sampling_logits :203-207
 //   find_first_misaligned_token_inds       :317-333 ('jacobi' scheme)
+//   TopPLogitsWarper3d                     scheduler/logit_processor_3dim.py:355-419  (block_top_p, after top-k)
 // torch.multinomial(p, 1) is argmax(p / Exp(1)) and torch.rand feeds the accept test; the noise tensors are
 // produced by the caller with the same torch.Generator calls the reference makes, so token streams are
 // reproducible against it.  The arithmetic deliberately avoids FMA contraction where the reference rounds
@@ -30,6 +31,7 @@ struct VerifyParams {
   const int* forced;     // [W] forced token id per window position, or -1
   const int* forced_resid;  // [W] forced id of the residual distribution at reject position j; null = forced
   int top_k;             // 0 = off
+  float top_p_thresh;    // float32(1 - top_p): ascending running probability <= this is removed; 0 = off
   int do_sample;         // 0 = argmax
   int scheme;            // 0 = speculative_jacobi, 1 = jacobi
   const int* draft;      // [W] window ids ([0] = last accepted token)
@@ -315,11 +317,160 @@ __device__ int block_topk_softmax_sample_regs(float (&s)[VPT], int v0, int lo, i
   return block_argmax(best, besti, sc);
 }
 
+
+// ---- top-p (nucleus) ---------------------------------------------------------------------------------------
+// TopPLogitsWarper3d (scheduler/logit_processor_3dim.py:406-419) sorts the scores ascending, takes the running sum of
+// their softmax and removes every entry whose running sum is <= 1 - top_p; the largest entry always stays.  Here the
+// row already holds that softmax (probabilities after top-k), so the removed set is "the smallest probabilities whose
+// sum stays <= thresh": a 3-pass radix descent over the float bits of the probability with a histogram of SUMS
+// finds the boundary value; sums are accumulated in 2^-44 fixed point (integer adds commute, so the result does
+// not depend on the order threads arrive in).  Entries tied with the boundary value are removed lowest id first,
+// as many as still fit (what a stable ascending sort gives).  The survivors are renormalised and the token redrawn.
+constexpr float kFx = 17592186044416.f;   // 2^44
+
+struct TopPScratch {
+  unsigned long long hsum[kHistBins];
+  unsigned long long below;   // fixed-point sum of everything under the current prefix
+  uint32_t sel_bin;           // selected bin, or 0xffffffff: nothing crosses the threshold
+  uint32_t warp_cnt[32];
+  uint32_t base;
+};
+
+__device__ int block_top_p(float* __restrict__ row, int V, float thresh, int do_sample, int greedy_tok,
+                           const float* __restrict__ noise_e, BlockScratch& sc, TopPScratch& tp) {
+  const unsigned long long thresh_fx = __float2ull_rd(thresh * kFx);
+  uint32_t prefix = 0, mask = 0;
+  const int shifts[3] = {21, 10, 0};
+  const int nbits[3] = {11, 11, 10};
+  if (threadIdx.x == 0) { tp.below = 0; tp.sel_bin = 0; }
+  bool none = false;
+  for (int pass = 0; pass < 3 && !none; ++pass) {
+    const int shift = shifts[pass];
+    const uint32_t nb = 1u << nbits[pass];
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) tp.hsum[i] = 0ull;
+    __syncthreads();
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float f = row[v];
+      if (f > 0.f) {
+        const uint32_t key = __float_as_uint(f);
+        if ((key & mask) == prefix) atomicAdd(&tp.hsum[(key >> shift) & (nb - 1)], __float2ull_rn(f * kFx));
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const uint32_t lane = threadIdx.x, per = nb / 32;
+      const unsigned long long below = tp.below;
+      unsigned long long csum = 0;
+      for (uint32_t j = 0; j < per; ++j) csum += tp.hsum[lane * per + j];   // lane 0 = smallest keys
+      unsigned long long incl = csum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= uint32_t(o)) incl += t;
+      }
+      const unsigned long long excl = incl - csum;
+      const bool mine = (below + excl <= thresh_fx) && (below + incl > thresh_fx);
+      const uint32_t any = __ballot_sync(0xffffffffu, mine);
+      if (any == 0u) {
+        if (lane == 0) tp.sel_bin = 0xffffffffu;
+      } else if (mine) {
+        unsigned long long run = below + excl;
+        for (uint32_t j = 0; j < per; ++j) {
+          const unsigned long long c = tp.hsum[lane * per + j];
+          if (run + c > thresh_fx) {
+            tp.sel_bin = lane * per + j;
+            tp.below = run;
+            break;
+          }
+          run += c;
+        }
+      }
+    }
+    __syncthreads();
+    if (tp.sel_bin == 0xffffffffu) none = true;
+    else {
+      prefix |= tp.sel_bin << shift;
+      mask |= (nb - 1) << shift;
+    }
+    __syncthreads();
+  }
+  float sum = 0.f;
+  if (none) {
+    // everything fits under the threshold (top_p ~ 0): only the last entry of the ascending order stays — the
+    // largest probability, highest id among equals
+    float mx = 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, row[v]);
+    mx = block_max(mx, sc);
+    int hi = -1;
+    for (int v = threadIdx.x; v < V; v += blockDim.x)
+      if (row[v] == mx) hi = v;
+    __syncthreads();
+    hi = -block_argmax(float(hi), -hi, sc);   // largest id: argmax of the id itself (exact in float for V < 2^24)
+    for (int v = threadIdx.x; v < V; v += blockDim.x) row[v] = (v == hi) ? 1.f : 0.f;
+    __syncthreads();
+    return do_sample ? hi : greedy_tok;
+  }
+  // boundary value `prefix`: tp.hsum[sel_bin] = (#ties) * fx(value); remove the first n_rm ties (ascending id)
+  const float bval = __uint_as_float(prefix);
+  const unsigned long long fx_b = __float2ull_rn(bval * kFx);
+  const unsigned long long room = thresh_fx - tp.below;
+  const uint32_t n_rm = fx_b ? uint32_t(room / fx_b) : 0u;
+  if (n_rm == 0u) {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float f = row[v];
+      const float keep = (f >= bval) ? f : 0.f;
+      row[v] = keep;
+      sum += keep;
+    }
+  } else {
+    if (threadIdx.x == 0) tp.base = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int v0 = 0; v0 < V; v0 += blockDim.x) {   // ids in ascending order, one slab of blockDim ids at a time
+      const int v = v0 + threadIdx.x;
+      const float f = v < V ? row[v] : 0.f;
+      const bool tie = (f == bval);
+      const uint32_t bal = __ballot_sync(0xffffffffu, tie);
+      if (lane == 0) tp.warp_cnt[wid] = __popc(bal);
+      __syncthreads();
+      uint32_t before = tp.base;
+      for (uint32_t w2 = 0; w2 < wid; ++w2) before += tp.warp_cnt[w2];
+      const uint32_t rank = before + __popc(bal & ((1u << lane) - 1u));
+      if (v < V) {
+        const float keep = (f > bval || (tie && rank >= n_rm)) ? f : 0.f;
+        row[v] = keep;
+        sum += keep;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (uint32_t w2 = 0; w2 < nw; ++w2) tot += tp.warp_cnt[w2];
+        tp.base += tot;
+      }
+      __syncthreads();
+    }
+  }
+  sum = block_sumf(sum, sc);
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float pr = row[v] / sum;
+    row[v] = pr;
+    if (do_sample) {
+      const float val = pr / noise_e[v];
+      if (val > best) { best = val; besti = v; }
+    }
+  }
+  const int tok = block_argmax(best, besti, sc);
+  return do_sample ? tok : greedy_tok;
+}
+
 constexpr int kRegVPT = 16;   // ids per thread held in registers: candidate ranges spanning up to 16 384 ids
 
 // One CTA per window position.
 __global__ void __launch_bounds__(kVerifyThreads) verify_rows_kernel(VerifyParams p) {
   __shared__ BlockScratch sc;
+  __shared__ TopPScratch tp;
   const int i = blockIdx.x;
   const int V = p.V;
   const float* c = p.logits + size_t(i) * V;
@@ -355,8 +506,12 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_rows_kernel(VerifyParam
     // everything outside the candidate range has probability zero
     for (int v = threadIdx.x; v < lo; v += blockDim.x) row[v] = 0.f;
     for (int v = hi + threadIdx.x; v < V; v += blockDim.x) row[v] = 0.f;
-    const int tok = block_topk_softmax_sample_regs<kRegVPT>(s, v0, lo, hi, p.top_k, p.do_sample,
-                                                            p.noise_e1 + size_t(i) * V, row, V, sc);
+    int tok = block_topk_softmax_sample_regs<kRegVPT>(s, v0, lo, hi, p.top_k, p.do_sample,
+                                                      p.noise_e1 + size_t(i) * V, row, V, sc);
+    if (p.top_p_thresh > 0.f) {
+      __syncthreads();   // the whole row of probabilities is in global memory
+      tok = block_top_p(row, V, p.top_p_thresh, p.do_sample, tok, p.noise_e1 + size_t(i) * V, sc, tp);
+    }
     if (threadIdx.x == 0) p.next_tokens[i] = tok;
     return;
   }
@@ -371,13 +526,18 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_rows_kernel(VerifyParam
     row[v] = s;
   }
   __syncthreads();
-  const int tok = block_topk_softmax_sample(row, V, p.top_k, p.do_sample, p.noise_e1 + size_t(i) * V, sc);
+  int tok = block_topk_softmax_sample(row, V, p.top_k, p.do_sample, p.noise_e1 + size_t(i) * V, sc);
+  if (p.top_p_thresh > 0.f) {
+    __syncthreads();
+    tok = block_top_p(row, V, p.top_p_thresh, p.do_sample, tok, p.noise_e1 + size_t(i) * V, sc, tp);
+  }
   if (threadIdx.x == 0) p.next_tokens[i] = tok;
 }
 
 // Single CTA: accept scan over the window, prefix match, residual resample at the first rejection.
 __global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyParams p) {
   __shared__ BlockScratch sc;
+  __shared__ TopPScratch tp;
   __shared__ int s_first;
   __shared__ int s_text_mode;
   const int W = p.W, V = p.V;
@@ -420,15 +580,32 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyPar
     const int xd = p.draft[first];
     const bool text = s_text_mode != 0;
     const int* fr = p.forced_resid ? p.forced_resid : p.forced;
-    const int forced = (!text && fr) ? fr[j] : -1;
+    // fr[j] >= 0: the grammar makes the residual one-hot at that id whatever its value (Lumina / Emu3 write 0 there
+    // and -inf elsewhere); fr[j] <= -2: "mask-forced" id f = -2 - fr[j] — every OTHER id is filled with finfo.min (the
+    // Anole processors, logit_processor_3dim.py:242-256): f wins if its residual is finite, else (p <= q there, i.e. f
+    // was outside the window's support) softmax sees V-1 equal finfo.min entries and the draw is uniform over them.
+    int forced = (!text && fr) ? fr[j] : -1;
+    bool mask_forced = false;
+    if (forced <= -2) { forced = -2 - forced; mask_forced = true; }
     const bool ranged = !text && (p.allow_hi > p.allow_lo);
     const int lo = ranged ? max(p.allow_lo, 0) : 0, hi = ranged ? min(p.allow_hi, V) : V;
     const int v0 = (lo / int(blockDim.x)) * int(blockDim.x);
     const int top_k = text ? p.text_top_k : p.top_k;
     int tok;
-    if (forced >= 0) {
+    if (forced >= 0 && mask_forced &&
+        !(__fsub_rn(a[forced], b ? b[forced] : (forced == xd ? 1.f : 0.f)) > 0.f)) {
+      const float pc = 1.f / float(V - 1);
+      float best = -INFINITY;
+      int besti = 0x7fffffff;
+      for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        if (v == forced) continue;
+        const float val = pc / p.noise_e2[v];
+        if (val > best) { best = val; besti = v; }
+      }
+      tok = block_argmax(best, besti, sc);
+    } else if (forced >= 0) {
       tok = forced;   // one-hot residual support after the grammar: the multinomial can only return it
-    } else if (hi - v0 <= int(blockDim.x) * kRegVPT) {
+    } else if (hi - v0 <= int(blockDim.x) * kRegVPT && !(p.top_p_thresh > 0.f)) {
       float s[kRegVPT];
 #pragma unroll
       for (int jj = 0; jj < kRegVPT; ++jj) {
@@ -452,6 +629,10 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyPar
       }
       __syncthreads();
       tok = block_topk_softmax_sample(p.resid, V, top_k, 1, p.noise_e2, sc);
+      if (p.top_p_thresh > 0.f) {   // the residual goes through the same processors (reject_sampling_single_token)
+        __syncthreads();
+        tok = block_top_p(p.resid, V, p.top_p_thresh, 1, tok, p.noise_e2, sc, tp);
+      }
     }
     if (threadIdx.x == 0) p.out_tokens[j] = tok;
   }

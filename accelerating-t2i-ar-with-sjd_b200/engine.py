@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as _np
 import torch
 
 from . import _lib
@@ -40,6 +41,7 @@ def verify_call(logits: torch.Tensor, W: int, V: int, desc: dict, draft: torch.T
     a.allow_lo, a.allow_hi = desc["allow"] if desc.get("allow") else (0, 0)
     a.forced = forced.data_ptr() if forced is not None else None
     a.top_k, a.do_sample, a.scheme = int(desc["top_k"]), int(do_sample), int(scheme)
+    a.top_p_thresh = top_p_threshold(desc.get("top_p", 1.0))
     a.draft = draft.data_ptr()
     a.q_row = q_row.data_ptr() if q_row is not None else None
     a.p_prev = p_prev.data_ptr() if p_prev is not None else None
@@ -62,6 +64,15 @@ def verify_call(logits: torch.Tensor, W: int, V: int, desc: dict, draft: torch.T
     return res
 
 
+def top_p_threshold(top_p: float) -> float:
+    """float32(1 - top_p), the value TopPLogitsWarper3d compares the ascending running probability with
+    (scheduler/logit_processor_3dim.py:411); 0 switches the filter off (top_p = 1 removes nothing)."""
+    top_p = float(top_p)
+    if top_p < 0 or top_p > 1.0:
+        raise ValueError(f"`top_p` has to be a float > 0 and < 1, but is {top_p}")
+    return float(_np.float32(1.0 - top_p)) if top_p < 1.0 else 0.0
+
+
 # =====================================================================================================
 # The SJD decode loop (host control only: integers, a few pinned-memory copies and two C calls per
 # Jacobi iteration).  Mirrors JacobiSampler._sample (scheduler/jacobi_iteration_lumina_mgpt.py:912-1249):
@@ -74,8 +85,6 @@ def verify_call(logits: torch.Tensor, W: int, V: int, desc: dict, draft: torch.T
 import random as _random
 import time as _time
 from dataclasses import dataclass, field
-
-import numpy as _np
 
 from .model import DeviceStack
 
@@ -194,14 +203,13 @@ class Emu3GrammarState:
 
 
 class PlainTopKState:
-    """No grammar: HF TopKLogitsWarper(k) [+ TopPLogitsWarper3d(1.0), a no-op] — LlamaGen
-    (llamagen/llamagen_solver.py:458-470)."""
+    """No grammar: HF TopKLogitsWarper(k) then TopPLogitsWarper3d(p) — LlamaGen (llamagen/llamagen_solver.py:458-470)."""
     eoi_token = -1
     text_top_k = 0
     no_cfg = False
 
-    def __init__(self, top_k=0):
-        self.top_k = top_k
+    def __init__(self, top_k=0, top_p=1.0):
+        self.top_k, self.top_p = top_k, top_p
 
     def reset(self):
         pass
@@ -210,7 +218,92 @@ class PlainTopKState:
         pass
 
     def describe(self, n: int) -> dict:
-        return {"allow": None, "forced": [-1] * n, "top_k": self.top_k}
+        return {"allow": None, "forced": [-1] * n, "top_k": self.top_k, "top_p": self.top_p}
+
+
+class AnoleGrammarState:
+    """Host-side state of the Anole "image-only" grammar: the five 3-D Chameleon processors installed by
+    renew_pipeline_anole.generate (scheduler/jacobi_iteration_anhole.py:200-240; classes at
+    scheduler/logit_processor_3dim.py:207-353) plus HF's TopKLogitsWarper.  Every one of them inspects the ACCEPTED
+    prefix only (its length, the token S+1 places from its end, whether begin-of-image is among its last S tokens) and
+    applies one decision to every window position, so a trip's grammar is one allowed-id set:
+        image ids [image_lo, image_hi)   while begin-of-image is within the last S accepted tokens,
+        {eoi}                            when begin-of-image sits exactly S+1 places back,
+        a subset of {eos, boi}           otherwise (boi until max_length - S - 1, eos except right at the start).
+    A window that straddles the end of the image keeps "image ids" for all its positions — the reference behaves the
+    same and truncates to image_seq_length afterwards (:309-311).  Sets the verify kernel cannot express (two special
+    ids at once, possible only when max_new_tokens exceeds S + 2) are refused.  CFG is never switched off (the first
+    processor has no image_start_token_id, jacobi_iteration_lumina_mgpt.py:1086-1096)."""
+    eoi_token = -1
+    text_top_k = 0
+    no_cfg = False
+
+    def __init__(self, boi, eoi, eos, image_lo, image_hi, image_seq_length, max_length, begin_index, top_k=50):
+        self.boi, self.eoi, self.eos = int(boi), int(eoi), int(eos)
+        self.allow = (int(image_lo), int(image_hi))
+        self.S, self.max_length, self.begin_index, self.top_k = int(image_seq_length), int(max_length), int(begin_index), int(top_k)
+        self.reset()
+
+    def reset(self):
+        self.n = 0          # accepted tokens so far
+        self.boi_at = []    # their positions holding begin-of-image
+
+    def observe(self, tokens):
+        for t in tokens:
+            if t == self.boi:
+                self.boi_at.append(self.n)
+            self.n += 1
+
+    def _decide(self, n: int):
+        """-> ('image', None) | ('forced', id) for an accepted prefix of length n (positions of boi as observed)."""
+        S = self.S
+        at_offset = n >= S + 1 and (n - (S + 1)) in self.boi_at          # input_ids[-(S+1)] == boi
+        in_window = any(n - min(S, n) <= p < n for p in self.boi_at)      # boi in input_ids[-min(S, n):]
+        if in_window:
+            if at_offset:
+                raise NotImplementedError("Anole grammar: two begin-of-image tokens S+1 apart leave no allowed id")
+            return "image", None
+        if at_offset:
+            return "forced", self.eoi
+        left = []
+        if not (self.begin_index <= n <= self.begin_index + 1):
+            left.append(self.eos)
+        if self.max_length - S - 1 > n:
+            left.append(self.boi)
+        if len(left) != 1:
+            raise NotImplementedError(f"Anole grammar: allowed set {left} after {n} tokens is not expressible on device "
+                                      "(use max_new_tokens = image_seq_length + 2 like the reference driver)")
+        return "forced", left[0]
+
+    def describe(self, n: int) -> dict:
+        kind, tok = self._decide(self.n)
+        if kind == "image":
+            return {"allow": self.allow, "forced": [-1] * n, "top_k": self.top_k}
+        return {"allow": None, "forced": [tok] * n, "top_k": self.top_k}
+
+    def describe_residual(self, n: int) -> list:
+        """Forced id (encoded -2 - id, see below) of the residual at reject position j: the processors are re-run on the prefix plus the j drafts
+        accepted before it (jacobi_iteration_lumina_mgpt.py:297-306); accepted drafts are image ids or the forced id, and
+        only begin-of-image moves the triggers, so the prefix length is all that changes."""
+        out = []
+        kind0, tok0 = self._decide(self.n)
+        keep = list(self.boi_at)
+        try:
+            for j in range(n):
+                if kind0 == "forced" and tok0 == self.boi and j > 0:
+                    self.boi_at.append(self.n + j - 1)   # the accepted drafts of a forced window are the forced id
+                kind, tok = self._decide(self.n + j)
+                if kind == "image" and kind0 != "image":
+                    tok = -2   # would need the image range while the window has none: not expressible, see below
+                out.append(-1 if kind == "image" and kind0 == "image" else tok)
+        finally:
+            self.boi_at = keep
+        if any(t == -2 for t in out[1:]) and n > 1:
+            raise NotImplementedError("Anole grammar: a multi-token window right at begin-of-image (use jacobi_loop_interval_l >= 1)")
+        # "mask-forced" code for sjd_verify (include/sjd_b200.h, forced_resid): these processors fill the other ids with
+        # finfo.min rather than writing a one-hot row, which matters when the forced id has no residual mass
+        out = [(-1 if t in (-1, -2) else -2 - t) for t in out]
+        return out
 
 
 @dataclass
@@ -419,6 +512,7 @@ class SJDEngine:
             a.forced = ds[base + 2 * self.Wmax:].data_ptr()
             a.forced_resid = ds[base + 3 * self.Wmax:].data_ptr() if resid_forced is not None else None
             a.top_k, a.do_sample, a.scheme = int(desc["top_k"]), int(do_sample), scheme
+            a.top_p_thresh = top_p_threshold(desc.get("top_p", 1.0))
             a.draft = d_draft.data_ptr()
             a.q_row = ds[base + self.Wmax:].data_ptr()
             a.p_prev, a.p_cur = self.pbuf[1 - cur].data_ptr(), self.pbuf[cur].data_ptr()

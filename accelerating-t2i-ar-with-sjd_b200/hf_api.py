@@ -8,6 +8,8 @@ scheduler/jacobi_iteration_lumina_mgpt.py:1340 renew_pipeline_sampler   renew_pi
                                           :1253 renew_backbone           renew_backbone (mask is index math in-kernel)
                                           :432  renew_pipeline           renew_pipeline (create_logits_processor)
 scheduler/logit_processor_3dim.py:45,158,355   3-D processors           descriptor classes, evaluated by sjd_verify
+scheduler/logit_processor_3dim.py:207-353      Anole 3-D processors     descriptor classes -> engine.AnoleGrammarState
+scheduler/jacobi_iteration_anhole.py:318       renew_pipeline_sampler   renew_pipeline_sampler_anole
 llamagen/llamagen_solver.py:196,349            renew_llamagen, LlamaGenSolver   same names
 
 `_sample(input_ids, logits_processor, stopping_criteria, generation_config, synced_gpus, streamer,
@@ -70,8 +72,8 @@ class MultiTokensInterleavedTopKLogitsWarper(_DeviceEvaluated):
 
 
 class TopPLogitsWarper3d(_DeviceEvaluated):
-    """scheduler/logit_processor_3dim.py:355-419.  top_p = 1.0 (every shipped driver) leaves the probabilities
-    unchanged; other values are not implemented on device yet and are rejected loudly."""
+    """scheduler/logit_processor_3dim.py:355-419.  Evaluated after top-k inside sjd_verify (block_top_p, csrc/verify.cu);
+    top_p = 1.0 (every shipped driver) removes nothing."""
 
     def __init__(self, top_p, filter_value=-float("Inf"), min_tokens_to_keep=1):
         top_p = float(top_p)
@@ -80,6 +82,86 @@ class TopPLogitsWarper3d(_DeviceEvaluated):
         if not isinstance(min_tokens_to_keep, int) or (min_tokens_to_keep < 1):
             raise ValueError(f"`min_tokens_to_keep` has to be a positive integer, but is {min_tokens_to_keep}")
         self.top_p = top_p
+        self.filter_value, self.min_tokens_to_keep = filter_value, min_tokens_to_keep
+        if min_tokens_to_keep != 1 or filter_value != -float("Inf"):
+            raise NotImplementedError("TopPLogitsWarper3d on device keeps exactly one token at least and fills with -inf")
+
+
+# ---- Anole: the 3-D variants of HF's Chameleon processors (scheduler/logit_processor_3dim.py:207-353) ----------------
+def _id_list(x):
+    return [int(t) for t in (x.flatten().tolist() if hasattr(x, "flatten") else x)]
+
+
+class AllowOnlyTokensAtRelativeOffsetLogitsProcessor3d(_DeviceEvaluated):
+    """:207-256"""
+
+    def __init__(self, trigger_token_id, allowed_token_ids, offset, exclusive=False, device="cpu"):
+        self.trigger_token_id, self.allowed_token_ids = int(trigger_token_id), _id_list(allowed_token_ids)
+        self.offset, self.exclusive = int(offset), bool(exclusive)
+
+
+class SuppressTokensInIndexRangeLogitsProcessor3d(_DeviceEvaluated):
+    """:258-286"""
+
+    def __init__(self, suppress_tokens, start_index, end_index=None, device="cpu"):
+        self.suppress_tokens = _id_list(suppress_tokens)
+        self.start_index = start_index
+        self.end_index = end_index if end_index is not None else math.inf
+
+
+class AllowOnlyTokensInRelativeWindowLogitsProcessor3d(_DeviceEvaluated):
+    """:288-338"""
+
+    def __init__(self, trigger_token_id, allowed_token_ids, window_width, exclusive=False, device="cpu"):
+        self.trigger_token_id, self.allowed_token_ids = int(trigger_token_id), _id_list(allowed_token_ids)
+        self.window_width, self.exclusive = int(window_width), bool(exclusive)
+
+
+class SuppressTokensAtBeginLogitsProcessor3d(SuppressTokensInIndexRangeLogitsProcessor3d):
+    """:340-349"""
+
+    def __init__(self, begin_suppress_tokens, begin_index, device="cpu"):
+        super().__init__(begin_suppress_tokens, begin_index, begin_index + 1, device=device)
+        self.begin_index = begin_index
+
+    def set_begin_index(self, begin_index):
+        self.start_index, self.end_index, self.begin_index = begin_index, begin_index + 1, begin_index
+
+
+class SuppressTokensLogitsProcessor3d(SuppressTokensInIndexRangeLogitsProcessor3d):
+    """:351-353"""
+
+    def __init__(self, suppress_tokens, device="cpu"):
+        super().__init__(suppress_tokens, 0, device=device)
+
+
+def _anole_grammar(procs, plain_k, vocab):
+    """The "image-only" processor set of renew_pipeline_anole.generate (scheduler/jacobi_iteration_anhole.py:200-240) ->
+    engine.AnoleGrammarState.  Any other combination of these processors has no device implementation."""
+    at = [p for p in procs if isinstance(p, AllowOnlyTokensAtRelativeOffsetLogitsProcessor3d)]
+    win = [p for p in procs if isinstance(p, AllowOnlyTokensInRelativeWindowLogitsProcessor3d)]
+    beg = [p for p in procs if isinstance(p, SuppressTokensAtBeginLogitsProcessor3d)]
+    rng = [p for p in procs if type(p) is SuppressTokensInIndexRangeLogitsProcessor3d]
+    sup = [p for p in procs if isinstance(p, SuppressTokensLogitsProcessor3d) or
+           (type(p).__name__ == "SuppressTokensLogitsProcessor" and hasattr(p, "suppress_tokens"))]
+    if not (len(at) == len(win) == len(beg) == len(rng) == len(sup) == 1):
+        raise NotImplementedError("only the Anole 'image-only' processor set (one of each 3-D Chameleon processor) "
+                                  "is implemented on device")
+    at, win, beg, rng, sup = at[0], win[0], beg[0], rng[0], sup[0]
+    S = win.window_width
+    lo, hi = _visual_range(win.allowed_token_ids)
+    ok = (at.exclusive and win.exclusive and at.trigger_token_id == win.trigger_token_id and at.offset == S + 1
+          and len(at.allowed_token_ids) == 1 and rng.suppress_tokens == [at.trigger_token_id]
+          and rng.end_index == math.inf and len(beg.suppress_tokens) == 1)
+    boi, eoi, eos = at.trigger_token_id, at.allowed_token_ids[0], beg.suppress_tokens[0]
+    if ok and vocab is not None:
+        kept = set(range(vocab)) - set(_id_list(sup.suppress_tokens))
+        ok = kept == set(range(lo, hi)) | {eos, boi, eoi}
+    if not ok:
+        raise NotImplementedError("Anole processors are not in the 'image-only' configuration of "
+                                  "scheduler/jacobi_iteration_anhole.py:200-240")
+    return _engine.AnoleGrammarState(boi, eoi, eos, lo, hi, S, max_length=int(rng.start_index) + S + 1,
+                                     begin_index=int(beg.begin_index), top_k=plain_k)
 
 
 def renew_end_of_line_logit_processor_3d(model_class):
@@ -99,10 +181,10 @@ def _visual_range(visual_tokens):
     return lo, hi
 
 
-def grammar_from_processors(processors):
+def grammar_from_processors(processors, vocab=None):
     """Translate the reference's processor list into the engine's grammar state."""
     vl = topk = emu = None
-    plain_k = 0
+    plain_k, top_p, anole = 0, 1.0, []
     for pr in processors or []:
         if getattr(pr, "_sjd_emu3_grammar", False):
             emu = pr
@@ -111,12 +193,23 @@ def grammar_from_processors(processors):
         elif isinstance(pr, MultiTokensInterleavedTopKLogitsWarper):
             topk = pr
         elif isinstance(pr, TopPLogitsWarper3d):
-            if pr.top_p != 1.0:
-                raise NotImplementedError("top_p < 1 is not implemented in sjd_verify")
+            top_p = pr.top_p   # sjd_verify applies it after top-k, the order every reference driver uses
         elif TopKLogitsWarper is not None and isinstance(pr, TopKLogitsWarper):
+            if top_p != 1.0:
+                raise NotImplementedError("top-k after top-p: sjd_verify applies top-k first")
             plain_k = int(pr.top_k)
+        elif isinstance(pr, (AllowOnlyTokensAtRelativeOffsetLogitsProcessor3d, SuppressTokensInIndexRangeLogitsProcessor3d,
+                             AllowOnlyTokensInRelativeWindowLogitsProcessor3d)) or \
+                type(pr).__name__ == "SuppressTokensLogitsProcessor":
+            anole.append(pr)
         else:
             raise NotImplementedError(f"logits processor {type(pr).__name__} has no device implementation")
+    if top_p != 1.0 and (emu is not None or vl is not None or anole):
+        raise NotImplementedError("top_p < 1 together with an image grammar")
+    if anole:
+        if emu is not None or vl is not None:
+            raise NotImplementedError("Anole processors mixed with another image grammar")
+        return _anole_grammar(anole, plain_k, vocab)
     if emu is not None:
         lo, hi = _visual_range(emu.visual_tokens)
         return _engine.Emu3GrammarState(int(emu.height), int(emu.width), int(emu.img_token), int(emu.eol_token),
@@ -126,7 +219,7 @@ def grammar_from_processors(processors):
         return _engine.LuminaGrammarState(
             image_start=vl.image_start_token_id, image_end=vl.image_end_token_id, eol=vl.image_next_line_token_id,
             image_top_k=topk.image_top_k if topk else 0, text_top_k=topk.text_top_k if topk else 0)
-    return _engine.PlainTopKState(top_k=plain_k)
+    return _engine.PlainTopKState(top_k=plain_k, top_p=top_p)
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -267,8 +360,8 @@ def renew_sampler(model_class):
             return st
 
         @torch.no_grad()
-        def _sample(self, input_ids, logits_processor, stopping_criteria, generation_config, synced_gpus, streamer,
-                    logits_warper=None, **model_kwargs):
+        def _sample(self, input_ids, logits_processor, stopping_criteria, generation_config, synced_gpus=False,
+                    streamer=None, logits_warper=None, **model_kwargs):
             assert not getattr(generation_config, "return_dict_in_generate", False)
             if input_ids.shape[0] != 1:
                 raise ValueError("the SJD sampler decodes one prompt per call (the reference's B>1 path is broken too)")
@@ -282,7 +375,8 @@ def renew_sampler(model_class):
             kv_len0 = int(getattr(self, "_sjd_kv_len0", 0))   # tokens already cached by a solver-side prefill
             cap = (max_length or (len(prompt) + 4096)) + self.max_num_new_tokens + kv_len0 + 8
             stack = self._sjd_stack(rows, int(-(-cap // 64) * 64), device)
-            grammar = grammar_from_processors(list(logits_processor or []) + list(logits_warper or []))
+            grammar = grammar_from_processors(list(logits_processor or []) + list(logits_warper or []),
+                                              vocab=stack.shape.vocab)
             eng = _engine.SJDEngine(stack, self._sjd_params(), grammar,
                                     self.img_vocab if self.img_vocab is not None else torch.arange(stack.shape.vocab))
             attn = model_kwargs.get("attention_mask")
@@ -419,6 +513,124 @@ def renew_pipeline_sampler(pipe_line, **kwargs):
     pipe_line.model.__class__ = renew_sampler(pipe_line.model.__class__)
     pipe_line.model._init_new_params(**kwargs)
     pipe_line.model.model.__class__ = renew_backbone(pipe_line.model.model.__class__)
+    return pipe_line
+
+
+# --------------------------------------------------------------------------------------------------------
+# Anole adaptor (scheduler/jacobi_iteration_anhole.py): HF ChameleonForConditionalGeneration as the pipeline
+# --------------------------------------------------------------------------------------------------------
+def renew_vocabulary_mapping(vocabulary_mapping):
+    """:45-97 — adds the ids the adaptor needs to HF's ChameleonImageVocabularyMapping (which only knows names)."""
+    from functools import cached_property
+
+    class IndexVocabularyMapping(vocabulary_mapping):
+        def _init_new_params(self, image_token_id=8711, boi_token_id=8197, eoi_token_id=8196):
+            for name, val in (("image_token_id", image_token_id), ("boi_token_id", boi_token_id),
+                              ("eoi_token_id", eoi_token_id)):
+                if not hasattr(self, name):
+                    setattr(self, name, val)
+
+        @cached_property
+        def image_token_ids(self):
+            return sorted(v for k, v in self.vocab_map.items() if k.startswith("IMGIMG"))
+
+    return IndexVocabularyMapping
+
+
+def renew_pipeline_anole(model_class):
+    """:99-285 — `generate(..., multimodal_generation_mode=...)` installs the 3-D Chameleon processors for the mode and
+    hands over to HF's generate, which ends in the renewed `_sample`."""
+    class JacobiPipeline(model_class):
+        def _init_new_params(self, guidance_scale=3.0, image_top_k=2000, text_top_k=10, **kwargs):
+            self.cfg, self.image_top_k, self.text_top_k = guidance_scale, image_top_k, text_top_k
+            self.vocabulary_mapping = self.model.vocabulary_mapping
+            self.vocabulary_mapping.__class__ = renew_vocabulary_mapping(self.vocabulary_mapping.__class__)
+            self.vocabulary_mapping._init_new_params()
+
+        @torch.no_grad()
+        def generate(self, inputs=None, generation_config=None, logits_processor=None, multimodal_generation_mode=None,
+                     **kwargs):
+            vm, S = self.vocabulary_mapping, int(self.model.image_seq_length)
+            mode = (multimodal_generation_mode or getattr(generation_config, "multimodal_generation_mode", None)
+                    or "text-only")
+            gc = generation_config if generation_config is not None else self.generation_config
+            no_len = kwargs.get("max_length") is None and kwargs.get("max_new_tokens") is None
+            if mode == "image-only" and no_len and generation_config is None:
+                kwargs["max_new_tokens"] = S + 2            # boi + image + eoi (:115-126)
+            input_ids = kwargs.get("input_ids", inputs)
+            P = int(input_ids.shape[-1])
+            if kwargs.get("max_new_tokens") is not None:
+                max_length = P + int(kwargs["max_new_tokens"])
+            elif kwargs.get("max_length") is not None:
+                max_length = int(kwargs["max_length"])
+            elif getattr(gc, "max_new_tokens", None) is not None:
+                max_length = P + int(gc.max_new_tokens)
+            else:
+                max_length = int(gc.max_length)
+            procs = LogitsProcessorList(list(logits_processor or []))
+            dev = self.device
+            image_ids = vm.image_token_ids
+            at_offset = AllowOnlyTokensAtRelativeOffsetLogitsProcessor3d(
+                trigger_token_id=vm.boi_token_id, allowed_token_ids=[vm.eoi_token_id], offset=S + 1, exclusive=True,
+                device=dev)
+            in_window = AllowOnlyTokensInRelativeWindowLogitsProcessor3d(
+                trigger_token_id=vm.boi_token_id, allowed_token_ids=image_ids, window_width=S, exclusive=True, device=dev)
+            no_late_image = SuppressTokensInIndexRangeLogitsProcessor3d(
+                suppress_tokens=[vm.boi_token_id], start_index=max_length - S - 1, device=dev)
+            if mode == "text-only":
+                procs.append(SuppressTokensLogitsProcessor3d(
+                    suppress_tokens=image_ids + [vm.boi_token_id, vm.eoi_token_id], device=dev))
+            elif mode == "image-only":
+                if max_length - P < S + 2:
+                    import warnings
+                    warnings.warn(f"image-only generation needs max_new_tokens >= {S + 2} (begin-of-image, {S} image "
+                                  f"tokens, end-of-image); got {max_length - P}")
+                allowed = set(image_ids) | {self.config.eos_token_id, vm.boi_token_id, vm.eoi_token_id}
+                procs.extend([at_offset, in_window, no_late_image,
+                              SuppressTokensLogitsProcessor3d(
+                                  suppress_tokens=[t for t in range(self.vocab_size) if t not in allowed], device=dev),
+                              SuppressTokensAtBeginLogitsProcessor3d(
+                                  begin_suppress_tokens=[self.config.eos_token_id], begin_index=P, device=dev)])
+            elif mode == "interleaved-text-image":
+                procs.extend([at_offset, in_window, no_late_image])
+            elif mode != "unrestricted":
+                raise ValueError(f"Unknown multimodal generation mode: {mode}. Please choose one of 'unrestricted', "
+                                 "'text-only', 'image-only', or 'interleaved-text-image'.")
+            return super().generate(inputs=inputs, generation_config=generation_config, logits_processor=procs, **kwargs)
+
+        @property
+        def vocab_size(self):
+            return int(self.config.vocab_size)
+
+        def decode_image_tokens(self, bpe_tokens):
+            return self.model.decode_image_tokens(bpe_tokens)
+
+    return JacobiPipeline
+
+
+def renew_backbone_adapt_anole(model_class):
+    """:287-316 — a multi-token accept can overshoot the image: keep the first image_seq_length tokens before the
+    VQ decoder (which is outside the SJD path and stays the model's own)."""
+    class JacobiBackboneAdaptedAnole(model_class):
+        def decode_image_tokens(self, bpe_tokens):
+            if bpe_tokens.shape[1] != self.image_seq_length:
+                bpe_tokens = bpe_tokens[:, : self.image_seq_length]
+            return self.vqmodel.decode(self.convert_bpe2img_tokens(bpe_tokens))
+
+    return JacobiBackboneAdaptedAnole
+
+
+def renew_pipeline_sampler_anole(pipe_line, processor, **kwargs):
+    """scheduler/jacobi_iteration_anhole.py:318-330 (exported there as renew_pipeline_sampler)."""
+    pipe_line.model.__class__ = renew_backbone(pipe_line.model.__class__)
+    pipe_line.model.__class__ = renew_backbone_adapt_anole(pipe_line.model.__class__)
+    if not hasattr(pipe_line.model, "image_seq_length"):
+        pipe_line.model.image_seq_length = processor.image_seq_length
+    print(pipe_line.model.image_seq_length)
+    pipe_line.__class__ = renew_pipeline_anole(pipe_line.__class__)
+    pipe_line._init_new_params(**kwargs)
+    pipe_line.__class__ = renew_sampler(pipe_line.__class__)
+    pipe_line._init_new_params(**kwargs)
     return pipe_line
 
 

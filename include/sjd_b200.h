@@ -69,8 +69,13 @@ typedef struct sjd_verify_args {
   const int32_t* forced;  /* [W] forced id per window position (EOL/EOI/...), -1 = free; may be NULL */
   const int32_t* forced_resid; /* [W] forced id of the RESIDUAL distribution when the draft after position j is rejected
                            * (the reference re-runs its processors on a 1-token window there, which a position-
-                           * and window-length-dependent grammar such as Emu3's answers differently); NULL = `forced` */
+                           * and window-length-dependent grammar such as Emu3's answers differently); NULL = `forced`.
+                           * A value <= -2 means "mask-forced" id f = -2 - value (Anole's processors fill every other id
+                           * with finfo.min instead of writing a one-hot row): f is returned when its residual is finite,
+                           * otherwise the draw is uniform over the other ids, as the reference's softmax makes it */
   int32_t top_k;          /* 0 = off; ties with the k-th largest are kept (scores < kth removed) */
+  float top_p_thresh;     /* TopPLogitsWarper3d (logit_processor_3dim.py:406-419), applied after top-k: float32(1 - top_p);
+                           * the smallest probabilities whose running sum stays <= this are removed; 0 = off (top_p = 1) */
   int32_t do_sample;      /* 0: argmax */
   int32_t scheme;         /* 0: 'speculative_jacobi', 1: 'jacobi' (:1032-1048) */
   const int32_t* draft;   /* [W] window ids, [0] = last accepted token */

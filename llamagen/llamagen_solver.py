@@ -54,8 +54,6 @@ class MaxlenCriteria(StoppingCriteria):
 
 def _first_token(logits_rows: torch.Tensor, cfg_scale: float, temperature=1.0, top_k=0, top_p=1.0, sample_logits=True):
     """prefill() + sample() of the reference (llamagen_solver.py:95-104, :75-84) on device: one [1, V] row."""
-    if top_p < 1.0:
-        raise NotImplementedError("top_p < 1 is not implemented on the SJD path")
     if cfg_scale > 1.0:
         c, u = logits_rows[0:1], logits_rows[1:2]
         lg = u + (c - u) * cfg_scale
@@ -65,6 +63,13 @@ def _first_token(logits_rows: torch.Tensor, cfg_scale: float, temperature=1.0, t
     if top_k > 0:
         k = min(max(top_k, 1), lg.shape[-1])
         lg = lg.masked_fill(lg < torch.topk(lg, k)[0][..., -1, None], float("-inf"))
+    if top_p < 1.0:
+        # the first token uses the gpt-fast nucleus of top_k_top_p_filtering (:56-71), not TopPLogitsWarper3d: descending
+        # order, drop what lies beyond the first entry whose running probability exceeds top_p
+        srt, order = torch.sort(lg, descending=True)
+        beyond = torch.cumsum(torch.softmax(srt, dim=-1), dim=-1) > top_p
+        beyond = torch.cat([torch.zeros_like(beyond[..., :1]), beyond[..., :-1]], dim=-1)
+        lg = lg.masked_fill(beyond.scatter(1, order, beyond), float("-inf"))
     probs = torch.softmax(lg, dim=-1)
     return torch.multinomial(probs, num_samples=1) if sample_logits else torch.topk(probs, k=1, dim=-1)[1]
 

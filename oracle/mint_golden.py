@@ -164,8 +164,27 @@ def run_reference_loop(case: dict, Cache) -> dict:
                                                  e["eof"], e["pad"], torch.arange(e["visual"][0], e["visual"][1]))
         fn.__class__ = E.renew_end_of_line_logit_processor_3d(fn.__class__)
         procs = LogitsProcessorList([fn, TopKLogitsWarper(top_k=case["image_top_k"])])
+    elif case["grammar"] == "anole":
+        # the processor list renew_pipeline_anole.generate builds for multimodal_generation_mode="image-only"
+        # (scheduler/jacobi_iteration_anhole.py:200-240); HF appends TopKLogitsWarper (GenerationConfig.top_k)
+        a = case["anole"]
+        image_ids = list(range(a["image"][0], a["image"][1]))
+        allowed = image_ids + [a["eos"], a["boi"], a["eoi"]]
+        S = a["image_seq_length"]
+        procs = LogitsProcessorList([
+            LP3.AllowOnlyTokensAtRelativeOffsetLogitsProcessor3d(trigger_token_id=a["boi"], allowed_token_ids=[a["eoi"]],
+                                                                 offset=S + 1, exclusive=True),
+            LP3.AllowOnlyTokensInRelativeWindowLogitsProcessor3d(trigger_token_id=a["boi"], allowed_token_ids=image_ids,
+                                                                 window_width=S, exclusive=True),
+            LP3.SuppressTokensInIndexRangeLogitsProcessor3d(suppress_tokens=[a["boi"]],
+                                                            start_index=case["max_length"] - S - 1),
+            LP3.SuppressTokensLogitsProcessor3d(suppress_tokens=[t for t in range(V) if t not in set(allowed)]),
+            LP3.SuppressTokensAtBeginLogitsProcessor3d(begin_suppress_tokens=[a["eos"]],
+                                                       begin_index=len(case["prompt"])),
+            TopKLogitsWarper(top_k=case["image_top_k"])])
     else:
-        procs = LogitsProcessorList([TopKLogitsWarper(top_k=case["image_top_k"]), TopPLogitsWarper3d(top_p=1.0)])
+        procs = LogitsProcessorList([TopKLogitsWarper(top_k=case["image_top_k"]),
+                                     TopPLogitsWarper3d(top_p=case.get("top_p", 1.0))])
     gc = GenerationConfig(max_new_tokens=case["max_length"], max_length=case["max_length"], temperature=1.0,
                           top_k=None, do_sample=case["do_sample"], eos_token_id=case["eos"] or None)
     gc._pad_token_tensor = torch.tensor(0) if case["eos"] else None
@@ -195,8 +214,36 @@ def run_reference_loop(case: dict, Cache) -> dict:
     return {"ids": [int(t) for t in out[0]], "trace": trace}
 
 
+_ANOLE = dict(boi=8197, eoi=8196, eos=2, image=[4, 8196], image_seq_length=24)
 _EMU3 = dict(height=4, width=6, img_token=900, eol=901, eof=902, eoi=903, eos=904, pad=905, visual=[1000, 3048])
 LOOP_CASES = {
+    # Anole (a12): five 3-D Chameleon processors + TopK(50); boi forced first, 24 image tokens, eoi only if a trip
+    # ends exactly on the offset (else the window jumps over it), max_new_tokens = S + 2 like model_loader.py:404-409
+    "anole_spec_w8": dict(V=9216, sharp=14.0, grammar="anole", anole=_ANOLE, image_top_k=50, text_top_k=10,
+                          prompt=[0, 300, 400, 500], img_vocab=[4, 8196], do_sample=True, eos=[2],
+                          max_length=4 + 24 + 2,
+                          jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=24 + 4, max_num_new_tokens=8,
+                                      guidance_scale=3.0, seed=6, multi_token_init_scheme="random", do_cfg=True,
+                                      prefix_token_sampler_scheme="speculative_jacobi")),
+    "anole_spec_w4_hits_eoi": dict(V=9216, sharp=9.0, grammar="anole", anole=_ANOLE, image_top_k=50, text_top_k=10,
+                                   prompt=[0, 300, 400], img_vocab=[4, 8196], do_sample=True, eos=[2],
+                                   max_length=3 + 24 + 2,
+                                   jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=20, max_num_new_tokens=4,
+                                               guidance_scale=7.0, seed=11, multi_token_init_scheme="random", do_cfg=True,
+                                               prefix_token_sampler_scheme="speculative_jacobi")),
+    # LlamaGen processors with a real nucleus: TopK(100) then TopPLogitsWarper3d(0.8) (a10)
+    "plain_topk_topp_spec_w16": dict(V=1024, sharp=12.0, grammar="plain", image_top_k=100, text_top_k=10, top_p=0.8,
+                                     prompt=[207], img_vocab=[0, 1024], do_sample=True, eos=[], max_length=100,
+                                     jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=90,
+                                                 max_num_new_tokens=16, guidance_scale=4.0, seed=1,
+                                                 multi_token_init_scheme="random", do_cfg=True,
+                                                 prefix_token_sampler_scheme="speculative_jacobi")),
+    "plain_topp_only_jacobi_w8": dict(V=1024, sharp=6.0, grammar="plain", image_top_k=1024, text_top_k=10, top_p=0.5,
+                                      prompt=[3], img_vocab=[0, 1024], do_sample=True, eos=[], max_length=60,
+                                      jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=50,
+                                                  max_num_new_tokens=8, guidance_scale=2.0, seed=4,
+                                                  multi_token_init_scheme="random", do_cfg=True,
+                                                  prefix_token_sampler_scheme="jacobi")),
     # Emu3 grammar (a11): 4 x 6 grid -> EOL after every 6 visual tokens, then EOF, EOI, EOS (stops the run)
     "emu3_spec_w8": dict(V=4096, sharp=14.0, grammar="emu3", emu3=_EMU3, image_top_k=512, text_top_k=10,
                          prompt=[5, 17, 23, 900], img_vocab=[1000, 3048], do_sample=True, eos=[904],
@@ -270,9 +317,11 @@ LOOP_CASES = {
 }
 
 
-def mint_loops(out_dir: Path):
+def mint_loops(out_dir: Path, only=None):
     Cache = apply_shims()
     for name, case in LOOP_CASES.items():
+        if only and name not in only:
+            continue
         res = run_reference_loop(case, Cache)
         nfe = len(res["trace"])
         n_new = len(res["ids"]) - len(case["prompt"])
@@ -288,7 +337,7 @@ if __name__ == "__main__":
     out.mkdir(parents=True, exist_ok=True)
     which = sys.argv[1:] or ["loops", "forward"]
     if "loops" in which:
-        mint_loops(out)
+        mint_loops(out, only=[w for w in which if w in LOOP_CASES])
     if "forward" in which:
         from oracle import mint_forward_golden as F
         F.mint_llamagen()

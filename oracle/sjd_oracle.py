@@ -123,9 +123,64 @@ class PlainTopK:
     """LlamaGen / Emu3-style processors without grammar: HF TopKLogitsWarper (+ TopPLogitsWarper3d with p = 1,
     a no-op on probabilities; llamagen/llamagen_solver.py:458-470)."""
     top_k: int = 0
+    top_p: float = 1.0
 
     def describe(self, ids: list[int], n: int) -> dict:
-        return {"in_image": True, "allow": None, "forced": [-1] * n, "top_k": self.top_k, "no_cfg": False}
+        return {"in_image": True, "allow": None, "forced": [-1] * n, "top_k": self.top_k, "no_cfg": False,
+                "top_p": self.top_p}
+
+
+@dataclass
+class AnoleGrammar:
+    """The five 3-D Chameleon processors the Anole adaptor installs for `multimodal_generation_mode="image-only"`
+    (scheduler/jacobi_iteration_anhole.py:200-240) followed by HF's TopKLogitsWarper, restated as ONE disallowed-id mask
+    per call: every processor looks at the ACCEPTED prefix only (its length / a token at a fixed distance from its end)
+    and applies its decision to every window position alike (logit_processor_3dim.py:242-256, :280-286, :323-338).
+    Disallowed ids are filled with finfo.min (not -inf).  A multi-token accept can therefore jump over the position
+    where end-of-image would have been forced; the adaptor truncates to image_seq_length afterwards
+    (jacobi_iteration_anhole.py:309-311)."""
+    vocab: int = 65536
+    boi: int = 8197
+    eoi: int = 8196
+    eos: int = 2
+    image_lo: int = 4
+    image_hi: int = 8196          # IMGIMG* ids of the Chameleon vocabulary: 4..8195
+    image_seq_length: int = 1024
+    max_length: int = 0           # generation_config.max_length (prompt + max_new_tokens)
+    begin_index: int = 0          # prompt length (SuppressTokensAtBegin)
+    top_k: int = 50               # HF default top_k when do_sample=True
+
+    def disallowed(self, ids: list[int]) -> np.ndarray:
+        V, S, cur = self.vocab, self.image_seq_length, len(ids)
+        img = np.zeros(V, bool)
+        img[self.image_lo:self.image_hi] = True
+        dis = np.zeros(V, bool)
+        # AllowOnlyTokensAtRelativeOffsetLogitsProcessor3d(boi, [eoi], offset=S+1, exclusive=True)  (:242-256)
+        not_eoi = np.ones(V, bool)
+        not_eoi[self.eoi] = False
+        off = S + 1
+        if cur < off:
+            dis |= ~not_eoi
+        else:
+            dis |= ~(not_eoi ^ (ids[-off] == self.boi))
+        # AllowOnlyTokensInRelativeWindowLogitsProcessor3d(boi, image ids, window_width=S, exclusive=True)  (:323-338)
+        ww = min(S, cur)
+        dis |= ~((~img) ^ (self.boi in ids[-ww:]))
+        # SuppressTokensInIndexRangeLogitsProcessor3d([boi], start=max_length - S - 1)  (:280-286)
+        if not (self.max_length - S - 1 > cur):
+            dis[self.boi] = True
+        # SuppressTokensLogitsProcessor3d(everything but image ids, eos, boi, eoi)
+        ok = img.copy()
+        ok[[self.eos, self.boi, self.eoi]] = True
+        dis |= ~ok
+        # SuppressTokensAtBeginLogitsProcessor3d([eos], begin_index): active for begin <= cur <= begin + 1  (:283)
+        if not (self.begin_index > cur or cur > self.begin_index + 1):
+            dis[self.eos] = True
+        return dis
+
+    def describe(self, ids: list[int], n: int) -> dict:
+        return {"in_image": True, "allow": None, "forced": [-1] * n, "top_k": self.top_k, "no_cfg": False,
+                "masked": self.disallowed(ids)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -148,6 +203,8 @@ def apply_grammar(scores: np.ndarray, desc: dict) -> np.ndarray:
         if tok >= 0:
             s[i, :] = NEG_INF
             s[i, tok] = F32(0)
+    if desc.get("masked") is not None:   # Anole processors: masked_fill(..., finfo.min)
+        s[:, desc["masked"]] = np.finfo(F32).min
     return s
 
 
@@ -160,6 +217,24 @@ def topk_filter(s: np.ndarray, k: int) -> np.ndarray:
     kth = np.partition(s, V - k, axis=-1)[..., V - k][..., None]
     out = s.copy()
     out[s < kth] = NEG_INF
+    return out
+
+
+def topp_filter(s: np.ndarray, top_p: float) -> np.ndarray:
+    """TopPLogitsWarper3d (logit_processor_3dim.py:406-419): ascending sort, softmax, running sum; entries whose
+    running sum is <= 1 - top_p are removed, the largest is always kept.  The comparison runs in float32 (a Python
+    scalar compared with a float32 tensor)."""
+    if top_p >= 1.0:
+        return s   # cumulative probability <= 0 only for entries that are -inf already
+    order = np.argsort(s, axis=-1, kind="stable")
+    srt = np.take_along_axis(s, order, axis=-1)
+    cum = np.cumsum(softmax(srt), axis=-1, dtype=F32)
+    rm_sorted = cum <= F32(1.0 - top_p)
+    rm_sorted[..., -1:] = False
+    rm = np.zeros_like(rm_sorted)
+    np.put_along_axis(rm, order, rm_sorted, axis=-1)
+    out = s.copy()
+    out[rm] = NEG_INF
     return out
 
 
@@ -182,6 +257,7 @@ def logits_to_probs(logits: np.ndarray, W: int, desc: dict, *, has_uncond: bool,
     if temperature != 1.0:
         s = (s / F32(temperature)).astype(F32)
     s = topk_filter(s, desc["top_k"])
+    s = topp_filter(s, desc.get("top_p", 1.0))
     return s
 
 
@@ -243,12 +319,14 @@ def verify(logits: np.ndarray, W: int, desc: dict, draft: np.ndarray, q_rows: li
         with np.errstate(divide="ignore"):
             rl = np.log(np.maximum((p[i - 1] - q).astype(F32), F32(0))).astype(F32)
         rdesc = residual_desc_fn([int(t) for t in tokens[: i - 1]]) if residual_desc_fn else \
-            {"allow": desc["allow"], "forced": [desc["forced"][i - 1]], "top_k": desc["top_k"]}
+            {"allow": desc["allow"], "forced": [desc["forced"][i - 1]], "top_k": desc["top_k"],
+             "top_p": desc.get("top_p", 1.0), "masked": desc.get("masked")}
         text_mode = bool(rdesc.get("text_mode", False))
         rs = apply_grammar(rl[None, :], rdesc)
         if temperature != 1.0:
             rs = (rs / F32(temperature)).astype(F32)
         rs = topk_filter(rs, rdesc["top_k"])
+        rs = topp_filter(rs, rdesc.get("top_p", 1.0))
         rp = softmax(rs)
         e2 = noise_e2() if callable(noise_e2) else noise_e2   # callable: drawn only now, like the reference
         tokens[i - 1] = int(multinomial1(rp, np.asarray(e2, F32).reshape(1, -1))[0])

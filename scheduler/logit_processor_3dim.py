@@ -6,4 +6,6 @@ import sys as _sys
 _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import sjd_b200  # noqa: E402,F401
 from sjd_b200.hf_api import (  # noqa: E402,F401
-    MultiTokensInterleavedTopKLogitsWarper, MultiTokensVLLogitsProcessor, TopPLogitsWarper3d)
+    AllowOnlyTokensAtRelativeOffsetLogitsProcessor3d, AllowOnlyTokensInRelativeWindowLogitsProcessor3d,
+    MultiTokensInterleavedTopKLogitsWarper, MultiTokensVLLogitsProcessor, SuppressTokensAtBeginLogitsProcessor3d,
+    SuppressTokensInIndexRangeLogitsProcessor3d, SuppressTokensLogitsProcessor3d, TopPLogitsWarper3d)

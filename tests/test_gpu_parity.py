@@ -90,7 +90,7 @@ def test_gemm_stream_k_grid_independence(env):
 
 # ---------------------------------------------------------------------------------------------- verify
 def _verify_case(env, seed, *, W=8, V=9216, scheme="speculative_jacobi", do_sample=True, guidance=3.0,
-                 has_uncond=True, apply_cfg=True, temperature=1.0, top_k=2000, grammar=True, u_scale=1.0):
+                 has_uncond=True, apply_cfg=True, temperature=1.0, top_k=2000, grammar=True, u_scale=1.0, top_p=1.0):
     O, dev, engine = env["O"], env["dev"], env["engine"]
     rng = np.random.default_rng(seed)
     logits = (rng.standard_normal(((2 if has_uncond else 1) * W, V)) * 1.5).astype(np.float32)
@@ -100,6 +100,7 @@ def _verify_case(env, seed, *, W=8, V=9216, scheme="speculative_jacobi", do_samp
         desc = g.describe(ids, W)
     else:
         desc = {"allow": None, "forced": [-1] * W, "top_k": top_k, "in_image": True, "no_cfg": False}
+    desc["top_p"] = top_p
     # distributions of this trip, to build plausible drafts: draft[i] ~ p[i-1], q = a perturbed p[i-1]
     s = O.logits_to_probs(logits, W, desc, has_uncond=has_uncond, apply_cfg=apply_cfg, guidance=guidance,
                           temperature=temperature)
@@ -160,6 +161,66 @@ def test_verify_variants_match_oracle(env, kw):
         assert np.abs(out["p"].cpu().numpy() - ref.p).max() <= 1e-6
 
 
+@pytest.mark.parametrize("kw", [
+    dict(top_p=0.9), dict(top_p=0.5, top_k=0), dict(top_p=0.8, grammar=False, V=16384, top_k=1000, W=16),
+    dict(top_p=0.95, scheme="jacobi"), dict(top_p=0.7, do_sample=False), dict(top_p=0.6, V=65536, grammar=False, top_k=0),
+    dict(top_p=0.85, temperature=0.8, u_scale=0.1),
+])
+def test_verify_top_p_matches_oracle(env, kw):
+    """TopPLogitsWarper3d after top-k (a10).  The reference's removed set is decided by an fp32 running sum in sorted
+    order; ours by an exact fixed-point sum, so an entry whose running sum lies within 2e-6 of 1 - top_p may fall on
+    either side.  Seeds whose boundary is that close are skipped (never more than one in three); everything else must
+    agree exactly: support, tokens, accepted count, probabilities to 1e-6."""
+    O = env["O"]
+    checked = 0
+    for seed in (1, 2, 3):
+        ref, out = _verify_case(env, 200 + seed, **kw)
+        p = out["p"].cpu().numpy()
+        if not np.array_equal(p > 0, ref.p > 0):
+            # is every disagreement a boundary case?  mass of the disputed entries relative to the threshold
+            diff = (p > 0) != (ref.p > 0)
+            rows = np.flatnonzero(diff.any(1))
+            for r in rows:
+                assert diff[r].sum() <= 1, "more than one disputed entry in a row"
+                kept = ref.p[r] > 0
+                srt = np.sort(np.where(kept | diff[r], np.maximum(ref.p[r], p[r]), 0.0))
+                assert np.abs(np.cumsum(srt[srt > 0]) / srt.sum() - (1 - kw["top_p"])).min() < 2e-6
+            continue
+        checked += 1
+        assert out["matched"] == ref.matched, kw
+        assert out["tokens"].cpu().numpy().tolist() == ref.tokens.tolist(), kw
+        assert np.abs(p - ref.p).max() <= 1e-6
+        n_allowed = 8192 if kw.get("grammar", True) else kw.get("V", 9216)
+        topk_only = min(kw.get("top_k", 2000) or n_allowed, n_allowed)
+        assert ((ref.p > 0).sum(1) < topk_only).all(), "top-p removed nothing: hollow case"
+    assert checked >= 2
+
+
+def test_verify_top_p_ties_removed_lowest_id_first(env):
+    """Equal probabilities straddling the threshold: a stable ascending sort removes the lowest ids first, as many as
+    fit under 1 - top_p; the largest entry always survives, even for top_p = 0."""
+    O, dev, engine = env["O"], env["dev"], env["engine"]
+    W, V = 3, 640
+    logits = np.full((W, V), -np.inf, np.float32)
+    logits[0, [3, 50, 200, 400, 639]] = [0.0, 0.0, 0.0, 0.0, np.log(4.0)]    # p = 1/8 x4, 1/2: top_p 0.7 removes ids 3, 50
+    logits[1, [7, 9]] = [1.0, 1.0]                                          # two equal entries, top_p 0.7: remove id 7? 0.5 > 0.3: none
+    logits[2, 100:110] = 0.0                                                # ten equal entries of 0.1: three removed (0.3 <= 0.3000000119)
+    e1 = np.ones((W, V), np.float32)
+    for top_p, want in ((0.7, [[200, 400, 639], [7, 9], list(range(103, 110))]), (0.0, [[639], [9], [109]])):
+        desc = {"allow": None, "forced": [-1] * W, "top_k": 0, "top_p": top_p}
+        ref = O.verify(logits, W, desc, np.array([0, 5, 5]), [None] * W, has_uncond=False, apply_cfg=False, guidance=1.0,
+                       do_sample=True, scheme="jacobi", noise_e1=e1)
+        out = engine.verify_call(torch.from_numpy(logits).to(dev), W, V, desc, torch.tensor([0, 5, 5], dtype=torch.int32, device=dev),
+                                 None, None, has_uncond=False, apply_cfg=False, guidance=1.0, temperature=1.0,
+                                 do_sample=True, scheme=1, noise_e1=torch.from_numpy(e1).to(dev))
+        p = out["p"].cpu().numpy()
+        for r in range(W):
+            assert np.flatnonzero(ref.p[r] > 0).tolist() == want[r], (top_p, r, np.flatnonzero(ref.p[r] > 0))
+            assert np.flatnonzero(p[r] > 0).tolist() == want[r], (top_p, r, np.flatnonzero(p[r] > 0))
+        assert np.abs(p - ref.p).max() <= 1e-6
+        assert out["tokens"].cpu().numpy().tolist() == ref.tokens.tolist()
+
+
 def test_verify_topk_ties_and_small_support(env):
     """Ties with the k-th largest score are kept; k beyond the finite support removes nothing."""
     O, dev, engine = env["O"], env["dev"], env["engine"]
@@ -200,8 +261,12 @@ def _engine_for_case(env, case, noise_dev="cpu"):
         e = case["emu3"]
         grammar = engine.Emu3GrammarState(e["height"], e["width"], e["img_token"], e["eol"], e["eof"], e["eoi"], e["eos"],
                                           e["pad"], e["visual"][0], e["visual"][1], top_k=case["image_top_k"])
+    elif case["grammar"] == "anole":
+        a = case["anole"]
+        grammar = engine.AnoleGrammarState(a["boi"], a["eoi"], a["eos"], a["image"][0], a["image"][1], a["image_seq_length"],
+                                           case["max_length"], len(case["prompt"]), top_k=case["image_top_k"])
     else:
-        grammar = engine.PlainTopKState(top_k=case["image_top_k"])
+        grammar = engine.PlainTopKState(top_k=case["image_top_k"], top_p=case.get("top_p", 1.0))
 
     class Eng(engine.SJDEngine):
         def _forward(self, row_tokens, kv_len, kv_lo, n_logit, embeds=None):
@@ -524,3 +589,68 @@ def test_forward_matches_hf_chameleon_bf16(env):
     err2 = (ours2[:, keep] - ref2[:, keep]).abs()
     assert err2.max().item() <= 3.0 * ulp, (err2.max().item(), ulp)
     stack.close()
+
+
+# ------------------------------------------------------------------------------- Anole boundary (config 5 family)
+def test_anole_adaptor_flow_on_gpu(env):
+    """scheduler.jacobi_iteration_anhole.renew_pipeline_sampler on a tiny HF ChameleonForConditionalGeneration (the module
+    tree Anole runs), through HF's own generate(): the five 3-D Chameleon processors + TopK evaluated by sjd_verify, CFG
+    with the hidden-prefix uncond row, real kernels end to end.  Engine output == oracle replay on the captured logits
+    (the oracle applies the reference processors as masks); begin-of-image first, then image ids only."""
+    from transformers import ChameleonConfig, ChameleonForConditionalGeneration
+    from scheduler.jacobi_iteration_anhole import renew_pipeline_sampler
+    O, model_mod, dev = env["O"], env["model"], env["dev"]
+    torch.manual_seed(2)
+    n_img, S, V = 200, 20, 512
+    names = {f"IMGIMG{chr(65 + i // 100)}{chr(65 + (i // 10) % 10)}{chr(65 + i % 10)}Z": 4 + i for i in range(n_img)}
+    cfg = ChameleonConfig(vocab_size=V, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                          num_attention_heads=2, num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-5,
+                          vocabulary_map={"<image>": 3, **names}, eos_token_id=2, bos_token_id=0, pad_token_id=1,
+                          vq_config={"embed_dim": 8, "num_embeddings": 16, "resolution": 32, "channel_multiplier": [1, 1],
+                                     "base_channels": 32, "num_res_blocks": 1, "latent_channels": 8})
+    m = ChameleonForConditionalGeneration(cfg)
+    with torch.no_grad():
+        for n_, p_ in m.named_parameters():
+            if "vqmodel" not in n_ and p_.dim() >= 2 and "norm" not in n_:
+                p_.normal_(0.0, 0.08)
+    m = m.to(dev, torch.bfloat16).eval()
+    boi, eoi = 300, 301
+    m.model.vocabulary_mapping.boi_token_id = boi
+    m.model.vocabulary_mapping.eoi_token_id = eoi
+
+    class Proc:
+        image_seq_length = S
+
+    jac = dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=S + 4, max_num_new_tokens=6, guidance_scale=3.0, seed=3,
+               multi_token_init_scheme="random", do_cfg=True, prefix_token_sampler_scheme="speculative_jacobi")
+    m = renew_pipeline_sampler(m, Proc(), image_top_k=50, text_top_k=10, **jac)
+    m.img_vocab = torch.arange(4, 4 + n_img)     # random drafts from this model's image ids
+    captured = []
+    orig_forward = model_mod.DeviceStack.forward
+
+    def spy(self, *a, **k):
+        lg = orig_forward(self, *a, **k)
+        captured.append(lg.detach().float().cpu().numpy().reshape(-1, V).copy())
+        return lg
+
+    prompt = [0, 400, 401, 402, 403]
+    ids_in = torch.tensor([prompt], device=dev)
+    model_mod.DeviceStack.forward = spy
+    try:
+        out = m.generate(input_ids=ids_in, attention_mask=torch.ones_like(ids_in),
+                         multimodal_generation_mode="image-only", max_new_tokens=S + 2, do_sample=True, top_k=40)
+    finally:
+        model_mod.DeviceStack.forward = orig_forward
+    ids = out[0].tolist()
+    P = len(prompt)
+    assert len(ids) == P + S + 2 and ids[P] == boi
+    assert all(4 <= t < 4 + n_img or t == eoi for t in ids[P + 1:]), ids
+    assert all(4 <= t < 4 + n_img for t in ids[P + 1:P + 1 + S]), ids
+    assert m.sjd_stats.nfe < S + 2, "Jacobi decoding must need fewer forwards than tokens"
+    it = iter(captured)
+    g = O.AnoleGrammar(vocab=V, boi=boi, eoi=eoi, eos=2, image_lo=4, image_hi=4 + n_img, image_seq_length=S,
+                       max_length=P + S + 2, begin_index=P, top_k=40)
+    ids_o, nfe_o = O.decode(lambda r, k, n: next(it), prompt, params=O.OracleParams(**jac), grammar=g,
+                            img_vocab=np.arange(4, 4 + n_img), max_length=P + S + 2, eos_ids=[2], rows=2,
+                            do_sample=True, noise=O.TorchNoise(jac["seed"], device=str(dev)))
+    assert ids_o == ids and nfe_o == m.sjd_stats.nfe

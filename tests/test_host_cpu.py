@@ -155,3 +155,168 @@ def test_two_rank_gloo_counter_gather(lib, tmp_path):
     out = json.loads(line)
     assert out == dict(world=2, total_tokens=sum(100 + i for i in range(8)), total_nfe=sum(10 + i for i in range(8)),
                        done=2, tmax=2.0)
+
+
+# ------------------------------------------------------------------------------------------- Anole grammar (a12)
+def _anole_pair(S=12, P=5, extra=2, top_k=50, V=9216):
+    from oracle import sjd_oracle as O
+    from sjd_b200 import engine
+    max_length = P + S + extra
+    o = O.AnoleGrammar(vocab=V, boi=8197, eoi=8196, eos=2, image_lo=4, image_hi=8196, image_seq_length=S,
+                       max_length=max_length, begin_index=P, top_k=top_k)
+    e = engine.AnoleGrammarState(8197, 8196, 2, 4, 8196, S, max_length, P, top_k=top_k)
+    return o, e
+
+
+def _allowed_from_desc(d, V):
+    """allowed-id set of window position 0 as the verify kernel will see it"""
+    if d["forced"][0] >= 0:
+        return {d["forced"][0]}
+    lo, hi = d["allow"]
+    return set(range(lo, hi))
+
+
+def test_anole_grammar_state_matches_oracle_masks():
+    """engine.AnoleGrammarState (what the kernel is told) == the five reference processors restated as masks in the
+    oracle, for every prefix length of an image-only generation — including prefixes a multi-token accept produced by
+    jumping over the end-of-image offset."""
+    rng = random.Random(0)
+    V, S, P = 9216, 12, 5
+    o, e = _anole_pair(S=S, P=P)
+    for overshoot in (False, True):
+        ids = [0, 300, 400, 500, 600]
+        e.reset()
+        e.observe(ids)
+        while len(ids) < P + S + 2:
+            d = e.describe(4)
+            allowed = set(np.flatnonzero(~o.disallowed(ids)).tolist())
+            assert _allowed_from_desc(d, V) == allowed, (len(ids), d["forced"][:1], sorted(allowed)[:4])
+            assert d["forced"] == [d["forced"][0]] * 4, "one decision for every window position"
+            # (the trip that forces begin-of-image is the window-1 trip after the prompt, jacobi_loop_interval_l >= 1)
+            resid = e.describe_residual(1 if allowed == {8197} else 3)
+            for j, f in enumerate(resid):   # residual at reject position j: prefix + j accepted drafts
+                acc = [7] * j if len(allowed) > 1 else [next(iter(allowed))] * j
+                want = set(np.flatnonzero(~o.disallowed(ids + acc)).tolist())
+                assert (want == {-2 - f}) if f <= -2 else (f == -1 and want == set(range(4, 8196))), (len(ids), j, f)
+            if len(allowed) == 1:
+                new = [next(iter(allowed))]
+            else:
+                n_new = rng.randint(1, 4) if overshoot else 1
+                new = [rng.randrange(4, 8196) for _ in range(n_new)]
+            ids += new
+            e.observe(new)
+        assert ids[P] == 8197
+        if not overshoot:
+            assert ids[P + S + 1] == 8196, "with single-token accepts end-of-image is forced at the offset"
+
+
+def test_anole_grammar_refuses_inexpressible_sets():
+    o, e = _anole_pair(S=4, P=2, extra=12)   # room for a second image: {eos, boi} after the first one
+    e.observe([0, 1, 8197, 10, 11, 12, 13, 8196])
+    with pytest.raises(NotImplementedError, match="not expressible"):
+        e.describe(1)
+
+
+def test_anole_processors_translate_to_grammar_state():
+    from sjd_b200 import engine, hf_api as H
+    from transformers.generation.logits_process import TopKLogitsWarper
+    V, S, P = 9216, 24, 4
+    image = list(range(4, 8196))
+    allowed = set(image) | {2, 8197, 8196}
+    procs = [H.AllowOnlyTokensAtRelativeOffsetLogitsProcessor3d(8197, [8196], offset=S + 1, exclusive=True),
+             H.AllowOnlyTokensInRelativeWindowLogitsProcessor3d(8197, image, window_width=S, exclusive=True),
+             H.SuppressTokensInIndexRangeLogitsProcessor3d([8197], start_index=P + S + 2 - S - 1),
+             H.SuppressTokensLogitsProcessor3d([t for t in range(V) if t not in allowed]),
+             H.SuppressTokensAtBeginLogitsProcessor3d([2], begin_index=P), TopKLogitsWarper(top_k=50)]
+    g = H.grammar_from_processors(procs, vocab=V)
+    assert isinstance(g, engine.AnoleGrammarState)
+    assert (g.boi, g.eoi, g.eos, g.allow, g.S, g.max_length, g.begin_index, g.top_k) == \
+        (8197, 8196, 2, (4, 8196), S, P + S + 2, P, 50)
+    with pytest.raises(RuntimeError, match="no host fallback"):
+        procs[0](torch.zeros(1, 3, dtype=torch.long), torch.zeros(1, 2, V))
+    with pytest.raises(NotImplementedError):
+        H.grammar_from_processors(procs[:2] + procs[3:], vocab=V)      # one processor of the set missing
+    procs[1] = H.AllowOnlyTokensInRelativeWindowLogitsProcessor3d(8197, image, window_width=S, exclusive=False)
+    with pytest.raises(NotImplementedError):
+        H.grammar_from_processors(procs, vocab=V)
+
+
+def test_top_p_processor_translates_and_validates():
+    from sjd_b200 import engine, hf_api as H
+    from transformers.generation.logits_process import TopKLogitsWarper
+    g = H.grammar_from_processors([TopKLogitsWarper(top_k=100), H.TopPLogitsWarper3d(top_p=0.8)])
+    assert isinstance(g, engine.PlainTopKState) and g.top_k == 100 and g.top_p == 0.8
+    assert g.describe(3)["top_p"] == 0.8
+    assert engine.top_p_threshold(1.0) == 0.0
+    assert engine.top_p_threshold(0.9) == float(np.float32(1.0 - 0.9))
+    with pytest.raises(ValueError):
+        H.TopPLogitsWarper3d(top_p=1.5)
+    with pytest.raises(NotImplementedError):
+        H.grammar_from_processors([H.TopPLogitsWarper3d(top_p=0.8), TopKLogitsWarper(top_k=100)])
+
+
+def test_top_p_oracle_follows_reference_formula():
+    """oracle.topp_filter against the reference arithmetic written out with torch (sort ascending, softmax, cumsum,
+    `<= 1 - top_p`, keep the last) — scheduler/logit_processor_3dim.py:406-419."""
+    from oracle import sjd_oracle as O
+    g = torch.Generator().manual_seed(3)
+    for top_p in (0.3, 0.8, 0.95):
+        s = torch.randn(4, 777, generator=g) * 3
+        s[0, 5:200] = -float("inf")
+        srt, idx = torch.sort(s, descending=False)
+        rm = srt.softmax(-1).cumsum(-1) <= (1 - top_p)
+        rm[..., -1:] = 0
+        want = s.masked_fill(rm.scatter(-1, idx, rm), -float("inf")).numpy()
+        got = O.topp_filter(s.numpy(), top_p)
+        assert np.array_equal(np.isinf(got), np.isinf(want))
+    assert O.topp_filter(s.numpy(), 1.0) is not None
+
+
+def test_anole_adaptor_generate_reaches_sample_with_the_image_only_grammar():
+    """scheduler.jacobi_iteration_anhole.renew_pipeline_sampler on a tiny HF ChameleonForConditionalGeneration: HF's own
+    generate() plumbing (this image: transformers 5.x) must end in the renewed `_sample` with the five 3-D processors
+    (+ HF's TopKLogitsWarper), which translate to the Anole grammar state.  `_sample` itself needs the GPU."""
+    from transformers import ChameleonConfig, ChameleonForConditionalGeneration
+    from scheduler.jacobi_iteration_anhole import renew_pipeline_sampler
+    from sjd_b200 import engine, hf_api as H
+    names = {f"IMGIMG{chr(65 + i // 10)}{chr(65 + i % 10)}Z": 4 + i for i in range(60)}
+    cfg = ChameleonConfig(vocab_size=128, hidden_size=128, intermediate_size=128, num_hidden_layers=1,
+                          num_attention_heads=1, num_key_value_heads=1, max_position_embeddings=64,
+                          vocabulary_map={"<image>": 3, **names}, eos_token_id=2, bos_token_id=0, pad_token_id=1,
+                          vq_config={"embed_dim": 8, "num_embeddings": 16, "resolution": 32, "channel_multiplier": [1, 1],
+                                     "base_channels": 32, "num_res_blocks": 1, "latent_channels": 8})
+    m = ChameleonForConditionalGeneration(cfg).eval()
+    m.model.vocabulary_mapping.boi_token_id = 70
+    m.model.vocabulary_mapping.eoi_token_id = 71
+
+    class Proc:
+        image_seq_length = 9
+
+    m = renew_pipeline_sampler(m, Proc(), jacobi_loop_interval_l=1, jacobi_loop_interval_r=20, max_num_new_tokens=4,
+                               guidance_scale=3.0, seed=0, multi_token_init_scheme="random", do_cfg=True,
+                               image_top_k=50, text_top_k=10, prefix_token_sampler_scheme="speculative_jacobi")
+    assert m.model.image_seq_length == 9 and m.vocabulary_mapping.image_token_ids == list(range(4, 64))
+    seen = {}
+
+    def fake_sample(self, *args, **kw):
+        import inspect
+        b = inspect.signature(orig).bind(self, *args, **kw)   # HF must be able to call the REAL _sample like this
+        b.apply_defaults()
+        input_ids, logits_processor = b.arguments["input_ids"], b.arguments["logits_processor"]
+        stopping_criteria, generation_config = b.arguments["stopping_criteria"], b.arguments["generation_config"]
+        seen["procs"], seen["gc"], seen["crit"] = logits_processor, generation_config, stopping_criteria
+        return input_ids
+
+    cls = type(m)
+    orig = cls._sample
+    cls._sample = fake_sample
+    try:
+        ids = torch.tensor([[0, 80, 81, 82]])
+        m.generate(input_ids=ids, attention_mask=torch.ones_like(ids), multimodal_generation_mode="image-only",
+                   do_sample=True, top_k=7)
+    finally:
+        cls._sample = orig
+    g = H.grammar_from_processors(list(seen["procs"]), vocab=cfg.vocab_size)
+    assert isinstance(g, engine.AnoleGrammarState)
+    assert (g.boi, g.eoi, g.eos, g.allow, g.S, g.max_length, g.begin_index, g.top_k) == (70, 71, 2, (4, 64), 9, 4 + 11, 4, 7)
+    assert int(seen["gc"].max_length) == 4 + 11

@@ -24,8 +24,13 @@ def run_oracle(case, max_trips=None):
         e = case["emu3"]
         grammar = O.Emu3Grammar(e["height"], e["width"], e["img_token"], e["eol"], e["eof"], e["eoi"], e["eos"], e["pad"],
                                 e["visual"][0], e["visual"][1], top_k=case["image_top_k"])
+    elif case["grammar"] == "anole":
+        a = case["anole"]
+        grammar = O.AnoleGrammar(vocab=V, boi=a["boi"], eoi=a["eoi"], eos=a["eos"], image_lo=a["image"][0],
+                                 image_hi=a["image"][1], image_seq_length=a["image_seq_length"],
+                                 max_length=case["max_length"], begin_index=len(case["prompt"]), top_k=case["image_top_k"])
     else:
-        grammar = O.PlainTopK(top_k=case["image_top_k"])
+        grammar = O.PlainTopK(top_k=case["image_top_k"], top_p=case.get("top_p", 1.0))
     trace = []
     do_cfg = j["do_cfg"] and j["guidance_scale"] != 1
     ids, nfe = O.decode(logits_fn, case["prompt"], params=params, grammar=grammar,
