@@ -64,7 +64,7 @@ struct BlockScratch {
 };
 
 // k-th largest key among the finite entries of row[0..V); caller guarantees k <= #finite.
-__device__ uint32_t block_kth_key(const float* __restrict__ row, int V, int k, BlockScratch& sc) {
+__device__ uint32_t block_kth_key(const float* __restrict__ row, int vb, int V, int k, BlockScratch& sc) {
   uint32_t prefix = 0, mask = 0;
   uint32_t remaining = uint32_t(k);
   const int shifts[3] = {21, 10, 0};
@@ -74,7 +74,7 @@ __device__ uint32_t block_kth_key(const float* __restrict__ row, int V, int k, B
     const uint32_t nb = 1u << nbits[pass];
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) sc.hist[i] = 0;
     __syncthreads();
-    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    for (int v = vb + threadIdx.x; v < V; v += blockDim.x) {
       const float f = row[v];
       if (f == -INFINITY) continue;
       const uint32_t key = f2key(f);
@@ -168,12 +168,15 @@ __device__ __forceinline__ int block_argmax(float v, int idx, BlockScratch& sc) 
 }
 
 // Shared tail: row[] holds processed scores (grammar applied). Applies top-k, softmax (in place -> probabilities)
-// and draws the token.  Returns the token (valid in every thread).
-__device__ int block_topk_softmax_sample(float* __restrict__ row, int V, int top_k, int do_sample,
+// and draws the token.  Returns the token (valid in every thread).  Only ids [vb, V) are visited: the caller passes the
+// grammar's candidate range (vb a multiple of blockDim, so that every thread walks the ids it would walk from 0, in
+// the same order — the block reductions, and with them every result, do not depend on vb) and has made everything
+// outside it -inf / probability 0.  `Vfull` is the vocabulary size (top-k is a no-op when k >= Vfull).
+__device__ int block_topk_softmax_sample(float* __restrict__ row, int vb, int V, int Vfull, int top_k, int do_sample,
                                          const float* __restrict__ noise_e, BlockScratch& sc) {
   float mx = -INFINITY;
   int nfin = 0;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+  for (int v = vb + threadIdx.x; v < V; v += blockDim.x) {
     const float f = row[v];
     mx = fmaxf(mx, f);
     nfin += (f != -INFINITY);
@@ -181,20 +184,20 @@ __device__ int block_topk_softmax_sample(float* __restrict__ row, int V, int top
   mx = block_max(mx, sc);
   nfin = block_sumi(nfin, sc);
   float thr = -INFINITY;  // scores < thr are removed
-  if (top_k > 0 && top_k < V && nfin > top_k) {
-    const uint32_t key = block_kth_key(row, V, top_k, sc);
+  if (top_k > 0 && top_k < Vfull && nfin > top_k) {
+    const uint32_t key = block_kth_key(row, vb, V, top_k, sc);
     const uint32_t u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
     thr = __uint_as_float(u);
   }
   float sum = 0.f;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+  for (int v = vb + threadIdx.x; v < V; v += blockDim.x) {
     const float f = row[v];
     if (f >= thr && f != -INFINITY) sum += expf(f - mx);
   }
   sum = block_sumf(sum, sc);
   float best = -INFINITY;
   int besti = 0x7fffffff;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+  for (int v = vb + threadIdx.x; v < V; v += blockDim.x) {
     const float f = row[v];
     const bool keep = (f >= thr && f != -INFINITY);
     const float pr = keep ? expf(f - mx) / sum : 0.f;
@@ -515,18 +518,25 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_rows_kernel(VerifyParam
     if (threadIdx.x == 0) p.next_tokens[i] = tok;
     return;
   }
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
-    float s = c[v];
-    if (mix) {
-      const float uu = u[v];
-      s = __fadd_rn(__fmul_rn(p.guidance, __fsub_rn(s, uu)), uu);
+  // candidate range too wide for registers (Emu3: 32 768 visual ids of 184 622): same passes over the row in global
+  // memory, but only over the blockDim-aligned span that covers [lo, hi); the rest of the row is probability 0
+  const int ve = min(V, ((hi + int(blockDim.x) - 1) / int(blockDim.x)) * int(blockDim.x));
+  for (int v = threadIdx.x; v < v0; v += blockDim.x) row[v] = 0.f;
+  for (int v = ve + threadIdx.x; v < V; v += blockDim.x) row[v] = 0.f;
+  for (int v = v0 + threadIdx.x; v < ve; v += blockDim.x) {
+    float s = -INFINITY;
+    if (v >= lo && v < hi) {
+      s = c[v];
+      if (mix) {
+        const float uu = u[v];
+        s = __fadd_rn(__fmul_rn(p.guidance, __fsub_rn(s, uu)), uu);
+      }
+      if (p.temperature != 1.f) s = s / p.temperature;
     }
-    if (ranged && (v < p.allow_lo || v >= p.allow_hi)) s = -INFINITY;
-    if (p.temperature != 1.f) s = s / p.temperature;
     row[v] = s;
   }
   __syncthreads();
-  int tok = block_topk_softmax_sample(row, V, p.top_k, p.do_sample, p.noise_e1 + size_t(i) * V, sc);
+  int tok = block_topk_softmax_sample(row, v0, ve, V, p.top_k, p.do_sample, p.noise_e1 + size_t(i) * V, sc);
   if (p.top_p_thresh > 0.f) {
     __syncthreads();
     tok = block_top_p(row, V, p.top_p_thresh, p.do_sample, tok, p.noise_e1 + size_t(i) * V, sc, tp);
@@ -620,16 +630,24 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyPar
       }
       tok = block_topk_softmax_sample_regs<kRegVPT>(s, v0, lo, hi, top_k, 1, p.noise_e2, nullptr, V, sc);
     } else {
-      for (int v = threadIdx.x; v < V; v += blockDim.x) {
-        const float q = b ? b[v] : (v == xd ? 1.f : 0.f);
-        float s = logf(fmaxf(__fsub_rn(a[v], q), 0.f));
-        if (ranged && (v < p.allow_lo || v >= p.allow_hi)) s = -INFINITY;
-        if (p.temperature != 1.f) s = s / p.temperature;
+      const int ve = min(V, ((hi + int(blockDim.x) - 1) / int(blockDim.x)) * int(blockDim.x));
+      const bool nucleus = p.top_p_thresh > 0.f;   // its pass walks the whole row: give it zeros outside the span
+      if (nucleus) {
+        for (int v = threadIdx.x; v < v0; v += blockDim.x) p.resid[v] = 0.f;
+        for (int v = ve + threadIdx.x; v < V; v += blockDim.x) p.resid[v] = 0.f;
+      }
+      for (int v = v0 + threadIdx.x; v < ve; v += blockDim.x) {
+        float s = -INFINITY;
+        if (v >= lo && v < hi) {
+          const float q = b ? b[v] : (v == xd ? 1.f : 0.f);
+          s = logf(fmaxf(__fsub_rn(a[v], q), 0.f));
+          if (p.temperature != 1.f) s = s / p.temperature;
+        }
         p.resid[v] = s;
       }
       __syncthreads();
-      tok = block_topk_softmax_sample(p.resid, V, top_k, 1, p.noise_e2, sc);
-      if (p.top_p_thresh > 0.f) {   // the residual goes through the same processors (reject_sampling_single_token)
+      tok = block_topk_softmax_sample(p.resid, v0, ve, V, top_k, 1, p.noise_e2, sc);
+      if (nucleus) {   // the residual goes through the same processors (reject_sampling_single_token)
         __syncthreads();
         tok = block_top_p(p.resid, V, p.top_p_thresh, 1, tok, p.noise_e2, sc, tp);
       }

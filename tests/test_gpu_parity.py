@@ -90,7 +90,8 @@ def test_gemm_stream_k_grid_independence(env):
 
 # ---------------------------------------------------------------------------------------------- verify
 def _verify_case(env, seed, *, W=8, V=9216, scheme="speculative_jacobi", do_sample=True, guidance=3.0,
-                 has_uncond=True, apply_cfg=True, temperature=1.0, top_k=2000, grammar=True, u_scale=1.0, top_p=1.0):
+                 has_uncond=True, apply_cfg=True, temperature=1.0, top_k=2000, grammar=True, u_scale=1.0, top_p=1.0,
+                 allow=None):
     O, dev, engine = env["O"], env["dev"], env["engine"]
     rng = np.random.default_rng(seed)
     logits = (rng.standard_normal(((2 if has_uncond else 1) * W, V)) * 1.5).astype(np.float32)
@@ -101,11 +102,14 @@ def _verify_case(env, seed, *, W=8, V=9216, scheme="speculative_jacobi", do_samp
     else:
         desc = {"allow": None, "forced": [-1] * W, "top_k": top_k, "in_image": True, "no_cfg": False}
     desc["top_p"] = top_p
+    if allow is not None:   # a wide candidate range (Emu3's 32 768 visual ids): the strided, range-restricted path
+        desc["allow"] = tuple(allow)
     # distributions of this trip, to build plausible drafts: draft[i] ~ p[i-1], q = a perturbed p[i-1]
     s = O.logits_to_probs(logits, W, desc, has_uncond=has_uncond, apply_cfg=apply_cfg, guidance=guidance,
                           temperature=temperature)
     p = O.softmax(s)
-    draft = rng.integers(4, min(8196, V), size=W).astype(np.int64)
+    d_lo, d_hi = allow if allow is not None else (4, min(8196, V))
+    draft = rng.integers(d_lo, d_hi, size=W).astype(np.int64)
     p_prev = np.zeros((W, V), np.float32)
     q_rows, q_idx = [None] * W, [-1] * W
     for i in range(1, W):
@@ -152,6 +156,8 @@ def test_verify_covers_accepts_and_rejects(env):
     dict(do_sample=False), dict(apply_cfg=False), dict(has_uncond=False, apply_cfg=False),
     dict(temperature=0.7), dict(top_k=0), dict(top_k=1), dict(top_k=50, grammar=False, V=1024),
     dict(W=1), dict(W=32, V=16384, grammar=False, top_k=1000), dict(W=16, V=65536), dict(u_scale=0.05),
+    dict(W=8, V=60000, grammar=False, allow=(20011, 52779), top_k=2048),            # range wider than the register path
+    dict(W=4, V=60000, grammar=False, allow=(1024, 40000), top_k=2048, top_p=0.9),  # ... with a nucleus on top
 ])
 def test_verify_variants_match_oracle(env, kw):
     for seed in (1, 2, 3):
