@@ -12,6 +12,7 @@
 #include "attention.cu"
 #include "block_ops.cu"
 #include "gemm_fused.cu"
+#include "attention_tc.cu"
 #include "verify.cu"
 
 namespace sjd {
@@ -59,6 +60,10 @@ struct sjd_ctx {
   // activation tensor maps per m_tile (index m_tile/16), built lazily
   sjd::TmapSet maps[17];   // w[]: qkv, o, gate_up, down, lm_head ; x[]: xn, attn, act, xl (box rows = m_tile)
   bool xmap_ok[17] = {false};
+  // tensor-core attention (attention_tc.cu): K / V cache maps (box 128 keys), q maps per row-slot count Wp (index Wp/8)
+  sjd::AttnTcMaps tcmaps[17];
+  bool tcmap_ok[17] = {false};
+  bool attn_tc = false;
 };
 
 namespace sjd {
@@ -86,6 +91,19 @@ static int ensure_xmaps(sjd_ctx* c, int m_tile) {
   if (make_tmap_bf16_2d(&t.x[2], c->act, SJD_MAX_TOKENS, g.d_ff, m_tile)) return SJD_E_TMAP;
   if (make_tmap_bf16_2d(&t.x[3], c->xl, SJD_MAX_TOKENS, g.d_model, m_tile)) return SJD_E_TMAP;
   c->xmap_ok[idx] = true;
+  return 0;
+}
+
+static int ensure_tcmaps(sjd_ctx* c, int Wp) {
+  const int idx = Wp / 8;
+  if (c->tcmap_ok[idx]) return 0;
+  const sjd_model_cfg& g = c->cfg;
+  AttnTcMaps& t = c->tcmaps[idx];
+  const uint64_t cache_rows = uint64_t(g.n_layers) * g.rows * g.n_kv_heads * uint64_t(g.max_len);
+  if (make_tmap_bf16_2d(&t.k, c->kcache, cache_rows, g.head_dim, kTcKeys)) return SJD_E_TMAP;
+  if (make_tmap_bf16_2d(&t.v, c->vcache, cache_rows, g.head_dim, kTcKeys)) return SJD_E_TMAP;
+  if (make_tmap_bf16_2d(&t.q, c->q, SJD_MAX_TOKENS, uint64_t(g.n_heads) * g.head_dim, uint32_t(Wp))) return SJD_E_TMAP;
+  c->tcmap_ok[idx] = true;
   return 0;
 }
 
@@ -278,6 +296,11 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
   c->ws_bytes = wsb;
   rc |= dmalloc(c, &c->ws, wsb);
   c->max_chunks = (g.max_len + kAttnSub - 1) / kAttnSub;   // upper bound on key splits
+  {
+    const char* e = getenv("SJD_ATTN");   // "tc": tcgen05 attention (attention_tc.cu); "mma": mma.sync kernel (attention.cu)
+    c->attn_tc = e ? (strcmp(e, "tc") == 0) : false;
+    if (uint64_t(g.n_layers) * g.rows * g.n_kv_heads * uint64_t(g.max_len) >= (1ull << 31)) c->attn_tc = false;
+  }
   rc |= dmalloc(c, &c->part_o, size_t(c->max_chunks) * T * hd * sizeof(float));
   rc |= dmalloc(c, &c->part_ml, size_t(c->max_chunks) * T * g.n_heads * 2 * sizeof(float));
   rc |= dmalloc(c, &c->fin, (kMaxChainOps + 2) * kCtrStride * 4);
@@ -389,6 +412,15 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
   }
   const size_t layer_cache = size_t(g.rows) * g.n_kv_heads * size_t(g.max_len) * g.head_dim;
   const size_t kvd = size_t(g.n_kv_heads) * g.head_dim;
+  // tcgen05 attention when the window fits one UMMA M tile per head; the mma.sync kernel otherwise
+  const bool use_tc = !gemm_only && c->attn_tc && W <= kTcRows;
+  AttnTcParams tp;
+  memset(&tp, 0, sizeof(tp));
+  if (use_tc) {
+    tp.a = ap;
+    attn_tc_plan(&tp, g.head_dim);
+    if (tp.a.n_chunks > c->max_chunks || ensure_tcmaps(c, tp.Wp)) return SJD_E_TMAP;
+  }
   GemmEpi base;
   memset(&base, 0, sizeof(base));
   base.M = M;
@@ -418,8 +450,15 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
       // which separates the cost of the two kernel boundaries from the cost of the attention kernel itself
       static const int dbg_attn = getenv("SJD_DEBUG_ATTN") ? atoi(getenv("SJD_DEBUG_ATTN")) : 0;
       if (dbg_attn != 1) {
-        rc |= attn_launch(ap, g.head_dim, false, s);   // the split merge rides in the next chain kernel (pre-op)
-        cb.ch.pre = attn_combine_desc(ap, g.head_dim);
+        if (use_tc) {
+          tp.a.k = ap.k; tp.a.v = ap.v;
+          tp.k_row0 = int(size_t(l) * g.rows * g.n_kv_heads * size_t(g.max_len));
+          rc |= attn_tc_launch(c->tcmaps[tp.Wp / 8], tp, s);
+          cb.ch.pre = attn_combine_desc(tp.a, g.head_dim);
+        } else {
+          rc |= attn_launch(ap, g.head_dim, false, s);   // the split merge rides in the next chain kernel (pre-op)
+          cb.ch.pre = attn_combine_desc(ap, g.head_dim);
+        }
         g_launches += 1;
       }
     }
