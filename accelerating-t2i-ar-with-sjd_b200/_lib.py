@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
     L.sjd_last_error.restype = C.c_char_p
     L.sjd_device_sm_count.restype = C.c_int
     L.sjd_launch_count.restype = C.c_uint64
+    L.sjd_debug_attn_stamps.restype = None
+    L.sjd_debug_attn_stamps.argtypes = [C.c_void_p]
     L.sjd_debug_gemm_stamps.restype = None
     L.sjd_debug_gemm_stamps.argtypes = [C.c_void_p, C.c_int]
     L.sjd_gemm_workspace_bytes.restype = C.c_size_t

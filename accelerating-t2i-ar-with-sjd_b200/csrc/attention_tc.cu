@@ -26,7 +26,6 @@ namespace sjd {
 
 constexpr int kTcKeys = 128;       // keys per CTA (UMMA N of the first product, K of the second)
 constexpr int kTcRows = 128;       // query-row slots per CTA (UMMA M)
-constexpr int kTcThreads = 160;    // warps 0..3: softmax / epilogue (TMEM lane quarter = warp), warp 4: TMA + MMA issue
 
 struct AttnTcParams {
   AttnParams a;          // geometry, partial buffers, kv_len / kv_lo (n_chunks = key tiles, span = kTcKeys)
@@ -34,7 +33,16 @@ struct AttnTcParams {
   int Wp;                // row slots per head: W rounded up to 8 (swizzle atom) — the Q tensor map's box height
   int hpc;               // heads stacked per CTA
   int k_row0;            // first row of this layer in the [layers*rows*Hkv*Lmax, Dh] view of the caches
+  long long* dbg;        // developer timing: CTA 0 writes clock64 stamps [unit < 8][16] (sjd_debug_attn_stamps)
+  // exact division by multiplication for the small non-negative ints the unit decode needs: x / d == umulhi(x, m)
+  uint32_t m_chunks, m_ny, m_mtiles, m_wp;
+  int ny, mtiles;
 };
+
+__host__ __device__ __forceinline__ uint32_t tc_magic(uint32_t d) { return uint32_t((0x100000000ull + d - 1) / d); }
+__device__ __forceinline__ int tc_div(int x, uint32_t magic, int d) {   // exact for 0 <= x < 2^16, 1 <= d < 2^16
+  return d == 1 ? x : int(__umulhi(uint32_t(x), magic));
+}
 
 // UMMA descriptor of an MN-major bf16 operand laid out by TMA with SWIZZLE_128B: rows are K (keys), each row holds 64
 // consecutive MN elements (128 bytes); 8-row groups are 1024 B apart (stride byte offset), the next 64 MN elements are
@@ -53,12 +61,67 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_bmn(uint32_t M, uint3
   return umma_idesc_bf16_f32(M, N) | (1u << 16);
 }
 
+// 2^x for x <= 0 (softmax exponents): one MUFU op; results below the normal range flush to zero
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// mbarrier wait with back-off for the single-thread roles: a hot try_wait loop would steal issue slots from the
+// softmax warp that shares its scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
+
 struct AttnTcMaps {
   CUtensorMap q, k, v;
 };
 
+// Work unit u -> (key tile, kv head x row tile, CFG row); key tiles run fastest so neighbouring CTAs share Q in L2.
+struct TcUnit {
+  int kt, hkv, h0, heads_here, b, key0, lo;
+  bool hidden;
+  // softmax-thread view (TMEM lane r = 32 * warp + lane)
+  int R, Rr, rep, g, rr, hs, qi;
+};
+
+__device__ __forceinline__ TcUnit tc_unit(const AttnTcParams& p, int u, int r) {
+  const AttnParams& a = p.a;
+  TcUnit t;
+  const int G = a.H / a.Hkv;
+  const int q1 = tc_div(u, p.m_chunks, a.n_chunks);          // u / n_chunks
+  t.kt = u - q1 * a.n_chunks;
+  t.b = tc_div(q1, p.m_ny, p.ny);                            // (u / n_chunks) / ny
+  const int y = q1 - t.b * p.ny;
+  t.hkv = tc_div(y, p.m_mtiles, p.mtiles);
+  const int mt = y - t.hkv * p.mtiles;
+  t.h0 = t.hkv * G + mt * p.hpc;
+  t.heads_here = min(p.hpc, G - mt * p.hpc);
+  t.key0 = t.kt * kTcKeys;
+  t.lo = a.kv_lo[t.b];
+  t.hidden = t.key0 + kTcKeys <= t.lo;     // whole tile inside the hidden prefix: nothing to load
+  t.R = t.heads_here * p.Wp;               // row slots in use
+  t.Rr = (t.R + 31) & ~31;                 // replica pitch: whole warps (tcgen05.ld is warp-collective: uniform columns)
+  t.rep = t.Rr <= 32 ? 4 : (t.Rr <= 64 ? 2 : 1);
+  t.g = t.Rr == 32 ? (r >> 5) : (t.Rr == 64 ? (r >> 6) : (r >= t.Rr ? 1 : 0));
+  t.rr = r - t.g * t.Rr;
+  t.hs = tc_div(t.rr, p.m_wp, p.Wp);
+  t.qi = t.rr - t.hs * p.Wp;
+  return t;
+}
+
+// Persistent: one CTA per SM walks units u = cta, cta + grid, ... through a two-stage pipeline
+//   warp 4 (TMA)  : loads Q, K (one barrier) and V (another) of unit n+1 as soon as the stage's previous product is done
+//   warp 5 (MMA)  : S(n) as soon as Q, K landed; then O(n-1) = P(n-1) V(n-1) once the softmax warps delivered P(n-1)
+//   warps 0..3, 8..11 : two softmax groups; group k owns pipeline stage k, i.e. every other unit: softmax of S(n) into
+//                   P(n), then the epilogue of its previous unit n-2 (whose O has long been ready)
+// so the K/V stream of the next tile, the tensor work of this one and the softmax of two tiles overlap.  TMEM: stage s owns columns
+// [256 s, 256 s + 128) for S and [256 s + 128, 256 s + 128 + Dh) for O.
+constexpr int kTcThreads2 = 384;   // warps 0..3 and 8..11: the two softmax groups; 4: TMA; 5: MMA; 6, 7: idle
+
 template <int DH>
-__global__ void __launch_bounds__(kTcThreads, 2)
+__global__ void __launch_bounds__(kTcThreads2, 1)
 attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
   constexpr int NDA = DH / 64;                            // 64-wide head-dim atoms
   constexpr uint32_t kQBytes = NDA * kTcRows * 128;       // Q tile: NDA atoms of [128 rows][128 B]
@@ -66,222 +129,389 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
   constexpr uint32_t kPBytes = 2 * kTcRows * 128;         // P tile: two 64-key atoms of [128 rows][128 B]
   constexpr uint32_t kKPBytes = kKBytes > kPBytes ? kKBytes : kPBytes;
   constexpr uint32_t kVBytes = NDA * kTcKeys * 128;       // V tile: NDA boxes of [128 keys][128 B]
+  constexpr uint32_t kStage = kQBytes + kKPBytes + kVBytes;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[4];
+  // per stage: qk landed, v landed, S done, P ready, O done, O drained
+  __shared__ __align__(8) uint64_t bars[12];
   __shared__ uint32_t tmem_holder;
+  __shared__ float xch_all[2 * 4 * kTcRows];              // per softmax group: {row max, row sum} across column replicas, two units deep
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = base + kQBytes, sV = sK + kKPBytes;
-  uint8_t* const genP = smem_raw + (sK - smem_u32(smem_raw));
-  const uint32_t bar_load = smem_u32(&bars[0]), bar_s = smem_u32(&bars[1]), bar_p = smem_u32(&bars[2]),
-                 bar_o = smem_u32(&bars[3]);
   const AttnParams& a = p.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x, b = blockIdx.z;
+  auto bar = [&](int which, int s) { return smem_u32(&bars[which * 2 + s]); };
+  enum { B_QK = 0, B_V = 1, B_S = 2, B_P = 3, B_O = 4, B_E = 5 };
   const int G = a.H / a.Hkv;
-  const int mtiles = (G + p.hpc - 1) / p.hpc;
-  const int hkv = blockIdx.y / mtiles, mt = blockIdx.y - hkv * mtiles;
-  const int h0 = hkv * G + mt * p.hpc;                      // first query head of this CTA
-  const int heads_here = min(p.hpc, G - mt * p.hpc);
-  const int T = a.kv_len + a.W, lo = a.kv_lo[b];
-  const int key0 = kt * kTcKeys;
-  const bool hidden = key0 + kTcKeys <= lo;                 // whole tile inside the hidden prefix: nothing to load
+  const int n_units = a.n_chunks * a.Hkv * ((G + p.hpc - 1) / p.hpc) * a.rows;
+  const int T = a.kv_len + a.W;
 
   if (warp == 4) {
     if (lane == 0) {
       tma_prefetch_desc(&maps.q);
       tma_prefetch_desc(&maps.k);
       tma_prefetch_desc(&maps.v);
-      mbar_init(bar_load, 1);
-      mbar_init(bar_s, 1);
-      mbar_init(bar_p, 4);
-      mbar_init(bar_o, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(bar(B_QK, s), 1);
+        mbar_init(bar(B_V, s), 1);
+        mbar_init(bar(B_S, s), 1);
+        mbar_init(bar(B_P, s), 4);
+        mbar_init(bar(B_O, s), 1);
+        mbar_init(bar(B_E, s), 4);
+      }
       fence_barrier_init();
     }
-    if (!hidden) {
-      tmem_alloc(smem_u32(&tmem_holder), 256);
-      tmem_relinquish();
-    }
+  } else if (warp == 5) {
+    tmem_alloc(smem_u32(&tmem_holder), 512);
+    tmem_relinquish();
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  // Keys below kv_len were cached by earlier forwards: the producer may stream the K/V tiles of its first two units
+  // while the previous kernel is still finishing (everything else — q, the window's own K/V rows, the partial
+  // buffers — belongs to the previous kernels until griddepcontrol.wait returns).
+  int early = 0;   // units whose K/V were requested before the wait (producer warp only)
+  if (warp == 4) {
+    // Everything this CTA will stream goes to L2 now (fire and forget; L2 is the coherence point, so rows the previous
+    // kernel is still writing are simply written into the prefetched lines): HBM works through the whole K/V span
+    // from the first microsecond, the pipeline below then loads from L2 with a third of the latency.
+    {
+      int i = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const TcUnit t = tc_unit(p, u, 0);
+        if (t.hidden) continue;
+        const int krow = p.k_row0 + (t.b * a.Hkv + t.hkv) * a.Lmax + t.key0;
+        for (int x = 0; x < 2 * NDA; ++x, ++i)
+          if ((i & 31) == lane) tma_prefetch_l2_2d(x < NDA ? &maps.k : &maps.v, (x % NDA) * 64, krow);
+      }
+    }
+    int n = 0;
+    for (int u = blockIdx.x; u < n_units && n < 2; u += gridDim.x) {
+      const TcUnit t = tc_unit(p, u, 0);
+      if (t.hidden) continue;
+      if (t.key0 + kTcKeys > a.kv_len) break;     // touches this window's keys: not before the wait
+      const int s = n & 1;
+      const uint32_t sK = base + uint32_t(s) * kStage + kQBytes, sV = sK + kKPBytes;
+      const int nq = t.rep * t.heads_here * NDA;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar(B_QK, s), uint32_t(nq) * uint32_t(p.Wp) * 128u + kKBytes);
+        mbar_arrive_expect_tx(bar(B_V, s), kVBytes);
+      }
+      __syncwarp();
+      const int krow = p.k_row0 + (t.b * a.Hkv + t.hkv) * a.Lmax + t.key0;
+      if (lane < NDA) tma_load_2d(sK + uint32_t(lane) * kTcKeys * 128, &maps.k, lane * 64, krow, bar(B_QK, s), kPolicyEvictFirst);
+      else if (lane < 2 * NDA)
+        tma_load_2d(sV + uint32_t(lane - NDA) * kTcKeys * 128, &maps.v, (lane - NDA) * 64, krow, bar(B_V, s), kPolicyEvictFirst);
+      ++n;
+    }
+    early = n;
+  }
   // Wait first, THEN let the next kernel in: releasing the dependents before the wait lets the whole forward cascade
   // into residency (chain l+1 behind attention l+1 behind chain l ...), which was measured to deadlock.
-  pdl_wait();   // q, this window's K/V rows and the partial buffers belong to the previous kernels until here
+  pdl_wait();
   pdl_launch_dependents();
-
-  // softmax thread r = TMEM lane: (column replica g, head slot hs, window position qi)
-  const int R = heads_here * p.Wp;                          // row slots in use
-  const int Rr = (R + 31) & ~31;                            // replica pitch: whole warps, so a warp never straddles two
-  const int rep = Rr <= 32 ? 4 : (Rr <= 64 ? 2 : 1);        //   replicas (tcgen05.ld is warp-collective: uniform columns)
-  const int r = warp * 32 + lane;
-  const int g = r / Rr, rr = r - g * Rr;
-  const int hs = rr / p.Wp, qi = rr - hs * p.Wp;
-  const bool row_ok = warp < 4 && rr < R && qi < a.W;       // this thread works on a real query row
-  const bool valid = row_ok && g == 0;                      // ... and owns its output
-  const size_t prow = valid ? ((size_t(kt) * a.rows + b) * a.H + (h0 + hs)) * size_t(a.W) + qi : 0;
-  const int ncol = kTcKeys / rep, col0 = g * ncol;          // this thread's slice of the row's 128 keys
-  __shared__ float xch[kTcRows];                            // row max, then row sum, across replicas
-
-  if (hidden) {   // uniform per CTA
-    if (valid) {
-      a.part_ml[prow * 2] = -INFINITY;
-      a.part_ml[prow * 2 + 1] = 0.f;
-    }
-    return;
-  }
-  const uint32_t tmem_base = tmem_holder;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[15] = clock64();   // start of work
 
   if (warp == 4) {
+    // ===== TMA producer: lane 0 arms the barriers, then every lane issues its share of the unit's box loads (a TMA
+    // issue costs a thread ~100 ns: K, V and the replicated Q boxes of a unit are up to a dozen) =====
+    int n = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const TcUnit t = tc_unit(p, u, 0);
+      if (t.hidden) continue;
+      const int s = n & 1, j = n >> 1;
+      const uint32_t sQ = base + uint32_t(s) * kStage, sK = sQ + kQBytes, sV = sK + kKPBytes;
+      const int nq = t.rep * t.heads_here * NDA;               // Q boxes
+      const bool kv_done = n < early;                        // K/V of this unit are in flight already
+      if (lane == 0 && !kv_done) {
+        if (j >= 1) mbar_wait_backoff(bar(B_O, s), uint32_t(j - 1) & 1u);   // the stage's previous P V has read its smem
+        mbar_arrive_expect_tx(bar(B_QK, s), uint32_t(nq) * uint32_t(p.Wp) * 128u + kKBytes);
+        mbar_arrive_expect_tx(bar(B_V, s), kVBytes);
+      }
+      __syncwarp();
+      const int krow = p.k_row0 + (t.b * a.Hkv + t.hkv) * a.Lmax + t.key0;
+      for (int l = lane; l < 2 * NDA + nq; l += 32) {
+        if (kv_done && (l < NDA || l >= NDA + nq)) continue;
+        if (l < NDA) {
+          tma_load_2d(sK + uint32_t(l) * kTcKeys * 128, &maps.k, l * 64, krow, bar(B_QK, s), kPolicyEvictFirst);
+        } else if (l < NDA + nq) {
+          const int x = l - NDA, d = x % NDA, gh = x / NDA;       // NDA is 1 or 2
+          const int gq = gh / t.heads_here, hs = gh - gq * t.heads_here;
+          tma_load_2d(sQ + uint32_t(d) * kTcRows * 128 + uint32_t(gq * t.Rr + hs * p.Wp) * 128, &maps.q,
+                      (t.h0 + hs) * DH + d * 64, t.b * a.W, bar(B_QK, s), kPolicyEvictLast);
+        } else {
+          const int d = l - NDA - nq;
+          tma_load_2d(sV + uint32_t(d) * kTcKeys * 128, &maps.v, d * 64, krow, bar(B_V, s), kPolicyEvictFirst);
+        }
+      }
+      if (p.dbg && blockIdx.x == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 0] = clock64();
+      ++n;
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
     if (lane == 0) {
-      // ---- loads ----
-      const uint32_t bytes = uint32_t(rep * heads_here) * NDA * uint32_t(p.Wp) * 128u + kKBytes + kVBytes;
-      mbar_arrive_expect_tx(bar_load, bytes);
-      const int krow = p.k_row0 + (b * a.Hkv + hkv) * a.Lmax + key0;
-#pragma unroll
-      for (int d = 0; d < NDA; ++d) {
-        tma_load_2d(sK + uint32_t(d) * kTcKeys * 128, &maps.k, d * 64, krow, bar_load, kPolicyEvictFirst);
-        tma_load_2d(sV + uint32_t(d) * kTcKeys * 128, &maps.v, d * 64, krow, bar_load, kPolicyEvictFirst);
-      }
-      for (int gq = 0; gq < rep; ++gq)
-        for (int s = 0; s < heads_here; ++s)
-#pragma unroll
-          for (int d = 0; d < NDA; ++d)
-            tma_load_2d(sQ + uint32_t(d) * kTcRows * 128 + uint32_t(gq * Rr + s * p.Wp) * 128, &maps.q,
-                        (h0 + s) * DH + d * 64, b * a.W, bar_load, kPolicyEvictLast);
-      mbar_wait(bar_load, 0);
-      tcgen05_fence_after();
-      // ---- S = Q K^T ----
       const uint32_t idesc_s = umma_idesc_bf16_f32(kTcRows, kTcKeys);
-      uint32_t acc = 0;
-#pragma unroll
-      for (int d = 0; d < NDA; ++d) {
-        const uint64_t da = umma_desc_sw128_kmajor(sQ + uint32_t(d) * kTcRows * 128);
-        const uint64_t db = umma_desc_sw128_kmajor(sK + uint32_t(d) * kTcKeys * 128);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_bf16_ss(tS, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc_s, acc);
-          acc = 1;
-        }
-      }
-      umma_commit(bar_s);
-      // ---- O = P V (P arrives in the smem the K tile occupied) ----
-      mbar_wait(bar_p, 0);
-      tcgen05_fence_after();
       const uint32_t idesc_o = umma_idesc_bf16_f32_bmn(kTcRows, DH);
-      acc = 0;
+      auto issue_pv = [&](int m) {   // O(m) = P(m) V(m)
+        const int s = m & 1, j = m >> 1;
+        const uint32_t sK = base + uint32_t(s) * kStage + kQBytes, sV = sK + kKPBytes;
+        mbar_wait_backoff(bar(B_V, s), uint32_t(j) & 1u);
+        mbar_wait_backoff(bar(B_P, s), uint32_t(j) & 1u);
+        if (j >= 1) mbar_wait_backoff(bar(B_E, s), uint32_t(j - 1) & 1u);   // the previous O of this stage has been drained
+        tcgen05_fence_after();
+        if (p.dbg && blockIdx.x == 0 && m < 8) p.dbg[m * 16 + 3] = clock64();
+        const uint32_t tO = tmem_base + uint32_t(s) * 256 + 128;
+        uint32_t acc = 0;
 #pragma unroll
-      for (int ka = 0; ka < 2; ++ka) {
-        const uint64_t da = umma_desc_sw128_kmajor(sK + uint32_t(ka) * kTcRows * 128);
+        for (int ka = 0; ka < 2; ++ka) {
+          const uint64_t da = umma_desc_sw128_kmajor(sK + uint32_t(ka) * kTcRows * 128);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t db = umma_desc_sw128_mnmajor(sV + uint32_t(ka * 64 + k * 16) * 128, kTcKeys * 128);
-          umma_bf16_ss(tO, da + uint64_t(2 * k), db, idesc_o, acc);
-          acc = 1;
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t db = umma_desc_sw128_mnmajor(sV + uint32_t(ka * 64 + k * 16) * 128, kTcKeys * 128);
+            umma_bf16_ss(tO, da + uint64_t(2 * k), db, idesc_o, acc);
+            acc = 1;
+          }
         }
+        umma_commit(bar(B_O, s));
+        if (p.dbg && blockIdx.x == 0 && m < 8) p.dbg[m * 16 + 4] = clock64();
+      };
+      auto issue_s = [&](int m) {    // S(m) = Q(m) K(m)^T
+        const int s = m & 1;
+        const uint32_t sQ = base + uint32_t(s) * kStage, sK = sQ + kQBytes;
+        tcgen05_fence_after();
+        const uint32_t tS = tmem_base + uint32_t(s) * 256;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int d = 0; d < NDA; ++d) {
+          const uint64_t da = umma_desc_sw128_kmajor(sQ + uint32_t(d) * kTcRows * 128);
+          const uint64_t db = umma_desc_sw128_kmajor(sK + uint32_t(d) * kTcKeys * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16_ss(tS, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc_s, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(bar(B_S, s));
+        if (p.dbg && blockIdx.x == 0 && m < 8) p.dbg[m * 16 + 2] = clock64();
+      };
+      int N = 0;   // units this CTA really runs
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) N += tc_unit(p, u, 0).hidden ? 0 : 1;
+      // Issue whichever product has its inputs first: S(ns) needs Q, K of unit ns (and the S accumulator of its stage,
+      // free once O(ns - 2) has been issued: that waited for P(ns - 2), i.e. for the last read of S); O(np) needs V and P
+      // of unit np and the drained O accumulator.  In-order issue would park a ready O behind the next tile's loads.
+      int ns = 0, np = 0;
+      while (np < N) {
+        bool did = false;
+        if (np < ns) {
+          const int s = np & 1, j = np >> 1;
+          if (mbar_try_wait(bar(B_P, s), uint32_t(j) & 1u) && mbar_try_wait(bar(B_V, s), uint32_t(j) & 1u) &&
+              (j < 1 || mbar_try_wait(bar(B_E, s), uint32_t(j - 1) & 1u))) {
+            issue_pv(np);
+            ++np;
+            did = true;
+          }
+        }
+        if (ns < N && ns - np < 2) {
+          const int s = ns & 1, j = ns >> 1;
+          if (mbar_try_wait(bar(B_QK, s), uint32_t(j) & 1u)) {
+            if (p.dbg && blockIdx.x == 0 && ns < 8) p.dbg[ns * 16 + 1] = clock64();
+            issue_s(ns);
+            ++ns;
+            did = true;
+          }
+        }
+        if (!did) __nanosleep(20);
       }
-      umma_commit(bar_o);
     }
-  } else {
-    // ---- softmax: one thread per query row, straight from the TMEM accumulator ----
-    mbar_wait(bar_s, 0);
-    tcgen05_fence_after();
-    const uint32_t t_row = (uint32_t(warp * 32) << 16);
-    // keys every query of this CTA sees: no per-element mask arithmetic for them
-    const bool interior = (key0 >= lo) && (key0 + kTcKeys - 1 <= a.kv_len) && (key0 + kTcKeys <= T);
-    const int j_hi = min(a.kv_len + qi, T - 1);   // last visible key of this row
-    float mx = -INFINITY;
-    if (g < rep) {
+  } else if (warp < 4 || warp >= 8) {
+    // ===== softmax + epilogue: one thread per query-row slot, straight from the TMEM accumulators.  Group `grp` takes
+    // the units that run through pipeline stage `grp` =====
+    const int grp = warp >> 3, qw = warp & 3;      // TMEM lane quarter = warp % 4
+    const int r = qw * 32 + lane;
+    const uint32_t t_row = (uint32_t(qw * 32) << 16);
+    float* const xch = xch_all + grp * 4 * kTcRows;
+    // state of the unit whose epilogue is still owed
+    bool e_row_ok = false, e_first = false;
+    size_t e_prow = 0;
+    float e_mx = 0.f, e_l = 0.f;
+    int e_c0 = 0, e_nc = 0, e_slot0 = 0, e_R = 0, e_h0 = 0;
+    size_t e_base = 0;
+    // per-warp transpose tile [32 rows][36 floats] behind the pipeline stages: TMEM hands a thread one ROW, global
+    // memory wants a warp to write whole 128-byte lines
+    float* const tile = reinterpret_cast<float*>(smem_raw + (base + 2 * kStage - smem_u32(smem_raw))) + (grp * 4 + qw) * (32 * 20);
+    // O(m): every replica row holds the full product (P is written into all of them), so replica g drains columns
+    // [g * Dh / rep, (g + 1) * Dh / rep) of its row: all four warps share the stores
+    auto epilogue = [&](int m) {
+      const int s = m & 1, j = m >> 1;
+      mbar_wait(bar(B_O, s), uint32_t(j) & 1u);
+      tcgen05_fence_after();
+      if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && m < 8) p.dbg[m * 16 + 8] = clock64();
+      const uint32_t tO = tmem_base + uint32_t(s) * 256 + 128;
 #pragma unroll 1
-      for (int c = col0; c < col0 + ncol; c += 16) {
+      for (int c = e_c0; c < e_c0 + e_nc; c += 16) {   // e_nc is a multiple of 16; warp-uniform
         uint32_t v[16];
-        tmem_ld_32x32b_x16(tS + t_row + uint32_t(c), v);
+        tmem_ld_32x32b_x16(tO + t_row + uint32_t(c), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int j = key0 + c + e;
-          const bool ok = interior || (j >= lo && j <= j_hi);
-          if (ok) mx = fmaxf(mx, __uint_as_float(v[e]));
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(tile + lane * 20 + 4 * q) =
+              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                          __uint_as_float(v[4 * q + 3]));
+        __syncwarp();
+        // lane -> (row of the tile, float4 of the row): 8 rows of 64 bytes per pass
+        const int q = lane & 3;
+#pragma unroll
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+          const int rw = r0 + (lane >> 2);
+          const int slot = e_slot0 + rw;                // row slot inside the replica
+          const int hs2 = tc_div(slot, p.m_wp, p.Wp), qi2 = slot - hs2 * p.Wp;
+          if (slot < e_R && qi2 < a.W) {
+            const float4 x = *reinterpret_cast<const float4*>(tile + rw * 20 + 4 * q);
+            *reinterpret_cast<float4*>(a.part_o + (e_base + size_t(e_h0 + hs2) * a.W + qi2) * DH + c + 4 * q) = x;
+          }
         }
+        __syncwarp();
       }
-    }
-    if (rep > 1) {   // uniform per CTA: the row max is spread over the replicas
-      xch[r] = mx;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (e_row_ok && e_first) {
+        a.part_ml[e_prow * 2] = e_mx;
+        a.part_ml[e_prow * 2 + 1] = e_l;
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_E, s));
+      if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && m < 8) p.dbg[m * 16 + 9] = clock64();
+    };
+    int n = 0, owed = -1;   // owed: this group's unit whose epilogue has not run yet
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const TcUnit t = tc_unit(p, u, r);
+      const bool row_ok = t.rr < t.R && t.qi < a.W && t.g < t.rep;   // this thread works on a real query row
+      const bool first = t.g == 0;                                   // replica 0 also owns {max, sum}
+      const size_t prow = row_ok ? ((size_t(t.kt) * a.rows + t.b) * a.H + (t.h0 + t.hs)) * size_t(a.W) + t.qi : 0;
+      if (t.hidden) {   // uniform per CTA
+        if (grp == 0 && row_ok && first) {
+          a.part_ml[prow * 2] = -INFINITY;
+          a.part_ml[prow * 2 + 1] = 0.f;
+        }
+        continue;
+      }
+      if ((n & 1) != grp) {   // the other group's unit
+        ++n;
+        continue;
+      }
+      const int s = n & 1, j = n >> 1;
+      const int lo = t.lo, key0 = t.key0, rep = t.rep, g = t.g, rr = t.rr;
+      const int ncol = kTcKeys / rep, col0 = g * ncol;       // this thread's slice of the row's 128 keys (32 | 64 | 128)
+      uint8_t* const genP = smem_raw + (base + uint32_t(s) * kStage + kQBytes - smem_u32(smem_raw));
+      const uint32_t tS = tmem_base + uint32_t(s) * 256;
+      float* const xmax = xch + (j & 1) * 2 * kTcRows;        // exchange buffers alternate between units: no barrier
+      float* const xsum = xmax + kTcRows;                     //   is needed to protect their reuse
+      // the group's previous unit first: its O has long been ready, and draining it now lets O(n) be issued the
+      // moment P(n) is delivered
+      if (owed >= 0) epilogue(owed);
+      mbar_wait(bar(B_S, s), uint32_t(j) & 1u);
+      tcgen05_fence_after();
+      if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 5] = clock64();
+      const int j_hi = min(a.kv_len + t.qi, T - 1);           // last visible key of this row
+      const float sc = a.scale_log2e;
+      // ---- pass 1: row max over this thread's columns (four independent chains) ----
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       if (g < rep) {
-        for (int g2 = 0; g2 < rep; ++g2) mx = fmaxf(mx, xch[g2 * Rr + rr]);
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    mx *= a.scale_log2e;                                    // scale > 0: max commutes with it
-    const float ms = (mx == -INFINITY) ? 0.f : mx;
-    float lsum = 0.f;
-    if (g < rep) {
 #pragma unroll 1
-      for (int c = col0; c < col0 + ncol; c += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tS + t_row + uint32_t(c), v);
-        tmem_ld_wait();
-        uint32_t pk[8];
+        for (int c = col0; c < col0 + ncol; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          tmem_ld_wait();
+          const int jk0 = key0 + c;
+          if (jk0 >= lo && jk0 + 31 <= j_hi) {                // every key of the chunk is visible to this row
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          const int j = key0 + c + e;
-          const bool ok0 = interior || (j >= lo && j <= j_hi), ok1 = interior || (j + 1 >= lo && j + 1 <= j_hi);
-          const float e0 = ok0 ? exp2f(__uint_as_float(v[e]) * a.scale_log2e - ms) : 0.f;
-          const float e1 = ok1 ? exp2f(__uint_as_float(v[e + 1]) * a.scale_log2e - ms) : 0.f;
-          const __nv_bfloat162 pb = __floats2bfloat162_rn(e0, e1);   // probabilities enter P*V as bf16
-          lsum += __low2float(pb) + __high2float(pb);
-          pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
-        }
-        if (row_ok) {
-          // row rr (replica 0's) of the K-major P tile: 64-key atom c / 64, 16-byte chunks (c % 64) / 8 and the next
-          // one, 128B-swizzled
-          uint8_t* rowp = genP + (c >> 6) * (kTcRows * 128) + rr * 128;
-          const int ch = (c & 63) >> 3;
-          *reinterpret_cast<uint4*>(rowp + (((ch) ^ (rr & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (rr & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            for (int e = 0; e < 32; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[e]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const bool ok = (jk0 + e >= lo) && (jk0 + e <= j_hi);
+              m4[e & 3] = fmaxf(m4[e & 3], ok ? __uint_as_float(v[e]) : -INFINITY);
+            }
+          }
         }
       }
-    }
-    if (rep > 1) {
-      xch[r] = lsum;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (g == 0) {
-        lsum = 0.f;
-        for (int g2 = 0; g2 < rep; ++g2) lsum += xch[g2 * Rr + rr];   // fixed order
+      float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      if (rep > 1) {   // uniform per CTA: the row max is spread over the replicas
+        xmax[r] = mx;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (g < rep) {
+          for (int g2 = 0; g2 < rep; ++g2) mx = fmaxf(mx, xmax[g2 * t.Rr + rr]);
+        }
       }
-    }
-    tcgen05_fence_before();
-    fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_p);
-    // ---- epilogue: unnormalised O row + {max, sum} as this split's partial ----
-    mbar_wait(bar_o, 0);
-    tcgen05_fence_after();
-    float* po = a.part_o + prow * DH;
+      mx *= sc;                                               // scale > 0: max commutes with it
+      if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 6] = clock64();
+      const float ms = (mx == -INFINITY) ? 0.f : mx;
+      // ---- pass 2: probabilities (bf16, like the reference's bf16 SDPA) into every replica's row of the P tile ----
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (g < rep) {
 #pragma unroll 1
-    for (int c = 0; c < DH; c += 16) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(tO + t_row + uint32_t(c), v);
-      tmem_ld_wait();
-      if (valid) {
+        for (int c = col0; c < col0 + ncol; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          tmem_ld_wait();
+          const int jk0 = key0 + c;
+          const bool all_ok = jk0 >= lo && jk0 + 31 <= j_hi;
+          uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 16; e += 4)
-          *reinterpret_cast<float4*>(po + c + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                                               __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          for (int e = 0; e < 32; e += 2) {
+            float e0 = ex2_approx(fmaf(__uint_as_float(v[e]), sc, -ms));
+            float e1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), sc, -ms));
+            if (!all_ok) {
+              if (!((jk0 + e >= lo) && (jk0 + e <= j_hi))) e0 = 0.f;
+              if (!((jk0 + e + 1 >= lo) && (jk0 + e + 1 <= j_hi))) e1 = 0.f;
+            }
+            const __nv_bfloat162 pb = __floats2bfloat162_rn(e0, e1);
+            l4[(e >> 1) & 3] += __low2float(pb) + __high2float(pb);
+            pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+          }
+          if (row_ok) {
+            // K-major P tile: 64-key atom c / 64, four 16-byte chunks from (c % 64) / 8, 128B-swizzled by the row
+            const int ch = (c & 63) >> 3;
+            for (int g2 = 0; g2 < rep; ++g2) {
+              const int prw = g2 * t.Rr + rr;
+              uint8_t* rowp = genP + (c >> 6) * (kTcRows * 128) + prw * 128;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(rowp + (((ch + q) ^ (prw & 7)) << 4)) =
+                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+          }
+        }
       }
+      float lsum = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      tcgen05_fence_before();
+      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_P, s));
+      if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 7] = clock64();
+      if (rep > 1) {
+        xsum[r] = lsum;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (g == 0) {
+          lsum = 0.f;
+          for (int g2 = 0; g2 < rep; ++g2) lsum += xsum[g2 * t.Rr + rr];   // fixed order
+        }
+      }
+      owed = n;
+      e_row_ok = row_ok; e_first = first; e_prow = prow; e_mx = mx; e_l = lsum;
+      e_nc = g < rep ? DH / rep : 0; e_c0 = g * e_nc;   // (a warp beyond the last replica drains nothing)
+      e_slot0 = qw * 32 - g * t.Rr; e_R = t.R; e_h0 = t.h0;
+      e_base = (size_t(t.kt) * a.rows + t.b) * a.H * size_t(a.W);
+      ++n;
     }
-    if (valid) {
-      a.part_ml[prow * 2] = mx;
-      a.part_ml[prow * 2 + 1] = lsum;
-    }
-    tcgen05_fence_before();
+    if (owed >= 0) epilogue(owed);
   }
+  tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 5) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -297,17 +527,25 @@ void attn_tc_plan(AttnTcParams* p, int head_dim) {
   p->hpc = hpc;
   a.span = kTcKeys;
   a.n_chunks = (T + kTcKeys - 1) / kTcKeys;
+  p->mtiles = (G + hpc - 1) / hpc;
+  p->ny = a.Hkv * p->mtiles;
+  p->m_chunks = tc_magic(uint32_t(a.n_chunks));
+  p->m_ny = tc_magic(uint32_t(p->ny));
+  p->m_mtiles = tc_magic(uint32_t(p->mtiles));
+  p->m_wp = tc_magic(uint32_t(p->Wp));
 }
 
-constexpr int attn_tc_smem(int head_dim) {
-  return 1024 + (head_dim / 64) * kTcRows * 128 + 2 * kTcRows * 128 + (head_dim / 64) * kTcKeys * 128;
+constexpr int attn_tc_smem(int head_dim) {   // two pipeline stages of {Q, K | P, V} + eight 32 x 20 fp32 transpose tiles
+  return 1024 + 2 * ((head_dim / 64) * kTcRows * 128 + 2 * kTcRows * 128 + (head_dim / 64) * kTcKeys * 128) + 8 * 32 * 20 * 4;
 }
 
 int attn_tc_launch(const AttnTcMaps& maps, const AttnTcParams& p, cudaStream_t stream) {
   const AttnParams& a = p.a;
   if (a.W > kTcRows || (p.head_dim != 64 && p.head_dim != 128)) return -3;
   const int G = a.H / a.Hkv, mtiles = (G + p.hpc - 1) / p.hpc;
-  dim3 grid(a.n_chunks, a.Hkv * mtiles, a.rows);
+  const int n_units = a.n_chunks * a.Hkv * mtiles * a.rows;
+  const int sms = device_num_sms();
+  dim3 grid(n_units < sms ? n_units : sms);
   static bool set = false;
   if (!set) {
     if (cudaFuncSetAttribute(attn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_tc_smem(128)) != cudaSuccess ||
@@ -315,8 +553,8 @@ int attn_tc_launch(const AttnTcMaps& maps, const AttnTcParams& p, cudaStream_t s
       return -5;
     set = true;
   }
-  if (p.head_dim == 128) return launch_pdl(attn_tc_kernel<128>, grid, dim3(kTcThreads), attn_tc_smem(128), stream, maps, p);
-  return launch_pdl(attn_tc_kernel<64>, grid, dim3(kTcThreads), attn_tc_smem(64), stream, maps, p);
+  if (p.head_dim == 128) return launch_pdl(attn_tc_kernel<128>, grid, dim3(kTcThreads2), attn_tc_smem(128), stream, maps, p);
+  return launch_pdl(attn_tc_kernel<64>, grid, dim3(kTcThreads2), attn_tc_smem(64), stream, maps, p);
 }
 
 }  // namespace sjd

@@ -63,7 +63,8 @@ struct sjd_ctx {
   // tensor-core attention (attention_tc.cu): K / V cache maps (box 128 keys), q maps per row-slot count Wp (index Wp/8)
   sjd::AttnTcMaps tcmaps[17];
   bool tcmap_ok[17] = {false};
-  bool attn_tc = false;
+  int attn_mode = 0;   // 0: pick per window (see forward_chain), 1: always tcgen05 (SJD_ATTN=tc), 2: always mma.sync (SJD_ATTN=mma)
+  bool attn_tc_ok = true;
 };
 
 namespace sjd {
@@ -173,6 +174,9 @@ int sjd_version(void) { return 200; }
 const char* sjd_last_error(void) { return g_err; }
 int sjd_device_sm_count(void) { return device_num_sms(); }
 uint64_t sjd_launch_count(void) { return g_launches.load(); }
+
+static long long* g_attn_dbg = nullptr;
+void sjd_debug_attn_stamps(void* device_buf) { g_attn_dbg = static_cast<long long*>(device_buf); }
 
 void sjd_debug_gemm_stamps(void* device_buf, int n_launches) {
   g_dbg_buf = static_cast<long long*>(device_buf);
@@ -298,8 +302,8 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
   c->max_chunks = (g.max_len + kAttnSub - 1) / kAttnSub;   // upper bound on key splits
   {
     const char* e = getenv("SJD_ATTN");   // "tc": tcgen05 attention (attention_tc.cu); "mma": mma.sync kernel (attention.cu)
-    c->attn_tc = e ? (strcmp(e, "tc") == 0) : false;
-    if (uint64_t(g.n_layers) * g.rows * g.n_kv_heads * uint64_t(g.max_len) >= (1ull << 31)) c->attn_tc = false;
+    c->attn_mode = !e ? 0 : (strcmp(e, "tc") == 0 ? 1 : (strcmp(e, "mma") == 0 ? 2 : 0));
+    if (uint64_t(g.n_layers) * g.rows * g.n_kv_heads * uint64_t(g.max_len) >= (1ull << 31)) c->attn_tc_ok = false;
   }
   rc |= dmalloc(c, &c->part_o, size_t(c->max_chunks) * T * hd * sizeof(float));
   rc |= dmalloc(c, &c->part_ml, size_t(c->max_chunks) * T * g.n_heads * 2 * sizeof(float));
@@ -412,8 +416,14 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
   }
   const size_t layer_cache = size_t(g.rows) * g.n_kv_heads * size_t(g.max_len) * g.head_dim;
   const size_t kvd = size_t(g.n_kv_heads) * g.head_dim;
-  // tcgen05 attention when the window fits one UMMA M tile per head; the mma.sync kernel otherwise
-  const bool use_tc = !gemm_only && c->attn_tc && W <= kTcRows;
+  // Two attention kernels.  The tcgen05 one wins when the query rows that share a kv head fill
+  // between half and all of one 128-row UMMA tile (measured: Lumina W=64, Emu3 W=32, profiles/r01g_config_sweep*); with
+  // fewer rows its softmax threads idle or duplicate work, with more the K/V tile is streamed once per row tile.
+  bool use_tc = false;
+  if (!gemm_only && c->attn_tc_ok && W <= kTcRows) {
+    const int rows_per_kv = (g.n_heads / g.n_kv_heads) * ((W + 7) & ~7);
+    use_tc = c->attn_mode == 1 || (c->attn_mode == 0 && rows_per_kv >= 64 && rows_per_kv <= kTcRows);
+  }
   AttnTcParams tp;
   memset(&tp, 0, sizeof(tp));
   if (use_tc) {
@@ -453,6 +463,7 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
         if (use_tc) {
           tp.a.k = ap.k; tp.a.v = ap.v;
           tp.k_row0 = int(size_t(l) * g.rows * g.n_kv_heads * size_t(g.max_len));
+          tp.dbg = g_attn_dbg;
           rc |= attn_tc_launch(c->tcmaps[tp.Wp / 8], tp, s);
           cb.ch.pre = attn_combine_desc(tp.a, g.head_dim);
         } else {

@@ -157,6 +157,9 @@ int sjd_ctx_gemm_only(sjd_ctx* ctx, int W, void* stream);
 /* Developer timing: when device_buf != NULL every following GEMM launch i writes clock64 stamps of its epilogue
  * stages to device_buf[(i % n_launches)][cta < 256][16] (int64).  NULL switches it off. */
 void sjd_debug_gemm_stamps(void* device_buf, int n_launches);
+/* Developer timing of the tensor-core attention: CTA 0 of every following launch writes clock64 stamps of its pipeline
+ * stages to device_buf[unit < 8][16] (int64; the last launch wins).  NULL switches it off. */
+void sjd_debug_attn_stamps(void* device_buf);
 /* counts kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t sjd_launch_count(void);
 
