@@ -26,6 +26,7 @@ struct AttnParams {
   int kv_lo[kAttnMaxRows];  // first visible key per row
   int n_chunks;             // key splits (one partial each)
   int span;                 // keys per split (multiple of kAttnSub)
+  int l2_prefetch;          // 1: every CTA sends its K/V span to L2 before the dependency wait
   float scale_log2e;        // softmax scale * log2(e)
 };
 
@@ -71,12 +72,25 @@ __global__ void __launch_bounds__(NTHREADS, MINB) attn_window_kernel(AttnParams 
   constexpr int ROWB = DH * 2 + 16;  // padded smem row (bytes): conflict-free ldmatrix
   constexpr int STAGE = kAttnSub * ROWB;
   extern __shared__ __align__(16) uint8_t smem[];
-  pdl_wait();
-  pdl_launch_dependents();
   uint8_t* sKb = smem;               // [2][kAttnSub][ROWB]
   uint8_t* sVb = smem + 2 * STAGE;   // [2][kAttnSub][ROWB]
 
   const int split = blockIdx.x, hkv = blockIdx.y % p.Hkv, tgroup = blockIdx.y / p.Hkv, b = blockIdx.z;
+  if (p.l2_prefetch && threadIdx.x == 0) {
+    // This CTA's key span is one contiguous piece of the K and of the V cache: send both to L2 while the previous
+    // kernel is still finishing (L2 is the coherence point, so rows that kernel is still writing are simply written
+    // into the prefetched lines); the cp.async stream below then pays L2 latency instead of HBM latency.
+    const int kb = max(split * p.span, (p.kv_lo[b] / kAttnSub) * kAttnSub);
+    const int ke = min(p.kv_len + p.W, split * p.span + p.span);
+    if (ke > kb) {
+      const size_t off = ((size_t(b) * p.Hkv + hkv) * size_t(p.Lmax) + kb) * DH;
+      const uint32_t bytes = uint32_t(ke - kb) * DH * 2;   // multiple of 16
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.k + off), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.v + off), "r"(bytes) : "memory");
+    }
+  }
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tiles_here = blockDim.x >> 6;
   const int T = p.kv_len + p.W;
   const int G = p.H / p.Hkv;

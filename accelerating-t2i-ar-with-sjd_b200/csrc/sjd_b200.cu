@@ -13,6 +13,7 @@
 #include "block_ops.cu"
 #include "gemm_fused.cu"
 #include "attention_tc.cu"
+#include "attention_tct.cu"
 #include "verify.cu"
 
 namespace sjd {
@@ -63,7 +64,8 @@ struct sjd_ctx {
   // tensor-core attention (attention_tc.cu): K / V cache maps (box 128 keys), q maps per row-slot count Wp (index Wp/8)
   sjd::AttnTcMaps tcmaps[17];
   bool tcmap_ok[17] = {false};
-  int attn_mode = 0;   // 0: pick per window (see forward_chain), 1: always tcgen05 (SJD_ATTN=tc), 2: always mma.sync (SJD_ATTN=mma)
+  int attn_mode = 0;   // 0: pick per window (see forward_chain); SJD_ATTN = tc -> 1, mma -> 2, tct -> 3 force one kernel
+  bool tct_auto = false;   // whether mode 0 may pick the transposed small-window kernel
   bool attn_tc_ok = true;
 };
 
@@ -302,7 +304,7 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
   c->max_chunks = (g.max_len + kAttnSub - 1) / kAttnSub;   // upper bound on key splits
   {
     const char* e = getenv("SJD_ATTN");   // "tc": tcgen05 attention (attention_tc.cu); "mma": mma.sync kernel (attention.cu)
-    c->attn_mode = !e ? 0 : (strcmp(e, "tc") == 0 ? 1 : (strcmp(e, "mma") == 0 ? 2 : 0));
+    c->attn_mode = !e ? 0 : (strcmp(e, "tc") == 0 ? 1 : (strcmp(e, "mma") == 0 ? 2 : (strcmp(e, "tct") == 0 ? 3 : 0)));
     if (uint64_t(g.n_layers) * g.rows * g.n_kv_heads * uint64_t(g.max_len) >= (1ull << 31)) c->attn_tc_ok = false;
   }
   rc |= dmalloc(c, &c->part_o, size_t(c->max_chunks) * T * hd * sizeof(float));
@@ -412,6 +414,8 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
     ap.rows = g.rows; ap.W = W; ap.H = g.n_heads; ap.Hkv = g.n_kv_heads; ap.Lmax = g.max_len; ap.kv_len = a->kv_len;
     for (int b = 0; b < kAttnMaxRows; ++b) ap.kv_lo[b] = b < g.rows ? a->kv_lo[b] : 0;
     attn_plan(&ap, device_num_sms());
+    static const int l2pf = getenv("SJD_ATTN_L2PF") ? atoi(getenv("SJD_ATTN_L2PF")) : 1;
+    ap.l2_prefetch = l2pf;
     ap.scale_log2e = 1.4426950408889634f / sqrtf(float(g.head_dim));
   }
   const size_t layer_cache = size_t(g.rows) * g.n_kv_heads * size_t(g.max_len) * g.head_dim;
@@ -419,16 +423,19 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
   // Two attention kernels.  The tcgen05 one wins when the query rows that share a kv head fill
   // between half and all of one 128-row UMMA tile (measured: Lumina W=64, Emu3 W=32, profiles/r01g_config_sweep*); with
   // fewer rows its softmax threads idle or duplicate work, with more the K/V tile is streamed once per row tile.
-  bool use_tc = false;
+  bool use_tc = false, use_tct = false;
   if (!gemm_only && c->attn_tc_ok && W <= kTcRows) {
     const int rows_per_kv = (g.n_heads / g.n_kv_heads) * ((W + 7) & ~7);
-    use_tc = c->attn_mode == 1 || (c->attn_mode == 0 && rows_per_kv >= 64 && rows_per_kv <= kTcRows);
+    const bool tct_fits = g.head_dim == 128 && ((W + 7) & ~7) <= kTctCols;
+    use_tct = tct_fits && (c->attn_mode == 3 || (c->attn_mode == 0 && rows_per_kv <= kTctCols && c->tct_auto));
+    use_tc = !use_tct && (c->attn_mode == 1 || (c->attn_mode == 0 && rows_per_kv >= 64 && rows_per_kv <= kTcRows));
   }
   AttnTcParams tp;
   memset(&tp, 0, sizeof(tp));
-  if (use_tc) {
+  if (use_tc || use_tct) {
     tp.a = ap;
-    attn_tc_plan(&tp, g.head_dim);
+    if (use_tct) attn_tct_plan(&tp);
+    else attn_tc_plan(&tp, g.head_dim);
     if (tp.a.n_chunks > c->max_chunks || ensure_tcmaps(c, tp.Wp)) return SJD_E_TMAP;
   }
   GemmEpi base;
@@ -460,11 +467,11 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
       // which separates the cost of the two kernel boundaries from the cost of the attention kernel itself
       static const int dbg_attn = getenv("SJD_DEBUG_ATTN") ? atoi(getenv("SJD_DEBUG_ATTN")) : 0;
       if (dbg_attn != 1) {
-        if (use_tc) {
+        if (use_tc || use_tct) {
           tp.a.k = ap.k; tp.a.v = ap.v;
           tp.k_row0 = int(size_t(l) * g.rows * g.n_kv_heads * size_t(g.max_len));
           tp.dbg = g_attn_dbg;
-          rc |= attn_tc_launch(c->tcmaps[tp.Wp / 8], tp, s);
+          rc |= use_tct ? attn_tct_launch(c->tcmaps[tp.Wp / 8], tp, s) : attn_tc_launch(c->tcmaps[tp.Wp / 8], tp, s);
           cb.ch.pre = attn_combine_desc(tp.a, g.head_dim);
         } else {
           rc |= attn_launch(ap, g.head_dim, false, s);   // the split merge rides in the next chain kernel (pre-op)

@@ -312,15 +312,16 @@ def _family(env, name):
         RF.rope_tables_rotate_half(128, 512, 1e6, True), [0, 5]
 
 
-@pytest.mark.parametrize("attn", ["auto", "tc", "mma"])
+@pytest.mark.parametrize("attn", ["auto", "tc", "tct", "mma"])
 @pytest.mark.parametrize("family", ["chameleon", "llamagen", "emu3"])
 def test_window_forward_matches_reference_stack(env, family, attn, monkeypatch):
     """Prefill, an AR step, two Jacobi windows with a 9-token roll-back in between, and a short window —
     logits within 4 bf16 ulp (mean well below one ulp) of the bf16-emulating reference, and no further from the exact
     fp32 forward than that bf16 reference itself is."""
     RF, model, dev = env["RF"], env["model"], env["dev"]
-    # both attention kernels on every shape (the context reads SJD_ATTN when it is created): "tc" = tcgen05 + TMEM
-    # (attention_tc.cu), "mma" = mma.sync (attention.cu), "auto" = the per-window choice the product makes
+    # every attention kernel on every shape it supports (the context reads SJD_ATTN when it is created): "tc" = tcgen05 +
+    # TMEM (attention_tc.cu), "tct" = its transposed small-window variant (attention_tct.cu; head dim 128, windows <= 64,
+    # else the next choice), "mma" = mma.sync (attention.cu), "auto" = the per-window choice the product makes
     if attn == "auto":
         monkeypatch.delenv("SJD_ATTN", raising=False)
     else:
