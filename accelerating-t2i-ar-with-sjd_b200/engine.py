@@ -390,6 +390,7 @@ class SJDEngine:
         self.pbuf = [torch.zeros(Wmax, self.V, dtype=torch.float32, device=self.dev) for _ in range(2)]
         n_i32 = 3 * _lib.SJD_MAX_TOKENS + 4 * Wmax + 16
         self.h_stage = torch.empty(n_i32, dtype=torch.int32).pin_memory()
+        self.h_np = self.h_stage.numpy()   # same pinned memory: filled with numpy (cheaper than torch.tensor per field)
         self.d_stage = torch.empty(n_i32, dtype=torch.int32, device=self.dev)
         self.d_out = torch.empty(4 + Wmax, dtype=torch.int32, device=self.dev)
         self.h_out = torch.empty(4 + Wmax, dtype=torch.int32).pin_memory()
@@ -403,16 +404,13 @@ class SJDEngine:
     def _forward(self, row_tokens, kv_len, kv_lo, n_logit, embeds=None):
         rows, W = self.rows, len(row_tokens[0])
         M = rows * W
-        hs = self.h_stage
-        flat = [t for r in row_tokens for t in r]
-        hs[:M] = torch.tensor(flat, dtype=torch.int32)
-        pos = list(range(kv_len, kv_len + W))
-        rp = []
+        hn = self.h_np
+        pos = _np.arange(kv_len, kv_len + W, dtype=_np.int32)
         for b in range(rows):
-            rp += [max(t - kv_lo[b], 0) for t in pos]
-        hs[M:2 * M] = torch.tensor(rp, dtype=torch.int32)
-        hs[2 * M:3 * M] = torch.tensor(pos * rows, dtype=torch.int32)
-        self.d_stage[:3 * M].copy_(hs[:3 * M], non_blocking=True)
+            hn[b * W:(b + 1) * W] = row_tokens[b]
+            _np.maximum(pos - kv_lo[b], 0, out=hn[M + b * W:M + (b + 1) * W])   # RoPE position = slot - first visible key
+            hn[2 * M + b * W:2 * M + (b + 1) * W] = pos
+        self.d_stage[:3 * M].copy_(self.h_stage[:3 * M], non_blocking=True)
         self.stats.h2d_bytes += 12 * M
         ds = self.d_stage
         return self.stack.forward(W, ds[M:2 * M], ds[2 * M:3 * M], kv_len, kv_lo,
@@ -491,15 +489,14 @@ class SJDEngine:
             # ---- verify ---------------------------------------------------------------------------------
             Wv = n_out
             desc = grammar.describe(Wv)
-            hs, ds = self.h_stage, self.d_stage
+            hs, ds, hn = self.h_stage, self.d_stage, self.h_np
             base = 3 * _lib.SJD_MAX_TOKENS
-            wv_ids = window[-Wv:]
-            hs[base:base + Wv] = torch.tensor(wv_ids, dtype=torch.int32)
-            hs[base + self.Wmax: base + self.Wmax + Wv] = torch.tensor(q_row[-Wv:], dtype=torch.int32)
-            hs[base + 2 * self.Wmax: base + 2 * self.Wmax + Wv] = torch.tensor(desc["forced"], dtype=torch.int32)
+            hn[base:base + Wv] = window[-Wv:]
+            hn[base + self.Wmax: base + self.Wmax + Wv] = q_row[-Wv:]
+            hn[base + 2 * self.Wmax: base + 2 * self.Wmax + Wv] = desc["forced"]
             resid_forced = grammar.describe_residual(Wv) if hasattr(grammar, "describe_residual") else None
             if resid_forced is not None:
-                hs[base + 3 * self.Wmax: base + 3 * self.Wmax + Wv] = torch.tensor(resid_forced, dtype=torch.int32)
+                hn[base + 3 * self.Wmax: base + 3 * self.Wmax + Wv] = resid_forced
             ds[base: base + 4 * self.Wmax].copy_(hs[base: base + 4 * self.Wmax], non_blocking=True)
             stats.h2d_bytes += 16 * self.Wmax
             d_draft = ds[base: base + Wv]
