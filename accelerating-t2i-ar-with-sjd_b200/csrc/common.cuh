@@ -7,6 +7,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef SJD_SPIN_NS0
+// back-off of a cross-CTA flag poll (ns): first sleep and cap.  Measured on the 8-layer Lumina chain (W=32):
+// 128/1024 -> 0.858 ms, 64/512 -> 0.841, 32/128 -> 0.833, 16/64 -> 0.832 (saturating; a hot poll starves the atomics)
+#define SJD_SPIN_NS0 16
+#define SJD_SPIN_NSMAX 64
+#endif
+
 namespace sjd {
 
 // ----------------------------------------------------------------------------------------
@@ -176,12 +183,12 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // Polite spin: relaxed polls with back-off (a hot line polled by 148 CTAs otherwise starves the L2 slice that also
 // serves the counters' atomics), one acquire fence once the value is there.
 __device__ __forceinline__ void spin_until_ge(const uint32_t* p, uint32_t target) {
-  uint32_t v, ns = 64;
+  uint32_t v, ns = SJD_SPIN_NS0;
   while (true) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     if (v >= target) break;
     __nanosleep(ns);
-    if (ns < 512) ns <<= 1;
+    if (ns < SJD_SPIN_NSMAX) ns <<= 1;
   }
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
