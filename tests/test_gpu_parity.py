@@ -739,3 +739,74 @@ def test_full_width_window_logits_do_not_depend_on_the_window(env):
         assert d <= 2.0 ** -6, (i, d)                   # bf16 logits of magnitude ~4: one ulp is 2^-6 .. 2^-5
     torch.cuda.synchronize()
     ds.close()
+
+
+# ------------------------------------------------------------------------- edges: long prompts, capacity, bad arguments
+def test_chunked_prefill_equals_one_pass_reference(env):
+    """A prompt longer than one forward call holds (rows * tokens <= 256) is prefilled in chunks through the same
+    kernels; the engine's first generated token and the cache it leaves behind must be what a single pass over the
+    whole prompt gives: last-position logits vs the oracle stack's one-pass logits, then one more window on top."""
+    RF, model, engine, dev = env["RF"], env["model"], env["engine"], env["dev"]
+    cfg, (cos, sin), _ = _family(env, "chameleon")
+    w = RF.random_weights(cfg, seed=7, device=dev)
+    shape = model.StackShape(cfg.n_layers, cfg.d_model, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cfg.d_ff,
+                             cfg.vocab, cfg.rms_eps, cfg.qk_norm, cfg.rope_interleaved)
+    P, rows, max_len = 300, 2, 448
+    ds = model.DeviceStack(shape, w, cos, sin, rows, max_len, dev)
+    ref = RF.RefStack(cfg, w, cos.to(dev), sin.to(dev), rows, max_len, emulate_bf16=True)
+    g = torch.Generator().manual_seed(9)
+    prompt = torch.randint(8900, 9200, (P,), generator=g).tolist()
+    kv_lo = [0, P - 1]
+    captured = []
+
+    class Eng(engine.SJDEngine):
+        def _forward(self, row_tokens, kv_len, kv_lo_, n_logit, embeds=None):
+            lg = super()._forward(row_tokens, kv_len, kv_lo_, n_logit, embeds)
+            captured.append((len(row_tokens[0]), kv_len, lg.detach().float().clone()))
+            return lg
+
+    kw = dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=64, max_num_new_tokens=8, guidance_scale=3.0, seed=0,
+              multi_token_init_scheme="random", do_cfg=True, prefix_token_sampler_scheme="speculative_jacobi")
+    eng = Eng(ds, engine.SJDParams(**kw), engine.PlainTopKState(top_k=50), torch.arange(4, 8196))
+    eng.generate(prompt, max_length=P + 10, kv_lo=kv_lo)
+    chunks = [c for c in captured if c[1] < P]
+    assert [c[0] for c in chunks] == [128, 128, 44] and [c[1] for c in chunks] == [0, 128, 256]
+    ids = torch.tensor([prompt, prompt], device=dev)
+    pos = torch.arange(P, device=dev)[None].repeat(rows, 1)
+    rope = torch.stack([(pos[b] - kv_lo[b]).clamp(min=0) for b in range(rows)])
+    lr = ref.forward(ids=ids, rope_pos=rope, kv_len=0, kv_lo=kv_lo, cache_pos=pos, n_logit_tokens=1)
+    ulp = 2.0 ** (torch.floor(torch.log2(lr.abs().max())).item() - 7)
+    assert (chunks[-1][2].view(rows, -1) - lr.view(rows, -1)).abs().max().item() <= 2.5 * ulp
+    # the first Jacobi window after the prefill reads the whole chunk-built cache
+    Wn, kv, lg = captured[len(chunks)]
+    assert kv == P
+    ds.close()
+
+
+def test_capacity_and_argument_errors_are_loud(env):
+    """KV cache overflow, too many token rows, missing noise: negative status from the C ABI -> RuntimeError in Python,
+    never a silent truncation."""
+    RF, model, engine, dev, lib = env["RF"], env["model"], env["engine"], env["dev"], env["lib"]
+    cfg, (cos, sin), _ = _family(env, "chameleon")
+    w = RF.random_weights(cfg, seed=2, device=dev)
+    shape = model.StackShape(cfg.n_layers, cfg.d_model, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cfg.d_ff,
+                             cfg.vocab, cfg.rms_eps, cfg.qk_norm, cfg.rope_interleaved)
+    ds = model.DeviceStack(shape, w, cos, sin, 2, 64, dev)
+    W = 16
+    ids = torch.zeros(2 * W, dtype=torch.int32, device=dev)
+    pos = torch.arange(W, dtype=torch.int32, device=dev).repeat(2)
+    with pytest.raises(RuntimeError, match="overflow"):
+        ds.forward(W, pos, pos, 56, [0, 0], ids=ids, n_logit_tokens=W)          # 56 + 16 > 64 slots
+    big = torch.zeros(2 * 129, dtype=torch.int32, device=dev)
+    with pytest.raises(RuntimeError, match="out of range"):
+        ds.forward(129, big, big, 0, [0, 0], ids=big, n_logit_tokens=1)         # 258 token rows > 256
+    eng = engine.SJDEngine(ds, engine.SJDParams(max_num_new_tokens=8, jacobi_loop_interval_r=40, seed=0),
+                           engine.PlainTopKState(top_k=10), torch.arange(4, 8196))
+    with pytest.raises(RuntimeError, match="KV cache too small"):
+        eng.generate([1, 2, 3], max_length=200, kv_lo=[0, 2])
+    logits = torch.zeros(2 * 4, 128, device=dev)
+    desc = {"allow": None, "forced": [-1] * 4, "top_k": 0}
+    with pytest.raises(RuntimeError, match="noise_e1"):
+        engine.verify_call(logits, 4, 128, desc, torch.zeros(4, dtype=torch.int32, device=dev), None, None,
+                           has_uncond=True, apply_cfg=True, guidance=3.0, temperature=1.0, do_sample=True, scheme=1)
+    ds.close()
