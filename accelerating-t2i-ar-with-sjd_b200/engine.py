@@ -391,6 +391,7 @@ class SJDEngine:
         n_i32 = 3 * _lib.SJD_MAX_TOKENS + 4 * Wmax + 16
         self.h_stage = torch.empty(n_i32, dtype=torch.int32).pin_memory()
         self.h_np = self.h_stage.numpy()   # same pinned memory: filled with numpy (cheaper than torch.tensor per field)
+        self._stage_copied = None          # event: the last H2D copy out of h_stage[:3M] has completed
         self.d_stage = torch.empty(n_i32, dtype=torch.int32, device=self.dev)
         self.d_out = torch.empty(4 + Wmax, dtype=torch.int32, device=self.dev)
         self.h_out = torch.empty(4 + Wmax, dtype=torch.int32).pin_memory()
@@ -404,6 +405,10 @@ class SJDEngine:
     def _forward(self, row_tokens, kv_len, kv_lo, n_logit, embeds=None):
         rows, W = self.rows, len(row_tokens[0])
         M = rows * W
+        # the pinned staging buffer is reused by every call: its previous async copy must have left it (a chunked
+        # prefill issues several forwards without a stream sync in between; in the decode loop the event is long done)
+        if self._stage_copied is not None:
+            self._stage_copied.synchronize()
         hn = self.h_np
         pos = _np.arange(kv_len, kv_len + W, dtype=_np.int32)
         for b in range(rows):
@@ -411,6 +416,9 @@ class SJDEngine:
             _np.maximum(pos - kv_lo[b], 0, out=hn[M + b * W:M + (b + 1) * W])   # RoPE position = slot - first visible key
             hn[2 * M + b * W:2 * M + (b + 1) * W] = pos
         self.d_stage[:3 * M].copy_(self.h_stage[:3 * M], non_blocking=True)
+        if self._stage_copied is None:
+            self._stage_copied = torch.cuda.Event()
+        self._stage_copied.record(torch.cuda.current_stream(self.dev))
         self.stats.h2d_bytes += 12 * M
         ds = self.d_stage
         return self.stack.forward(W, ds[M:2 * M], ds[2 * M:3 * M], kv_len, kv_lo,
