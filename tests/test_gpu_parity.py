@@ -810,3 +810,39 @@ def test_capacity_and_argument_errors_are_loud(env):
         engine.verify_call(logits, 4, 128, desc, torch.zeros(4, dtype=torch.int32, device=dev), None, None,
                            has_uncond=True, apply_cfg=True, guidance=3.0, temperature=1.0, do_sample=True, scheme=1)
     ds.close()
+
+
+def test_full_size_config2_image_is_deterministic_and_grammatical(env):
+    """BASELINE config 2 at FULL size: Lumina-mGPT-7B shape (32 layers, 13.5 GB of weights), one 768 x 768 image
+    (48 rows of 48 tokens + end-of-line, end-of-image), window 32, cfg 3.0, top-k 2000, fixed seed — decoded twice.
+    Identical token streams and accepted-count traces (bit-reproducible kernels), the grammar exactly in place over all
+    2 353 image-region tokens, accepted tokens per forward > 1, and the KV cache never rewound below the accepted prefix."""
+    from sjd_b200 import families
+    engine, model, dev = env["engine"], env["model"], env["dev"]
+    shape = families.lumina_7b()
+    w = families.random_weights(shape, seed=0, device=dev)
+    cos, sin = families.rope_rotate_half(128, 2560, 10000.0, True)
+    ds = model.DeviceStack(shape, w, cos, sin, 2, 2560, dev)
+    del w
+    torch.cuda.empty_cache()
+    g = 48
+    gen = torch.Generator().manual_seed(1000)
+    prompt = torch.randint(8900, 65000, (64,), generator=gen).tolist() + [8197, 8804 + g // 2, 8804 + g // 2]
+    kw = dict(jacobi_loop_interval_l=3, jacobi_loop_interval_r=g * g + g - 10, max_num_new_tokens=32, guidance_scale=3.0,
+              seed=0, multi_token_init_scheme="random", do_cfg=True, prefix_token_sampler_scheme="speculative_jacobi")
+    runs = []
+    for _ in range(2):
+        eng = engine.SJDEngine(ds, engine.SJDParams(**kw), engine.LuminaGrammarState(image_top_k=2000), torch.arange(4, 8196))
+        ids = eng.generate(prompt, max_length=len(prompt) + g * (g + 1) + 2, eos_token_ids=[8710],
+                           kv_lo=[0, len(prompt) - 1], collect_trace=True)
+        runs.append((ids, list(eng.stats.trace), eng.stats.nfe))
+    assert runs[0] == runs[1]
+    ids, trace, nfe = runs[0]
+    img = ids[len(prompt):]
+    n = g * (g + 1)
+    assert len(img) >= n + 1 and img[n] == 8196
+    assert all(img[i] == 8803 for i in range(g, n, g + 1))
+    assert all(4 <= t < 8196 for i, t in enumerate(img[:n]) if i % (g + 1) != g)
+    assert sum(t[1] for t in trace) == len(img) and nfe < len(img)
+    assert all(1 <= t[1] <= t[0] for t in trace), "accepted count outside [1, window]"
+    ds.close()
