@@ -39,9 +39,12 @@ attn_tct_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[12];               // per stage: qk landed, v landed, S done, P ready, O done, O drained
   __shared__ uint32_t tmem_holder;
-  __shared__ int xmax_all[2 * 2 * 4 * kTctCols];           // [group][unit parity][warp][column] warp maxima (ordered ints)
+  __shared__ __align__(16) float xmf_all[2 * kTctCols];                  // [group][column] tile-wide column max (scaled log2 domain)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sOnes = base + 2 * kStage;
+  // per softmax group: a [128 keys][33] fp32 staging tile (+8 floats per 32 keys) for the column maxima
+  constexpr uint32_t kStBytes = (kTcKeys * 33 + 32) * 4;
+  const uint32_t sSt = sOnes + kTcRows * 128;
   const AttnParams& a = p.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar = [&](int which, int s) { return smem_u32(&bars[which * 2 + s]); };
@@ -236,7 +239,10 @@ attn_tct_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       tcgen05_fence_after();
       if (p.dbg && blockIdx.x == 0 && grp == (m & 1) && qw == 0 && lane == 0 && m < 8) p.dbg[m * 16 + 8] = clock64();
       const uint32_t tO = tmem_base + uint32_t(s) * 256 + 64, tL = tO + 64;
-      int hs = 0, qi = 0;                                   // slot c -> (head slot, window position), walked incrementally
+      // slot c -> partial row: rows of one head are consecutive (512 bytes apart for this lane's element), the next
+      // head starts W rows later: one pointer walked with adds, no per-element address arithmetic
+      float* pcol = a.part_o + (e_base + size_t(e_h0) * a.W) * DH + kl;
+      int qi = 0;
 #pragma unroll 1
       for (int c0 = 0; c0 < e_R; c0 += 16) {
         uint32_t v[16];
@@ -244,9 +250,9 @@ attn_tct_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          if (qi < a.W && c0 + e < e_R)                     // uniform: lanes = 32 consecutive floats of one output row
-            a.part_o[(e_base + size_t(e_h0 + hs) * a.W + qi) * DH + kl] = __uint_as_float(v[e]);
-          if (++qi == p.Wp) { qi = 0; ++hs; }
+          if (qi < a.W && c0 + e < e_R) *pcol = __uint_as_float(v[e]);   // uniform: a warp writes 128 contiguous bytes
+          pcol += DH;
+          if (++qi == p.Wp) { qi = 0; pcol -= (p.Wp - a.W) * DH; }
         }
       }
       if (qw == 0) {   // row sums: every lane of L holds them; lane c (and 32 + c) of warp 0 writes column c's
@@ -296,7 +302,6 @@ attn_tct_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       if (owed >= 0) epilogue(owed);
       uint8_t* const genP = smem_raw + (base + uint32_t(s) * kStage - smem_u32(smem_raw));
       const uint32_t tS = tmem_base + uint32_t(s) * 256;
-      int* const xm = xmax_all + ((grp * 2 + (j & 1)) * 4) * kTctCols;   // [warp][column]
       mbar_wait(bar(B_S, s), uint32_t(j) & 1u);
       tcgen05_fence_after();
       if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 5] = clock64();
@@ -305,83 +310,87 @@ attn_tct_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       const bool key_ok = jk >= lo && jk < T;
       // every (key, query) pair of the tile visible: no mask arithmetic
       const bool interior = (t.key0 >= lo) && (t.key0 + kTcKeys - 1 <= a.kv_len) && (t.key0 + kTcKeys <= T);
-      // ---- pass 1: per-column max over the 32 keys of this warp (redux), lanes c and c - 32 keep columns c ----
-      int wm0 = f2ord(-INFINITY), wm1 = wm0;
-      {
-        int hs = 0, qi = 0;
+      float* const st = reinterpret_cast<float*>(smem_raw + (sSt + uint32_t(grp) * kStBytes - smem_u32(smem_raw)));
+      float* const xmf = xmf_all + grp * kTctCols;
+      uint8_t* rowp = genP + kl * 128;
+      // 32 columns at a time: (a) every key thread parks its 32 scores in the staging tile; (b) thread (quarter q, column
+      // c) takes the max over the 32 keys of quarter q — no cross-lane traffic, its mask is a key range — and two
+      // shuffles merge the quarters; (c) the 32 column maxima go back through shared memory and every key thread turns
+      // its scores into probabilities
 #pragma unroll 1
-        for (int c0 = 0; c0 < R; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c0), v);
-          tmem_ld_wait();
+      for (int ch0 = 0; ch0 < R; ch0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x16(tS + t_row + uint32_t(ch0), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_ld_32x32b_x16(tS + t_row + uint32_t(ch0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        tmem_ld_wait();
+        {
+          float* row = st + kl * 33 + 8 * qw;               // +8 floats per 32 keys: step (b) reads without bank conflicts
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const bool ok = interior ? (qi < a.W) : (key_ok && jk <= a.kv_len + qi && qi < a.W);
-            const int o = __reduce_max_sync(0xffffffffu, f2ord(ok ? __uint_as_float(v[e]) : -INFINITY));
-            if ((lane & 15) == e && (lane >> 4) == ((c0 >> 4) & 1)) {
-              if (c0 < 32) wm0 = o; else wm1 = o;
-            }
-            if (++qi == p.Wp) { qi = 0; ++hs; }
+          for (int e = 0; e < 32; ++e) row[e] = __uint_as_float(v[e]);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        {
+          const int q = lane >> 3, c = ch0 + 8 * qw + (lane & 7);       // this thread: keys [32 q, 32 q + 32) of column c
+          const int hs2 = tc_div(c, p.m_wp, p.Wp), qi2 = c - hs2 * p.Wp;
+          // visible keys of this column inside the quarter: [k_lo, k_hi]
+          const int jq = t.key0 + 32 * q;
+          int k_lo = 0, k_hi = 31;
+          if (!interior) {
+            k_lo = max(lo - jq, 0);
+            k_hi = min(min(a.kv_len + qi2, T - 1) - jq, 31);
+          }
+          if (qi2 >= a.W || c >= R) k_hi = -1;
+          const float* col = st + (32 * q) * 33 + 8 * q + (c - ch0);
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = col[k * 33];
+            m4[k & 3] = fmaxf(m4[k & 3], (k >= k_lo && k <= k_hi) ? x : -INFINITY);
+          }
+          float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+          if (q == 0) {
+            const float ms = mx * sc;                        // scale > 0: max commutes with it
+            xmf[c] = ms;
+            if (qi2 < a.W && c < R) a.part_ml[(ubase + size_t(t.h0 + hs2) * a.W + qi2) * 2] = ms;
           }
         }
-      }
-      xm[qw * kTctCols + lane] = wm0;
-      xm[qw * kTctCols + 32 + lane] = wm1;
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-      // lane holds the tile-wide max of columns `lane` and `32 + lane`, already in the scaled log2 domain
-      float fm0, fm1;
-      {
-        int m0 = xm[lane], m1 = xm[32 + lane];
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 6] = clock64();
+        // (c) probabilities of this key for the 32 columns (bf16, q contiguous) -> four 16-byte chunks of its P^T row
+        {
+          float mcol[32];
 #pragma unroll
-        for (int w2 = 1; w2 < 4; ++w2) {
-          m0 = max(m0, xm[w2 * kTctCols + lane]);
-          m1 = max(m1, xm[w2 * kTctCols + 32 + lane]);
-        }
-        fm0 = ord2f(m0) * sc;
-        fm1 = ord2f(m1) * sc;
-      }
-      if (qw == 0) {   // {max} of the partial: columns lane and 32 + lane
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = h * 32 + lane;
-          if (c < R) {
-            const int hs2 = tc_div(c, p.m_wp, p.Wp), qi2 = c - hs2 * p.Wp;
-            if (qi2 < a.W) a.part_ml[(ubase + size_t(t.h0 + hs2) * a.W + qi2) * 2] = h ? fm1 : fm0;
+          for (int e = 0; e < 32; e += 4) {
+            const float4 m = *reinterpret_cast<const float4*>(xmf + ch0 + e);
+            mcol[e] = m.x; mcol[e + 1] = m.y; mcol[e + 2] = m.z; mcol[e + 3] = m.w;
           }
-        }
-      }
-      if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 6] = clock64();
-      // ---- pass 2: P^T row of this key (bf16, q contiguous): 16 columns = two 16-byte chunks per step ----
-      {
-        int hs = 0, qi = 0;
-        uint8_t* rowp = genP + kl * 128;
-#pragma unroll 1
-        for (int c0 = 0; c0 < R; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c0), v);
-          tmem_ld_wait();
-          const float fm = c0 < 32 ? fm0 : fm1;
-          uint32_t pk[8];
+          int qi = ch0 % p.Wp;                               // ch0 is 0 or 32; Wp divides 64 boundaries only when it divides 32
+          uint32_t pk[16];
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) {
+          for (int e = 0; e < 32; e += 2) {
             float pe[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const float mc = __shfl_sync(0xffffffffu, fm, ((c0 & 16) + e + h));
-              const float ms = (mc == -INFINITY) ? 0.f : mc;
+              const float ms = (mcol[e + h] == -INFINITY) ? 0.f : mcol[e + h];
               const bool ok = interior ? (qi < a.W) : (key_ok && jk <= a.kv_len + qi && qi < a.W);
               pe[h] = ok ? ex2_approx(fmaf(__uint_as_float(v[e + h]), sc, -ms)) : 0.f;
-              if (++qi == p.Wp) { qi = 0; ++hs; }
+              if (++qi == p.Wp) qi = 0;
             }
             const __nv_bfloat162 pb = __floats2bfloat162_rn(pe[0], pe[1]);
             pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
           }
-          const int ch = c0 >> 3;
-          *reinterpret_cast<uint4*>(rowp + (((ch) ^ (kl & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (kl & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          const int ch = ch0 >> 3;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(rowp + (((ch + q4) ^ (kl & 7)) << 4)) =
+                make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
         }
+      }
+      {
         // slots beyond R feed accumulator columns nobody reads; zero them once per unit so they stay finite
-        for (int c0 = (R + 15) & ~15; c0 < kTctCols; c0 += 8)
+        for (int c0 = (R + 31) & ~31; c0 < kTctCols; c0 += 8)
           *reinterpret_cast<uint4*>(rowp + (((c0 >> 3) ^ (kl & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
       }
       tcgen05_fence_before();
@@ -423,7 +432,9 @@ void attn_tct_plan(AttnTcParams* p) {
   p->m_wp = tc_magic(uint32_t(p->Wp));
 }
 
-constexpr int attn_tct_smem() { return 1024 + 2 * (2 * kTcKeys * 128 + 2 * kTcKeys * 128 + 2 * kTctCols * 128) + kTcRows * 128; }
+constexpr int attn_tct_smem() {   // two stages of {K | P^T, V, Q}, the ones tile, two staging tiles for the column maxima
+  return 1024 + 2 * (2 * kTcKeys * 128 + 2 * kTcKeys * 128 + 2 * kTctCols * 128) + kTcRows * 128 + 2 * (kTcKeys * 33 + 32) * 4;
+}
 
 int attn_tct_launch(const AttnTcMaps& maps, const AttnTcParams& p, cudaStream_t stream) {
   const AttnParams& a = p.a;
