@@ -3,8 +3,10 @@
 // Same contract as attention.cu (key j visible to window query i of CFG row b iff kv_lo[b] <= j <= kv_len + i; one
 // fp32 partial {sum p*v, max, sum p} per key split, merged by attn_combine_row in the next chain kernel), different
 // machine mapping:
-//   * one CTA per (128-key tile, kv head [x query-row tile], CFG row); two CTAs share an SM (97 KB smem, 256 TMEM
-//     columns each), so one CTA's TMA latency hides behind the other's math;
+//   * work unit = (128-key tile, kv head [x query-row tile], CFG row); one persistent CTA per SM deals itself the
+//     units cta, cta + grid, ... and runs them through a two-stage pipeline (TMA producer warp, one MMA-issuing thread,
+//     two softmax groups of four warps — see the kernel's comment), so the K/V stream of the next tile, the tensor work
+//     of this one and the softmax of two tiles overlap;
 //   * the query rows of up to 128 / Wp heads that share the kv head are stacked along UMMA M (GQA: the K/V tile is
 //     loaded once for all of them); rows beyond the stack are garbage that only ever produces garbage rows;
 //   * S[128 q x 128 keys] = Q K^T :  A = Q tile, B = K tile, both K-major (head dim contiguous), SWIZZLE_128B boxes
@@ -16,16 +18,17 @@
 //     an MN-major operand — no transposed cache, no smem transpose;
 //   * when the stacked rows fill only 1/rep of the 128 TMEM lanes (MHA, window 32: a quarter), Q is loaded rep times
 //     and replica g takes columns [128 g / rep, 128 (g+1) / rep) of every row: all four softmax warps work, row max and
-//     row sum meet in shared memory, and every replica writes its slice of P into replica 0's row;
-//   * a CTA sees its whole key span at once, so there is no online rescaling: max, exponentials, one product.
+//     row sum meet in shared memory, every replica writes its slice of P into ALL replica rows, and replica g drains
+//     its slice of the columns of O;
+//   * a unit sees its whole key span at once, so there is no online rescaling: max, exponentials, one product.
 // Reference semantics: SDPA over the additive window mask (modeling_chameleon.py:567-574, mask from
 // scheduler/jacobi_iteration_lumina_mgpt.py:1256-1336; llamagen/llamagen.py:269-273).
 #include "common.cuh"
 
 namespace sjd {
 
-constexpr int kTcKeys = 128;       // keys per CTA (UMMA N of the first product, K of the second)
-constexpr int kTcRows = 128;       // query-row slots per CTA (UMMA M)
+constexpr int kTcKeys = 128;       // keys per unit (UMMA N of the first product, K of the second)
+constexpr int kTcRows = 128;       // query-row slots per unit (UMMA M)
 
 struct AttnTcParams {
   AttnParams a;          // geometry, partial buffers, kv_len / kv_lo (n_chunks = key tiles, span = kTcKeys)
