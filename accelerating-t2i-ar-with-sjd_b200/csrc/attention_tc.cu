@@ -121,10 +121,14 @@ __device__ __forceinline__ TcUnit tc_unit(const AttnTcParams& p, int u, int r) {
 //                   P(n), then the epilogue of its previous unit n-2 (whose O has long been ready)
 // so the K/V stream of the next tile, the tensor work of this one and the softmax of two tiles overlap.  TMEM: stage s owns columns
 // [256 s, 256 s + 128) for S and [256 s + 128, 256 s + 128 + Dh) for O.
-constexpr int kTcThreads2 = 384;   // warps 0..3 and 8..11: the two softmax groups; 4: TMA; 5: MMA; 6, 7: idle
+constexpr int kTcThreads2 = 384;   // (attention_tct.cu) warps 0..3 and 8..11: the two softmax groups; 4: TMA; 5: MMA; 6, 7: idle
+// attn_tc_kernel: each softmax group has EIGHT warps — two per TMEM lane quarter, each taking half of the row's columns
+// (a lone warp per scheduler runs at ~0.2 IPC; the halves meet through the same shared-memory exchange as the replicas):
+// warps 0..3 / 12..15 = group 0 halves 0 / 1, warps 8..11 / 16..19 = group 1 halves 0 / 1, 4 = TMA, 5 = MMA, 6, 7 idle
+constexpr int kTcThreads3 = 640;
 
 template <int DH>
-__global__ void __launch_bounds__(kTcThreads2, 1)
+__global__ void __launch_bounds__(kTcThreads3, 1)
 attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
   constexpr int NDA = DH / 64;                            // 64-wide head-dim atoms
   constexpr uint32_t kQBytes = NDA * kTcRows * 128;       // Q tile: NDA atoms of [128 rows][128 B]
@@ -137,7 +141,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
   // per stage: qk landed, v landed, S done, P ready, O done, O drained
   __shared__ __align__(8) uint64_t bars[12];
   __shared__ uint32_t tmem_holder;
-  __shared__ float xch_all[2 * 4 * kTcRows];              // per softmax group: {row max, row sum} across column replicas, two units deep
+  __shared__ float xch_all[2 * 8 * kTcRows];              // per softmax group: {row max, row sum} x 2 column halves x 128 lanes, two units deep
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const AttnParams& a = p.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -156,7 +160,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
         mbar_init(bar(B_QK, s), 1);
         mbar_init(bar(B_V, s), 1);
         mbar_init(bar(B_S, s), 1);
-        mbar_init(bar(B_P, s), 4);
+        mbar_init(bar(B_P, s), 8);
         mbar_init(bar(B_O, s), 1);
         mbar_init(bar(B_E, s), 4);
       }
@@ -307,8 +311,8 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
         bool did = false;
         if (np < ns) {
           const int s = np & 1, j = np >> 1;
-          if (mbar_try_wait(bar(B_P, s), uint32_t(j) & 1u) && mbar_try_wait(bar(B_V, s), uint32_t(j) & 1u) &&
-              (j < 1 || mbar_try_wait(bar(B_E, s), uint32_t(j - 1) & 1u))) {
+          if (mbar_test_wait(bar(B_P, s), uint32_t(j) & 1u) && mbar_test_wait(bar(B_V, s), uint32_t(j) & 1u) &&
+              (j < 1 || mbar_test_wait(bar(B_E, s), uint32_t(j - 1) & 1u))) {
             issue_pv(np);
             ++np;
             did = true;
@@ -316,7 +320,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
         }
         if (ns < N && ns - np < 2) {
           const int s = ns & 1, j = ns >> 1;
-          if (mbar_try_wait(bar(B_QK, s), uint32_t(j) & 1u)) {
+          if (mbar_test_wait(bar(B_QK, s), uint32_t(j) & 1u)) {
             if (p.dbg && blockIdx.x == 0 && ns < 8) p.dbg[ns * 16 + 1] = clock64();
             issue_s(ns);
             ++ns;
@@ -329,10 +333,11 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
   } else if (warp < 4 || warp >= 8) {
     // ===== softmax + epilogue: one thread per query-row slot, straight from the TMEM accumulators.  Group `grp` takes
     // the units that run through pipeline stage `grp` =====
-    const int grp = warp >> 3, qw = warp & 3;      // TMEM lane quarter = warp % 4
+    const int widx = warp < 4 ? warp : warp - 4;   // 0..15
+    const int qw = widx & 3, grp = (widx >> 2) & 1, half = widx >> 3;   // TMEM lane quarter = warp % 4
     const int r = qw * 32 + lane;
     const uint32_t t_row = (uint32_t(qw * 32) << 16);
-    float* const xch = xch_all + grp * 4 * kTcRows;
+    float* const xch = xch_all + grp * 8 * kTcRows;
     // state of the unit whose epilogue is still owed
     bool e_row_ok = false, e_first = false;
     size_t e_prow = 0;
@@ -348,7 +353,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       const int s = m & 1, j = m >> 1;
       mbar_wait(bar(B_O, s), uint32_t(j) & 1u);
       tcgen05_fence_after();
-      if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && m < 8) p.dbg[m * 16 + 8] = clock64();
+      if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && m < 8) p.dbg[m * 16 + 8] = clock64();   // (half 0 only runs this)
       const uint32_t tO = tmem_base + uint32_t(s) * 256 + 128;
 #pragma unroll 1
       for (int c = e_c0; c < e_c0 + e_nc; c += 16) {   // e_nc is a multiple of 16; warp-uniform
@@ -388,10 +393,10 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const TcUnit t = tc_unit(p, u, r);
       const bool row_ok = t.rr < t.R && t.qi < a.W && t.g < t.rep;   // this thread works on a real query row
-      const bool first = t.g == 0;                                   // replica 0 also owns {max, sum}
+      const bool first = t.g == 0 && half == 0;                      // replica 0, half 0 also owns {max, sum}
       const size_t prow = row_ok ? ((size_t(t.kt) * a.rows + t.b) * a.H + (t.h0 + t.hs)) * size_t(a.W) + t.qi : 0;
       if (t.hidden) {   // uniform per CTA
-        if (grp == 0 && row_ok && first) {
+        if (grp == 0 && row_ok && first) {   // (first implies half 0)
           a.part_ml[prow * 2] = -INFINITY;
           a.part_ml[prow * 2 + 1] = 0.f;
         }
@@ -403,86 +408,76 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       }
       const int s = n & 1, j = n >> 1;
       const int lo = t.lo, key0 = t.key0, rep = t.rep, g = t.g, rr = t.rr;
-      const int ncol = kTcKeys / rep, col0 = g * ncol;       // this thread's slice of the row's 128 keys (32 | 64 | 128)
+      const int ncol = kTcKeys / rep / 2, col0 = g * (kTcKeys / rep) + half * ncol;   // this thread's slice of the row's 128 keys (16 | 32 | 64)
       uint8_t* const genP = smem_raw + (base + uint32_t(s) * kStage + kQBytes - smem_u32(smem_raw));
       const uint32_t tS = tmem_base + uint32_t(s) * 256;
-      float* const xmax = xch + (j & 1) * 2 * kTcRows;        // exchange buffers alternate between units: no barrier
-      float* const xsum = xmax + kTcRows;                     //   is needed to protect their reuse
+      float* const xmax = xch + (j & 1) * 4 * kTcRows;        // exchange buffers alternate between units: no barrier
+      float* const xsum = xmax + 2 * kTcRows;                 //   is needed to protect their reuse; [half][lane]
       // the group's previous unit first: its O has long been ready, and draining it now lets O(n) be issued the
       // moment P(n) is delivered
-      if (owed >= 0) epilogue(owed);
+      if (half == 0 && owed >= 0) epilogue(owed);
       mbar_wait(bar(B_S, s), uint32_t(j) & 1u);
       tcgen05_fence_after();
-      if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 5] = clock64();
+      if (p.dbg && blockIdx.x == 0 && half == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 5] = clock64();
       const int j_hi = min(a.kv_len + t.qi, T - 1);           // last visible key of this row
       const float sc = a.scale_log2e;
-      // ---- pass 1: row max over this thread's columns (four independent chains) ----
+      // ---- pass 1: row max over this thread's columns (four independent chains), 16 columns per step ----
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       if (g < rep) {
 #pragma unroll 1
-        for (int c = col0; c < col0 + ncol; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        for (int c = col0; c < col0 + ncol; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c), v);
           tmem_ld_wait();
           const int jk0 = key0 + c;
-          if (jk0 >= lo && jk0 + 31 <= j_hi) {                // every key of the chunk is visible to this row
+          const int e_lo = lo - jk0, e_hi = j_hi - jk0;   // visible columns of the step: [e_lo, e_hi]
 #pragma unroll
-            for (int e = 0; e < 32; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[e]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const bool ok = (jk0 + e >= lo) && (jk0 + e <= j_hi);
-              m4[e & 3] = fmaxf(m4[e & 3], ok ? __uint_as_float(v[e]) : -INFINITY);
-            }
-          }
+          for (int e = 0; e < 16; ++e)
+            m4[e & 3] = fmaxf(m4[e & 3], (e >= e_lo && e <= e_hi) ? __uint_as_float(v[e]) : -INFINITY);
         }
       }
       float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      if (rep > 1) {   // uniform per CTA: the row max is spread over the replicas
-        xmax[r] = mx;
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      {   // the row max is spread over the column halves and the replicas
+        xmax[half * kTcRows + r] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
         if (g < rep) {
-          for (int g2 = 0; g2 < rep; ++g2) mx = fmaxf(mx, xmax[g2 * t.Rr + rr]);
+          for (int g2 = 0; g2 < rep; ++g2)
+            mx = fmaxf(mx, fmaxf(xmax[g2 * t.Rr + rr], xmax[kTcRows + g2 * t.Rr + rr]));
         }
       }
       mx *= sc;                                               // scale > 0: max commutes with it
-      if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 6] = clock64();
+      if (p.dbg && blockIdx.x == 0 && half == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 6] = clock64();
       const float ms = (mx == -INFINITY) ? 0.f : mx;
       // ---- pass 2: probabilities (bf16, like the reference's bf16 SDPA) into every replica's row of the P tile ----
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
       if (g < rep) {
 #pragma unroll 1
-        for (int c = col0; c < col0 + ncol; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        for (int c = col0; c < col0 + ncol; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tS + t_row + uint32_t(c), v);
           tmem_ld_wait();
           const int jk0 = key0 + c;
-          const bool all_ok = jk0 >= lo && jk0 + 31 <= j_hi;
-          uint32_t pk[16];
+          const int e_lo = lo - jk0, e_hi = j_hi - jk0;
+          uint32_t pk[8];
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+          for (int e = 0; e < 16; e += 2) {
             float e0 = ex2_approx(fmaf(__uint_as_float(v[e]), sc, -ms));
             float e1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), sc, -ms));
-            if (!all_ok) {
-              if (!((jk0 + e >= lo) && (jk0 + e <= j_hi))) e0 = 0.f;
-              if (!((jk0 + e + 1 >= lo) && (jk0 + e + 1 <= j_hi))) e1 = 0.f;
-            }
-            const __nv_bfloat162 pb = __floats2bfloat162_rn(e0, e1);
+            if (!(e >= e_lo && e <= e_hi)) e0 = 0.f;
+            if (!(e + 1 >= e_lo && e + 1 <= e_hi)) e1 = 0.f;
+            const __nv_bfloat162 pb = __floats2bfloat162_rn(e0, e1);   // probabilities enter P*V as bf16
             l4[(e >> 1) & 3] += __low2float(pb) + __high2float(pb);
             pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
           }
           if (row_ok) {
-            // K-major P tile: 64-key atom c / 64, four 16-byte chunks from (c % 64) / 8, 128B-swizzled by the row
+            // K-major P tile: 64-key atom c / 64, two 16-byte chunks from (c % 64) / 8, 128B-swizzled by the row;
+            // written into every replica's row
             const int ch = (c & 63) >> 3;
             for (int g2 = 0; g2 < rep; ++g2) {
               const int prw = g2 * t.Rr + rr;
               uint8_t* rowp = genP + (c >> 6) * (kTcRows * 128) + prw * 128;
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(rowp + (((ch + q) ^ (prw & 7)) << 4)) =
-                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              *reinterpret_cast<uint4*>(rowp + (((ch) ^ (prw & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (prw & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
           }
         }
@@ -492,23 +487,23 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_P, s));
-      if (p.dbg && blockIdx.x == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 7] = clock64();
-      if (rep > 1) {
-        xsum[r] = lsum;
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-        if (g == 0) {
+      if (p.dbg && blockIdx.x == 0 && half == 0 && qw == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 7] = clock64();
+      {
+        xsum[half * kTcRows + r] = lsum;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
+        if (first) {
           lsum = 0.f;
-          for (int g2 = 0; g2 < rep; ++g2) lsum += xsum[g2 * t.Rr + rr];   // fixed order
+          for (int g2 = 0; g2 < rep; ++g2) lsum += xsum[g2 * t.Rr + rr] + xsum[kTcRows + g2 * t.Rr + rr];   // fixed order
         }
       }
-      owed = n;
+      if (half == 0) owed = n;
       e_row_ok = row_ok; e_first = first; e_prow = prow; e_mx = mx; e_l = lsum;
       e_nc = g < rep ? DH / rep : 0; e_c0 = g * e_nc;   // (a warp beyond the last replica drains nothing)
       e_slot0 = qw * 32 - g * t.Rr; e_R = t.R; e_h0 = t.h0;
       e_base = (size_t(t.kt) * a.rows + t.b) * a.H * size_t(a.W);
       ++n;
     }
-    if (owed >= 0) epilogue(owed);
+    if (half == 0 && owed >= 0) epilogue(owed);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -556,8 +551,8 @@ int attn_tc_launch(const AttnTcMaps& maps, const AttnTcParams& p, cudaStream_t s
       return -5;
     set = true;
   }
-  if (p.head_dim == 128) return launch_pdl(attn_tc_kernel<128>, grid, dim3(kTcThreads2), attn_tc_smem(128), stream, maps, p);
-  return launch_pdl(attn_tc_kernel<64>, grid, dim3(kTcThreads2), attn_tc_smem(64), stream, maps, p);
+  if (p.head_dim == 128) return launch_pdl(attn_tc_kernel<128>, grid, dim3(kTcThreads3), attn_tc_smem(128), stream, maps, p);
+  return launch_pdl(attn_tc_kernel<64>, grid, dim3(kTcThreads3), attn_tc_smem(64), stream, maps, p);
 }
 
 }  // namespace sjd

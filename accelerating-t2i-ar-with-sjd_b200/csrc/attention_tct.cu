@@ -205,8 +205,8 @@ attn_tct_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
         bool did = false;
         if (np < ns) {
           const int s = np & 1, j = np >> 1;
-          if (mbar_try_wait(bar(B_P, s), uint32_t(j) & 1u) && mbar_try_wait(bar(B_V, s), uint32_t(j) & 1u) &&
-              (j < 1 || mbar_try_wait(bar(B_E, s), uint32_t(j - 1) & 1u))) {
+          if (mbar_test_wait(bar(B_P, s), uint32_t(j) & 1u) && mbar_test_wait(bar(B_V, s), uint32_t(j) & 1u) &&
+              (j < 1 || mbar_test_wait(bar(B_E, s), uint32_t(j - 1) & 1u))) {
             issue_pv(np);
             ++np;
             did = true;
@@ -214,7 +214,7 @@ attn_tct_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
         }
         if (ns < N && ns - np < 2) {
           const int s = ns & 1, j = ns >> 1;
-          if (mbar_try_wait(bar(B_QK, s), uint32_t(j) & 1u)) {
+          if (mbar_test_wait(bar(B_QK, s), uint32_t(j) & 1u)) {
             if (p.dbg && blockIdx.x == 0 && ns < 8) p.dbg[ns * 16 + 1] = clock64();
             issue_s(ns);
             ++ns;
