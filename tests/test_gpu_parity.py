@@ -846,3 +846,52 @@ def test_full_size_config2_image_is_deterministic_and_grammatical(env):
     assert sum(t[1] for t in trace) == len(img) and nfe < len(img)
     assert all(1 <= t[1] <= t[0] for t in trace), "accepted count outside [1, window]"
     ds.close()
+
+
+def test_config4_width_long_cache_kernels_agree(env):
+    """BASELINE config 4 at full width (Emu3-Gen: 32 query / 8 kv heads, d_ff 14 336, V = 184 622; 2 layers deep) over a
+    4 096-token cache: the same 64 draft tokens fed as one window of 64 (mma.sync attention, 256 stacked rows per kv
+    head), as two windows of 32 (tcgen05 attention, 128 rows) and one by one (window 1) must give the same logits to
+    bf16 rounding — three attention kernels / split plans, two GEMM row counts, one answer.  Then the wide verify:
+    tokens restricted to the 32 768 visual ids."""
+    from sjd_b200 import families
+    model, engine, dev = env["model"], env["engine"], env["dev"]
+    shape = families.emu3_gen()
+    shape.n_layers = 2
+    w = families.random_weights(shape, seed=5, std=0.03, device=dev)
+    max_len = 4352
+    cos, sin = families.rope_rotate_half(128, max_len, 1e6, True)
+    ds = model.DeviceStack(shape, w, cos, sin, 2, max_len, dev)
+    del w
+    V, L, kv_lo = shape.vocab, 4096, [0, 16]
+    gen = torch.Generator().manual_seed(8)
+
+    def fwd(ids2, kv_len):
+        Wn = ids2.shape[1]
+        pos = torch.arange(kv_len, kv_len + Wn, dtype=torch.int32, device=dev)
+        rope = torch.cat([(pos - kv_lo[b]).clamp(min=0) for b in range(2)]).int().contiguous()
+        return ds.forward(Wn, rope, pos.repeat(2).contiguous(), kv_len, kv_lo, ids=ids2.flatten().contiguous(),
+                          n_logit_tokens=Wn).clone()
+
+    for s in range(0, L, 128):   # fill the cache
+        fwd(torch.randint(0, V, (2, 128), generator=gen).int().to(dev), s)
+    win = torch.randint(151854, 151854 + 32768, (1, 64), generator=gen).int().repeat(2, 1).to(dev)
+    big = fwd(win, L)                                                     # [2, 64, V], window 64
+    halves = torch.cat([fwd(win[:, :32].contiguous(), L), fwd(win[:, 32:].contiguous(), L + 32)], 1)
+    ulp = 2.0 ** (torch.floor(torch.log2(big.abs().max())).item() - 7)
+    assert (halves - big).abs().max().item() <= 2.0 * ulp, ((halves - big).abs().max().item(), ulp)
+    for i in (0, 1, 31, 32, 63):                                          # the cache holds win[:, :64] from the calls above
+        one = fwd(win[:, i:i + 1].contiguous(), L + i)
+        assert (one[:, 0] - big[:, i]).abs().max().item() <= 2.0 * ulp, i
+    # verify over the 184 622-wide vocabulary with Emu3's 32 768-id visual range (strided, range-restricted path)
+    W = 64
+    desc = {"allow": (151854, 151854 + 32768), "forced": [-1] * W, "top_k": 2048}
+    e1 = torch.empty(W, V, device=dev).exponential_(generator=torch.Generator(dev).manual_seed(1))
+    out = engine.verify_call(big.view(-1, V), W, V, desc, win[0].contiguous(), None, None, has_uncond=True, apply_cfg=True,
+                             guidance=3.0, temperature=1.0, do_sample=True, scheme=1, noise_e1=e1)
+    toks = out["tokens"].cpu()
+    p = out["p"]
+    assert bool(((toks >= 151854) & (toks < 151854 + 32768)).all())   # (ties with the k-th logit are kept: bf16 logits tie often)
+    assert bool(((p > 0).sum(1) <= 2048 + 128).all()) and torch.allclose(p.sum(1), torch.ones(W, device=dev), atol=1e-4)
+    assert float(p[:, :151854].sum()) == 0.0 and float(p[:, 151854 + 32768:].sum()) == 0.0
+    ds.close()
