@@ -12,8 +12,9 @@
 //   * S[128 q x 128 keys] = Q K^T :  A = Q tile, B = K tile, both K-major (head dim contiguous), SWIZZLE_128B boxes
 //     straight from the q buffer / K cache by TMA;
 //   * softmax on the TMEM accumulator with one thread per query row (row max and row sum are thread-local): two
-//     passes of tcgen05.ld, probabilities rounded to bf16 like the reference's bf16 SDPA and written into the smem the K
-//     tile occupied, as the K-major A operand of the second product;
+//     passes of tcgen05.ld, probabilities rounded to bf16 like the reference's bf16 SDPA and written into the smem the Q
+//     tile occupied (so the K tile is free for the next unit's K as soon as S exists), as the K-major A operand of the
+//     second product;
 //   * O[128 q x Dh] = P V :  B = the V tile exactly as TMA lands it ([key][head dim], head dim contiguous), consumed as
 //     an MN-major operand — no transposed cache, no smem transpose;
 //   * when the stacked rows fill only 1/rep of the 128 TMEM lanes (MHA, window 32: a quarter), Q is loaded rep times
@@ -115,7 +116,7 @@ __device__ __forceinline__ TcUnit tc_unit(const AttnTcParams& p, int u, int r) {
 }
 
 // Persistent: one CTA per SM walks units u = cta, cta + grid, ... through a two-stage pipeline
-//   warp 4 (TMA)  : loads Q, K (one barrier) and V (another) of unit n+1 as soon as the stage's previous product is done
+//   warp 4 (TMA)  : K of unit n+2 as soon as S(n) exists; Q and V of unit n+2 once O(n) has read P (which sits on Q) and V
 //   warp 5 (MMA)  : S(n) as soon as Q, K landed; then O(n-1) = P(n-1) V(n-1) once the softmax warps delivered P(n-1)
 //   warps 0..3, 8..11 : two softmax groups; group k owns pipeline stage k, i.e. every other unit: softmax of S(n) into
 //                   P(n), then the epilogue of its previous unit n-2 (whose O has long been ready)
@@ -134,19 +135,21 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
   constexpr uint32_t kQBytes = NDA * kTcRows * 128;       // Q tile: NDA atoms of [128 rows][128 B]
   constexpr uint32_t kKBytes = NDA * kTcKeys * 128;       // K tile, same shape
   constexpr uint32_t kPBytes = 2 * kTcRows * 128;         // P tile: two 64-key atoms of [128 rows][128 B]
-  constexpr uint32_t kKPBytes = kKBytes > kPBytes ? kKBytes : kPBytes;
+  // P is written where Q was (both are dead / born at "S done"), so the K tile is free the moment S has been computed
+  // and the next unit's K can land while this unit's softmax runs; Q (from L2) and V follow once P V has drained
+  constexpr uint32_t kQPBytes = kQBytes > kPBytes ? kQBytes : kPBytes;
   constexpr uint32_t kVBytes = NDA * kTcKeys * 128;       // V tile: NDA boxes of [128 keys][128 B]
-  constexpr uint32_t kStage = kQBytes + kKPBytes + kVBytes;
+  constexpr uint32_t kStage = kQPBytes + kKBytes + kVBytes;
   extern __shared__ uint8_t smem_raw[];
-  // per stage: qk landed, v landed, S done, P ready, O done, O drained
-  __shared__ __align__(8) uint64_t bars[12];
+  // per stage: q landed, v landed, S done, P ready, O done, O drained, k landed
+  __shared__ __align__(8) uint64_t bars[14];
   __shared__ uint32_t tmem_holder;
   __shared__ float xch_all[2 * 8 * kTcRows];              // per softmax group: {row max, row sum} x 2 column halves x 128 lanes, two units deep
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const AttnParams& a = p.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar = [&](int which, int s) { return smem_u32(&bars[which * 2 + s]); };
-  enum { B_QK = 0, B_V = 1, B_S = 2, B_P = 3, B_O = 4, B_E = 5 };
+  enum { B_Q = 0, B_V = 1, B_S = 2, B_P = 3, B_O = 4, B_E = 5, B_K = 6 };
   const int G = a.H / a.Hkv;
   const int n_units = a.n_chunks * a.Hkv * ((G + p.hpc - 1) / p.hpc) * a.rows;
   const int T = a.kv_len + a.W;
@@ -157,7 +160,8 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       tma_prefetch_desc(&maps.k);
       tma_prefetch_desc(&maps.v);
       for (int s = 0; s < 2; ++s) {
-        mbar_init(bar(B_QK, s), 1);
+        mbar_init(bar(B_Q, s), 1);
+        mbar_init(bar(B_K, s), 1);
         mbar_init(bar(B_V, s), 1);
         mbar_init(bar(B_S, s), 1);
         mbar_init(bar(B_P, s), 8);
@@ -198,15 +202,14 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       if (t.hidden) continue;
       if (t.key0 + kTcKeys > a.kv_len) break;     // touches this window's keys: not before the wait
       const int s = n & 1;
-      const uint32_t sK = base + uint32_t(s) * kStage + kQBytes, sV = sK + kKPBytes;
-      const int nq = t.rep * t.heads_here * NDA;
+      const uint32_t sK = base + uint32_t(s) * kStage + kQPBytes, sV = sK + kKBytes;
       if (lane == 0) {
-        mbar_arrive_expect_tx(bar(B_QK, s), uint32_t(nq) * uint32_t(p.Wp) * 128u + kKBytes);
+        mbar_arrive_expect_tx(bar(B_K, s), kKBytes);
         mbar_arrive_expect_tx(bar(B_V, s), kVBytes);
       }
       __syncwarp();
       const int krow = p.k_row0 + (t.b * a.Hkv + t.hkv) * a.Lmax + t.key0;
-      if (lane < NDA) tma_load_2d(sK + uint32_t(lane) * kTcKeys * 128, &maps.k, lane * 64, krow, bar(B_QK, s), kPolicyEvictFirst);
+      if (lane < NDA) tma_load_2d(sK + uint32_t(lane) * kTcKeys * 128, &maps.k, lane * 64, krow, bar(B_K, s), kPolicyEvictFirst);
       else if (lane < 2 * NDA)
         tma_load_2d(sV + uint32_t(lane - NDA) * kTcKeys * 128, &maps.v, (lane - NDA) * 64, krow, bar(B_V, s), kPolicyEvictFirst);
       ++n;
@@ -227,27 +230,35 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       const TcUnit t = tc_unit(p, u, 0);
       if (t.hidden) continue;
       const int s = n & 1, j = n >> 1;
-      const uint32_t sQ = base + uint32_t(s) * kStage, sK = sQ + kQBytes, sV = sK + kKPBytes;
+      const uint32_t sQ = base + uint32_t(s) * kStage, sK = sQ + kQPBytes, sV = sK + kKBytes;
       const int nq = t.rep * t.heads_here * NDA;               // Q boxes
       const bool kv_done = n < early;                        // K/V of this unit are in flight already
-      if (lane == 0 && !kv_done) {
-        if (j >= 1) mbar_wait_backoff(bar(B_O, s), uint32_t(j - 1) & 1u);   // the stage's previous P V has read its smem
-        mbar_arrive_expect_tx(bar(B_QK, s), uint32_t(nq) * uint32_t(p.Wp) * 128u + kKBytes);
-        mbar_arrive_expect_tx(bar(B_V, s), kVBytes);
+      const int krow = p.k_row0 + (t.b * a.Hkv + t.hkv) * a.Lmax + t.key0;
+      // K first: its smem is free as soon as the stage's previous S has been computed
+      if (!kv_done) {
+        if (lane == 0) {
+          if (j >= 1) mbar_wait_backoff(bar(B_S, s), uint32_t(j - 1) & 1u);
+          mbar_arrive_expect_tx(bar(B_K, s), kKBytes);
+        }
+        __syncwarp();
+        if (lane < NDA)
+          tma_load_2d(sK + uint32_t(lane) * kTcKeys * 128, &maps.k, lane * 64, krow, bar(B_K, s), kPolicyEvictFirst);
+      }
+      // Q (it lands where the previous P was) and V: once the stage's previous P V has read them
+      if (lane == 0) {
+        if (j >= 1) mbar_wait_backoff(bar(B_O, s), uint32_t(j - 1) & 1u);
+        mbar_arrive_expect_tx(bar(B_Q, s), uint32_t(nq) * uint32_t(p.Wp) * 128u);
+        if (!kv_done) mbar_arrive_expect_tx(bar(B_V, s), kVBytes);
       }
       __syncwarp();
-      const int krow = p.k_row0 + (t.b * a.Hkv + t.hkv) * a.Lmax + t.key0;
-      for (int l = lane; l < 2 * NDA + nq; l += 32) {
-        if (kv_done && (l < NDA || l >= NDA + nq)) continue;
-        if (l < NDA) {
-          tma_load_2d(sK + uint32_t(l) * kTcKeys * 128, &maps.k, l * 64, krow, bar(B_QK, s), kPolicyEvictFirst);
-        } else if (l < NDA + nq) {
-          const int x = l - NDA, d = x % NDA, gh = x / NDA;       // NDA is 1 or 2
+      for (int l = lane; l < NDA + nq; l += 32) {
+        if (l < nq) {
+          const int d = l % NDA, gh = l / NDA;                  // NDA is 1 or 2
           const int gq = gh / t.heads_here, hs = gh - gq * t.heads_here;
           tma_load_2d(sQ + uint32_t(d) * kTcRows * 128 + uint32_t(gq * t.Rr + hs * p.Wp) * 128, &maps.q,
-                      (t.h0 + hs) * DH + d * 64, t.b * a.W, bar(B_QK, s), kPolicyEvictLast);
-        } else {
-          const int d = l - NDA - nq;
+                      (t.h0 + hs) * DH + d * 64, t.b * a.W, bar(B_Q, s), kPolicyEvictLast);
+        } else if (!kv_done) {
+          const int d = l - nq;
           tma_load_2d(sV + uint32_t(d) * kTcKeys * 128, &maps.v, d * 64, krow, bar(B_V, s), kPolicyEvictFirst);
         }
       }
@@ -261,7 +272,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       const uint32_t idesc_o = umma_idesc_bf16_f32_bmn(kTcRows, DH);
       auto issue_pv = [&](int m) {   // O(m) = P(m) V(m)
         const int s = m & 1, j = m >> 1;
-        const uint32_t sK = base + uint32_t(s) * kStage + kQBytes, sV = sK + kKPBytes;
+        const uint32_t sP = base + uint32_t(s) * kStage, sV = sP + kQPBytes + kKBytes;
         mbar_wait_backoff(bar(B_V, s), uint32_t(j) & 1u);
         mbar_wait_backoff(bar(B_P, s), uint32_t(j) & 1u);
         if (j >= 1) mbar_wait_backoff(bar(B_E, s), uint32_t(j - 1) & 1u);   // the previous O of this stage has been drained
@@ -271,7 +282,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
         uint32_t acc = 0;
 #pragma unroll
         for (int ka = 0; ka < 2; ++ka) {
-          const uint64_t da = umma_desc_sw128_kmajor(sK + uint32_t(ka) * kTcRows * 128);
+          const uint64_t da = umma_desc_sw128_kmajor(sP + uint32_t(ka) * kTcRows * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t db = umma_desc_sw128_mnmajor(sV + uint32_t(ka * 64 + k * 16) * 128, kTcKeys * 128);
@@ -284,7 +295,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       };
       auto issue_s = [&](int m) {    // S(m) = Q(m) K(m)^T
         const int s = m & 1;
-        const uint32_t sQ = base + uint32_t(s) * kStage, sK = sQ + kQBytes;
+        const uint32_t sQ = base + uint32_t(s) * kStage, sK = sQ + kQPBytes;
         tcgen05_fence_after();
         const uint32_t tS = tmem_base + uint32_t(s) * 256;
         uint32_t acc = 0;
@@ -320,7 +331,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
         }
         if (ns < N && ns - np < 2) {
           const int s = ns & 1, j = ns >> 1;
-          if (mbar_test_wait(bar(B_QK, s), uint32_t(j) & 1u)) {
+          if (mbar_test_wait(bar(B_K, s), uint32_t(j) & 1u) && mbar_test_wait(bar(B_Q, s), uint32_t(j) & 1u)) {
             if (p.dbg && blockIdx.x == 0 && ns < 8) p.dbg[ns * 16 + 1] = clock64();
             issue_s(ns);
             ++ns;
@@ -409,7 +420,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
       const int s = n & 1, j = n >> 1;
       const int lo = t.lo, key0 = t.key0, rep = t.rep, g = t.g, rr = t.rr;
       const int ncol = kTcKeys / rep / 2, col0 = g * (kTcKeys / rep) + half * ncol;   // this thread's slice of the row's 128 keys (16 | 32 | 64)
-      uint8_t* const genP = smem_raw + (base + uint32_t(s) * kStage + kQBytes - smem_u32(smem_raw));
+      uint8_t* const genP = smem_raw + (base + uint32_t(s) * kStage - smem_u32(smem_raw));   // over the Q tile
       const uint32_t tS = tmem_base + uint32_t(s) * 256;
       float* const xmax = xch + (j & 1) * 4 * kTcRows;        // exchange buffers alternate between units: no barrier
       float* const xsum = xmax + 2 * kTcRows;                 //   is needed to protect their reuse; [half][lane]
@@ -533,7 +544,7 @@ void attn_tc_plan(AttnTcParams* p, int head_dim) {
   p->m_wp = tc_magic(uint32_t(p->Wp));
 }
 
-constexpr int attn_tc_smem(int head_dim) {   // two pipeline stages of {Q, K | P, V} + eight 32 x 20 fp32 transpose tiles
+constexpr int attn_tc_smem(int head_dim) {   // two pipeline stages of {Q | P, K, V} + eight 32 x 20 fp32 transpose tiles
   return 1024 + 2 * ((head_dim / 64) * kTcRows * 128 + 2 * kTcRows * 128 + (head_dim / 64) * kTcKeys * 128) + 8 * 32 * 20 * 4;
 }
 
