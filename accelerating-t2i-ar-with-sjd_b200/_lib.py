@@ -65,6 +65,7 @@ class VerifyArgs(C.Structure):
         ("noise_e1", C.c_void_p), ("noise_u", C.c_void_p), ("noise_e2", C.c_void_p),
         ("eoi_token", C.c_int32), ("text_top_k", C.c_int32),
         ("resid", C.c_void_p), ("next_tokens", C.c_void_p), ("out_tokens", C.c_void_p), ("out_info", C.c_void_p),
+        ("sync_ws", C.c_void_p),
     ]
 
 

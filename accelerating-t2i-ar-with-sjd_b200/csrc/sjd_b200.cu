@@ -240,7 +240,8 @@ int sjd_verify(const sjd_verify_args* a, void* stream) {
   p.q_row = a->q_row; p.p_prev = a->p_prev; p.p_cur = a->p_cur; p.noise_e1 = a->noise_e1; p.noise_u = a->noise_u;
   p.noise_e2 = a->noise_e2; p.eoi_token = a->eoi_token; p.text_top_k = a->text_top_k; p.resid = a->resid;
   p.next_tokens = a->next_tokens; p.out_tokens = a->out_tokens; p.out_info = a->out_info;
-  g_launches += 2;
+  p.sync_ws = a->sync_ws;
+  g_launches += a->sync_ws ? 1 : 2;
   int rc = verify_launch(p, static_cast<cudaStream_t>(stream));
   return rc ? fail(rc, "verify_launch") : 0;
 }

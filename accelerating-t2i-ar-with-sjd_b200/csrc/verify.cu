@@ -1,7 +1,7 @@
 // Speculative-Jacobi verify step: everything the reference does between "logits are back" and
 // "how many draft tokens survived" — CFG mix, grammar mask, top-k, softmax, sampling, probabilistic
-// accept/reject scan, residual resample, prefix match — as two launches with no host round trip and
-// no Python loop.  Restates, on device:
+// accept/reject scan, residual resample, prefix match — as ONE launch with no host round trip and
+// no Python loop (the CTA that finishes its window position last runs the accept scan).  Restates, on device:
 //   sampling_logits2tokens                 scheduler/jacobi_iteration_lumina_mgpt.py:82-132
 //   MultiTokensVLLogitsProcessor           scheduler/logit_processor_3dim.py:45-155   (as allow-range + forced ids)
 //   MultiTokensInterleavedTopKLogitsWarper scheduler/logit_processor_3dim.py:158-204  (scores < k-th largest removed)
@@ -47,6 +47,7 @@ struct VerifyParams {
   int* next_tokens;      // [W] scratch: tokens sampled from p_cur
   int* out_tokens;       // [W] tokens after accept / resample
   int* out_info;         // [4] matched, rejected(0/1), first_reject, reserved
+  unsigned int* sync_ws; // one zero-initialised word: lets the last row CTA run the accept scan in the same launch
 };
 
 __device__ __forceinline__ uint32_t f2key(float f) {
@@ -471,10 +472,7 @@ __device__ int block_top_p(float* __restrict__ row, int V, float thresh, int do_
 constexpr int kRegVPT = 16;   // ids per thread held in registers: candidate ranges spanning up to 16 384 ids
 
 // One CTA per window position.
-__global__ void __launch_bounds__(kVerifyThreads) verify_rows_kernel(VerifyParams p) {
-  __shared__ BlockScratch sc;
-  __shared__ TopPScratch tp;
-  const int i = blockIdx.x;
+__device__ void verify_row(const VerifyParams& p, int i, BlockScratch& sc, TopPScratch& tp) {
   const int V = p.V;
   const float* c = p.logits + size_t(i) * V;
   const float* u = p.logits + size_t(p.W + i) * V;
@@ -545,9 +543,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_rows_kernel(VerifyParam
 }
 
 // Single CTA: accept scan over the window, prefix match, residual resample at the first rejection.
-__global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyParams p) {
-  __shared__ BlockScratch sc;
-  __shared__ TopPScratch tp;
+__device__ void verify_accept(const VerifyParams& p, BlockScratch& sc, TopPScratch& tp) {
   __shared__ int s_first;
   __shared__ int s_text_mode;
   const int W = p.W, V = p.V;
@@ -662,10 +658,45 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyPar
   }
 }
 
+// One launch for the whole verify step: every CTA processes its window position, the CTA that finishes LAST (a counter
+// in sync_ws, which it leaves zero again) runs the accept scan — it then sees every row's probabilities and samples.
+__global__ void __launch_bounds__(kVerifyThreads) verify_kernel(VerifyParams p) {
+  __shared__ BlockScratch sc;
+  __shared__ TopPScratch tp;
+  __shared__ int s_last;
+  verify_row(p, blockIdx.x, sc, tp);
+  __syncthreads();                       // the whole row (p_cur, next_tokens) has been written by this CTA
+  if (threadIdx.x == 0) {
+    __threadfence();                     // ... and is visible device-wide before the count goes up
+    s_last = atomicAdd(p.sync_ws, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) *p.sync_ws = 0u; // re-arm for the next launch
+  __threadfence();                       // acquire side: the other CTAs' rows
+  verify_accept(p, sc, tp);
+}
+
+// two-launch form for callers that pass no sync word
+__global__ void __launch_bounds__(kVerifyThreads) verify_rows_kernel(VerifyParams p) {
+  __shared__ BlockScratch sc;
+  __shared__ TopPScratch tp;
+  verify_row(p, blockIdx.x, sc, tp);
+}
+__global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyParams p) {
+  __shared__ BlockScratch sc;
+  __shared__ TopPScratch tp;
+  verify_accept(p, sc, tp);
+}
+
 int verify_launch(const VerifyParams& p, cudaStream_t stream) {
   if (p.W < 1 || p.W > kVerifyThreads) return -3;
-  verify_rows_kernel<<<p.W, kVerifyThreads, 0, stream>>>(p);
-  verify_accept_kernel<<<1, kVerifyThreads, 0, stream>>>(p);
+  if (p.sync_ws) {
+    verify_kernel<<<p.W, kVerifyThreads, 0, stream>>>(p);
+  } else {
+    verify_rows_kernel<<<p.W, kVerifyThreads, 0, stream>>>(p);
+    verify_accept_kernel<<<1, kVerifyThreads, 0, stream>>>(p);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 

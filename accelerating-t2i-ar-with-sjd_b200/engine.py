@@ -55,6 +55,10 @@ def verify_call(logits: torch.Tensor, W: int, V: int, desc: dict, draft: torch.T
     out_tok = torch.empty(W, dtype=torch.int32, device=dev)
     info = torch.empty(4, dtype=torch.int32, device=dev)
     a.resid, a.next_tokens, a.out_tokens, a.out_info = resid.data_ptr(), nxt.data_ptr(), out_tok.data_ptr(), info.data_ptr()
+    k = ("sync_ws", str(dev))
+    if k not in _scratch:
+        _scratch[k] = torch.zeros(1, dtype=torch.int32, device=dev)   # zero once; the kernel leaves it zero
+    a.sync_ws = _scratch[k].data_ptr()
     stream = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(L.sjd_verify(C.byref(a), C.c_void_p(stream)), "sjd_verify")
     res = {"tokens": out_tok, "next_tokens": nxt, "info": info, "p": p_cur, "_keep": (forced,)}
@@ -397,6 +401,7 @@ class SJDEngine:
         self.h_out = torch.empty(4 + Wmax, dtype=torch.int32).pin_memory()
         self.d_nxt = torch.empty(Wmax, dtype=torch.int32, device=self.dev)
         self.resid = torch.empty(self.V, dtype=torch.float32, device=self.dev)
+        self.d_sync = torch.zeros(1, dtype=torch.int32, device=self.dev)   # sjd_verify's last-CTA counter (stays zero)
         self.noise_factory = noise_factory or NoiseSource
         self.lib = _lib.lib()
         self.stats = SJDStats()
@@ -535,6 +540,7 @@ class SJDEngine:
             a.eoi_token, a.text_top_k = int(grammar.eoi_token), int(grammar.text_top_k)
             a.resid, a.next_tokens = self.resid.data_ptr(), self.d_nxt.data_ptr()
             a.out_info, a.out_tokens = self.d_out.data_ptr(), self.d_out[4:].data_ptr()
+            a.sync_ws = self.d_sync.data_ptr()
             stream = torch.cuda.current_stream(dev)
             _lib.check(self.lib.sjd_verify(C.byref(a), C.c_void_p(stream.cuda_stream)), "sjd_verify")
             self.h_out[:4 + Wv].copy_(self.d_out[:4 + Wv], non_blocking=True)

@@ -91,6 +91,9 @@ typedef struct sjd_verify_args {
   int32_t* next_tokens;   /* [W] scratch */
   int32_t* out_tokens;    /* [W] tokens after accept/resample: first `matched` are final, rest are next drafts */
   int32_t* out_info;      /* [4]: matched, rejected, first_reject, residual_text_mode */
+  uint32_t* sync_ws;      /* one device word, ZERO before its first use (the kernel leaves it zero): with it the whole step
+                           * is ONE launch — the CTA that finishes its window position last runs the accept scan.  NULL:
+                           * two launches (rows, then accept).  Not to be shared by calls in flight on different streams. */
 } sjd_verify_args;
 
 int sjd_verify(const sjd_verify_args* args, void* stream);
