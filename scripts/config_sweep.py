@@ -33,9 +33,9 @@ def ev_time(fn, n=8, warm=3):
     return e0.elapsed_time(e1) / n
 
 
-def run(name, shape, points, max_len, prompt=67, allow=(4, 8196), top_k=2000):
+def run(name, shape, points, max_len, prompt=67, allow=(4, 8196), top_k=2000, rope=None):
     w = families.random_weights(shape, seed=0, device=dev)
-    cos, sin = families.rope_rotate_half(shape.head_dim, max_len, 10000.0, True)
+    cos, sin = rope if rope is not None else families.rope_rotate_half(shape.head_dim, max_len, 10000.0, True)
     st = model.DeviceStack(shape, w, cos, sin, rows=2, max_len=max_len, device=dev)
     del w
     torch.cuda.empty_cache()
@@ -91,3 +91,6 @@ if "lumina" in which:
 if "emu3" in which:
     run("emu3-gen", families.emu3_gen(), [(64, 4096), (64, 8000), (32, 4096)], 8320, prompt=48,
         allow=(151854, 151854 + 32768), top_k=2048)
+if "llamagen" in which:   # config 1: LlamaGen GPT-B class-conditional 256 x 256 (16 x 16 latent grid + 1 condition token), window 16
+    run("llamagen-gpt-b", families.llamagen("GPT-B"), [(16, 64), (16, 200), (1, 200)], 320, prompt=1, allow=(0, 16384),
+        top_k=1000, rope=families.rope_llamagen_2d(16, 64, 10000, 1))
