@@ -272,6 +272,8 @@ struct GemmOp {
 struct Chain {
   int n_ops, num_stages;
   int lookahead;   // weight units prefetched into L2 beyond the ring
+  int pf_always;   // 1: keep the L2 prefetch frontier `lookahead` units ahead in steady state too (0: only while the ring is blocked)
+  int dbg_xskip;   // developer timing only (SJD_DEBUG_XSKIP=1): skip the activation-tile loads after the ring's first fill (results are garbage)
   uint32_t tmem_cols;
   uint32_t* fin;   // [(kMaxChainOps + 2) * kCtrStride] rows finalised per op, exit counter, pre-op counter; zero between launches
   // optional pre-op run by the (otherwise idle) epilogue warps before op 0: merge the attention's key-split partials
@@ -343,6 +345,7 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
       int pf_i = 0;                 // prefetch cursor (op, unit), never behind the issue cursor
       uint32_t pf_u = ch.ops[0].sk.begin(cta);
       int pf_ahead = 0;             // units the prefetch cursor is ahead of the issue cursor
+      int n_issued = 0;
       auto w_coords = [&](const GemmOp& op, uint32_t u, int& c0, int& c1) {
         if (op.w_tiled) { c0 = 0; c1 = (op.w_row0 + int(u)) * kBlockN; }
         else { const uint32_t KB = uint32_t(op.sk.kb), tile = u / KB; c0 = int((u - tile * KB) * kBlockK); c1 = op.w_row0 + int(tile * kBlockN); }
@@ -373,9 +376,22 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
           }
           int c0, c1;
           w_coords(op, u, c0, c1);
-          mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+          mbar_arrive_expect_tx(full_bar(stage), (ch.dbg_xskip && n_issued >= num_stages) ? kATileBytes : stage_bytes);
           tma_load_2d(smem_base + uint32_t(stage) * stage_bytes, tw, c0, c1, full_bar(stage), kPolicyEvictFirst);
+          ++n_issued;
           if (pf_ahead > 0) --pf_ahead;
+          if (ch.pf_always) {   // top the L2 frontier up: at most two prefetches per load issued
+            if (pf_ahead == 0) { pf_i = i; pf_u = u + 1; }
+            for (int k = 0; k < 2; ++k) {
+              pf_normalise();
+              if (pf_ahead >= ch.lookahead || pf_i >= ch.n_ops) break;
+              int p0, p1;
+              w_coords(ch.ops[pf_i], pf_u, p0, p1);
+              tma_prefetch_l2_2d(&maps.w[ch.ops[pf_i].wmap], p0, p1);
+              ++pf_u;
+              ++pf_ahead;
+            }
+          }
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -385,6 +401,7 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int n_issued = 0;
       for (int i = 0; i < ch.n_ops; ++i) {
         const GemmOp& op = ch.ops[i];
         const CUtensorMap* tx = &maps.x[op.xmap];
@@ -406,8 +423,10 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
         for (uint32_t u = u0; u < u1; ++u) {
           const uint32_t kb = u % KB;
           mbar_wait(empty_bar(stage), phase ^ 1);
-          tma_load_2d(smem_base + uint32_t(stage) * stage_bytes + kATileBytes, tx, int(kb * kBlockK), 0,
-                      full_bar(stage), kPolicyEvictLast);
+          if (!(ch.dbg_xskip && n_issued >= num_stages))
+            tma_load_2d(smem_base + uint32_t(stage) * stage_bytes + kATileBytes, tx, int(kb * kBlockK), 0,
+                        full_bar(stage), kPolicyEvictLast);
+          ++n_issued;
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -862,6 +881,10 @@ int chain_launch(const TmapSet& maps, Chain ch, cudaStream_t stream) {
     lookahead = e ? atoi(e) : kLookahead;
   }
   ch.lookahead = lookahead;
+  static const int pf_always = getenv("SJD_GEMM_PF_ALWAYS") ? atoi(getenv("SJD_GEMM_PF_ALWAYS")) : 0;
+  static const int xskip = getenv("SJD_DEBUG_XSKIP") ? atoi(getenv("SJD_DEBUG_XSKIP")) : 0;
+  ch.pf_always = pf_always;
+  ch.dbg_xskip = xskip;
   int grid = 0;
   for (int i = 0; i < ch.n_ops; ++i) {
     if (ch.ops[i].sk.m_tile != ch.ops[0].sk.m_tile || ch.ops[i].sk.grid < 1) return -3;

@@ -125,6 +125,16 @@ class LuminaGrammarState:
     def no_cfg(self) -> bool:
         return self.n_start == self.n_end
 
+    def note_residual_call(self, accepted):
+        """On a rejection the reference re-runs its processors on the prefix plus the accepted drafts
+        (reject_sampling_single_token, :209-241); if those close the image the processor forgets h and w right there
+        (logit_processor_3dim.py:89-92), which the NEXT window's draft initialisation reads (:1069) before any other
+        processor call."""
+        n_start = self.n_start + sum(1 for t in accepted if t == self.image_start)
+        n_end = self.n_end + sum(1 for t in accepted if t == self.image_end)
+        if n_start == n_end:
+            self.h = self.w = None
+
     def describe(self, n: int) -> dict:
         in_img = self.n_start == self.n_end + 1
         d = {"allow": None, "forced": [-1] * n, "top_k": self.image_top_k if in_img else self.text_top_k}
@@ -333,6 +343,47 @@ class SJDStats:
     d2h_bytes: int = 0                          # device -> pinned-host bytes (accepted tokens, counters)
 
 
+def check_init_scheme(scheme: str):
+    """multi_token_init_scheme as get_multi_token_for_preparation reads it (jacobi_iteration_lumina_mgpt.py:502-594):
+    'random', or a name containing 'horizon' and 'repeat'.  'vertical' asserts upstream (:560); 'sample_horizon' (like
+    'repeat_horizon') dies upstream with an IndexError as soon as the Lumina grammar knows the image width (:577) — here
+    'repeat_horizon' runs with the semantics the code states (see horizon_init) and 'sample_horizon' is refused."""
+    if scheme == "random":
+        return
+    if "horizon" not in scheme:
+        raise ValueError(f"multi_token_init_scheme should be 'horizon' or 'vertical', but got {scheme}")
+    if "sample" in scheme:
+        raise NotImplementedError("multi_token_init_scheme 'sample_horizon' crashes in the reference (IndexError, "
+                                  "jacobi_iteration_lumina_mgpt.py:577) and has no implementation here; use "
+                                  "'repeat_horizon' or 'random'")
+    if "repeat" not in scheme:
+        raise ValueError(f"multi_token_init_scheme should be 'sample' or 'repeat', but got {scheme}")
+
+
+def horizon_init(fresh, scheme, ids, carried, img_w, prefill_num):
+    """Spatial draft initialisation, get_multi_token_for_preparation's non-'random' branch (:516-594).  The fresh tokens
+    are drawn uniformly first in every scheme (:517-523, same RNG consumption).  Once the grammar knows the latent
+    width w, a fresh draft at absolute sequence index a whose column (a - origin) % (w + 1) is not the first of its row
+    becomes a copy of its left neighbour, the token at index a - 1 of [accepted ids | carried drafts] — clamped to the
+    last known token (:570-574), so the fresh drafts of one window repeat the last known token up to the next row
+    start.  origin = prefill_num + 3 (:536).  Grammars without a width (LlamaGen, Emu3, Anole) keep the random drafts,
+    like the reference (img_width = 0, :533-537)."""
+    if scheme == "random" or not fresh or img_w is None:
+        return fresh
+    width, origin = int(img_w) + 1, prefill_num + 3
+    a0 = len(ids) + len(carried)
+    if a0 < origin:
+        return fresh
+    out = list(fresh)
+    n_known = len(ids) + len(carried)
+    for r in range(len(fresh)):
+        a = a0 + r
+        if (a - origin) % width - 1 >= 0:
+            j = min(a - 1, n_known - 1)
+            out[r] = int(ids[j]) if j < len(ids) else int(carried[j - len(ids)])
+    return out
+
+
 def set_seed(seed: int):
     """jacobi_iteration_lumina_mgpt.py:36-45"""
     _random.seed(seed)
@@ -446,6 +497,8 @@ class SJDEngine:
         scheme = {"speculative_jacobi": 0, "jacobi": 1}.get(p.prefix_token_sampler_scheme)
         if scheme is None:
             raise ValueError(f"prefix_token_sampler_scheme: {p.prefix_token_sampler_scheme}")
+        check_init_scheme(p.multi_token_init_scheme)
+        prefill_num = cur_len - 1   # attention_mask.shape[1] - 1 at entry (:1000)
         if p.seed is not None:
             set_seed(p.seed)   # python / numpy / torch global RNGs: the CPU one drives the fresh-draft randint
         noise = self.noise_factory(p.seed, dev)
@@ -479,11 +532,19 @@ class SJDEngine:
                 if n_rand > 0:
                     r = torch.randint(0, len(self.img_vocab), (1, n_rand))   # CPU global RNG, like :505-509
                     fresh = self.img_vocab[r[0]].tolist()
+                    fresh = horizon_init(fresh, p.multi_token_init_scheme, ids, carried, getattr(grammar, "w", None),
+                                         prefill_num)
                 window = [ids[-1]] + keep + fresh
                 q_row = [-1] + [carried_row0 + j for j in range(len(keep))] + [-1] * n_rand
             W = len(window)
             if kv_len + W > self.stack.max_len:
                 raise RuntimeError(f"KV cache too small: need {kv_len + W}, have {self.stack.max_len}")
+            n_rope = getattr(self.stack, "n_rope_pos", None)
+            if n_rope is not None and kv_len + W - min(kv_lo) > n_rope:
+                # the reference fails loudly on freqs_cis[input_pos] (llamagen/llamagen.py:386); reading past the table
+                # on the device would accept garbage drafts instead
+                raise RuntimeError(f"RoPE table too small: position {kv_len + W - min(kv_lo) - 1} needed, table has "
+                                   f"{n_rope} rows (jacobi_loop_interval_r / max_num_new_tokens reach past the image)")
             no_cfg = bool(grammar.no_cfg)
             # ---- forward (prefill may be chunked; only the last `n_out` positions need logits) ----------
             n_out = out_W
@@ -564,6 +625,8 @@ class SJDEngine:
             next_W = (min(p.max_num_new_tokens, lr[1] - cur_len)
                       if (cur_len >= lr[0] and cur_len < lr[1]) else 1)
             ids += new
+            if rejected and hasattr(grammar, "note_residual_call"):
+                grammar.note_residual_call(new[:-1])
             grammar.observe(new)
             kv_len += n_cached
             stats.nfe += 1

@@ -29,11 +29,12 @@ from . import engine as _engine
 from .model import DeviceStack, StackShape
 
 try:  # HF is plumbing for the boundary only
-    from transformers.generation.logits_process import LogitsProcessor, LogitsProcessorList, TopKLogitsWarper
+    from transformers.generation.logits_process import (LogitsProcessor, LogitsProcessorList, TemperatureLogitsWarper,
+                                                        TopKLogitsWarper, TopPLogitsWarper)
 except Exception:  # pragma: no cover
     LogitsProcessor = object
     LogitsProcessorList = list
-    TopKLogitsWarper = None
+    TopKLogitsWarper = TemperatureLogitsWarper = TopPLogitsWarper = None
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -182,10 +183,30 @@ def _visual_range(visual_tokens):
 
 
 def grammar_from_processors(processors, vocab=None):
-    """Translate the reference's processor list into the engine's grammar state."""
+    """Translate the reference's processor list into the engine's grammar state.  HF's own warpers, which
+    `generate()` appends for `temperature != 1` / `top_p < 1` / `top_k`, are consumed too: the returned state carries
+    `.temperature` (1.0 when no TemperatureLogitsWarper is in the list — the reference's _sample applies only what the
+    list holds, never generation_config.temperature by itself)."""
+    g = _grammar_from_processors(processors, vocab)
+    g.temperature = 1.0
+    for pr in processors or []:
+        if TemperatureLogitsWarper is not None and isinstance(pr, TemperatureLogitsWarper):
+            g.temperature *= float(pr.temperature)
+    return g
+
+
+def _grammar_from_processors(processors, vocab=None):
     vl = topk = emu = None
     plain_k, top_p, anole = 0, 1.0, []
     for pr in processors or []:
+        if TemperatureLogitsWarper is not None and isinstance(pr, TemperatureLogitsWarper):
+            continue      # a positive scale commutes with the grammar masks and the top-k selection: applied in sjd_verify
+        if TopPLogitsWarper is not None and isinstance(pr, TopPLogitsWarper):
+            # HF's 2-D nucleus warper == TopPLogitsWarper3d on every window row (logit_processor_3dim.py:355-419 is its port)
+            if getattr(pr, "min_tokens_to_keep", 1) != 1 or getattr(pr, "filter_value", -float("inf")) != -float("inf"):
+                raise NotImplementedError("TopPLogitsWarper on device keeps exactly one token at least and fills with -inf")
+            top_p = float(pr.top_p)
+            continue
         if getattr(pr, "_sjd_emu3_grammar", False):
             emu = pr
         elif isinstance(pr, MultiTokensVLLogitsProcessor):
@@ -346,18 +367,45 @@ def renew_sampler(model_class):
                                      self.guidance_scale, self.seed, self.multi_token_init_scheme, self.do_cfg,
                                      self.prefix_token_sampler_scheme)
 
-        def _sjd_stack(self, rows, max_len, device):
-            """Weights are packed once per (rows, capacity); a larger cached context is reused as is, so a solver-side
-            prefill and the following _sample share one KV cache."""
+        def _sjd_fingerprint(self):
+            """(data_ptr, version, dtype) of every parameter: changes on load_state_dict, in-place edits (LoRA merges),
+            .to(dtype) and re-allocation — the engine holds a private re-laid-out copy of the weights."""
+            return tuple((p.data_ptr(), p._version, p.dtype) for p in self.parameters())
+
+        def sjd_invalidate(self):
+            """Drop the engine's packed copy of the weights (and its KV cache); the next call re-packs."""
             st = getattr(self, "_sjd_stack_cache", None)
-            if st is not None and st.rows == rows and st.max_len >= max_len and st.ctx is not None:
-                return st
             if st is not None:
                 st.close()
+            object.__setattr__(self, "_sjd_stack_cache", None)
+            object.__setattr__(self, "_sjd_engine_cache", None)
+
+        def _sjd_stack(self, rows, max_len, device):
+            """Weights are packed once per (rows, capacity); a larger cached context is reused as is, so a solver-side
+            prefill and the following _sample share one KV cache.  A change of the module's parameters since the pack
+            (fingerprint above) re-packs instead of silently decoding with stale weights."""
+            st = getattr(self, "_sjd_stack_cache", None)
+            fp = self._sjd_fingerprint()
+            if st is not None and st.rows == rows and st.max_len >= max_len and st.ctx is not None and \
+                    getattr(st, "_sjd_fp", None) == fp:
+                return st
+            self.sjd_invalidate()
             packer = pack_llamagen if hasattr(self, "tok_embeddings") else pack_hf_decoder
             st = packer(self, max_len, rows, device)
+            st._sjd_fp = fp
             object.__setattr__(self, "_sjd_stack_cache", st)
             return st
+
+        def _sjd_engine(self, stack, grammar):
+            """One SJDEngine (two [W, V] fp32 probability buffers + pinned staging) per packed stack, reused across calls."""
+            eng = getattr(self, "_sjd_engine_cache", None)
+            vocab = self.img_vocab if self.img_vocab is not None else torch.arange(stack.shape.vocab)
+            if eng is None or eng.stack is not stack:
+                eng = _engine.SJDEngine(stack, self._sjd_params(), grammar, vocab)
+                object.__setattr__(self, "_sjd_engine_cache", eng)
+            else:
+                eng.p, eng.grammar, eng.img_vocab = self._sjd_params(), grammar, vocab.cpu().long()
+            return eng
 
         @torch.no_grad()
         def _sample(self, input_ids, logits_processor, stopping_criteria, generation_config, synced_gpus=False,
@@ -367,6 +415,12 @@ def renew_sampler(model_class):
                 raise ValueError("the SJD sampler decodes one prompt per call (the reference's B>1 path is broken too)")
             if self.prefix_token_sampler_scheme not in ("speculative_jacobi", "jacobi"):
                 raise ValueError(f"prefix_token_sampler_scheme: {self.prefix_token_sampler_scheme}")
+            for name in ("pixel_values", "inputs_embeds"):
+                if model_kwargs.get(name) is not None:
+                    # the reference feeds them to its first forward (prepare_inputs_for_generation_jacobi, :715-724)
+                    raise NotImplementedError(f"`{name}` (image-conditioned prompts) is not supported by the SJD engine: "
+                                              "the prefill would run on raw placeholder ids")
+            _engine.check_init_scheme(self.multi_token_init_scheme)
             device = input_ids.device
             do_cfg = bool(self.do_cfg) and self.guidance_scale != 1
             rows = 2 if do_cfg else 1
@@ -377,8 +431,7 @@ def renew_sampler(model_class):
             stack = self._sjd_stack(rows, int(-(-cap // 64) * 64), device)
             grammar = grammar_from_processors(list(logits_processor or []) + list(logits_warper or []),
                                               vocab=stack.shape.vocab)
-            eng = _engine.SJDEngine(stack, self._sjd_params(), grammar,
-                                    self.img_vocab if self.img_vocab is not None else torch.arange(stack.shape.vocab))
+            eng = self._sjd_engine(stack, grammar)
             attn = model_kwargs.get("attention_mask")
             prefill_num = (attn.shape[1] - 1) if attn is not None else len(prompt) - 1
             kv_lo = [0, prefill_num] if (rows == 2 and not self._init_doubled_attn_mask_cfg
@@ -407,7 +460,7 @@ def renew_sampler(model_class):
             t1.record()
             ids = eng.generate(prompt, max_length=max_length or (len(prompt) + 4096), eos_token_ids=eos,
                                do_sample=bool(generation_config.do_sample), kv_len0=kv_len0, kv_lo=kv_lo,
-                               temperature=float(getattr(generation_config, "temperature", 1.0) or 1.0),
+                               temperature=float(grammar.temperature),
                                stop_fn=stop_fn, uncond_input_ids=uncond)
             t2.record()
             torch.cuda.synchronize()

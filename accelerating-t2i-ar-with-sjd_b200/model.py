@@ -49,6 +49,7 @@ class DeviceStack:
         self.rope_cos = put(rope_cos, torch.float32)
         self.rope_sin = put(rope_sin, torch.float32)
         assert self.rope_cos.shape[1] == shape.head_dim // 2
+        self.n_rope_pos = int(self.rope_cos.shape[0])
         cfg = _lib.ModelCfg(shape.n_layers, shape.d_model, shape.n_heads, shape.n_kv_heads, shape.head_dim,
                             shape.d_ff, shape.vocab, shape.rms_eps, int(shape.qk_norm),
                             int(shape.rope_interleaved), rows, max_len, self.rope_cos.shape[0],

@@ -180,6 +180,19 @@ def run_ours(args):
     # 4*n_layers + 1 GEMMs with their fused epilogues), attention skipped.
     roof = None
     cpu_base = None
+    gpu_ref = None
+
+    def one_image_bounded(window, n_img_tokens, seed):
+        """our engine on the first n_img_tokens of an image with the given window (the span the eager reference leg times)"""
+        e2 = engine.SJDEngine(stack, engine.SJDParams(**sjd_params(window, seed)), grammar, torch.arange(4, 8196))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        ids = e2.generate(synthetic_prompt(seed), max_length=P + n_img_tokens, eos_token_ids=[8710], kv_lo=[0, P - 1])
+        b.record()
+        torch.cuda.synchronize()
+        return {"seconds": a.elapsed_time(b) / 1e3, "nfe": e2.stats.nfe, "new_tokens": len(ids) - P}
+
     if rank == 0:
         M = 2 * args.window
         st = torch.cuda.current_stream().cuda_stream
@@ -217,6 +230,8 @@ def run_ours(args):
                 "us_per_gemm": round(t_launch * n_launch / n_gemm * 1e6, 2)}
         if world == 1 and not args.no_cpu_baseline:
             cpu_base = cpu_reference(args, budget_s=args.cpu_budget)
+        if world == 1 and not args.no_gpu_reference:
+            gpu_ref = gpu_eager_reference(args, dev, eng, one_image_bounded)
 
     if rank == 0:
         line = {
@@ -230,7 +245,7 @@ def run_ours(args):
             "e2e": {"value": round(e_tot / t_e2e, 2), "unit": UNIT, "h2d_bytes_per_step": e_h2d // args.steps,
                     "d2h_bytes_per_step": e_d2h // args.steps, "api": "SyntheticLuminaSolver.generate (host ids in, host ids out)"},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu_base,
+            "roofline": roof, "cpu_baseline": cpu_base, "gpu_eager_reference": gpu_ref,
         }
         print(json.dumps(line), flush=True)
     stack.close()
@@ -238,6 +253,54 @@ def run_ours(args):
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ===================================================== the reference's own PyTorch-eager SJD on this GPU (north_star's denominator)
+def gpu_eager_reference(args, dev, eng, ours_bounded):
+    """BASELINE north_star: ">= 2x the reference's own single-GPU PyTorch SJD image-tokens/sec on Lumina-mGPT-7B 768x768".
+    Runs the UNMODIFIED reference (baseline/_ref: scheduler/jacobi_iteration_lumina_mgpt.py + vendored Chameleon, HF-5.5
+    name shims only) on this GPU at the same 7B shape / bf16 / cfg / top-k, on the first `--ref-tokens` image tokens of one
+    768x768 image (a bounded sample: the whole image takes the reference ~2 minutes), for windows 32 and 16, timed by
+    the reference's own CUDA-event timer; then our engine on the SAME span.  `speedup` = reference ms/NFE over ours
+    (acceptance is a property of the weights, identical for both)."""
+    sys.path.insert(0, str(ROOT / "baseline"))
+    try:
+        import ref_gpu_eager as RG
+    except Exception as ex:   # pragma: no cover
+        return {"unavailable": f"baseline/ref_gpu_eager.py import failed: {ex!r}"[:200]}
+    why = RG.available()
+    if why:
+        return {"unavailable": why}
+    out = {"impl": "unmodified reference (JacobiSampler._sample + vendored ChameleonForConditionalGeneration, sdpa), "
+                   "PyTorch eager, bf16, same GPU", "torch": torch.__version__, "sample":
+           f"first {args.ref_tokens} image tokens of one 768x768 image per window (prefill + AR steps + Jacobi windows)",
+           "timer": "reference's own CUDA events (jacobi_iteration_lumina_mgpt.py:1050-1055,1213-1223)", "windows": {}}
+    try:
+        t0 = time.perf_counter()
+        model, mods = RG.build_model(dev, seed=0)
+        out["build_s"] = round(time.perf_counter() - t0, 1)
+        P = PROMPT_TEXT + 3
+        for window in (args.window, 16) if args.window != 16 else (16,):
+            RG.run(model, mods, prompt=synthetic_prompt(77), max_length=P + 24, window=window, guidance=CFG,
+                   image_top_k=TOP_K, seed=77, grid=GRID)                      # warm-up (cuBLAS heuristics, allocator)
+            r = RG.run(model, mods, prompt=synthetic_prompt(0), max_length=P + args.ref_tokens, window=window,
+                       guidance=CFG, image_top_k=TOP_K, seed=0, grid=GRID)
+            ours_bounded(window, 24, 77)
+            o = ours_bounded(window, args.ref_tokens, 0)
+            out["windows"][str(window)] = {
+                "reference_ms_per_nfe": round(r["ms_per_nfe"], 3), "reference_nfe": r["nfe"],
+                "reference_new_tokens": r["new_tokens"], "reference_tokens_per_s": round(r["tokens_per_s"], 2),
+                "ours_ms_per_nfe": round(o["seconds"] / o["nfe"] * 1e3, 3), "ours_nfe": o["nfe"],
+                "ours_new_tokens": o["new_tokens"], "ours_tokens_per_s": round(o["new_tokens"] / o["seconds"], 2),
+                "speedup_ms_per_nfe": round(r["ms_per_nfe"] / (o["seconds"] / o["nfe"] * 1e3), 3),
+                "speedup_tokens_per_s": round((o["new_tokens"] / o["seconds"]) / r["tokens_per_s"], 3)}
+        del model
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        import traceback
+        out["error"] = f"{ex!r}"[:300]
+        out["traceback_tail"] = traceback.format_exc()[-600:]
+    return out
 
 
 # ================================================================= reference arm / cpu baseline (oracle port)
@@ -316,6 +379,8 @@ def main():
     ap.add_argument("--window", type=int, default=WINDOW)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference's eager SJD on this GPU")
+    ap.add_argument("--ref-tokens", type=int, default=192, help="image tokens decoded by the eager-reference leg per window")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

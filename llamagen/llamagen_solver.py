@@ -131,6 +131,43 @@ class LlamaGenSolver:
         return generated
 
 
-def generate(*args, **kwargs):
-    """The reference's non-Jacobi AR sampler (llamagen_solver.py:144-194) is not part of the SJD hot path."""
-    raise NotImplementedError("plain AR `generate` is not provided; use LlamaGenSolver (window 1 gives AR decoding)")
+@torch.no_grad()
+def generate(model, cond, max_new_tokens, emb_masks=None, cfg_scale=1.0, cfg_interval=-1, **sampling_kwargs):
+    """The reference's plain AR sampler (llamagen_solver.py:144-194: prefill, then decode_n_tokens one token at a time,
+    CFG switched off after `cfg_interval` steps, every token drawn from the GLOBAL torch generator by sample(), :75-84)
+    on the engine: window-1 forwards over the static KV cache.  Same signature, same return ([1, max_new_tokens])."""
+    device = cond.device
+    if device.type != "cuda":
+        raise RuntimeError("the SJD engine needs the model and its inputs on a CUDA device (no CPU fallback)")
+    if cond.shape[0] != 1:
+        raise ValueError("one prompt per call")
+    do_cfg = cfg_scale > 1.0
+    if model.model_type == "c2i":
+        cond_combined = torch.cat([cond, torch.ones_like(cond) * model.num_classes]) if do_cfg else cond
+        T = 1
+    elif model.model_type == "t2i":
+        cond_combined = torch.cat([cond, torch.zeros_like(cond) + model.cls_embedding.uncond_embedding]) if do_cfg else cond
+        T = cond.shape[1]
+        if emb_masks is not None and not bool(emb_masks.bool().all()):
+            raise NotImplementedError("caption padding masks (emb_masks with zeros) are not implemented on the SJD path")
+    else:
+        raise Exception("please check model type")
+    cond_embeds = model.cls_embedding(cond_combined, train=False)[:, : model.cls_token_num]
+    rows = 2 if do_cfg else 1
+    model.setup_caches(max_batch_size=rows, max_seq_length=T + max_new_tokens, dtype=model.tok_embeddings.weight.dtype)
+    cap = T + max_new_tokens + int(getattr(model, "max_num_new_tokens", 1)) + 8
+    if not hasattr(model, "_sjd_stack"):
+        raise RuntimeError("wrap the model with scheduler.jacobi_iteration_lumina_mgpt.renew_sampler first (it owns the engine)")
+    stack = model._sjd_stack(rows, int(-(-cap // 64) * 64), device)
+    pos = torch.arange(T, dtype=torch.int32, device=device).repeat(rows)
+    logits = stack.forward(T, pos, pos, 0, [0] * rows, embeds=cond_embeds.to(torch.bfloat16).contiguous(), n_logit_tokens=1)
+    tok = _first_token(logits[:, 0].float(), cfg_scale, **sampling_kwargs)
+    out = [tok]
+    for i in range(max_new_tokens - 1):
+        scale = cfg_scale if not (cfg_interval > -1 and i > cfg_interval) else 1.0   # cfg_flag (:134-136)
+        ids = tok.to(torch.int32).reshape(1).repeat(rows).contiguous()
+        p1 = torch.full((rows,), T + i, dtype=torch.int32, device=device)
+        logits = stack.forward(1, p1, p1, T + i, [0] * rows, ids=ids, n_logit_tokens=1)
+        tok = _first_token(logits[:, 0].float(), scale, **sampling_kwargs)
+        out.append(tok)
+    return torch.cat(out, dim=1).to(torch.int)

@@ -36,7 +36,7 @@ def first_token(logits_2rows: np.ndarray, cfg_scale: float, temperature: float, 
     return int(torch.multinomial(probs, num_samples=1)[0, 0])
 
 
-def generate(case: dict, ff: int, norm_eps: float, rope_base: float, trace=None):
+def generate(case: dict, ff: int, norm_eps: float, rope_base: float, trace=None, max_trips=None):
     cfg, w, cls_table, cos, sin = build_stack(case, ff, norm_eps, rope_base)
     T, n_new = case["cls_token_num"], case["grid"] ** 2
     stack = RF.RefStack(cfg, w, cos, sin, rows=2, max_len=T + n_new + case["jacobi"]["max_num_new_tokens"] + 2,
@@ -56,5 +56,5 @@ def generate(case: dict, ff: int, norm_eps: float, rope_base: float, trace=None)
 
     ids, nfe = O.decode(logits_fn, [tok0], params=O.OracleParams(**case["jacobi"]), grammar=O.PlainTopK(top_k=case["top_k"]),
                         img_vocab=np.arange(case["vocab"]), max_length=n_new, eos_ids=[], rows=2, do_sample=True,
-                        temperature=1.0, kv_len0=T, trace=trace)
-    return ids[-n_new:], nfe
+                        temperature=1.0, kv_len0=T, trace=trace, max_trips=max_trips)
+    return (ids[-n_new:] if max_trips is None else ids), nfe

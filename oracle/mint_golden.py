@@ -317,6 +317,30 @@ LOOP_CASES = {
 }
 
 
+# Spatial draft initialisation with the Lumina grammar (the only grammar that knows the latent width).  The UNMODIFIED
+# reference CRASHES on these (IndexError at jacobi_iteration_lumina_mgpt.py:577: it indexes the [B, 1, V] score tensor
+# with sequence positions before it reaches the 'repeat' / 'sample' branch), which is why its own drivers use 'random'
+# for Lumina (test_lumina_mgpt.py:59) and 'repeat_horizon' only for LlamaGen, where no width is known and the scheme
+# degenerates to 'random' (golden plain_topk_spec_w16).  No golden can be minted; tests/ run engine vs oracle on them and
+# tests/test_host_cpu.py shows the crash.  (python oracle/mint_golden.py crash  reproduces it.)
+UNPINNED_CASES = {
+    "lumina_spec_w8_repeat_horizon": dict(V=9216, sharp=16.0, grammar="lumina", image_top_k=2000, text_top_k=10,
+                                          prompt=[1, 100, 200, 8197, 8808, 8808], img_vocab=[4, 8196], do_sample=True,
+                                          eos=[8710], max_length=6 + 8 * 9 + 3,
+                                          jacobi=dict(jacobi_loop_interval_l=3, jacobi_loop_interval_r=8 * 8 + 8 - 10,
+                                                      max_num_new_tokens=8, guidance_scale=3.0, seed=0,
+                                                      multi_token_init_scheme="repeat_horizon", do_cfg=True,
+                                                      prefix_token_sampler_scheme="speculative_jacobi")),
+    "lumina_jacobi_w16_repeat_horizon": dict(V=9216, sharp=10.0, grammar="lumina", image_top_k=500, text_top_k=10,
+                                             prompt=[7, 8197, 8807, 8809], img_vocab=[4, 8196], do_sample=True, eos=[8710],
+                                             max_length=4 + 6 * 11 + 12,
+                                             jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=200,
+                                                         max_num_new_tokens=16, guidance_scale=3.0, seed=3,
+                                                         multi_token_init_scheme="repeat_horizon", do_cfg=True,
+                                                         prefix_token_sampler_scheme="jacobi")),
+}
+
+
 def mint_loops(out_dir: Path, only=None):
     Cache = apply_shims()
     for name, case in LOOP_CASES.items():
@@ -338,6 +362,14 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["loops", "forward"]
     if "loops" in which:
         mint_loops(out, only=[w for w in which if w in LOOP_CASES])
+    if "crash" in which:
+        Cache = apply_shims()
+        for name, case in UNPINNED_CASES.items():
+            try:
+                run_reference_loop(case, Cache)
+                print(name, "ran (unexpected)")
+            except IndexError as e:
+                print(name, "-> reference raises IndexError:", e)
     if "forward" in which:
         from oracle import mint_forward_golden as F
         F.mint_llamagen()

@@ -30,8 +30,20 @@ CASE = dict(dim=256, n_layer=2, n_head=4, vocab=1024, grid=8, num_classes=10, cl
                         prefix_token_sampler_scheme="speculative_jacobi"))
 
 
+# BASELINE config 1 at its stated size: class-conditional GPT-B (12 layers, d 768, 12 heads, 16 384 codes), 256 x 256 ->
+# 16 x 16 = 256 image tokens, window 16, cfg 4, top-k 1000 (test_llamagen.py:27-50 uses window 16 / top-k 1000 as well)
+CASE_GPTB = dict(dim=768, n_layer=12, n_head=12, vocab=16384, grid=16, num_classes=1000, cls_token_num=1,
+                 weights_seed=311, weights_std=0.04, cls_seed=312, class_id=207, cfg_scale=4.0, temperature=1.0,
+                 top_k=1000, top_p=1.0, global_seed=78,
+                 jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=16 * 16 - 16 - 2, max_num_new_tokens=16,
+                             guidance_scale=4.0, seed=6, multi_token_init_scheme="random", do_cfg=True,
+                             prefix_token_sampler_scheme="speculative_jacobi"))
+CASES = {"toy": (CASE, "llamagen_flow.json"), "gptb": (CASE_GPTB, "llamagen_flow_gptb.json")}
+
+
 @torch.no_grad()
-def main():
+def main(which="toy"):
+    CASE, fname = CASES[which]
     from oracle.mint_golden import apply_shims, load_reference_scheduler
     apply_shims()
     J, _ = load_reference_scheduler()
@@ -67,9 +79,10 @@ def main():
     out = solver.generate(torch.tensor([c["class_id"]]), c["grid"] ** 2, None, cfg_scale=c["cfg_scale"],
                           temperature=c["temperature"], top_k=c["top_k"], top_p=c["top_p"], sample_logits=True)
     res = {"tokens": out[0].tolist(), "ff": ff, "norm_eps": args.norm_eps, "rope_base": args.rope_base}
-    (REPO / "tests" / "golden" / "llamagen_flow.json").write_text(json.dumps({"case": c, "result": res}, separators=(",", ":")))
-    print("llamagen_flow.json:", len(res["tokens"]), "tokens", res["tokens"][:12])
+    (REPO / "tests" / "golden" / fname).write_text(json.dumps({"case": c, "result": res}, separators=(",", ":")))
+    print(fname + ":", len(res["tokens"]), "tokens", res["tokens"][:12])
 
 
 if __name__ == "__main__":
-    main()
+    for name in (sys.argv[1:] or ["toy", "gptb"]):
+        main(name)

@@ -379,6 +379,36 @@ class TorchNoise:
                                generator=self.g)[0].cpu().numpy()
 
 
+def horizon_init(fresh, scheme, ids, carried, img_w, prefill_num):
+    """get_multi_token_for_preparation's non-'random' branch (:516-594).  The fresh tokens have already been drawn
+    uniformly (the reference draws them first in every scheme, :517-523).  When the grammar knows the latent width, a
+    fresh draft at absolute index a whose column (a - origin) % (w + 1) is not 0 becomes a copy of the token at index
+    a - 1 of [accepted ids | carried drafts] — clamped to the last known token, so every such draft of one window
+    repeats the last known token ('repeat'; :565-586).  origin = prefill_num + 3 (:536)."""
+    if scheme == "random" or not fresh:
+        return fresh
+    if img_w is None:
+        return fresh
+    width, origin = int(img_w) + 1, prefill_num + 3
+    a0 = len(ids) + len(carried)
+    if a0 < origin:
+        return fresh
+    if "horizon" not in scheme:
+        raise AssertionError(f"multi_token_init_scheme should be 'horizon' or 'vertical', but got {scheme}")
+    if "sample" in scheme:
+        raise NotImplementedError("'sample_horizon' indexes a [B, 1, V] score tensor with sequence positions upstream "
+                                  "and crashes; not restated")
+    if "repeat" not in scheme:
+        raise AssertionError(f"multi_token_init_scheme should be 'sample' or 'repeat', but got {scheme}")
+    known = list(ids) + list(carried)
+    out = list(fresh)
+    for r in range(len(fresh)):
+        a = a0 + r
+        if (a - origin) % width - 1 >= 0:
+            out[r] = int(known[min(a - 1, len(known) - 1)])
+    return out
+
+
 def decode(logits_fn, input_ids, *, params: OracleParams, grammar, img_vocab, max_length, eos_ids=(), rows=2,
            do_sample=True, temperature=1.0, noise=None, max_trips=None, trace=None, stop_fn=None, kv_len0=0):
     """Run the SJD loop.  logits_fn(row_tokens: list[list[int]], kv_len: int, n_logit: int) -> float32
@@ -391,6 +421,7 @@ def decode(logits_fn, input_ids, *, params: OracleParams, grammar, img_vocab, ma
     do_cfg = bool(p.do_cfg) and p.guidance_scale != 1 and rows == 2
     noise = noise or TorchNoise(p.seed)
     lr = (cur_len + p.jacobi_loop_interval_l, cur_len + p.jacobi_loop_interval_r)
+    prefill_num = cur_len - 1      # attention_mask.shape[1] - 1 at entry (:1000)
     out_W = 1
     carried_tokens: list[int] = []
     carried_q: list = []          # distributions the carried drafts were sampled from
@@ -406,6 +437,8 @@ def decode(logits_fn, input_ids, *, params: OracleParams, grammar, img_vocab, ma
             keep_t, keep_q = carried_tokens[:n_fill], carried_q[:n_fill]
             n_rand = max(n_fill - len(carried_tokens), 0)
             fresh = [int(img_vocab[j]) for j in noise.randint(len(img_vocab), n_rand)] if n_rand > 0 else []
+            fresh = horizon_init(fresh, p.multi_token_init_scheme, ids, carried_tokens, getattr(grammar, "w", None),
+                                 prefill_num)
             window = [ids[-1]] + keep_t + fresh
             q_rows = [None] + keep_q + [None] * n_rand
         W = len(window)

@@ -21,7 +21,8 @@ def ev_time(fn, n=10):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-for W in (32, 16, 64):
+Ws = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [32, 16, 64]
+for W in Ws:
     L, P = 1200, 67
     ids = torch.randint(4, 8196, (2 * W,), dtype=torch.int32).to(dev)
     pos = torch.arange(L, L + W, dtype=torch.int32)

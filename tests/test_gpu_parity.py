@@ -405,8 +405,10 @@ def test_engine_on_real_stack_matches_oracle_replay(env):
 
 
 # ------------------------------------------------------------------------------- LlamaGen boundary (config 1)
-def test_llamagen_solver_flow_on_gpu(env):
-    """The reference's test_llamagen.py call sequence against this repo's drop-in modules, on the GPU:
+@pytest.mark.parametrize("golden", ["llamagen_flow.json", "llamagen_flow_gptb.json"])
+def test_llamagen_solver_flow_on_gpu(env, golden):
+    """(llamagen_flow_gptb.json = BASELINE config 1 at its stated size: GPT-B, 256 tokens, window 16, cfg 4, top-k 1000.)
+    The reference's test_llamagen.py call sequence against this repo's drop-in modules, on the GPU:
     llamagen.llamagen.Transformer -> renew_llamagen -> renew_sampler -> LlamaGenSolver.generate.  Every forward's
     logits are captured and the oracle flow (pinned to the reference by tests/golden/llamagen_flow.json) is replayed on
     them with the same generators: identical image tokens."""
@@ -417,7 +419,7 @@ def test_llamagen_solver_flow_on_gpu(env):
     from scheduler.jacobi_iteration_lumina_mgpt import renew_sampler
     from oracle import llamagen_flow
     RF, O, model_mod, dev = env["RF"], env["O"], env["model"], env["dev"]
-    g = json.loads((GOLDEN / "llamagen_flow.json").read_text())
+    g = json.loads((GOLDEN / golden).read_text())
     case, ref = g["case"], g["result"]
     args = ModelArgs(dim=case["dim"], n_layer=case["n_layer"], n_head=case["n_head"], vocab_size=case["vocab"],
                      block_size=case["grid"] ** 2, cls_token_num=case["cls_token_num"], num_classes=case["num_classes"],

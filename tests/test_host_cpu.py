@@ -320,3 +320,170 @@ def test_anole_adaptor_generate_reaches_sample_with_the_image_only_grammar():
     assert isinstance(g, engine.AnoleGrammarState)
     assert (g.boi, g.eoi, g.eos, g.allow, g.S, g.max_length, g.begin_index, g.top_k) == (70, 71, 2, (4, 64), 9, 4 + 11, 4, 7)
     assert int(seen["gc"].max_length) == 4 + 11
+
+
+# ------------------------------------------------------------------------ round 2: draft initialisation schemes (f2)
+def _ref_root():
+    for p in (ROOT / "baseline" / "_ref", Path("/root/reference")):
+        if (p / "scheduler" / "jacobi_iteration_lumina_mgpt.py").exists():
+            return p
+    return None
+
+
+def test_multi_token_init_scheme_is_validated_not_ignored(lib):
+    """every non-'random' scheme used to mean 'random' silently.  Now: 'repeat_horizon' is implemented (engine ==
+    oracle restatement of jacobi_iteration_lumina_mgpt.py:516-594), anything the reference asserts on raises ValueError, and
+    'sample_horizon' (an IndexError upstream) is refused."""
+    from sjd_b200 import engine
+    from oracle import sjd_oracle as O
+    engine.check_init_scheme("random")
+    engine.check_init_scheme("repeat_horizon")
+    for bad in ("vertical", "repeat_vertical", "horizon"):
+        with pytest.raises(ValueError):
+            engine.check_init_scheme(bad)
+    with pytest.raises(NotImplementedError):
+        engine.check_init_scheme("sample_horizon")
+    # width 8 (+1 for the end-of-line slot), prompt of 6 tokens -> origin = (6 - 1) + 3 = 8
+    ids = list(range(100, 120))            # 20 accepted tokens
+    carried = [7001, 7002]
+    fresh = [1, 2, 3, 4, 5, 6]
+    out = engine.horizon_init(fresh, "repeat_horizon", ids, carried, 8, 5)
+    # absolute indices 22..27 -> columns (a - 8) % 9 = 5, 6, 7, 8, 0, 1: copies of the last known token except at column 0
+    assert out == [7002, 7002, 7002, 7002, 5, 7002]
+    assert engine.horizon_init(fresh, "random", ids, carried, 8, 5) == fresh
+    assert engine.horizon_init(fresh, "repeat_horizon", ids, carried, None, 5) == fresh      # no width (LlamaGen, Emu3)
+    rng = random.Random(0)
+    for _ in range(200):
+        n_ids, n_c, n_f = rng.randint(1, 60), rng.randint(0, 9), rng.randint(0, 9)
+        a = [rng.randint(4, 8195) for _ in range(n_ids)]
+        c = [rng.randint(4, 8195) for _ in range(n_c)]
+        f = [rng.randint(4, 8195) for _ in range(n_f)]
+        w, pre = rng.choice([None, 4, 6, 48]), rng.randint(0, 12)
+        assert engine.horizon_init(f, "repeat_horizon", a, c, w, pre) == O.horizon_init(f, "repeat_horizon", a, c, w, pre)
+
+
+def test_reference_itself_crashes_on_lumina_horizon_schemes():
+    """Why 'repeat_horizon' + the Lumina grammar has no reference-minted golden: the unmodified reference raises
+    IndexError at jacobi_iteration_lumina_mgpt.py:577 as soon as a window inside the image needs fresh drafts."""
+    ref = _ref_root()
+    if ref is None:
+        pytest.skip("no reference checkout / baseline/_ref here")
+    code = ("import os, sys; sys.dont_write_bytecode = True; sys.path.insert(0, %r); os.environ['SJD_REFERENCE'] = %r\n"
+            "from oracle import mint_golden as M\nM.REF = __import__('pathlib').Path(%r)\nC = M.apply_shims()\n"
+            "case = M.UNPINNED_CASES['lumina_spec_w8_repeat_horizon']\n"
+            "try:\n    M.run_reference_loop(case, C); print('RAN')\nexcept IndexError as e:\n    print('INDEXERROR', e)\n"
+            % (str(ROOT), str(ref), str(ref)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "INDEXERROR" in r.stdout, (r.stdout[-500:], r.stderr[-800:])
+
+
+def test_oracle_repeat_horizon_changes_the_drafts_only_inside_the_image():
+    """Oracle loop with the spatial initialisation on the two unpinned cases: it must differ from 'random' (the scheme
+    is live), keep the grammar intact, and leave the greedy-Jacobi fixed point untouched."""
+    from oracle import mint_golden as M
+    from test_oracle_golden import run_oracle
+    differs = 0
+    for name, case in M.UNPINNED_CASES.items():
+        ids_h, nfe_h, tr_h = run_oracle(case)
+        rnd = dict(case, jacobi=dict(case["jacobi"], multi_token_init_scheme="random"))
+        ids_r, nfe_r, tr_r = run_oracle(rnd)
+        differs += int([t["n_new"] for t in tr_h] != [t["n_new"] for t in tr_r] or ids_h != ids_r)
+        P = len(case["prompt"])
+        h, w = (case["prompt"][-2] - 8804) * 2, (case["prompt"][-1] - 8804) * 2
+        img = ids_h[P:]
+        assert all(img[i] == 8803 for i in range(w, min(len(img), h * (w + 1)), w + 1)), name
+    assert differs >= 1, "the spatial initialisation never changed a run: the scheme is not live"
+
+
+# ------------------------------------------------------------------------ round 2: the drop-in boundary, for real
+_IMPORT_BLOCKS = {
+    # the import lines of the three reference demo scripts that touch modules this repository shadows or must not shadow
+    "test_llamagen.py:16-20": ["from llamagen.tokenizer.tokenizer_image.vq_model import VQ_models",
+                               "from llamagen.language.t5 import T5Embedder",
+                               "from llamagen.llamagen import GPT_models",
+                               "from llamagen.llamagen_solver import LlamaGenSolver, renew_llamagen, generate",
+                               "from scheduler.jacobi_iteration_lumina_mgpt import renew_sampler"],
+    "test_lumina_mgpt.py:10,101": ["from lumina_mgpt.inference_solver import FlexARInferenceSolver",
+                                   "from scheduler.jacobi_iteration_lumina_mgpt import renew_pipeline_sampler"],
+    "test_emu3.py:16,145": ["from emu3.mllm.processing_emu3 import Emu3Processor",
+                            "from scheduler.jacobi_iteration_emu3 import renew_solver"],
+}
+
+
+def test_reference_demo_scripts_import_blocks_resolve_with_this_repo_first():
+    """README's drop-in claim: with this repository AHEAD of a reference checkout on sys.path (the reference's scripts
+    append ./ and ./lumina_mgpt/ themselves, test_lumina_mgpt.py:4-5), every import of test_llamagen.py / test_lumina_mgpt.py
+    / test_emu3.py resolves — scheduler.* / llamagen.llamagen / llamagen.llamagen_solver to THIS repository, the VQ
+    decoder, T5 embedder, FlexARInferenceSolver and Emu3Processor to the reference's own files (round 1 shadowed
+    llamagen.tokenizer / llamagen.language with a regular package).  HF-5.5 name shims of SURVEY App. C applied first;
+    a missing third-party dependency of the reference (ftfy for its T5 text cleaner) is reported, not a failure."""
+    ref = _ref_root()
+    if ref is None:
+        pytest.skip("no reference checkout / baseline/_ref here")
+    lines = [l for block in _IMPORT_BLOCKS.values() for l in block]
+    code = ("import sys, json; sys.dont_write_bytecode = True\n"
+            "sys.path[:0] = [%r, %r, %r]\n"
+            "from oracle.mint_golden import apply_shims; apply_shims()\n"
+            "out = {}\n"
+            "for l in %r:\n"
+            "    try:\n"
+            "        exec(l, {}); out[l] = sys.modules[l.split()[1]].__file__\n"
+            "    except ModuleNotFoundError as e:\n"
+            "        out[l] = 'MISSING:' + str(e.name)\n"
+            "    except Exception as e:\n"
+            "        out[l] = 'ERROR:' + repr(e)[:200]\n"
+            "print('RESULT' + json.dumps(out))\n" % (str(ROOT), str(ref), str(ref / "lumina_mgpt"), lines))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd="/tmp")
+    import json
+    res = json.loads(r.stdout.split("RESULT", 1)[1])
+    ours = ("scheduler.", "llamagen.llamagen ", "llamagen.llamagen_solver ")
+    for line, where in res.items():
+        if where.startswith("MISSING:"):
+            # only third-party packages the reference itself needs may be missing, never a module of either repository
+            assert where.split(":", 1)[1].split(".")[0] not in ("llamagen", "scheduler", "lumina_mgpt", "emu3", "model",
+                                                                  "xllmx", "data"), (line, where)
+            continue
+        assert not where.startswith("ERROR:"), (line, where)
+        mine = any(line.split()[1].startswith(o.strip()) and (o.endswith(".") or line.split()[1] == o.strip()) for o in ours)
+        assert where.startswith(str(ROOT / "baseline")) != mine or str(ref) not in where, (line, where)
+        if mine:
+            assert where.startswith(str(ROOT)) and "baseline" not in where, (line, where)
+        else:
+            assert where.startswith(str(ref)), (line, where)
+
+
+def test_llamagen_renew_calls_of_the_demo_script_on_a_stub_checkpoint():
+    """test_llamagen.py:72-88 on CPU: GPT_models[...]() -> renew_llamagen -> renew_sampler -> _init_new_params(**dict with the
+    script's extra keys) -> load_state_dict of a stub checkpoint -> LlamaGenSolver(...).  (The forward needs the GPU.)"""
+    from llamagen.llamagen import GPT_models
+    from llamagen.llamagen_solver import LlamaGenSolver, renew_llamagen
+    from scheduler.jacobi_iteration_lumina_mgpt import renew_sampler
+    gpt = GPT_models["GPT-B"](block_size=16 ** 2, cls_token_num=1, model_type="c2i", num_classes=10, vocab_size=512)
+    jd = dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=(256 // 16) ** 2 - 16 - 2, max_num_new_tokens=16,
+              guidance_scale=7.5, seed=None, multi_token_init_scheme="repeat_horizon", do_cfg=True, image_top_k=1000,
+              text_top_k=10, prefix_token_sampler_scheme="speculative_jacobi")
+    gpt.__class__ = renew_llamagen(gpt.__class__)
+    gpt._init_new_params(**jd)
+    gpt.__class__ = renew_sampler(gpt.__class__)
+    gpt._init_new_params(**jd)
+    sd = {k: v.clone() for k, v in gpt.state_dict().items()}
+    missing = gpt.load_state_dict(sd, strict=False)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    solver = LlamaGenSolver(model=gpt, image_top_k=jd["image_top_k"], image_top_p=1.0)
+    assert [type(p).__name__ for p in solver.create_logits_processor()] == ["TopKLogitsWarper", "TopPLogitsWarper3d"]
+    assert gpt.multi_token_init_scheme == "repeat_horizon" and gpt.max_num_new_tokens == 16
+    with pytest.raises(RuntimeError, match="CUDA"):
+        solver.generate(torch.tensor([3]), 256, None, cfg_scale=7.5, temperature=1.0, top_k=1000, top_p=1.0)
+
+
+def test_hf_warpers_are_consumed_by_the_grammar_translation():
+    """HF generate() appends TemperatureLogitsWarper / TopPLogitsWarper / TopKLogitsWarper for non-default
+    sampling settings; they must reach sjd_verify instead of raising, and the kernel temperature must come from the list."""
+    from transformers.generation.logits_process import TemperatureLogitsWarper, TopKLogitsWarper, TopPLogitsWarper
+    from sjd_b200 import engine, hf_api
+    g = hf_api.grammar_from_processors([TopKLogitsWarper(50), TemperatureLogitsWarper(0.7), TopPLogitsWarper(0.9)])
+    assert isinstance(g, engine.PlainTopKState) and g.top_k == 50 and abs(g.top_p - 0.9) < 1e-12
+    assert abs(g.temperature - 0.7) < 1e-12
+    g = hf_api.grammar_from_processors([hf_api.MultiTokensVLLogitsProcessor(8197, 8196, 8803, 32, 65536),
+                                        hf_api.MultiTokensInterleavedTopKLogitsWarper(2000, 10, 8197, 8196)])
+    assert isinstance(g, engine.LuminaGrammarState) and g.temperature == 1.0

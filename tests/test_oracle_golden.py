@@ -156,3 +156,41 @@ def test_llamagen_flow_oracle_matches_reference():
     tokens, nfe = llamagen_flow.generate(case, ref["ff"], ref["norm_eps"], ref["rope_base"])
     assert tokens == ref["tokens"]
     assert nfe < len(tokens)
+
+
+def test_llamagen_flow_oracle_matches_reference_at_gptb_size():
+    """BASELINE config 1 at its stated size (class-conditional GPT-B: 12 layers, d 768, 16 384 codes; 16 x 16 tokens,
+    window 16, cfg 4, top-k 1000): tests/golden/llamagen_flow_gptb.json is the UNMODIFIED reference's test_llamagen.py
+    flow on CPU (oracle/mint_llamagen_flow.py gptb, 243 forwards).  The whole flow takes minutes on CPU, so the oracle
+    flow is checked on its first 10 forwards here (condition prefill, first token, nine Jacobi windows); the GPU test
+    replays the full length."""
+    import json
+    from conftest import GOLDEN
+    from oracle import llamagen_flow
+    g = json.loads((GOLDEN / "llamagen_flow_gptb.json").read_text())
+    case, ref = g["case"], g["result"]
+    ids, nfe = llamagen_flow.generate(case, ref["ff"], ref["norm_eps"], ref["rope_base"], max_trips=9)
+    assert nfe == 9 and len(ids) >= 9
+    assert ids == ref["tokens"][:len(ids)]
+
+
+@pytest.mark.parametrize("emulate_bf16", [False, True])
+@pytest.mark.parametrize("name", ["cfg3_4x4", "nocfg_6x6"])
+def test_forward_included_end_to_end_golden(name, emulate_bf16):
+    """tests/golden/e2e_chameleon_greedy_jacobi_*.json (oracle/mint_e2e_golden.py): the UNMODIFIED reference — vendored
+    Chameleon forward + renewed mask + JacobiSampler._sample, greedy, 'jacobi', window 8 — run on a tiny decoder, with
+    CFG 3 (two rows, hidden prompt prefix) and without.  The loop oracle driving the forward oracle must emit the same
+    tokens and, in fp32, the same accepted-count trace; with the bf16 rounding points emulated the tokens must still be
+    the same (every decisive argmax leads by several bf16 ulp of the logit scale — that is what lets the GPU test demand
+    token equality with the forward included)."""
+    import json
+    from conftest import GOLDEN
+    from oracle import e2e_case
+    g = json.loads((GOLDEN / f"e2e_chameleon_greedy_jacobi_{name}.json").read_text())
+    trace = []
+    ids, nfe = e2e_case.oracle_decode(g["case"], emulate_bf16, trace=trace)
+    assert ids == g["result"]["ids"]
+    assert g["result"]["min_margin_ulp_fp32"] >= (8.0 if name.startswith("cfg") else 3.5)
+    if not emulate_bf16:
+        assert [t["n_new"] for t in trace] == [t["n_new"] for t in g["result"]["trace"]]
+        assert nfe == len(g["result"]["trace"])
