@@ -66,6 +66,7 @@ class VerifyArgs(C.Structure):
         ("eoi_token", C.c_int32), ("text_top_k", C.c_int32),
         ("resid", C.c_void_p), ("next_tokens", C.c_void_p), ("out_tokens", C.c_void_p), ("out_info", C.c_void_p),
         ("sync_ws", C.c_void_p),
+        ("rng_mode", C.c_int32), ("rng_seed", C.c_uint64), ("rng_off", C.c_uint64 * 3), ("rng_span", C.c_uint32 * 3),
     ]
 
 
@@ -123,6 +124,8 @@ def lib() -> C.CDLL:
                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     L.sjd_verify.restype = C.c_int
     L.sjd_verify.argtypes = [C.POINTER(VerifyArgs), C.c_void_p]
+    L.sjd_debug_philox.restype = C.c_int
+    L.sjd_debug_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
     L.sjd_ctx_create.restype = C.c_int
     L.sjd_ctx_create.argtypes = [C.POINTER(ModelCfg), C.POINTER(C.c_void_p)]
     L.sjd_ctx_destroy.restype = None

@@ -57,15 +57,17 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_b
   for (int i = threadIdx.x; i < d / 8; i += blockDim.x) o[i] = s[i];
 }
 
-// One-time weight re-layout into contiguous GEMM tiles: dst[(tile*KB + kb)][128][64] <- src[row(tile, r)][kb*64 ..],
-// so that every TMA box of the weight stream is one contiguous 16 KB block of HBM.  Rows beyond N are zero.
+// One-time weight re-layout into contiguous GEMM units: dst[(group*KB + kb)][h][128][64] <- src[row(tile, r)][kb*64 ..]
+// with tile = group * tpu + h, so that every stream-K unit (tpu tiles against one activation tile, streamk.cuh) is one
+// contiguous tpu * 16 KB block of HBM.  Rows beyond N (and the missing tiles of a ragged last group) are zero.
 // gate_up != 0 additionally interleaves gate/up rows (src = [gate rows; up rows], ff rows each): tile row 4l+e is
 // gate[64*tile + 2l + e] for e < 2 and up[64*tile + 2l + e - 2] otherwise, so that lane l of the GEMM epilogue holds
 // gate and up of act columns 2l, 2l+1.
 __global__ void pack_tiles_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int K,
-                                  int gate_up_ff) {
+                                  int gate_up_ff, int tpu) {
   const int KB = K / 64;
   const int r = blockIdx.x & 127, tile = blockIdx.x >> 7;
+  const int grp = tile / tpu, hh = tile - grp * tpu;
   int srow;
   if (gate_up_ff) {
     const int l = r >> 2, e = r & 3;
@@ -77,7 +79,7 @@ __global__ void pack_tiles_kernel(const __nv_bfloat16* __restrict__ src, __nv_bf
     const int kb = i >> 3, c = i & 7;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (srow < N) v = *reinterpret_cast<const uint4*>(src + size_t(srow) * K + size_t(i) * 8);
-    *reinterpret_cast<uint4*>(dst + ((size_t(tile) * KB + kb) * 128 + r) * 64 + c * 8) = v;
+    *reinterpret_cast<uint4*>(dst + (((size_t(grp) * KB + kb) * tpu + hh) * 128 + r) * 64 + c * 8) = v;
   }
 }
 
@@ -89,9 +91,9 @@ int embed_rmsnorm_rows(const int* ids, const __nv_bfloat16* table, const __nv_bf
 int gather_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int rows, int W, int n, int d, cudaStream_t s) {
   return launch_pdl(gather_rows_kernel, dim3(rows * n), dim3(128), 0, s, src, dst, W, n, d);
 }
-int pack_tiles(const __nv_bfloat16* src, __nv_bfloat16* dst, int N, int K, int gate_up_ff, cudaStream_t s) {
-  const int n_tiles = (N + 127) / 128;
-  pack_tiles_kernel<<<n_tiles * 128, 128, 0, s>>>(src, dst, N, K, gate_up_ff);
+int pack_tiles(const __nv_bfloat16* src, __nv_bfloat16* dst, int N, int K, int gate_up_ff, int tpu, cudaStream_t s) {
+  const int n_tiles = ((N + 127) / 128 + tpu - 1) / tpu * tpu;   // whole groups: the tiles of a ragged last group are zero
+  pack_tiles_kernel<<<n_tiles * 128, 128, 0, s>>>(src, dst, N, K, gate_up_ff, tpu);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 

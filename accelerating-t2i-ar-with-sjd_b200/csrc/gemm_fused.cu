@@ -43,7 +43,8 @@ constexpr int kGemmThreads = 128 + kEpiThreads;  // warp 0 weight TMA, 1 MMA, 2 
 constexpr int kBlockN = 128;  // weight rows per tile (UMMA M)
 constexpr int kBlockK = 64;   // bf16 K elements per stage = one 128-byte swizzle row
 constexpr int kMaxStages = 12;
-constexpr uint32_t kATileBytes = kBlockN * kBlockK * 2;  // 16 KB
+constexpr uint32_t kATileBytes = kBlockN * kBlockK * 2;  // 16 KB per weight tile; a unit carries tpu of them
+constexpr int kMaxTpu = 4;
 constexpr int kCtrStride = 64;                            // u32 between hot counters: one 256-byte region each
 constexpr int kTileCtrStride = 8;                         // u32 per tile {arrived, done, pad..}: 32 bytes
 constexpr int kLookahead = 32;                            // weight units (16 KB) prefetched into L2 beyond the ring
@@ -275,6 +276,7 @@ struct Chain {
   int pf_always;   // 1: keep the L2 prefetch frontier `lookahead` units ahead in steady state too (0: only while the ring is blocked)
   int dbg_xskip;   // developer timing only (SJD_DEBUG_XSKIP=1): skip the activation-tile loads after the ring's first fill (results are garbage)
   uint32_t tmem_cols;
+  int nbuf;        // accumulator sets in TMEM
   uint32_t* fin;   // [(kMaxChainOps + 2) * kCtrStride] rows finalised per op, exit counter, pre-op counter; zero between launches
   // optional pre-op run by the (otherwise idle) epilogue warps before op 0: merge the attention's key-split partials
   // into the bf16 rows that op 0 (o_proj) reads; pre.n_chunks == 0 switches it off
@@ -296,9 +298,12 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_stages = ch.num_stages;
   const int m_tile = ch.ops[0].sk.m_tile;   // common to the chain
+  const int tpu = ch.ops[0].sk.tpu;         // weight tiles per unit, common to the chain
+  const int nbuf = ch.nbuf;                 // accumulator sets in TMEM (2, or 1 when 2 * tpu * m_tile > 512 columns)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_tile_bytes = uint32_t(m_tile) * kBlockK * 2;
-  const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
+  const uint32_t a_bytes = uint32_t(tpu) * kATileBytes;
+  const uint32_t stage_bytes = a_bytes + b_tile_bytes;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
@@ -346,9 +351,11 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
       uint32_t pf_u = ch.ops[0].sk.begin(cta);
       int pf_ahead = 0;             // units the prefetch cursor is ahead of the issue cursor
       int n_issued = 0;
+      // a unit = tpu tiles of 128 weight rows: one TMA box of 128 * min(tpu, 2) rows, two boxes when tpu = 4
+      const int box_rows = kBlockN * (tpu < 2 ? tpu : 2), n_box = (tpu + 1) / 2;
       auto w_coords = [&](const GemmOp& op, uint32_t u, int& c0, int& c1) {
-        if (op.w_tiled) { c0 = 0; c1 = (op.w_row0 + int(u)) * kBlockN; }
-        else { const uint32_t KB = uint32_t(op.sk.kb), tile = u / KB; c0 = int((u - tile * KB) * kBlockK); c1 = op.w_row0 + int(tile * kBlockN); }
+        if (op.w_tiled) { c0 = 0; c1 = (op.w_row0 + int(u)) * kBlockN * tpu; }
+        else { const uint32_t KB = uint32_t(op.sk.kb), grp = u / KB; c0 = int((u - grp * KB) * kBlockK); c1 = op.w_row0 + int(grp) * kBlockN * tpu; }
       };
       auto pf_normalise = [&]() {   // skip exhausted ops
         while (pf_i < ch.n_ops && pf_u >= ch.ops[pf_i].sk.begin(cta + 1)) {
@@ -367,7 +374,7 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
             if (pf_ahead < ch.lookahead && pf_i < ch.n_ops) {
               int c0, c1;
               w_coords(ch.ops[pf_i], pf_u, c0, c1);
-              tma_prefetch_l2_2d(&maps.w[ch.ops[pf_i].wmap], c0, c1);
+              for (int j = 0; j < n_box; ++j) tma_prefetch_l2_2d(&maps.w[ch.ops[pf_i].wmap], c0, c1 + j * box_rows);
               ++pf_u;
               ++pf_ahead;
             } else {
@@ -376,8 +383,10 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
           }
           int c0, c1;
           w_coords(op, u, c0, c1);
-          mbar_arrive_expect_tx(full_bar(stage), (ch.dbg_xskip && n_issued >= num_stages) ? kATileBytes : stage_bytes);
-          tma_load_2d(smem_base + uint32_t(stage) * stage_bytes, tw, c0, c1, full_bar(stage), kPolicyEvictFirst);
+          mbar_arrive_expect_tx(full_bar(stage), (ch.dbg_xskip && n_issued >= num_stages) ? a_bytes : stage_bytes);
+          for (int j = 0; j < n_box; ++j)
+            tma_load_2d(smem_base + uint32_t(stage) * stage_bytes + uint32_t(j) * 2u * kATileBytes, tw, c0, c1 + j * box_rows,
+                        full_bar(stage), kPolicyEvictFirst);
           ++n_issued;
           if (pf_ahead > 0) --pf_ahead;
           if (ch.pf_always) {   // top the L2 frontier up: at most two prefetches per load issued
@@ -387,7 +396,7 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
               if (pf_ahead >= ch.lookahead || pf_i >= ch.n_ops) break;
               int p0, p1;
               w_coords(ch.ops[pf_i], pf_u, p0, p1);
-              tma_prefetch_l2_2d(&maps.w[ch.ops[pf_i].wmap], p0, p1);
+              for (int j = 0; j < n_box; ++j) tma_prefetch_l2_2d(&maps.w[ch.ops[pf_i].wmap], p0, p1 + j * box_rows);
               ++pf_u;
               ++pf_ahead;
             }
@@ -424,7 +433,7 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
           const uint32_t kb = u % KB;
           mbar_wait(empty_bar(stage), phase ^ 1);
           if (!(ch.dbg_xskip && n_issued >= num_stages))
-            tma_load_2d(smem_base + uint32_t(stage) * stage_bytes + kATileBytes, tx, int(kb * kBlockK), 0,
+            tma_load_2d(smem_base + uint32_t(stage) * stage_bytes + a_bytes, tx, int(kb * kBlockK), 0,
                         full_bar(stage), kPolicyEvictLast);
           ++n_issued;
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
@@ -444,30 +453,32 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
         const uint32_t u0 = op.sk.begin(cta), u1 = op.sk.begin(cta + 1), KB = uint32_t(op.sk.kb);
         uint32_t u = u0;
         while (u < u1) {
-          const uint32_t tile = u / KB;
-          const uint32_t seg_end = min(u1, (tile + 1) * KB);
+          const uint32_t grp = u / KB;
+          const uint32_t seg_end = min(u1, (grp + 1) * KB);
           mbar_wait(tempty_bar(acc), acc_phase ^ 1);
           tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + uint32_t(acc) * uint32_t(m_tile);
+          const uint32_t d_tmem = tmem_base + uint32_t(acc * tpu) * uint32_t(m_tile);
           uint32_t accumulate = 0;
           for (; u < seg_end; ++u) {
             mbar_wait(full_bar(stage), phase);
             tcgen05_fence_after();
             const uint32_t sa = smem_base + uint32_t(stage) * stage_bytes;
-            const uint64_t da = umma_desc_sw128_kmajor(sa);
-            const uint64_t db = umma_desc_sw128_kmajor(sa + kATileBytes);
+            const uint64_t db = umma_desc_sw128_kmajor(sa + a_bytes);
+#pragma unroll 1
+            for (int h = 0; h < tpu; ++h) {   // the tiles of the unit share the activation tile (B operand)
+              const uint64_t da = umma_desc_sw128_kmajor(sa + uint32_t(h) * kATileBytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-              umma_bf16_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < kBlockK / 16; ++k)
+                // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                umma_bf16_ss(d_tmem + uint32_t(h * m_tile), da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
+                             (k == 0) ? accumulate : 1u);
             }
+            accumulate = 1;
             umma_commit(empty_bar(stage));
             if (++stage == num_stages) { stage = 0; phase ^= 1; }
           }
           umma_commit(tfull_bar(acc));
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
+          if (++acc == nbuf) { acc = 0; acc_phase ^= 1; }
         }
       }
     }
@@ -534,26 +545,32 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
       uint32_t my_rows = 0;   // (tile, token row) pairs this CTA made final
 #pragma unroll 1
       while (u < u1) {
-        const uint32_t tile = u / KB;
-        const uint32_t seg_end = min(u1, (tile + 1) * KB);
-        const bool head = (tile * KB >= u0);                    // this CTA owns the tile's first k-block
-        const bool whole = head && ((tile + 1) * KB <= u1);
+        const uint32_t grp = u / KB;
+        const uint32_t seg_end = min(u1, (grp + 1) * KB);
+        const bool head = (grp * KB >= u0);                     // this CTA owns the group's first k-block
+        const bool whole = head && ((grp + 1) * KB <= u1);
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
         if (dbg) dbg[(seg_end == u1) ? 2 : 1] = clock64();   // accumulator of a (1) non-last / (2) last segment ready
-        const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc) * uint32_t(sk.m_tile);
+        const uint32_t t_acc = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * tpu) * uint32_t(sk.m_tile);
+        const int seg = (u == u0) ? 0 : 1;
         if (row_mode || !head) {
-          // park the partial.  slot 2*cta: the CTA's first segment; 2*cta+1: its last (row mode only, <= 2 segments)
-          const int slot = 2 * cta + ((u == u0) ? 0 : 1);
-          float* dst = ep.ws + size_t(slot) * slot_floats + nrow;
+          // park the partials.  slots (2*cta + seg) * tpu + h: seg 0 = the CTA's first segment, 1 = its last (row mode
+          // only, <= 2 segments); h = tile of the group
 #pragma unroll 1
-          for (int m0 = 16 * cgrp; m0 < sk.m_tile; m0 += 64) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(t_addr + uint32_t(m0), v);
-            tmem_ld_wait();
-            if (m0 < ep.M) {
+          for (int h = 0; h < tpu; ++h) {
+            if (int(grp) * tpu + h >= sk.n_tiles) break;        // a ragged last group: nothing behind the missing tiles
+            float* dst = ep.ws + size_t((2 * cta + seg) * tpu + h) * slot_floats + nrow;
+            const uint32_t t_addr = t_acc + uint32_t(h * sk.m_tile);
+#pragma unroll 1
+            for (int m0 = 16 * cgrp; m0 < sk.m_tile; m0 += 64) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(t_addr + uint32_t(m0), v);
+              tmem_ld_wait();
+              if (m0 < ep.M) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) __stcg(dst + size_t(m0 + j) * 128, __uint_as_float(v[j]));
+                for (int j = 0; j < 16; ++j) __stcg(dst + size_t(m0 + j) * 128, __uint_as_float(v[j]));
+              }
             }
           }
           tcgen05_fence_before();
@@ -563,63 +580,69 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
             epi_bar();   // every warp's partial stores happen-before thread 0's (cumulative) fence + flag
             if (tid_e == 0) {
               __threadfence();
-              atomicAdd(&ep.tile_arrive[kTileCtrStride * tile], 1u);
+              atomicAdd(&ep.tile_arrive[kTileCtrStride * grp], 1u);
             }
           }
         } else {
-          // head segment (whole tile, or the finisher's part of a split tile): stage, add the parked partials, finish
-          const int c_last = whole ? cta : sk.last_cta(int(tile));
+          // head segment (whole group, or the finisher's part of a split group): stage, add the parked partials, finish
+          const int c_last = whole ? cta : sk.last_cta(int(grp));
           if (c_last > cta && tid_e == 0) {
-            spin_until_ge(&ep.tile_arrive[kTileCtrStride * tile], uint32_t(c_last - cta));
-            ep.tile_arrive[kTileCtrStride * tile] = 0;   // leave it zero for the next launch
+            spin_until_ge(&ep.tile_arrive[kTileCtrStride * grp], uint32_t(c_last - cta));
+            ep.tile_arrive[kTileCtrStride * grp] = 0;   // leave it zero for the next launch
           }
-          const EpiTileConst tc = epi_tile_const(ep, int(tile), lane);
 #pragma unroll 1
-          for (int c0m = 0; c0m < sk.m_tile; c0m += kEpiChunk) {
-            const int cw = min(kEpiChunk, sk.m_tile - c0m);
+          for (int h = 0; h < tpu; ++h) {
+            const int tile = int(grp) * tpu + h;
+            const bool last_h = (h == tpu - 1) || (tile + 1 >= sk.n_tiles);
+            if (tile >= sk.n_tiles) break;
+            const uint32_t t_addr = t_acc + uint32_t(h * sk.m_tile);
+            const EpiTileConst tc = epi_tile_const(ep, tile, lane);
 #pragma unroll 1
-            for (int j0 = 16 * cgrp; j0 < cw; j0 += 64) {
-              uint32_t v[16];
-              tmem_ld_32x32b_x16(t_addr + uint32_t(c0m + j0), v);
-              tmem_ld_wait();
+            for (int c0m = 0; c0m < sk.m_tile; c0m += kEpiChunk) {
+              const int cw = min(kEpiChunk, sk.m_tile - c0m);
+#pragma unroll 1
+              for (int j0 = 16 * cgrp; j0 < cw; j0 += 64) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(t_addr + uint32_t(c0m + j0), v);
+                tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) stage_tile[(j0 + j) * kBlockN + nrow] = __uint_as_float(v[j]);
-            }
-            if (c0m + kEpiChunk >= sk.m_tile) {  // accumulator fully drained
-              tcgen05_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tempty_bar(acc));
-            }
-            epi_bar();  // staging tile complete; also orders thread 0's acquire before everybody's partial reads
-#pragma unroll 1
-            for (int ml = ew; ml < cw; ml += kEpiWarps) {   // one token row per warp at a time
-              const int m = c0m + ml;
-              if (m >= ep.M) break;
-              const EpiAux aux = epi_load_aux(ep, tc, int(tile), m, lane, s_pos);
-              const float4 t = *reinterpret_cast<const float4*>(stage_tile + ml * kBlockN + 4 * lane);
-              float v[4] = {t.x, t.y, t.z, t.w};
-              constexpr int C = 4;   // partials in flight
-#pragma unroll 1
-              for (int cb = cta + 1; cb <= c_last; cb += C) {
-                float4 pv[C];
-#pragma unroll
-                for (int cc = 0; cc < C; ++cc) {   // unconditional (clamped) loads so that they batch
-                  const int c = min(cb + cc, c_last);
-                  pv[cc] = __ldcg(reinterpret_cast<const float4*>(ep.ws + size_t(2 * c) * slot_floats + size_t(m) * 128 + 4 * lane));
-                }
-#pragma unroll
-                for (int cc = 0; cc < C; ++cc)   // CTA order: bit-reproducible
-                  if (cb + cc <= c_last) { v[0] += pv[cc].x; v[1] += pv[cc].y; v[2] += pv[cc].z; v[3] += pv[cc].w; }
+                for (int j = 0; j < 16; ++j) stage_tile[(j0 + j) * kBlockN + nrow] = __uint_as_float(v[j]);
               }
-              epi_apply(ep, tc, aux, int(tile), m, lane, v, sk.m_tile);
+              if (last_h && c0m + kEpiChunk >= sk.m_tile) {  // every accumulator of the group fully drained
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+              }
+              epi_bar();  // staging tile complete; also orders thread 0's acquire before everybody's partial reads
+#pragma unroll 1
+              for (int ml = ew; ml < cw; ml += kEpiWarps) {   // one token row per warp at a time
+                const int m = c0m + ml;
+                if (m >= ep.M) break;
+                const EpiAux aux = epi_load_aux(ep, tc, tile, m, lane, s_pos);
+                const float4 t = *reinterpret_cast<const float4*>(stage_tile + ml * kBlockN + 4 * lane);
+                float v[4] = {t.x, t.y, t.z, t.w};
+                constexpr int C = 4;   // partials in flight
+#pragma unroll 1
+                for (int cb = cta + 1; cb <= c_last; cb += C) {
+                  float4 pv[C];
+#pragma unroll
+                  for (int cc = 0; cc < C; ++cc) {   // unconditional (clamped) loads so that they batch
+                    const int c = min(cb + cc, c_last);
+                    pv[cc] = __ldcg(reinterpret_cast<const float4*>(ep.ws + size_t(2 * c * tpu + h) * slot_floats + size_t(m) * 128 + 4 * lane));
+                  }
+#pragma unroll
+                  for (int cc = 0; cc < C; ++cc)   // CTA order: bit-reproducible
+                    if (cb + cc <= c_last) { v[0] += pv[cc].x; v[1] += pv[cc].y; v[2] += pv[cc].z; v[3] += pv[cc].w; }
+                }
+                epi_apply(ep, tc, aux, tile, m, lane, v, sk.m_tile);
+              }
+              epi_bar();  // rows done before the next chunk overwrites the staging tile
             }
-            epi_bar();  // rows done before the next chunk overwrites the staging tile
+            my_rows += uint32_t(ep.M);
           }
-          my_rows += uint32_t(ep.M);
         }
         u = seg_end;
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == nbuf) { acc = 0; acc_phase ^= 1; }
       }
       if (dbg) dbg[3] = clock64();   // all segments drained / parked
       // ---- EPI_RESID_NORM: one CTA per token row finishes the row across all tiles -----------------------------
@@ -650,8 +673,9 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
             for (int i = 0; i < TPW; ++i) {
               const int t = ew + kEpiWarps * i;
               if (t < sk.n_tiles) {
-                const int c_first = sk.first_cta(t), c_last = sk.last_cta(t);
-                const bool first_uses_last_slot = (sk.begin(c_first) / KB) != uint32_t(t);
+                const int grp = t / tpu, hh = t - grp * tpu;
+                const int c_first = sk.first_cta(grp), c_last = sk.last_cta(grp);
+                const bool first_uses_last_slot = (sk.begin(c_first) / KB) != uint32_t(grp);
                 const size_t off = size_t(m) * ep.N + size_t(t) * kBlockN + 4 * lane;
                 const uint2 hraw = *reinterpret_cast<const uint2*>(ep.h + off);
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -662,7 +686,7 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
 #pragma unroll
                   for (int cc = 0; cc < C; ++cc) {
                     const int c = min(cb + cc, c_last);
-                    const int slot = 2 * c + ((c == c_first && first_uses_last_slot) ? 1 : 0);
+                    const int slot = (2 * c + ((c == c_first && first_uses_last_slot) ? 1 : 0)) * tpu + hh;
                     pv[cc] = __ldcg(reinterpret_cast<const float4*>(ep.ws + size_t(slot) * slot_floats + size_t(m) * 128 + 4 * lane));
                   }
 #pragma unroll
@@ -775,9 +799,24 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
-// tiled weights: [units * 128 rows, 64 cols] bf16, one box = one contiguous 16 KB tile
+// weight tiles per stream-K unit (streamk.cuh).  Fixed per process: the context packs its weights for it.
+// SJD_GEMM_TPU = 1 | 2 | 4 (developer A/B switch); default 2.
+int gemm_tpu() {
+  static int tpu = 0;
+  if (!tpu) {
+    tpu = 2;
+    if (const char* e = getenv("SJD_GEMM_TPU")) {
+      const int v = atoi(e);
+      if (v == 1 || v == 2 || v == 4) tpu = v;
+    }
+  }
+  return tpu;
+}
+static inline uint32_t weight_box_rows() { return uint32_t(kBlockN * (gemm_tpu() < 2 ? gemm_tpu() : 2)); }
+
+// tiled weights: [units * tpu * 128 rows, 64 cols] bf16; one unit = tpu contiguous 16 KB tiles = one or two boxes
 int make_tmap_tiled(CUtensorMap* out, const void* ptr, uint64_t units) {
-  return make_tmap_bf16_2d(out, ptr, units * kBlockN, kBlockK, kBlockN);
+  return make_tmap_bf16_2d(out, ptr, units * uint64_t(kBlockN) * gemm_tpu(), kBlockK, weight_box_rows());
 }
 
 static int g_num_sms = 0;
@@ -795,15 +834,17 @@ StreamK gemm_partition(int N, int K, int m_tile, int grid_limit) {
   sk.n_tiles = (N + kBlockN - 1) / kBlockN;
   sk.kb = K / kBlockK;
   sk.m_tile = m_tile;
+  sk.tpu = gemm_tpu();
+  sk.n_groups = (sk.n_tiles + sk.tpu - 1) / sk.tpu;
   int g = grid_limit > 0 ? grid_limit : device_num_sms();
-  uint32_t U = uint32_t(sk.n_tiles) * uint32_t(sk.kb);
+  uint32_t U = uint32_t(sk.n_groups) * uint32_t(sk.kb);
   sk.grid = int(U < uint32_t(g) ? U : uint32_t(g));
   if (uint64_t(U) * uint64_t(sk.grid) >= (1ull << 31)) sk.grid = 0;   // 32-bit partition math would overflow: rejected by the caller
   return sk;
 }
 
 // workspace layout (counters FIRST, so their place does not move with m_tile / grid and they stay zero):
-//   [2 KB of counters, one per 256 B: stats {in, done}, stand-alone chain counters][tile {arrive, done}: 32 B each][ssq: n_tiles * m_tile floats][2*grid partial slots]
+//   [2 KB of counters, one per 256 B: stats {in, done}, stand-alone chain counters][tile {arrive, done}: 32 B each][ssq: n_tiles * m_tile floats][2*grid*tpu partial slots]
 struct GemmWorkspace {
   size_t ctr_off, arrive_off, ssq_off, slots_off, bytes;
 };
@@ -816,12 +857,13 @@ GemmWorkspace gemm_workspace(const StreamK& sk, int arrive_cap = 0) {
   w.arrive_off = 2048;
   w.ssq_off = w.arrive_off + size_t(cap) * kTileCtrStride * 4;
   w.slots_off = w.ssq_off + size_t(sk.n_tiles) * sk.m_tile * 4;
-  w.bytes = w.slots_off + 2 * size_t(sk.grid) * sk.slot_floats() * 4;
+  w.bytes = w.slots_off + 2 * size_t(sk.grid) * size_t(sk.tpu) * sk.slot_floats() * 4;
   return w;
 }
 
 struct ChainShape {
   int num_stages;
+  int nbuf;
   uint32_t tmem_cols;
   uint32_t smem_bytes;
 };
@@ -841,14 +883,17 @@ int gemm_smem_budget() {
 // ring depth / TMEM columns / dynamic smem for a given m_tile
 int gemm_shape(ChainShape* g, int m_tile) {
   if (m_tile % 16 != 0 || m_tile < 16 || m_tile > 256) return -3;
-  const uint32_t stage_bytes = kATileBytes + uint32_t(m_tile) * kBlockK * 2;
+  const int tpu = gemm_tpu();
+  if (tpu * m_tile > 512) return -3;
+  const uint32_t stage_bytes = uint32_t(tpu) * kATileBytes + uint32_t(m_tile) * kBlockK * 2;
   const uint32_t budget = uint32_t(gemm_smem_budget()) - 1024 - kEpiStageBytes;
   int stages = int(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return -4;
   g->num_stages = stages;
+  g->nbuf = (2 * tpu * m_tile <= 512) ? 2 : 1;   // double-buffered accumulators while they fit the 512 TMEM columns
   uint32_t cols = 32;
-  while (cols < uint32_t(2 * m_tile)) cols <<= 1;
+  while (cols < uint32_t(g->nbuf * tpu * m_tile)) cols <<= 1;
   g->tmem_cols = cols;
   g->smem_bytes = uint32_t(stages) * stage_bytes + kEpiStageBytes + 1024;
   return 0;
@@ -875,6 +920,7 @@ int chain_launch(const TmapSet& maps, Chain ch, cudaStream_t stream) {
   if (gemm_shape(&shp, ch.ops[0].sk.m_tile)) return -4;
   ch.num_stages = shp.num_stages;
   ch.tmem_cols = shp.tmem_cols;
+  ch.nbuf = shp.nbuf;
   static int lookahead = -1;
   if (lookahead < 0) {
     const char* e = getenv("SJD_GEMM_LOOKAHEAD");
@@ -891,6 +937,7 @@ int chain_launch(const TmapSet& maps, Chain ch, cudaStream_t stream) {
     if (ch.ops[i].ep.mode == EPI_RESID_NORM) {   // row-owner scheme: <= 2 segments per CTA, <= 64 tiles per row
       const StreamK& k = ch.ops[i].sk;
       if (k.n_tiles > 64 || (k.units() + uint32_t(k.grid) - 1) / uint32_t(k.grid) > uint32_t(k.kb)) return -3;
+      if (k.tpu != ch.ops[0].sk.tpu) return -3;
     }
     grid = ch.ops[i].sk.grid > grid ? ch.ops[i].sk.grid : grid;
     ch.ops[i].ep.dbg = g_dbg_buf ? g_dbg_buf + size_t(g_dbg_idx++ % uint64_t(g_dbg_cap)) * 256 * 16 : nullptr;

@@ -110,11 +110,12 @@ static int ensure_tcmaps(sjd_ctx* c, int Wp) {
   return 0;
 }
 
-// weights are stored tile-packed: [layers][n_tiles][K/64][128][64] (pack_tiles_kernel)
-static size_t packed_elems(int N, int K) { return size_t((N + kBlockN - 1) / kBlockN) * kBlockN * size_t(K); }
+// weights are stored unit-packed: [layers][n_groups][K/64][tpu][128][64] (pack_tiles_kernel)
+static int n_groups_of(int N) { return ((N + kBlockN - 1) / kBlockN + gemm_tpu() - 1) / gemm_tpu(); }
+static size_t packed_elems(int N, int K) { return size_t(n_groups_of(N)) * gemm_tpu() * kBlockN * size_t(K); }
 static int set_wmap(WeightMap* wm, const void* ptr, int layers, int N, int K) {
   if (!ptr || K % kBlockK) return SJD_E_ARG;
-  const uint64_t units = uint64_t(layers) * uint64_t((N + kBlockN - 1) / kBlockN) * uint64_t(K / kBlockK);
+  const uint64_t units = uint64_t(layers) * uint64_t(n_groups_of(N)) * uint64_t(K / kBlockK);
   if (make_tmap_tiled(&wm->map, ptr, units)) return SJD_E_TMAP;
   wm->N = N;
   wm->K = K;
@@ -152,7 +153,7 @@ struct ChainBuilder {
     op.xmap = xmap;
     op.sk = gemm_partition(wm.N, wm.K, m_tile, 0);
     op.w_tiled = 1;
-    op.w_row0 = layer * op.sk.n_tiles * op.sk.kb;   // first unit of this layer's weights
+    op.w_row0 = layer * op.sk.n_groups * op.sk.kb;   // first unit of this layer's weights
     if (gemm_workspace(op.sk, c->arrive_cap).bytes > c->ws_bytes) rc |= SJD_E_ARG;
     ep.N = wm.N;
     bind_ws(c, op.sk, &ep);
@@ -199,7 +200,8 @@ int sjd_gemm_bf16(const void* w, int N, int K, const void* x, int x_rows, int M,
   const StreamK sk = gemm_partition(N, K, m_tile, grid_limit);
   TmapSet maps;
   memset(&maps, 0, sizeof(maps));
-  if (make_tmap_bf16_2d(&maps.w[0], w, uint64_t(N), uint64_t(K), kBlockN)) return fail(SJD_E_TMAP, "weight tensor map");
+  if (make_tmap_bf16_2d(&maps.w[0], w, uint64_t(N), uint64_t(K), uint32_t(kBlockN * (gemm_tpu() < 2 ? gemm_tpu() : 2))))
+    return fail(SJD_E_TMAP, "weight tensor map");
   if (make_tmap_bf16_2d(&maps.x[0], x, uint64_t(x_rows), uint64_t(K), uint32_t(m_tile)))
     return fail(SJD_E_TMAP, "activation tensor map");
   Chain ch;
@@ -230,8 +232,12 @@ int sjd_verify(const sjd_verify_args* a, void* stream) {
     return fail(SJD_E_ARG, "sjd_verify: null argument");
   if (a->W < 1 || a->W > SJD_MAX_TOKENS || a->V < 2) return fail(SJD_E_ARG, "sjd_verify: bad W/V");
   if (!(a->top_p_thresh >= 0.f && a->top_p_thresh <= 1.f)) return fail(SJD_E_ARG, "sjd_verify: top_p_thresh outside [0, 1]");
-  if (a->do_sample && !a->noise_e1) return fail(SJD_E_ARG, "sjd_verify: noise_e1 required when sampling");
-  if (a->scheme == 0 && a->W > 1 && (!a->noise_u || !a->noise_e2 || !a->q_row))
+  if (a->rng_mode != 0 && a->rng_mode != 1) return fail(SJD_E_ARG, "sjd_verify: rng_mode");
+  if (a->rng_mode == 1 && (!a->rng_span[0] || !a->rng_span[1] || !a->rng_span[2] || (a->rng_off[0] & 3) ||
+                           (a->rng_off[1] & 3) || (a->rng_off[2] & 3)))
+    return fail(SJD_E_ARG, "sjd_verify: rng_span must be non-zero and rng_off multiples of 4");
+  if (a->do_sample && !a->rng_mode && !a->noise_e1) return fail(SJD_E_ARG, "sjd_verify: noise_e1 required when sampling");
+  if (a->scheme == 0 && a->W > 1 && (!a->q_row || (!a->rng_mode && (!a->noise_u || !a->noise_e2))))
     return fail(SJD_E_ARG, "sjd_verify: speculative scheme needs noise_u, noise_e2, q_row");
   VerifyParams p;
   p.logits = a->logits; p.W = a->W; p.V = a->V; p.has_uncond = a->has_uncond; p.apply_cfg = a->apply_cfg;
@@ -241,9 +247,17 @@ int sjd_verify(const sjd_verify_args* a, void* stream) {
   p.noise_e2 = a->noise_e2; p.eoi_token = a->eoi_token; p.text_top_k = a->text_top_k; p.resid = a->resid;
   p.next_tokens = a->next_tokens; p.out_tokens = a->out_tokens; p.out_info = a->out_info;
   p.sync_ws = a->sync_ws;
+  p.rng_mode = a->rng_mode; p.rng_seed = a->rng_seed;
+  for (int k = 0; k < 3; ++k) { p.rng_off[k] = a->rng_off[k]; p.rng_span[k] = a->rng_span[k]; }
   g_launches += a->sync_ws ? 1 : 2;
   int rc = verify_launch(p, static_cast<cudaStream_t>(stream));
   return rc ? fail(rc, "verify_launch") : 0;
+}
+
+int sjd_debug_philox(float* out, uint64_t numel, uint64_t seed, uint64_t offset, uint32_t span, int kind, void* stream) {
+  if (!out || !span || (offset & 3)) return fail(SJD_E_ARG, "sjd_debug_philox: bad argument");
+  const int rc = philox_fill(out, numel, seed, offset, span, kind, static_cast<cudaStream_t>(stream));
+  return rc ? fail(rc, "philox_fill") : 0;
 }
 
 int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
@@ -354,10 +368,11 @@ int sjd_ctx_set_layer(sjd_ctx* c, int layer, const sjd_layer_weights* w) {
   };
   int prc = 0;
   auto bfp = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
-  prc |= pack_tiles(bfp(w->wqkv), c->wqkv + l * packed_elems(int(nqkv), g.d_model), int(nqkv), g.d_model, 0, 0);
-  prc |= pack_tiles(bfp(w->wo), c->wo + l * packed_elems(g.d_model, int(hd)), g.d_model, int(hd), 0, 0);
-  prc |= pack_tiles(bfp(w->w_down), c->wdown + l * packed_elems(g.d_model, g.d_ff), g.d_model, g.d_ff, 0, 0);
-  prc |= pack_tiles(bfp(w->w_gate_up), c->wgu + l * packed_elems(2 * g.d_ff, g.d_model), 2 * g.d_ff, g.d_model, g.d_ff, 0);
+  const int tpu = gemm_tpu();
+  prc |= pack_tiles(bfp(w->wqkv), c->wqkv + l * packed_elems(int(nqkv), g.d_model), int(nqkv), g.d_model, 0, tpu, 0);
+  prc |= pack_tiles(bfp(w->wo), c->wo + l * packed_elems(g.d_model, int(hd)), g.d_model, int(hd), 0, tpu, 0);
+  prc |= pack_tiles(bfp(w->w_down), c->wdown + l * packed_elems(g.d_model, g.d_ff), g.d_model, g.d_ff, 0, tpu, 0);
+  prc |= pack_tiles(bfp(w->w_gate_up), c->wgu + l * packed_elems(2 * g.d_ff, g.d_model), 2 * g.d_ff, g.d_model, g.d_ff, tpu, 0);
   if (prc) return fail(SJD_E_LAUNCH, "sjd_ctx_set_layer: pack_tiles");
   cp(c->attn_norm + l * d, w->attn_norm, d * 2);
   cp(c->ffn_norm + l * d, w->ffn_norm, d * 2);
@@ -380,7 +395,7 @@ int sjd_ctx_set_globals(sjd_ctx* c, const void* embed, const void* final_norm, c
   const size_t vd = size_t(g.vocab) * g.d_model * 2, rb = size_t(g.n_rope_pos) * (g.head_dim / 2) * 4;
   cudaError_t e = cudaSuccess;
   if (embed) e = cudaMemcpy(c->embed, embed, vd, cudaMemcpyDeviceToDevice);
-  if (e == cudaSuccess && pack_tiles(static_cast<const __nv_bfloat16*>(lm_head), c->lm_head, g.vocab, g.d_model, 0, 0))
+  if (e == cudaSuccess && pack_tiles(static_cast<const __nv_bfloat16*>(lm_head), c->lm_head, g.vocab, g.d_model, 0, gemm_tpu(), 0))
     e = cudaErrorUnknown;
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(c->final_norm, final_norm, size_t(g.d_model) * 2, cudaMemcpyDeviceToDevice);

@@ -48,12 +48,87 @@ struct VerifyParams {
   int* out_tokens;       // [W] tokens after accept / resample
   int* out_info;         // [4] matched, rejected(0/1), first_reject, reserved
   unsigned int* sync_ws; // one zero-initialised word: lets the last row CTA run the accept scan in the same launch
+  // device-side noise (rng_mode = 1): the kernel computes, for exactly the elements it consumes, the values torch's CUDA
+  // generator would have written into the three noise tensors (Philox4x32-10, torch's element -> (thread, counter) map)
+  int rng_mode;
+  unsigned long long rng_seed;
+  unsigned long long rng_off[3];   // philox offset at the start of the e1 / u / e2 draw
+  unsigned int rng_span[3];        // blockDim * gridDim of torch's launch for that draw (its grid-stride)
 };
+
+// ---- torch-compatible Philox noise ------------------------------------------------------------------------------
+// torch.Tensor.exponential_ / torch.rand on a CUDA generator run distribution_elementwise_grid_stride_kernel
+// (ATen/native/cuda/DistributionTemplates.h): thread t = blockIdx * 256 + threadIdx calls curand_init(seed, t, offset)
+// and, in grid-stride iteration k, one curand_uniform4 whose four values go to the elements t + span * (4k + j),
+// j = 0..3, span = 256 * grid.  So element e sits at thread e % span, iteration (e / span) / 4, lane (e / span) % 4, and
+// its value is Philox4x32-10(counter = {offset / 4 + iteration, subsequence = thread}, key = seed)[lane].
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// curand_uniform: (0, 1]
+__device__ __forceinline__ float torch_uniform_raw(unsigned long long seed, unsigned long long offset, uint32_t span,
+                                                   unsigned long long e) {
+  const unsigned long long q = e / span;
+  const uint32_t t = uint32_t(e - q * span), lane = uint32_t(q & 3ull);
+  const unsigned long long ctr = (offset >> 2) + (q >> 2);
+  const uint4 r = philox4x32_10(make_uint4(uint32_t(ctr), uint32_t(ctr >> 32), t, 0u),
+                                make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+  const uint32_t x = lane == 0 ? r.x : (lane == 1 ? r.y : (lane == 2 ? r.z : r.w));
+  return __fmaf_rn(float(x), 2.3283064e-10f, 2.3283064e-10f / 2.0f);
+}
+// torch.rand: reverse_bounds maps 1.0 to 0.0 (uniform_and_transform, from = 0, to = 1)
+__device__ __forceinline__ float torch_rand(unsigned long long seed, unsigned long long offset, uint32_t span,
+                                            unsigned long long e) {
+  const float u = torch_uniform_raw(seed, offset, span, e);
+  return u == 1.0f ? 0.0f : u;
+}
+// exponential_(1): -log(u), with u >= 1 - eps/2 mapped to eps/2 (transformation::exponential, TransformationHelper.h)
+__device__ __forceinline__ float torch_exponential(unsigned long long seed, unsigned long long offset, uint32_t span,
+                                                   unsigned long long e) {
+  const float u = torch_uniform_raw(seed, offset, span, e);
+  const float lg = (u >= 1.0f - 1.1920929e-07f / 2.0f) ? -1.1920929e-07f / 2.0f : logf(u);
+  return -1.0f * lg;
+}
+
+// The Exp(1) noise of one multinomial row: either a tensor the caller filled, or computed on the fly.
+struct NoiseRow {
+  const float* ptr;               // rng_mode 0
+  unsigned long long seed, off, base;   // rng_mode 1: element index = base + v
+  uint32_t span;
+  __device__ __forceinline__ float operator[](int v) const {
+    return ptr ? ptr[v] : torch_exponential(seed, off, span, base + uint32_t(v));
+  }
+};
+__device__ __forceinline__ NoiseRow noise_row_e1(const struct VerifyParams& p, int i);
+__device__ __forceinline__ NoiseRow noise_row_e2(const struct VerifyParams& p);
 
 __device__ __forceinline__ uint32_t f2key(float f) {
   if (f == 0.f) return 0x80000000u;  // -0 == +0 for "<"
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ NoiseRow noise_row_e1(const VerifyParams& p, int i) {
+  NoiseRow n;
+  n.ptr = p.rng_mode ? nullptr : p.noise_e1 + size_t(i) * p.V;
+  n.seed = p.rng_seed; n.off = p.rng_off[0]; n.span = p.rng_span[0];
+  n.base = (unsigned long long)(i) * (unsigned long long)(p.V);
+  return n;
+}
+__device__ __forceinline__ NoiseRow noise_row_e2(const VerifyParams& p) {
+  NoiseRow n;
+  n.ptr = p.rng_mode ? nullptr : p.noise_e2;
+  n.seed = p.rng_seed; n.off = p.rng_off[2]; n.span = p.rng_span[2];
+  n.base = 0ull;
+  return n;
 }
 
 struct BlockScratch {
@@ -174,7 +249,7 @@ __device__ __forceinline__ int block_argmax(float v, int idx, BlockScratch& sc) 
 // the same order — the block reductions, and with them every result, do not depend on vb) and has made everything
 // outside it -inf / probability 0.  `Vfull` is the vocabulary size (top-k is a no-op when k >= Vfull).
 __device__ int block_topk_softmax_sample(float* __restrict__ row, int vb, int V, int Vfull, int top_k, int do_sample,
-                                         const float* __restrict__ noise_e, BlockScratch& sc) {
+                                         const NoiseRow noise_e, BlockScratch& sc) {
   float mx = -INFINITY;
   int nfin = 0;
   for (int v = vb + threadIdx.x; v < V; v += blockDim.x) {
@@ -204,7 +279,7 @@ __device__ int block_topk_softmax_sample(float* __restrict__ row, int vb, int V,
     const float pr = keep ? expf(f - mx) / sum : 0.f;
     row[v] = pr;
     float val;
-    if (do_sample) val = pr / noise_e[v];
+    if (do_sample) val = pr > 0.f ? pr / noise_e[v] : 0.f;   // 0 / noise = 0: no need to draw it
     else val = keep ? f : -INFINITY;
     if (val > best) { best = val; besti = v; }  // ascending v per thread keeps the lowest index on ties
   }
@@ -278,7 +353,7 @@ __device__ uint32_t block_kth_key_regs(const float (&s)[VPT], int k, BlockScratc
 // probabilities of ids [lo, hi) to p_out (the caller zeroes the rest of the row) and returns the token.
 template <int VPT>
 __device__ int block_topk_softmax_sample_regs(float (&s)[VPT], int v0, int lo, int hi, int top_k, int do_sample,
-                                              const float* __restrict__ noise_e, float* __restrict__ p_out,
+                                              const NoiseRow noise_e, float* __restrict__ p_out,
                                               int V, BlockScratch& sc) {
   float mx = -INFINITY;
   int nfin = 0;
@@ -311,7 +386,7 @@ __device__ int block_topk_softmax_sample_regs(float (&s)[VPT], int v0, int lo, i
       const float pr = keep ? expf(f - mx) / sum : 0.f;
       if (p_out) p_out[v] = pr;
       float val;
-      if (do_sample) val = pr / noise_e[v];
+      if (do_sample) val = pr > 0.f ? pr / noise_e[v] : 0.f;   // 0 / noise = 0: no need to draw it
       else val = keep ? f : -INFINITY;
       if (val > best) { best = val; besti = v; }  // ascending v per thread keeps the lowest index on ties
     }
@@ -341,7 +416,7 @@ struct TopPScratch {
 };
 
 __device__ int block_top_p(float* __restrict__ row, int V, float thresh, int do_sample, int greedy_tok,
-                           const float* __restrict__ noise_e, BlockScratch& sc, TopPScratch& tp) {
+                           const NoiseRow noise_e, BlockScratch& sc, TopPScratch& tp) {
   const unsigned long long thresh_fx = __float2ull_rd(thresh * kFx);
   uint32_t prefix = 0, mask = 0;
   const int shifts[3] = {21, 10, 0};
@@ -461,7 +536,7 @@ __device__ int block_top_p(float* __restrict__ row, int V, float thresh, int do_
     const float pr = row[v] / sum;
     row[v] = pr;
     if (do_sample) {
-      const float val = pr / noise_e[v];
+      const float val = pr > 0.f ? pr / noise_e[v] : 0.f;
       if (val > best) { best = val; besti = v; }
     }
   }
@@ -507,11 +582,10 @@ __device__ void verify_row(const VerifyParams& p, int i, BlockScratch& sc, TopPS
     // everything outside the candidate range has probability zero
     for (int v = threadIdx.x; v < lo; v += blockDim.x) row[v] = 0.f;
     for (int v = hi + threadIdx.x; v < V; v += blockDim.x) row[v] = 0.f;
-    int tok = block_topk_softmax_sample_regs<kRegVPT>(s, v0, lo, hi, p.top_k, p.do_sample,
-                                                      p.noise_e1 + size_t(i) * V, row, V, sc);
+    int tok = block_topk_softmax_sample_regs<kRegVPT>(s, v0, lo, hi, p.top_k, p.do_sample, noise_row_e1(p, i), row, V, sc);
     if (p.top_p_thresh > 0.f) {
       __syncthreads();   // the whole row of probabilities is in global memory
-      tok = block_top_p(row, V, p.top_p_thresh, p.do_sample, tok, p.noise_e1 + size_t(i) * V, sc, tp);
+      tok = block_top_p(row, V, p.top_p_thresh, p.do_sample, tok, noise_row_e1(p, i), sc, tp);
     }
     if (threadIdx.x == 0) p.next_tokens[i] = tok;
     return;
@@ -534,10 +608,10 @@ __device__ void verify_row(const VerifyParams& p, int i, BlockScratch& sc, TopPS
     row[v] = s;
   }
   __syncthreads();
-  int tok = block_topk_softmax_sample(row, v0, ve, V, p.top_k, p.do_sample, p.noise_e1 + size_t(i) * V, sc);
+  int tok = block_topk_softmax_sample(row, v0, ve, V, p.top_k, p.do_sample, noise_row_e1(p, i), sc);
   if (p.top_p_thresh > 0.f) {
     __syncthreads();
-    tok = block_top_p(row, V, p.top_p_thresh, p.do_sample, tok, p.noise_e1 + size_t(i) * V, sc, tp);
+    tok = block_top_p(row, V, p.top_p_thresh, p.do_sample, tok, noise_row_e1(p, i), sc, tp);
   }
   if (threadIdx.x == 0) p.next_tokens[i] = tok;
 }
@@ -557,7 +631,10 @@ __device__ void verify_accept(const VerifyParams& p, BlockScratch& sc, TopPScrat
       const float px = p.p_cur[size_t(i - 1) * V + x];
       const int qr = p.q_row[i];
       const float qx = qr < 0 ? 1.f : p.p_prev[size_t(qr) * V + x];
-      accept = p.noise_u[i] < fminf(px / qx, 1.f);
+      const float ui = p.rng_mode ? torch_rand(p.rng_seed, p.rng_off[1], p.rng_span[1],
+                                               (unsigned long long)(i) * (unsigned long long)(V) + uint32_t(x))
+                                  : p.noise_u[i];
+      accept = ui < fminf(px / qx, 1.f);
     } else {
       accept = (x == p.next_tokens[i - 1]);
     }
@@ -605,7 +682,7 @@ __device__ void verify_accept(const VerifyParams& p, BlockScratch& sc, TopPScrat
       int besti = 0x7fffffff;
       for (int v = threadIdx.x; v < V; v += blockDim.x) {
         if (v == forced) continue;
-        const float val = pc / p.noise_e2[v];
+        const float val = pc / noise_row_e2(p)[v];
         if (val > best) { best = val; besti = v; }
       }
       tok = block_argmax(best, besti, sc);
@@ -624,7 +701,7 @@ __device__ void verify_accept(const VerifyParams& p, BlockScratch& sc, TopPScrat
         }
         s[jj] = sv;
       }
-      tok = block_topk_softmax_sample_regs<kRegVPT>(s, v0, lo, hi, top_k, 1, p.noise_e2, nullptr, V, sc);
+      tok = block_topk_softmax_sample_regs<kRegVPT>(s, v0, lo, hi, top_k, 1, noise_row_e2(p), nullptr, V, sc);
     } else {
       const int ve = min(V, ((hi + int(blockDim.x) - 1) / int(blockDim.x)) * int(blockDim.x));
       const bool nucleus = p.top_p_thresh > 0.f;   // its pass walks the whole row: give it zeros outside the span
@@ -642,10 +719,10 @@ __device__ void verify_accept(const VerifyParams& p, BlockScratch& sc, TopPScrat
         p.resid[v] = s;
       }
       __syncthreads();
-      tok = block_topk_softmax_sample(p.resid, v0, ve, V, top_k, 1, p.noise_e2, sc);
+      tok = block_topk_softmax_sample(p.resid, v0, ve, V, top_k, 1, noise_row_e2(p), sc);
       if (nucleus) {   // the residual goes through the same processors (reject_sampling_single_token)
         __syncthreads();
-        tok = block_top_p(p.resid, V, p.top_p_thresh, 1, tok, p.noise_e2, sc, tp);
+        tok = block_top_p(p.resid, V, p.top_p_thresh, 1, tok, noise_row_e2(p), sc, tp);
       }
     }
     if (threadIdx.x == 0) p.out_tokens[j] = tok;
@@ -687,6 +764,19 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyPar
   __shared__ BlockScratch sc;
   __shared__ TopPScratch tp;
   verify_accept(p, sc, tp);
+}
+
+// developer / test entry: what the kernel would draw for every element of a [numel] noise tensor
+__global__ void philox_fill_kernel(float* out, unsigned long long numel, unsigned long long seed, unsigned long long off,
+                                   uint32_t span, int kind) {
+  for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < numel;
+       e += (unsigned long long)gridDim.x * blockDim.x)
+    out[e] = kind == 0 ? torch_exponential(seed, off, span, e) : torch_rand(seed, off, span, e);
+}
+int philox_fill(float* out, unsigned long long numel, unsigned long long seed, unsigned long long off, uint32_t span,
+                int kind, cudaStream_t stream) {
+  philox_fill_kernel<<<1024, 256, 0, stream>>>(out, numel, seed, off, span, kind);
+  return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 
 int verify_launch(const VerifyParams& p, cudaStream_t stream) {

@@ -430,6 +430,41 @@ class NoiseSource:
         gen.set_state(state)
 
 
+class PhiloxNoise:
+    """The same three draws as NoiseSource on a torch.Generator(device='cuda').manual_seed(seed), but nothing is
+    generated on the host side: sjd_verify (rng_mode = 1) computes the consumed elements itself from (seed, philox
+    offset, torch's launch geometry).  This object only does torch's bookkeeping: every draw of `numel` elements moves
+    the generator's offset by ((numel - 1) // (span * 4) + 1) * 4 with span = 256 * min(SMs * maxThreadsPerSM // 256,
+    ceil(numel / 256)) (calc_execution_policy, ATen/native/cuda/DistributionTemplates.h).  Bit parity with torch is
+    tested on the GPU (tests/test_gpu_parity.py::test_device_philox_matches_torch_generator)."""
+
+    def __init__(self, seed: int, device):
+        self.seed, self.offset = int(seed) & 0xFFFFFFFFFFFFFFFF, 0
+        pr = torch.cuda.get_device_properties(device)
+        self.max_grid = pr.multi_processor_count * (pr.max_threads_per_multi_processor // 256)
+
+    def span(self, numel: int) -> int:
+        return 256 * min(self.max_grid, -(-numel // 256))
+
+    def peek(self, numel: int):
+        return self.offset, self.span(numel)
+
+    def draw(self, numel: int):
+        off, span = self.offset, self.span(numel)
+        self.offset += ((numel - 1) // (span * 4) + 1) * 4
+        return off, span
+
+
+def default_noise(seed, device):
+    """Device-side Philox noise when the reference would use a seeded CUDA generator; the torch-tensor path otherwise
+    (seed None = torch's global generator, or SJD_HOST_NOISE=1)."""
+    import os
+    dev = torch.device(device)
+    if seed is not None and dev.type == "cuda" and os.environ.get("SJD_HOST_NOISE", "0") != "1":
+        return PhiloxNoise(seed, dev)
+    return NoiseSource(seed, dev)
+
+
 class SJDEngine:
     """One prompt, `rows` CFG rows (cond [+ uncond]) — the reference's effective batch."""
 
@@ -453,7 +488,7 @@ class SJDEngine:
         self.d_nxt = torch.empty(Wmax, dtype=torch.int32, device=self.dev)
         self.resid = torch.empty(self.V, dtype=torch.float32, device=self.dev)
         self.d_sync = torch.zeros(1, dtype=torch.int32, device=self.dev)   # sjd_verify's last-CTA counter (stays zero)
-        self.noise_factory = noise_factory or NoiseSource
+        self.noise_factory = noise_factory or default_noise
         self.lib = _lib.lib()
         self.stats = SJDStats()
 
@@ -589,15 +624,27 @@ class SJDEngine:
             a.p_prev, a.p_cur = self.pbuf[1 - cur].data_ptr(), self.pbuf[cur].data_ptr()
             keep_alive = []
             undo = None
-            if do_sample:
-                e1 = noise.multinomial_noise(Wv, V)
-                keep_alive.append(e1)
-                a.noise_e1 = e1.data_ptr()
-            if scheme == 0 and Wv > 1:
-                u = noise.accept_noise(Wv, V, d_draft)
-                e2, undo = noise.residual_noise_speculative(V)
-                keep_alive += [u, e2]
-                a.noise_u, a.noise_e2 = u.data_ptr(), e2.data_ptr()
+            pending_e2 = False
+            if isinstance(noise, PhiloxNoise):
+                a.rng_mode, a.rng_seed = 1, noise.seed
+                for k in range(3):
+                    a.rng_off[k], a.rng_span[k] = 0, 256
+                if do_sample:
+                    a.rng_off[0], a.rng_span[0] = noise.draw(Wv * V)
+                if scheme == 0 and Wv > 1:
+                    a.rng_off[1], a.rng_span[1] = noise.draw(Wv * V)
+                    a.rng_off[2], a.rng_span[2] = noise.peek(V)    # consumed (and counted) only on a rejection
+                    pending_e2 = True
+            else:
+                if do_sample:
+                    e1 = noise.multinomial_noise(Wv, V)
+                    keep_alive.append(e1)
+                    a.noise_e1 = e1.data_ptr()
+                if scheme == 0 and Wv > 1:
+                    u = noise.accept_noise(Wv, V, d_draft)
+                    e2, undo = noise.residual_noise_speculative(V)
+                    keep_alive += [u, e2]
+                    a.noise_u, a.noise_e2 = u.data_ptr(), e2.data_ptr()
             a.eoi_token, a.text_top_k = int(grammar.eoi_token), int(grammar.text_top_k)
             a.resid, a.next_tokens = self.resid.data_ptr(), self.d_nxt.data_ptr()
             a.out_info, a.out_tokens = self.d_out.data_ptr(), self.d_out[4:].data_ptr()
@@ -612,6 +659,8 @@ class SJDEngine:
             toks = res[4:4 + Wv]
             if undo is not None and not rejected:
                 noise.undo(undo)
+            if pending_e2 and rejected:
+                noise.draw(V)
             # ---- bookkeeping ----------------------------------------------------------------------------
             if first_trip or out_W <= 1:
                 n_cached = W            # every fed token is now a valid cache entry

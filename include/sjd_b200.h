@@ -94,9 +94,23 @@ typedef struct sjd_verify_args {
   uint32_t* sync_ws;      /* one device word, ZERO before its first use (the kernel leaves it zero): with it the whole step
                            * is ONE launch — the CTA that finishes its window position last runs the accept scan.  NULL:
                            * two launches (rows, then accept).  Not to be shared by calls in flight on different streams. */
+  /* Device-side noise.  rng_mode = 1: noise_e1 / noise_u / noise_e2 are ignored; the kernel computes, for exactly the
+   * elements it consumes, the values the reference's torch.Generator(device='cuda') would have written into them
+   * (jacobi_iteration_lumina_mgpt.py:118 multinomial -> exponential_ [W,V]; :260 rand [1,W,V]; :237-240 multinomial ->
+   * exponential_ [1,V]): Philox4x32-10 keyed by rng_seed, counter from rng_off[k] (the generator's philox offset when
+   * draw k starts, in 32-bit outputs) and torch's element -> (thread, iteration) mapping with grid-stride rng_span[k]
+   * = 256 * min(SMs * maxThreadsPerSM / 256, ceil(numel / 256)).  The caller advances its offset exactly like torch:
+   * by ((numel - 1) / (rng_span * 4) + 1) * 4 per draw. */
+  int32_t rng_mode;
+  uint64_t rng_seed;
+  uint64_t rng_off[3];
+  uint32_t rng_span[3];
 } sjd_verify_args;
 
 int sjd_verify(const sjd_verify_args* args, void* stream);
+/* Test / developer entry: fills out[0..numel) with what rng_mode = 1 draws for a noise tensor of numel elements:
+ * kind 0 = exponential_(1), kind 1 = rand.  Bit-compared against torch on the GPU by the parity tests. */
+int sjd_debug_philox(float* out, uint64_t numel, uint64_t seed, uint64_t offset, uint32_t span, int kind, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Model context: the fused transformer stack of the draft-window forward with a static KV cache.

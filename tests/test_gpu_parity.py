@@ -908,3 +908,33 @@ def test_config4_width_long_cache_kernels_agree(env):
     assert bool(((p > 0).sum(1) <= 2048 + 128).all()) and torch.allclose(p.sum(1), torch.ones(W, device=dev), atol=1e-4)
     assert float(p[:, :151854].sum()) == 0.0 and float(p[:, 151854 + 32768:].sum()) == 0.0
     ds.close()
+
+
+# ------------------------------------------------------------------------------------------ device-side noise (round 2)
+@pytest.mark.parametrize("shape", [(32, 65536), (1, 65536), (8, 9216), (64, 184622), (1, 184622), (3, 1000), (16, 16384)])
+def test_device_philox_matches_torch_generator(env, shape):
+    """sjd_verify's rng_mode = 1 must draw, element for element and bit for bit, what the reference's seeded
+    torch.Generator(device='cuda') writes into the noise tensors: exponential_ [W, V] (torch.multinomial), rand [1, W, V]
+    (accept test), exponential_ [1, V] (residual multinomial) — in that order from one generator, with the offset
+    bookkeeping engine.PhiloxNoise does on the host."""
+    L, _lib, engine, dev = env["lib"], env["_lib"], env["engine"], env["dev"]
+    W, V = shape
+    seed = 1234 + W
+    g = torch.Generator(dev).manual_seed(seed)
+    ph = engine.PhiloxNoise(seed, dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for rep in range(2):   # two trips: the offsets must keep tracking torch's generator
+        for kind, numel, make in ((0, W * V, lambda: torch.empty(W, V, device=dev).exponential_(1.0, generator=g)),
+                                  (1, W * V, lambda: torch.rand(1, W, V, device=dev, generator=g)),
+                                  (0, V, lambda: torch.empty(1, V, device=dev).exponential_(1.0, generator=g))):
+            ref = make().flatten()
+            off, span = ph.draw(numel)
+            out = torch.empty(numel, device=dev)
+            _lib.check(L.sjd_debug_philox(out.data_ptr(), numel, seed, off, span, kind, st), "philox")
+            torch.cuda.synchronize()
+            same = torch.equal(out, ref)
+            if not same:
+                bad = (out != ref).nonzero().flatten()
+                raise AssertionError(f"kind {kind} numel {numel} rep {rep}: {bad.numel()} of {numel} differ, first at "
+                                     f"{int(bad[0])}: {float(out[bad[0]])!r} vs {float(ref[bad[0]])!r}")
+        assert ph.offset == g.get_offset(), (ph.offset, g.get_offset())
