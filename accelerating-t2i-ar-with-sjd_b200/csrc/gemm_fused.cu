@@ -274,7 +274,6 @@ struct Chain {
   int n_ops, num_stages;
   int lookahead;   // weight units prefetched into L2 beyond the ring
   int pf_always;   // 1: keep the L2 prefetch frontier `lookahead` units ahead in steady state too (0: only while the ring is blocked)
-  int dbg_xskip;   // developer timing only (SJD_DEBUG_XSKIP=1): skip the activation-tile loads after the ring's first fill (results are garbage)
   uint32_t tmem_cols;
   int nbuf;        // accumulator sets in TMEM
   uint32_t* fin;   // [(kMaxChainOps + 2) * kCtrStride] rows finalised per op, exit counter, pre-op counter; zero between launches
@@ -350,7 +349,6 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
       int pf_i = 0;                 // prefetch cursor (op, unit), never behind the issue cursor
       uint32_t pf_u = ch.ops[0].sk.begin(cta);
       int pf_ahead = 0;             // units the prefetch cursor is ahead of the issue cursor
-      int n_issued = 0;
       // a unit = tpu tiles of 128 weight rows: one TMA box of 128 * min(tpu, 2) rows, two boxes when tpu = 4
       const int box_rows = kBlockN * (tpu < 2 ? tpu : 2), n_box = (tpu + 1) / 2;
       auto w_coords = [&](const GemmOp& op, uint32_t u, int& c0, int& c1) {
@@ -383,11 +381,10 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
           }
           int c0, c1;
           w_coords(op, u, c0, c1);
-          mbar_arrive_expect_tx(full_bar(stage), (ch.dbg_xskip && n_issued >= num_stages) ? a_bytes : stage_bytes);
+          mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
           for (int j = 0; j < n_box; ++j)
             tma_load_2d(smem_base + uint32_t(stage) * stage_bytes + uint32_t(j) * 2u * kATileBytes, tw, c0, c1 + j * box_rows,
                         full_bar(stage), kPolicyEvictFirst);
-          ++n_issued;
           if (pf_ahead > 0) --pf_ahead;
           if (ch.pf_always) {   // top the L2 frontier up: at most two prefetches per load issued
             if (pf_ahead == 0) { pf_i = i; pf_u = u + 1; }
@@ -410,7 +407,6 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int n_issued = 0;
       for (int i = 0; i < ch.n_ops; ++i) {
         const GemmOp& op = ch.ops[i];
         const CUtensorMap* tx = &maps.x[op.xmap];
@@ -432,10 +428,8 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
         for (uint32_t u = u0; u < u1; ++u) {
           const uint32_t kb = u % KB;
           mbar_wait(empty_bar(stage), phase ^ 1);
-          if (!(ch.dbg_xskip && n_issued >= num_stages))
-            tma_load_2d(smem_base + uint32_t(stage) * stage_bytes + a_bytes, tx, int(kb * kBlockK), 0,
-                        full_bar(stage), kPolicyEvictLast);
-          ++n_issued;
+          tma_load_2d(smem_base + uint32_t(stage) * stage_bytes + a_bytes, tx, int(kb * kBlockK), 0,
+                      full_bar(stage), kPolicyEvictLast);
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -928,9 +922,7 @@ int chain_launch(const TmapSet& maps, Chain ch, cudaStream_t stream) {
   }
   ch.lookahead = lookahead;
   static const int pf_always = getenv("SJD_GEMM_PF_ALWAYS") ? atoi(getenv("SJD_GEMM_PF_ALWAYS")) : 0;
-  static const int xskip = getenv("SJD_DEBUG_XSKIP") ? atoi(getenv("SJD_DEBUG_XSKIP")) : 0;
   ch.pf_always = pf_always;
-  ch.dbg_xskip = xskip;
   int grid = 0;
   for (int i = 0; i < ch.n_ops; ++i) {
     if (ch.ops[i].sk.m_tile != ch.ops[0].sk.m_tile || ch.ops[i].sk.grid < 1) return -3;
