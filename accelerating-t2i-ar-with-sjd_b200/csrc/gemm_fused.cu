@@ -270,6 +270,16 @@ struct GemmOp {
   StreamK sk;
   GemmEpi ep;
 };
+// K/V cache spans the attention kernel that FOLLOWS this chain will stream: sent to L2 by the weight producer once it
+// has issued its last weight load, i.e. while the chain's last cross-CTA tail and the kernel boundary leave HBM idle.
+struct KvPrefetch {
+  const __nv_bfloat16* k;   // layer base [rows][Hkv][Lmax][Dh]; null = off
+  const __nv_bfloat16* v;
+  int rows, Hkv, Lmax, Dh;
+  int kv_len;               // cached keys (the window's own keys are written by this chain's QKV epilogue)
+  int lo[8];                // first visible key per row
+};
+
 struct Chain {
   int n_ops, num_stages;
   int lookahead;   // weight units prefetched into L2 beyond the ring
@@ -280,6 +290,7 @@ struct Chain {
   // optional pre-op run by the (otherwise idle) epilogue warps before op 0: merge the attention's key-split partials
   // into the bf16 rows that op 0 (o_proj) reads; pre.n_chunks == 0 switches it off
   AttnCombine pre;
+  KvPrefetch kvpf;
   GemmOp ops[kMaxChainOps];
 };
 
@@ -399,6 +410,26 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
             }
           }
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (ch.kvpf.k != nullptr) {
+        // every weight load of the chain has been issued: HBM idles through the last op's tail and the kernel
+        // boundary — send this CTA's share of the next attention's K/V span to L2 (32 KB pieces, round-robin)
+        const KvPrefetch& kp = ch.kvpf;
+        constexpr uint32_t kPiece = 32768;
+        const int n_span = kp.rows * kp.Hkv * 2;
+        for (int sp = 0; sp < n_span; ++sp) {
+          const int bh = sp >> 1, b = bh / kp.Hkv;
+          const int lo = (kp.lo[b] / 64) * 64;
+          if (kp.kv_len <= lo) continue;
+          const size_t bytes = size_t(kp.kv_len - lo) * kp.Dh * 2;
+          const char* base = reinterpret_cast<const char*>((sp & 1) ? kp.v : kp.k) + (size_t(bh) * kp.Lmax + lo) * kp.Dh * 2;
+          const uint32_t n_piece = uint32_t((bytes + kPiece - 1) / kPiece);
+          for (uint32_t pc = uint32_t((cta + sp) % int(gridDim.x)); pc < n_piece; pc += gridDim.x) {
+            const size_t off = size_t(pc) * kPiece;
+            const uint32_t nb = uint32_t(bytes - off < kPiece ? bytes - off : kPiece);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(nb) : "memory");
+          }
         }
       }
     }
@@ -794,11 +825,14 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
 }
 
 // weight tiles per stream-K unit (streamk.cuh).  Fixed per process: the context packs its weights for it.
-// SJD_GEMM_TPU = 1 | 2 | 4 (developer A/B switch); default 2.
+// SJD_GEMM_TPU = 1 | 2 | 4 (developer A/B switch).  Default 1: measured on the B200 (profiles/r02b_chain_experiments.txt),
+// sharing the activation tile between 2 or 4 weight tiles does NOT pay — with ~1 tile per CTA and op the wider stream-K
+// groups are split over 2-4x more CTAs, and the extra fp32 partial traffic / fix-up fan-in costs more than the saved
+// L2 -> SM activation re-reads (Lumina-7B, 64 token rows: 4256 GB/s at tpu 1, 3792 at tpu 2, 2296 at tpu 4).
 int gemm_tpu() {
   static int tpu = 0;
   if (!tpu) {
-    tpu = 2;
+    tpu = 1;
     if (const char* e = getenv("SJD_GEMM_TPU")) {
       const int v = atoi(e);
       if (v == 1 || v == 2 || v == 4) tpu = v;

@@ -474,8 +474,16 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
     return e;
   };
   cb.add(c->m_qkv, ChainBuilder::W_QKV, 0, ChainBuilder::X_XN, qkv_epi(0));
+  static const int kv_pf = getenv("SJD_KV_PF") ? atoi(getenv("SJD_KV_PF")) : 1;
   for (int l = 0; l < g.n_layers && !rc; ++l) {
     if (!gemm_only) {
+      if (kv_pf && a->kv_len > 0) {   // the chain about to be flushed ends right before layer l's attention
+        KvPrefetch& kp = cb.ch.kvpf;
+        kp.k = c->kcache + size_t(l) * layer_cache;
+        kp.v = c->vcache + size_t(l) * layer_cache;
+        kp.rows = g.rows; kp.Hkv = g.n_kv_heads; kp.Lmax = g.max_len; kp.Dh = g.head_dim; kp.kv_len = a->kv_len;
+        for (int b = 0; b < 8; ++b) kp.lo[b] = b < g.rows ? a->kv_lo[b] : 0;
+      }
       cb.flush();
       ap.k = c->kcache + size_t(l) * layer_cache;
       ap.v = c->vcache + size_t(l) * layer_cache;

@@ -62,7 +62,7 @@ struct VerifyParams {
 // and, in grid-stride iteration k, one curand_uniform4 whose four values go to the elements t + span * (4k + j),
 // j = 0..3, span = 256 * grid.  So element e sits at thread e % span, iteration (e / span) / 4, lane (e / span) % 4, and
 // its value is Philox4x32-10(counter = {offset / 4 + iteration, subsequence = thread}, key = seed)[lane].
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+__device__ __noinline__ uint4 philox4x32_10(uint4 c, uint2 k) {   // one copy: the callers sit in unrolled loops
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
@@ -767,11 +767,31 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_accept_kernel(VerifyPar
 }
 
 // developer / test entry: what the kernel would draw for every element of a [numel] noise tensor
+// kind: 0 = exponential_ as the verify kernel draws it, 1 = rand as the verify kernel draws it; developer variants used to
+// pin the transform against torch on the GPU: 16 + v: exponential with log variant v (0 logf, 1 __logf, 2 __log2f * ln 2),
+// +8: uniform conversion as separate multiply and add instead of one FMA
 __global__ void philox_fill_kernel(float* out, unsigned long long numel, unsigned long long seed, unsigned long long off,
                                    uint32_t span, int kind) {
   for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < numel;
-       e += (unsigned long long)gridDim.x * blockDim.x)
-    out[e] = kind == 0 ? torch_exponential(seed, off, span, e) : torch_rand(seed, off, span, e);
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    if (kind == 0) { out[e] = torch_exponential(seed, off, span, e); continue; }
+    if (kind == 1) { out[e] = torch_rand(seed, off, span, e); continue; }
+    float u = torch_uniform_raw(seed, off, span, e);
+    if (kind & 8) {   // recompute the uniform without contraction
+      const unsigned long long q = e / span;
+      const uint32_t t = uint32_t(e - q * span), lane = uint32_t(q & 3ull);
+      const unsigned long long ctr = (off >> 2) + (q >> 2);
+      const uint4 r = philox4x32_10(make_uint4(uint32_t(ctr), uint32_t(ctr >> 32), t, 0u), make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+      const uint32_t x = lane == 0 ? r.x : (lane == 1 ? r.y : (lane == 2 ? r.z : r.w));
+      u = __fadd_rn(__fmul_rn(float(x), 2.3283064e-10f), 2.3283064e-10f / 2.0f);
+    }
+    const int v = kind & 7;
+    if (kind & 32) { out[e] = (u == 1.0f) ? 0.0f : u; continue; }   // rand with the chosen uniform
+    float lg;
+    if (u >= 1.0f - 1.1920929e-07f / 2.0f) lg = -1.1920929e-07f / 2.0f;
+    else lg = v == 0 ? logf(u) : (v == 1 ? __logf(u) : __log2f(u) * 0.6931471805599453f);
+    out[e] = -1.0f * lg;
+  }
 }
 int philox_fill(float* out, unsigned long long numel, unsigned long long seed, unsigned long long off, uint32_t span,
                 int kind, cudaStream_t stream) {

@@ -341,6 +341,7 @@ class SJDStats:
     trace: list = field(default_factory=list)   # per trip (W, matched, rejected)
     h2d_bytes: int = 0                          # pinned-host -> device bytes copied by the loop
     d2h_bytes: int = 0                          # device -> pinned-host bytes (accepted tokens, counters)
+    kv_read_tokens: int = 0                     # sum over forwards of the keys each CFG row's window attended to
 
 
 def check_init_scheme(scheme: str):
@@ -677,6 +678,7 @@ class SJDEngine:
             if rejected and hasattr(grammar, "note_residual_call"):
                 grammar.note_residual_call(new[:-1])
             grammar.observe(new)
+            stats.kv_read_tokens += sum(kv_len + W - lo_ for lo_ in kv_lo)
             kv_len += n_cached
             stats.nfe += 1
             if collect_trace:

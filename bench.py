@@ -93,6 +93,33 @@ class ClockSampler:
                 "power_w": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
+def stack_bytes(shape, rows):
+    """(weight bytes of one forward incl. lm_head, KV bytes per attended key token summed over layers and K+V)"""
+    d, ff, V, hd = shape.d_model, shape.d_ff, shape.vocab, shape.n_heads * shape.head_dim
+    qkv_n = (shape.n_heads + 2 * shape.n_kv_heads) * shape.head_dim
+    w = shape.n_layers * (qkv_n * d + d * hd + 2 * ff * d + d * ff) * 2 + V * d * 2
+    kv_per_token = shape.n_layers * 2 * shape.n_kv_heads * shape.head_dim * 2
+    return w, kv_per_token
+
+
+def whole_trip_roofline(shape, rows, nfe, kv_read_tokens, seconds):
+    """Algorithmic HBM bytes of the whole decode (every forward streams all weights once and reads the visible K/V of
+    every CFG row once) over the device time, against the measured HBM peak."""
+    w, kvt = stack_bytes(shape, rows)
+    alg = nfe * w + kv_read_tokens * kvt
+    peak, src = measured_peaks()
+    ach = alg / seconds / 1e9
+    return {"bound": "hbm", "alg_bytes_per_nfe": int(alg / max(nfe, 1)), "weights_bytes": int(w),
+            "kv_bytes_per_nfe": int(kv_read_tokens * kvt / max(nfe, 1)), "achieved": round(ach, 1), "peak": peak,
+            "unit": "GB/s", "frac": round(ach / peak, 4), "peak_source": src}
+
+
+def projected(ms_per_nfe):
+    """tokens/s at the acceptance the reference publishes for real checkpoints (README: 2.1-2.4 accepted tokens per
+    forward with window 16-32): random-init weights accept ~1.06, so the measured tokens/s is an AR-rate number."""
+    return {f"{a:.1f}": round(a / ms_per_nfe * 1e3, 1) for a in (2.1, 2.4)}
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -142,11 +169,11 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     tok = nfe = 0
-    h2d = d2h = 0
+    h2d = d2h = kvr = 0
     for i in range(args.steps):
         t, n, st = one_image(rank + i * world)
         tok, nfe = tok + t, nfe + n
-        h2d, d2h = h2d + st.h2d_bytes, d2h + st.d2h_bytes
+        h2d, d2h, kvr = h2d + st.h2d_bytes, d2h + st.d2h_bytes, kvr + st.kv_read_tokens
     e1.record()
     torch.cuda.synchronize()
     replicas.barrier()
@@ -241,6 +268,10 @@ def run_ours(args):
             "config": bench_config(world, args.window),
             "accepted_tokens_per_iter": round(tot_tok / tot_nfe, 3), "nfe_per_image": round(tot_nfe / (args.steps * world), 1),
             "ms_per_nfe": round(t_dev / (tot_nfe / world) * 1e3, 3),
+            "whole_trip_roofline": whole_trip_roofline(shape, 2, nfe, kvr, e0.elapsed_time(e1) / 1e3),
+            "projected_tokens_per_sec_per_gpu_at_published_acceptance": projected(t_dev / (tot_nfe / world) * 1e3),
+            "vs_reference_note": "the --impl reference arm is ONE host's CPU cores whatever N is: its ratio is meaningful at "
+                                 "N=1 only; the GPU-vs-GPU number is gpu_eager_reference",
             "clocks": clk,
             "e2e": {"value": round(e_tot / t_e2e, 2), "unit": UNIT, "h2d_bytes_per_step": e_h2d // args.steps,
                     "d2h_bytes_per_step": e_d2h // args.steps, "api": "SyntheticLuminaSolver.generate (host ids in, host ids out)"},
@@ -370,6 +401,92 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ======================================================================== BASELINE configs 1 / 4 / 5 (own lines)
+CONFIGS = {
+    1: dict(model="synthetic/llamagen-gpt-b", window=16, kw=dict(guidance_scale=4.0, image_top_k=1000, target_size=256),
+            name="LlamaGen GPT-B (12L d768), 256x256 (256 tokens), window 16, cfg 4, top-k 1000"),
+    4: dict(model="synthetic/emu3-gen", window=64, kw=dict(guidance_scale=3.0, image_top_k=2048, target_size=720),
+            name="Emu3-Gen shape (32L d4096 GQA 32:8 ff14336 V184622), 720x720 (90x91 tokens), window 64, cfg 3, top-k 2048"),
+    5: dict(model="synthetic/anole-7b-512", window=32, kw=dict(guidance_scale=3.0, image_top_k=2000, target_size=512),
+            name="Anole / Chameleon-7B shape, 512x512 (1024 image tokens, Anole grammar), cfg 3, top-k 2000",
+            sweep=(8, 16, 32, 64, 128)),
+}
+
+
+def run_config(args):
+    """One JSON line for BASELINE config 1, 4 or 5 through the public loader API (model_wrappers.model_loader:
+    load_pretrained_model / get_forward_func on the synthetic family; host prompt string in, host token tensor out, so
+    `value` and `e2e` are the same measurement).  Config 5 sweeps the window."""
+    import sjd_b200  # noqa: F401
+    from sjd_b200 import _lib, replicas
+    from model_wrappers.model_loader import get_forward_func, load_pretrained_model
+    rank, world, local = replicas.init_process_group()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    C = CONFIGS[args.config]
+    lib = _lib.lib()
+    windows = C.get("sweep", (C["window"],)) if args.window == WINDOW else (args.window,)
+    rows_out = []
+    clk = None
+    for window in windows:
+        solver = load_pretrained_model(C["model"], device=dev, seed=0, max_num_new_tokens=window, **C["kw"])
+        fwd = get_forward_func(C["model"], solver)
+        for i in range(args.warmup):
+            solver.engine.p.seed = 10_000 + i
+            fwd(f"warm-up prompt {rank} {i}")
+        clocks = ClockSampler(local)
+        clocks.start()
+        l0 = lib.sjd_launch_count()
+        replicas.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tok = nfe = kvr = h2d = d2h = 0
+        for i in range(args.steps):
+            solver.engine.p.seed = rank + i * world
+            out = fwd(f"prompt {rank + i * world}")
+            st = solver.engine.stats
+            tok, nfe, kvr = tok + int(out.numel()), nfe + st.nfe, kvr + st.kv_read_tokens
+            h2d, d2h = h2d + st.h2d_bytes, d2h + st.d2h_bytes
+        e1.record()
+        torch.cuda.synchronize()
+        replicas.barrier()
+        t = replicas.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+        clk = clocks.stop()
+        cnt = replicas.gather_counters(tok, nfe, 1, dev)
+        T, N = int(cnt[:, 0].sum()), int(cnt[:, 1].sum())
+        rows_out.append({"window": window, "tokens_per_s": round(T / t, 2), "accepted_tokens_per_iter": round(T / N, 3),
+                         "ms_per_nfe": round(t / (N / world) * 1e3, 3), "nfe_per_image": round(N / (args.steps * world), 1),
+                         "whole_trip_roofline": whole_trip_roofline(solver.stack.shape, 2, nfe, kvr, e0.elapsed_time(e1) / 1e3),
+                         "projected_tokens_per_sec_per_gpu_at_published_acceptance": projected(t / (N / world) * 1e3),
+                         "gpu_launches": int(lib.sjd_launch_count() - l0), "seconds": round(t, 3),
+                         "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps})
+        solver.stack.close()
+        del solver, fwd
+        torch.cuda.empty_cache()
+    if rank == 0:
+        head = next((r for r in rows_out if r["window"] == C["window"]), rows_out[0])
+        line = {"metric": METRIC, "value": head["tokens_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(head["seconds"] / args.steps * 1e3, 2), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"BASELINE config {args.config}: {C['name']}; 1 prompt per GPU per step",
+                           "window": head["window"], "parallelism": f"replicas x{world}",
+                           "weights": "random-init N(0,0.02) bf16", "l2": "weights per trip >> 126 MB L2 (no flush needed)"
+                           if args.config != 1 else "GPT-B weights (0.2 GB) exceed the 126 MB L2; no flush"},
+                "accepted_tokens_per_iter": head["accepted_tokens_per_iter"], "ms_per_nfe": head["ms_per_nfe"],
+                "nfe_per_image": head["nfe_per_image"], "clocks": clk,
+                "e2e": {"value": head["tokens_per_s"], "unit": UNIT, "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": head["d2h_bytes_per_step"],
+                        "api": "model_wrappers.model_loader.get_forward_func(...)(prompt: str) -> LongTensor (host)"},
+                "gpu_launches": head["gpu_launches"], "roofline": head["whole_trip_roofline"], "cpu_baseline": None,
+                "window_sweep": rows_out if len(rows_out) > 1 else None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -381,9 +498,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference's eager SJD on this GPU")
     ap.add_argument("--ref-tokens", type=int, default=192, help="image tokens decoded by the eager-reference leg per window")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE config: 2 (default; 3 is the same workload at --gpus 8), 1 = LlamaGen GPT-B, 4 = Emu3-Gen, "
+                         "5 = Anole window sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config in (1, 4, 5):
+        run_config(args)
     else:
         run_ours(args)
 

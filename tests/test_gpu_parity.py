@@ -932,9 +932,16 @@ def test_device_philox_matches_torch_generator(env, shape):
             out = torch.empty(numel, device=dev)
             _lib.check(L.sjd_debug_philox(out.data_ptr(), numel, seed, off, span, kind, st), "philox")
             torch.cuda.synchronize()
-            same = torch.equal(out, ref)
-            if not same:
+            if not torch.equal(out, ref):
                 bad = (out != ref).nonzero().flatten()
+                # which transform variant WOULD match (developer aid; see philox_fill_kernel)
+                hits = []
+                for var in ([16, 17, 18, 24, 25, 26] if kind == 0 else [32, 40]):
+                    o2 = torch.empty(numel, device=dev)
+                    L.sjd_debug_philox(o2.data_ptr(), numel, seed, off, span, var, st)
+                    torch.cuda.synchronize()
+                    hits.append((var, int((o2 != ref).sum())))
                 raise AssertionError(f"kind {kind} numel {numel} rep {rep}: {bad.numel()} of {numel} differ, first at "
-                                     f"{int(bad[0])}: {float(out[bad[0]])!r} vs {float(ref[bad[0]])!r}")
+                                     f"{int(bad[0])}: {float(out[bad[0]])!r} vs {float(ref[bad[0]])!r}; mismatches per "
+                                     f"variant {hits}")
         assert ph.offset == g.get_offset(), (ph.offset, g.get_offset())
