@@ -67,7 +67,12 @@ class VerifyArgs(C.Structure):
         ("resid", C.c_void_p), ("next_tokens", C.c_void_p), ("out_tokens", C.c_void_p), ("out_info", C.c_void_p),
         ("sync_ws", C.c_void_p),
         ("rng_mode", C.c_int32), ("rng_seed", C.c_uint64), ("rng_off", C.c_uint64 * 3), ("rng_span", C.c_uint32 * 3),
+        ("allow_mode", C.c_int32), ("ban", C.c_int32 * 2),
     ]
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.ban[0] = self.ban[1] = -1      # "no extra removed id"
 
 
 class ModelCfg(C.Structure):

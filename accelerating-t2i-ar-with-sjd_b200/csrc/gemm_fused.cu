@@ -47,7 +47,11 @@ constexpr uint32_t kATileBytes = kBlockN * kBlockK * 2;  // 16 KB per weight til
 constexpr int kMaxTpu = 4;
 constexpr int kCtrStride = 64;                            // u32 between hot counters: one 256-byte region each
 constexpr int kTileCtrStride = 8;                         // u32 per tile {arrived, done, pad..}: 32 bytes
-constexpr int kLookahead = 32;                            // weight units (16 KB) prefetched into L2 beyond the ring
+constexpr int kLookahead = 0;                             // weight units (16 KB) prefetched into L2 beyond the ring while it is
+                                                          // blocked.  Round 2 sweep on the B200 (profiles/r02c_chain_experiments.txt):
+                                                          // 0 is best at <= 64 token rows (4354 GB/s vs 4278 at 32), 64 and the
+                                                          // 'always ahead' mode are clearly worse: L2 prefetch requests queue
+                                                          // ahead of the ring's demand loads
 constexpr int kEpiChunk = 64;                             // token columns staged per epilogue pass
 constexpr uint32_t kEpiStageBytes = kEpiChunk * kBlockN * 4;  // 16 KB
 

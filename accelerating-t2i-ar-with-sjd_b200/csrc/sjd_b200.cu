@@ -247,6 +247,10 @@ int sjd_verify(const sjd_verify_args* a, void* stream) {
   p.noise_e2 = a->noise_e2; p.eoi_token = a->eoi_token; p.text_top_k = a->text_top_k; p.resid = a->resid;
   p.next_tokens = a->next_tokens; p.out_tokens = a->out_tokens; p.out_info = a->out_info;
   p.sync_ws = a->sync_ws;
+  if (a->allow_mode < 0 || a->allow_mode > 4 || (a->allow_mode == 3 && (a->ban[0] < 0 || a->ban[1] < 0)) ||
+      (a->allow_mode == 2 && a->allow_hi < a->allow_lo))
+    return fail(SJD_E_ARG, "sjd_verify: allow_mode / ban");
+  p.allow_mode = a->allow_mode; p.ban[0] = a->ban[0]; p.ban[1] = a->ban[1];
   p.rng_mode = a->rng_mode; p.rng_seed = a->rng_seed;
   for (int k = 0; k < 3; ++k) { p.rng_off[k] = a->rng_off[k]; p.rng_span[k] = a->rng_span[k]; }
   g_launches += a->sync_ws ? 1 : 2;
@@ -474,7 +478,10 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
     return e;
   };
   cb.add(c->m_qkv, ChainBuilder::W_QKV, 0, ChainBuilder::X_XN, qkv_epi(0));
-  static const int kv_pf = getenv("SJD_KV_PF") ? atoi(getenv("SJD_KV_PF")) : 1;
+  // Sending the next attention's K/V span to L2 from the chain's producer (SJD_KV_PF=1) was measured on the B200 and is
+  // OFF: attention + boundaries went from 22.9 to 40.4 us per layer (W = 32, 1 200 keys; profiles/r02c_chain_experiments.txt)
+  // — 40 MB of bulk prefetches drain slower than the attention's own demand loads, which then queue behind them.
+  static const int kv_pf = getenv("SJD_KV_PF") ? atoi(getenv("SJD_KV_PF")) : 0;
   for (int l = 0; l < g.n_layers && !rc; ++l) {
     if (!gemm_only) {
       if (kv_pf && a->kv_len > 0) {   // the chain about to be flushed ends right before layer l's attention

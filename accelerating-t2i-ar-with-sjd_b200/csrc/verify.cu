@@ -28,6 +28,9 @@ struct VerifyParams {
   float guidance;
   float temperature;     // scores / temperature when != 1
   int allow_lo, allow_hi;  // ids outside [lo,hi) -> -inf; disabled when hi <= lo
+  int allow_mode;          // 0: [lo,hi) if hi > lo (ban ignored); 1: same minus ban[]; 2: complement of [lo,hi) minus ban[];
+                           // 3: only the ids ban[0], ban[1]; 4: everything minus ban[]
+  int ban[2];              // removed ids (-1 = none); mode 3: the kept ids
   const int* forced;     // [W] forced token id per window position, or -1
   const int* forced_resid;  // [W] forced id of the residual distribution at reject position j; null = forced
   int top_k;             // 0 = off
@@ -90,11 +93,14 @@ __device__ __forceinline__ float torch_rand(unsigned long long seed, unsigned lo
   const float u = torch_uniform_raw(seed, offset, span, e);
   return u == 1.0f ? 0.0f : u;
 }
-// exponential_(1): -log(u), with u >= 1 - eps/2 mapped to eps/2 (transformation::exponential, TransformationHelper.h)
+// exponential_(1): -log(u), with u >= 1 - eps/2 mapped to eps/2 (transformation::exponential, TransformationHelper.h).
+// torch's CUDA build evaluates that log with the FAST intrinsic (__logf = lg2.approx * ln 2) — pinned on the B200 against
+// torch 2.11: with logf 85 % of the elements differ in the last bit or two, with __logf none does
+// (tests/test_gpu_parity.py::test_device_philox_matches_torch_generator, profiles/r02c notes).
 __device__ __forceinline__ float torch_exponential(unsigned long long seed, unsigned long long offset, uint32_t span,
                                                    unsigned long long e) {
   const float u = torch_uniform_raw(seed, offset, span, e);
-  const float lg = (u >= 1.0f - 1.1920929e-07f / 2.0f) ? -1.1920929e-07f / 2.0f : logf(u);
+  const float lg = (u >= 1.0f - 1.1920929e-07f / 2.0f) ? -1.1920929e-07f / 2.0f : __logf(u);
   return -1.0f * lg;
 }
 
@@ -114,6 +120,34 @@ __device__ __forceinline__ uint32_t f2key(float f) {
   if (f == 0.f) return 0x80000000u;  // -0 == +0 for "<"
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// The grammar's candidate set of a window (the Chameleon / Anole processors of logit_processor_3dim.py:207-353 reduce to
+// one of these per call): [lo, hi) (mode 1, also Lumina / Emu3), its complement minus two ids (mode 2: text between
+// images), a set of one or two ids (mode 3), or everything minus two ids (mode 0).
+struct Cand {
+  int kind;   // 0: everything, 1: [lo, hi), 2: complement of [lo, hi), 3: only b0 / b1; kinds 0-2 also drop b0, b1
+  int lo, hi, b0, b1, span_lo, span_hi;
+  __device__ __forceinline__ bool ok(int v) const {
+    if (kind == 3) return v == b0 || v == b1;
+    if (v == b0 || v == b1) return false;
+    const bool in = v >= lo && v < hi;
+    return kind == 1 ? in : (kind == 2 ? !in : true);
+  }
+};
+__device__ __forceinline__ Cand make_cand(const VerifyParams& p, bool text_mode) {
+  Cand c;
+  const bool ranged = !text_mode && (p.allow_hi > p.allow_lo);
+  const int m = text_mode ? 0 : p.allow_mode;
+  c.kind = m == 2 ? 2 : (m == 3 ? 3 : ((m == 4 || !ranged) ? 0 : 1));
+  c.lo = ranged ? max(p.allow_lo, 0) : 0;
+  c.hi = ranged ? min(p.allow_hi, p.V) : p.V;
+  const bool bans = !text_mode && m >= 1;     // mode 0 = the zero-initialised legacy form: ban[] is not looked at
+  c.b0 = bans ? p.ban[0] : -1;
+  c.b1 = bans ? p.ban[1] : -1;
+  c.span_lo = c.kind == 1 ? c.lo : 0;
+  c.span_hi = c.kind == 1 ? c.hi : p.V;
+  return c;
 }
 
 __device__ __forceinline__ NoiseRow noise_row_e1(const VerifyParams& p, int i) {
@@ -553,7 +587,6 @@ __device__ void verify_row(const VerifyParams& p, int i, BlockScratch& sc, TopPS
   const float* u = p.logits + size_t(p.W + i) * V;
   float* row = p.p_cur + size_t(i) * V;
   const int forced = p.forced ? p.forced[i] : -1;
-  const bool ranged = p.allow_hi > p.allow_lo;
   const bool mix = p.has_uncond && p.apply_cfg;
   if (forced >= 0) {
     // forced position: the distribution is one-hot whatever the logits are (0 -> exp(0)/1 = 1)
@@ -561,7 +594,8 @@ __device__ void verify_row(const VerifyParams& p, int i, BlockScratch& sc, TopPS
     if (threadIdx.x == 0) p.next_tokens[i] = forced;
     return;
   }
-  const int lo = ranged ? max(p.allow_lo, 0) : 0, hi = ranged ? min(p.allow_hi, V) : V;
+  const Cand cd = make_cand(p, false);
+  const int lo = cd.span_lo, hi = cd.span_hi;
   const int v0 = (lo / int(blockDim.x)) * int(blockDim.x);
   if (hi - v0 <= int(blockDim.x) * kRegVPT) {
     float s[kRegVPT];
@@ -569,7 +603,7 @@ __device__ void verify_row(const VerifyParams& p, int i, BlockScratch& sc, TopPS
     for (int j = 0; j < kRegVPT; ++j) {
       const int v = v0 + j * blockDim.x + threadIdx.x;
       float sv = -INFINITY;
-      if (v >= lo && v < hi) {
+      if (v >= lo && v < hi && cd.ok(v)) {
         sv = c[v];
         if (mix) {
           const float uu = u[v];
@@ -597,7 +631,7 @@ __device__ void verify_row(const VerifyParams& p, int i, BlockScratch& sc, TopPS
   for (int v = ve + threadIdx.x; v < V; v += blockDim.x) row[v] = 0.f;
   for (int v = v0 + threadIdx.x; v < ve; v += blockDim.x) {
     float s = -INFINITY;
-    if (v >= lo && v < hi) {
+    if (v >= lo && v < hi && cd.ok(v)) {
       s = c[v];
       if (mix) {
         const float uu = u[v];
@@ -670,8 +704,8 @@ __device__ void verify_accept(const VerifyParams& p, BlockScratch& sc, TopPScrat
     int forced = (!text && fr) ? fr[j] : -1;
     bool mask_forced = false;
     if (forced <= -2) { forced = -2 - forced; mask_forced = true; }
-    const bool ranged = !text && (p.allow_hi > p.allow_lo);
-    const int lo = ranged ? max(p.allow_lo, 0) : 0, hi = ranged ? min(p.allow_hi, V) : V;
+    const Cand cd = make_cand(p, text);
+    const int lo = cd.span_lo, hi = cd.span_hi;
     const int v0 = (lo / int(blockDim.x)) * int(blockDim.x);
     const int top_k = text ? p.text_top_k : p.top_k;
     int tok;
@@ -694,7 +728,7 @@ __device__ void verify_accept(const VerifyParams& p, BlockScratch& sc, TopPScrat
       for (int jj = 0; jj < kRegVPT; ++jj) {
         const int v = v0 + jj * blockDim.x + threadIdx.x;
         float sv = -INFINITY;
-        if (v >= lo && v < hi) {
+        if (v >= lo && v < hi && cd.ok(v)) {
           const float q = b ? b[v] : (v == xd ? 1.f : 0.f);
           sv = logf(fmaxf(__fsub_rn(a[v], q), 0.f));
           if (p.temperature != 1.f) sv = sv / p.temperature;
@@ -711,7 +745,7 @@ __device__ void verify_accept(const VerifyParams& p, BlockScratch& sc, TopPScrat
       }
       for (int v = v0 + threadIdx.x; v < ve; v += blockDim.x) {
         float s = -INFINITY;
-        if (v >= lo && v < hi) {
+        if (v >= lo && v < hi && cd.ok(v)) {
           const float q = b ? b[v] : (v == xd ? 1.f : 0.f);
           s = logf(fmaxf(__fsub_rn(a[v], q), 0.f));
           if (p.temperature != 1.f) s = s / p.temperature;

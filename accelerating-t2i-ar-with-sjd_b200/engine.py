@@ -39,6 +39,8 @@ def verify_call(logits: torch.Tensor, W: int, V: int, desc: dict, draft: torch.T
     a.has_uncond, a.apply_cfg = int(has_uncond), int(apply_cfg)
     a.guidance, a.temperature = float(guidance), float(temperature)
     a.allow_lo, a.allow_hi = desc["allow"] if desc.get("allow") else (0, 0)
+    a.allow_mode = int(desc.get("allow_mode", 0))
+    a.ban[0], a.ban[1] = desc.get("ban", (-1, -1))
     a.forced = forced.data_ptr() if forced is not None else None
     a.top_k, a.do_sample, a.scheme = int(desc["top_k"]), int(do_sample), int(scheme)
     a.top_p_thresh = top_p_threshold(desc.get("top_p", 1.0))
@@ -236,26 +238,35 @@ class PlainTopKState:
 
 
 class AnoleGrammarState:
-    """Host-side state of the Anole "image-only" grammar: the five 3-D Chameleon processors installed by
-    renew_pipeline_anole.generate (scheduler/jacobi_iteration_anhole.py:200-240; classes at
-    scheduler/logit_processor_3dim.py:207-353) plus HF's TopKLogitsWarper.  Every one of them inspects the ACCEPTED
-    prefix only (its length, the token S+1 places from its end, whether begin-of-image is among its last S tokens) and
-    applies one decision to every window position, so a trip's grammar is one allowed-id set:
-        image ids [image_lo, image_hi)   while begin-of-image is within the last S accepted tokens,
-        {eoi}                            when begin-of-image sits exactly S+1 places back,
-        a subset of {eos, boi}           otherwise (boi until max_length - S - 1, eos except right at the start).
+    """Host-side state of the Anole / HF-Chameleon grammar: the 3-D Chameleon processors that
+    renew_pipeline_anole.generate installs per `multimodal_generation_mode` (scheduler/jacobi_iteration_anhole.py:170-265;
+    classes at scheduler/logit_processor_3dim.py:207-353) plus HF's TopKLogitsWarper.  Every one of them inspects the
+    ACCEPTED prefix only (its length, the token S+1 places from its end, whether begin-of-image is among its last S
+    tokens) and applies one decision to every window position, so a trip's grammar is one candidate set:
+
+      image-only              image ids [image_lo, image_hi)  while begin-of-image is within the last S accepted tokens,
+                              {eoi}                            when begin-of-image sits exactly S+1 places back,
+                              a subset of {eos, boi}           otherwise (boi until max_length - S - 1, eos except at the start)
+      interleaved-text-image  image ids / {eoi} as above; otherwise everything EXCEPT image ids, eoi and — from index
+                              max_length - S - 1 on — boi
+      text-only               everything except image ids, boi and eoi
+      unrestricted            everything (hf_api maps it to PlainTopKState)
+
     A window that straddles the end of the image keeps "image ids" for all its positions — the reference behaves the
-    same and truncates to image_seq_length afterwards (:309-311).  Sets the verify kernel cannot express (two special
-    ids at once, possible only when max_new_tokens exceeds S + 2) are refused.  CFG is never switched off (the first
-    processor has no image_start_token_id, jacobi_iteration_lumina_mgpt.py:1086-1096)."""
+    same and truncates to image_seq_length afterwards (:309-311).  CFG is never switched off (the first processor has no
+    image_start_token_id, jacobi_iteration_lumina_mgpt.py:1086-1096)."""
     eoi_token = -1
     text_top_k = 0
     no_cfg = False
 
-    def __init__(self, boi, eoi, eos, image_lo, image_hi, image_seq_length, max_length, begin_index, top_k=50):
+    def __init__(self, boi, eoi, eos, image_lo, image_hi, image_seq_length, max_length, begin_index, top_k=50,
+                 mode="image-only"):
+        if mode not in ("image-only", "interleaved-text-image", "text-only"):
+            raise ValueError(f"Unknown multimodal generation mode: {mode}")
         self.boi, self.eoi, self.eos = int(boi), int(eoi), int(eos)
         self.allow = (int(image_lo), int(image_hi))
         self.S, self.max_length, self.begin_index, self.top_k = int(image_seq_length), int(max_length), int(begin_index), int(top_k)
+        self.mode = mode
         self.reset()
 
     def reset(self):
@@ -269,55 +280,77 @@ class AnoleGrammarState:
             self.n += 1
 
     def _decide(self, n: int):
-        """-> ('image', None) | ('forced', id) for an accepted prefix of length n (positions of boi as observed)."""
+        """Candidate set after an accepted prefix of length n (positions of boi as observed):
+        ('image',) | ('forced', id) | ('pair', id, id) | ('text', ban0, ban1)."""
         S = self.S
+        if self.mode == "text-only":
+            return ("text", self.boi, self.eoi)
         at_offset = n >= S + 1 and (n - (S + 1)) in self.boi_at          # input_ids[-(S+1)] == boi
         in_window = any(n - min(S, n) <= p < n for p in self.boi_at)      # boi in input_ids[-min(S, n):]
+        late = not (self.max_length - S - 1 > n)                          # begin-of-image suppressed from here on
         if in_window:
             if at_offset:
                 raise NotImplementedError("Anole grammar: two begin-of-image tokens S+1 apart leave no allowed id")
-            return "image", None
+            return ("image",)
         if at_offset:
-            return "forced", self.eoi
+            return ("forced", self.eoi)
+        if self.mode == "interleaved-text-image":
+            return ("text", self.eoi, self.boi if late else -1)
         left = []
         if not (self.begin_index <= n <= self.begin_index + 1):
             left.append(self.eos)
-        if self.max_length - S - 1 > n:
+        if not late:
             left.append(self.boi)
-        if len(left) != 1:
-            raise NotImplementedError(f"Anole grammar: allowed set {left} after {n} tokens is not expressible on device "
-                                      "(use max_new_tokens = image_seq_length + 2 like the reference driver)")
-        return "forced", left[0]
+        if len(left) == 1:
+            return ("forced", left[0])
+        if len(left) == 2:
+            return ("pair", left[0], left[1])
+        raise NotImplementedError(f"Anole grammar: no id is allowed after {n} tokens (max_length too small for an image)")
+
+    def _desc(self, d, n):
+        if d[0] == "image":
+            return {"allow": self.allow, "forced": [-1] * n, "top_k": self.top_k, "allow_mode": 1, "ban": [-1, -1]}
+        if d[0] == "forced":
+            return {"allow": None, "forced": [d[1]] * n, "top_k": self.top_k, "allow_mode": 0, "ban": [-1, -1]}
+        if d[0] == "pair":
+            return {"allow": None, "forced": [-1] * n, "top_k": self.top_k, "allow_mode": 3, "ban": [d[1], d[2]]}
+        return {"allow": self.allow, "forced": [-1] * n, "top_k": self.top_k, "allow_mode": 2, "ban": [d[1], d[2]]}
 
     def describe(self, n: int) -> dict:
-        kind, tok = self._decide(self.n)
-        if kind == "image":
-            return {"allow": self.allow, "forced": [-1] * n, "top_k": self.top_k}
-        return {"allow": None, "forced": [tok] * n, "top_k": self.top_k}
+        return self._desc(self._decide(self.n), n)
 
-    def describe_residual(self, n: int) -> list:
-        """Forced id (encoded -2 - id, see below) of the residual at reject position j: the processors are re-run on the prefix plus the j drafts
-        accepted before it (jacobi_iteration_lumina_mgpt.py:297-306); accepted drafts are image ids or the forced id, and
-        only begin-of-image moves the triggers, so the prefix length is all that changes."""
+    def describe_residual(self, n: int, drafts=None) -> list:
+        """Forced id (encoded -2 - id, see below) of the residual at reject position j: the processors are re-run on the
+        prefix plus the j drafts accepted before it (jacobi_iteration_lumina_mgpt.py:297-306).  `drafts` = the window's
+        tokens ([0] = last accepted token); only begin-of-image among them moves the triggers.  The kernel applies the
+        WINDOW's candidate set to the residual unless a forced id is given, so a residual set that differs from the
+        window's and is not a single id cannot be expressed and is refused."""
         out = []
-        kind0, tok0 = self._decide(self.n)
+        d0 = self._decide(self.n)
         keep = list(self.boi_at)
         try:
             for j in range(n):
-                if kind0 == "forced" and tok0 == self.boi and j > 0:
-                    self.boi_at.append(self.n + j - 1)   # the accepted drafts of a forced window are the forced id
-                kind, tok = self._decide(self.n + j)
-                if kind == "image" and kind0 != "image":
-                    tok = -2   # would need the image range while the window has none: not expressible, see below
-                out.append(-1 if kind == "image" and kind0 == "image" else tok)
+                if j > 0:
+                    tok = drafts[j] if drafts is not None else (d0[1] if d0[0] == "forced" else None)
+                    if tok == self.boi:
+                        self.boi_at.append(self.n + j - 1)
+                d = self._decide(self.n + j)
+                if d == d0 and d[0] != "forced":
+                    out.append(-1)
+                elif d[0] == "forced":
+                    out.append(-2 - d[1])   # "mask-forced" code of sjd_verify (include/sjd_b200.h, forced_resid): these
+                    # processors fill the other ids with finfo.min rather than writing a one-hot row, which matters when
+                    # the forced id has no residual mass
+                else:
+                    out.append(None)        # a different multi-id set: not expressible
         finally:
             self.boi_at = keep
-        if any(t == -2 for t in out[1:]) and n > 1:
-            raise NotImplementedError("Anole grammar: a multi-token window right at begin-of-image (use jacobi_loop_interval_l >= 1)")
-        # "mask-forced" code for sjd_verify (include/sjd_b200.h, forced_resid): these processors fill the other ids with
-        # finfo.min rather than writing a one-hot row, which matters when the forced id has no residual mass
-        out = [(-1 if t in (-1, -2) else -2 - t) for t in out]
-        return out
+        if any(t is None for t in out[1:]) and n > 1:
+            raise NotImplementedError("Anole grammar: the candidate set changes inside this window in a way the verify "
+                                      "kernel cannot express (a window right at begin-of-image, or one that straddles "
+                                      "index max_length - image_seq_length - 1 in interleaved mode); use "
+                                      "jacobi_loop_interval_l >= 1 / a window of 1 there")
+        return [(-1 if t is None else t) for t in out]
 
 
 @dataclass
@@ -604,7 +637,12 @@ class SJDEngine:
             hn[base:base + Wv] = window[-Wv:]
             hn[base + self.Wmax: base + self.Wmax + Wv] = q_row[-Wv:]
             hn[base + 2 * self.Wmax: base + 2 * self.Wmax + Wv] = desc["forced"]
-            resid_forced = grammar.describe_residual(Wv) if hasattr(grammar, "describe_residual") else None
+            resid_forced = None
+            if hasattr(grammar, "describe_residual"):
+                try:
+                    resid_forced = grammar.describe_residual(Wv, window[-Wv:])
+                except TypeError:
+                    resid_forced = grammar.describe_residual(Wv)
             if resid_forced is not None:
                 hn[base + 3 * self.Wmax: base + 3 * self.Wmax + Wv] = resid_forced
             ds[base: base + 4 * self.Wmax].copy_(hs[base: base + 4 * self.Wmax], non_blocking=True)
@@ -616,6 +654,8 @@ class SJDEngine:
             a.has_uncond, a.apply_cfg = int(rows == 2), int(do_cfg and not no_cfg)
             a.guidance, a.temperature = float(p.guidance_scale), float(temperature)
             a.allow_lo, a.allow_hi = desc["allow"] if desc["allow"] else (0, 0)
+            a.allow_mode = int(desc.get("allow_mode", 0))
+            a.ban[0], a.ban[1] = desc.get("ban", (-1, -1))
             a.forced = ds[base + 2 * self.Wmax:].data_ptr()
             a.forced_resid = ds[base + 3 * self.Wmax:].data_ptr() if resid_forced is not None else None
             a.top_k, a.do_sample, a.scheme = int(desc["top_k"]), int(do_sample), scheme

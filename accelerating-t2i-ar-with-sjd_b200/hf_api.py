@@ -137,24 +137,53 @@ class SuppressTokensLogitsProcessor3d(SuppressTokensInIndexRangeLogitsProcessor3
 
 
 def _anole_grammar(procs, plain_k, vocab):
-    """The "image-only" processor set of renew_pipeline_anole.generate (scheduler/jacobi_iteration_anhole.py:200-240) ->
-    engine.AnoleGrammarState.  Any other combination of these processors has no device implementation."""
+    """The processor sets renew_pipeline_anole.generate builds per multimodal_generation_mode
+    (scheduler/jacobi_iteration_anhole.py:170-265) -> engine.AnoleGrammarState(mode):
+        image-only              at-offset + in-window + no-late-image + suppress(everything else) + suppress-at-begin(eos)
+        interleaved-text-image  at-offset + in-window + no-late-image
+        text-only               suppress(image ids + boi + eoi)
+    ("unrestricted" installs none of them and never reaches this function.)  Any other combination has no device
+    implementation."""
     at = [p for p in procs if isinstance(p, AllowOnlyTokensAtRelativeOffsetLogitsProcessor3d)]
     win = [p for p in procs if isinstance(p, AllowOnlyTokensInRelativeWindowLogitsProcessor3d)]
     beg = [p for p in procs if isinstance(p, SuppressTokensAtBeginLogitsProcessor3d)]
     rng = [p for p in procs if type(p) is SuppressTokensInIndexRangeLogitsProcessor3d]
     sup = [p for p in procs if isinstance(p, SuppressTokensLogitsProcessor3d) or
            (type(p).__name__ == "SuppressTokensLogitsProcessor" and hasattr(p, "suppress_tokens"))]
-    if not (len(at) == len(win) == len(beg) == len(rng) == len(sup) == 1):
-        raise NotImplementedError("only the Anole 'image-only' processor set (one of each 3-D Chameleon processor) "
-                                  "is implemented on device")
-    at, win, beg, rng, sup = at[0], win[0], beg[0], rng[0], sup[0]
+    counts = (len(at), len(win), len(rng), len(sup), len(beg))
+    if counts == (0, 0, 0, 1, 0):
+        # text-only: the suppressed ids are one contiguous image-id run plus begin- and end-of-image
+        ids = sorted(_id_list(sup[0].suppress_tokens))
+        runs, start = [], 0
+        for i in range(1, len(ids) + 1):
+            if i == len(ids) or ids[i] != ids[i - 1] + 1:
+                runs.append((ids[start], ids[i - 1] + 1))
+                start = i
+        big = max(runs, key=lambda r: r[1] - r[0])
+        rest = [t for lo_, hi_ in runs if (lo_, hi_) != big for t in range(lo_, hi_)]
+        if len(rest) > 2:
+            raise NotImplementedError("text-only Anole grammar: more than two suppressed ids outside the image-id range")
+        rest += [-1] * (2 - len(rest))
+        return _engine.AnoleGrammarState(rest[0], rest[1], -1, big[0], big[1], 0, max_length=0, begin_index=0,
+                                         top_k=plain_k, mode="text-only")
+    if counts[:3] != (1, 1, 1) or counts[3:] not in ((1, 1), (0, 0)):
+        raise NotImplementedError("this combination of 3-D Chameleon processors is none of the Anole adaptor's modes "
+                                  "(scheduler/jacobi_iteration_anhole.py:170-265)")
+    at, win, rng = at[0], win[0], rng[0]
     S = win.window_width
     lo, hi = _visual_range(win.allowed_token_ids)
     ok = (at.exclusive and win.exclusive and at.trigger_token_id == win.trigger_token_id and at.offset == S + 1
           and len(at.allowed_token_ids) == 1 and rng.suppress_tokens == [at.trigger_token_id]
-          and rng.end_index == math.inf and len(beg.suppress_tokens) == 1)
-    boi, eoi, eos = at.trigger_token_id, at.allowed_token_ids[0], beg.suppress_tokens[0]
+          and rng.end_index == math.inf)
+    boi, eoi = at.trigger_token_id, at.allowed_token_ids[0]
+    if counts[3:] == (0, 0):
+        if not ok:
+            raise NotImplementedError("Anole processors are not in the 'interleaved-text-image' configuration")
+        return _engine.AnoleGrammarState(boi, eoi, -1, lo, hi, S, max_length=int(rng.start_index) + S + 1, begin_index=0,
+                                         top_k=plain_k, mode="interleaved-text-image")
+    beg, sup = beg[0], sup[0]
+    ok = ok and len(beg.suppress_tokens) == 1
+    eos = beg.suppress_tokens[0]
     if ok and vocab is not None:
         kept = set(range(vocab)) - set(_id_list(sup.suppress_tokens))
         ok = kept == set(range(lo, hi)) | {eos, boi, eoi}

@@ -105,6 +105,14 @@ typedef struct sjd_verify_args {
   uint64_t rng_seed;
   uint64_t rng_off[3];
   uint32_t rng_span[3];
+  /* Candidate sets beyond one id range — what the 3-D Chameleon / Anole processors (scheduler/logit_processor_3dim.py:
+   * 207-353, installed per multimodal_generation_mode by scheduler/jacobi_iteration_anhole.py:170-265) reduce to for one
+   * call.  allow_mode 0 (a zero-initialised struct): [allow_lo, allow_hi) as above, ban[] not looked at; 1: the same
+   * minus the ids ban[0], ban[1] (-1 = none); 2: every id EXCEPT [allow_lo, allow_hi) and ban[] (text between images:
+   * image ids, end-of-image and, late, begin-of-image removed); 3: only the ids ban[0] and ban[1] (both >= 0) are kept;
+   * 4: every id except ban[]. */
+  int32_t allow_mode;
+  int32_t ban[2];
 } sjd_verify_args;
 
 int sjd_verify(const sjd_verify_args* args, void* stream);

@@ -171,17 +171,24 @@ def run_reference_loop(case: dict, Cache) -> dict:
         image_ids = list(range(a["image"][0], a["image"][1]))
         allowed = image_ids + [a["eos"], a["boi"], a["eoi"]]
         S = a["image_seq_length"]
-        procs = LogitsProcessorList([
+        three = [
             LP3.AllowOnlyTokensAtRelativeOffsetLogitsProcessor3d(trigger_token_id=a["boi"], allowed_token_ids=[a["eoi"]],
                                                                  offset=S + 1, exclusive=True),
             LP3.AllowOnlyTokensInRelativeWindowLogitsProcessor3d(trigger_token_id=a["boi"], allowed_token_ids=image_ids,
                                                                  window_width=S, exclusive=True),
             LP3.SuppressTokensInIndexRangeLogitsProcessor3d(suppress_tokens=[a["boi"]],
-                                                            start_index=case["max_length"] - S - 1),
-            LP3.SuppressTokensLogitsProcessor3d(suppress_tokens=[t for t in range(V) if t not in set(allowed)]),
-            LP3.SuppressTokensAtBeginLogitsProcessor3d(begin_suppress_tokens=[a["eos"]],
-                                                       begin_index=len(case["prompt"])),
-            TopKLogitsWarper(top_k=case["image_top_k"])])
+                                                            start_index=case["max_length"] - S - 1)]
+        mode = a.get("mode", "image-only")
+        if mode == "text-only":            # jacobi_iteration_anhole.py:190-198
+            plist = [LP3.SuppressTokensLogitsProcessor3d(suppress_tokens=image_ids + [a["boi"], a["eoi"]])]
+        elif mode == "interleaved-text-image":   # :241-248
+            plist = three
+        else:                              # image-only, :200-240
+            plist = three + [
+                LP3.SuppressTokensLogitsProcessor3d(suppress_tokens=[t for t in range(V) if t not in set(allowed)]),
+                LP3.SuppressTokensAtBeginLogitsProcessor3d(begin_suppress_tokens=[a["eos"]],
+                                                           begin_index=len(case["prompt"]))]
+        procs = LogitsProcessorList(plist + [TopKLogitsWarper(top_k=case["image_top_k"])])
     else:
         procs = LogitsProcessorList([TopKLogitsWarper(top_k=case["image_top_k"]),
                                      TopPLogitsWarper3d(top_p=case.get("top_p", 1.0))])
@@ -215,6 +222,8 @@ def run_reference_loop(case: dict, Cache) -> dict:
 
 
 _ANOLE = dict(boi=8197, eoi=8196, eos=2, image=[4, 8196], image_seq_length=24)
+_ANOLE_TEXT = dict(_ANOLE, mode="text-only")
+_ANOLE_MIX = dict(_ANOLE, mode="interleaved-text-image")
 _EMU3 = dict(height=4, width=6, img_token=900, eol=901, eof=902, eoi=903, eos=904, pad=905, visual=[1000, 3048])
 LOOP_CASES = {
     # Anole (a12): five 3-D Chameleon processors + TopK(50); boi forced first, 24 image tokens, eoi only if a trip
@@ -231,6 +240,21 @@ LOOP_CASES = {
                                    jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=20, max_num_new_tokens=4,
                                                guidance_scale=7.0, seed=11, multi_token_init_scheme="random", do_cfg=True,
                                                prefix_token_sampler_scheme="speculative_jacobi")),
+    # Anole's other generation modes (a12, round 2): text-only = everything but image ids / boi / eoi; interleaved = image
+    # ids for S tokens after a begin-of-image, end-of-image forced right after, text (no image ids, no eoi, boi only early)
+    # elsewhere.  The interleaved prompt ends in begin-of-image so that the run crosses image -> eoi -> text.
+    "anole_text_only_w8": dict(V=9216, sharp=12.0, grammar="anole", anole=_ANOLE_TEXT, image_top_k=50, text_top_k=10,
+                               prompt=[0, 300, 400, 500], img_vocab=[4, 8196], do_sample=True, eos=[2],
+                               max_length=4 + 40,
+                               jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=30, max_num_new_tokens=8,
+                                           guidance_scale=3.0, seed=8, multi_token_init_scheme="random", do_cfg=True,
+                                           prefix_token_sampler_scheme="speculative_jacobi")),
+    "anole_interleaved_w6": dict(V=9216, sharp=12.0, grammar="anole", anole=_ANOLE_MIX, image_top_k=50, text_top_k=10,
+                                 prompt=[0, 300, 400, 8197], img_vocab=[4, 8196], do_sample=True, eos=[2],
+                                 max_length=4 + 24 + 1 + 70,
+                                 jacobi=dict(jacobi_loop_interval_l=1, jacobi_loop_interval_r=24 + 1 + 9, max_num_new_tokens=6,
+                                             guidance_scale=3.0, seed=12, multi_token_init_scheme="random", do_cfg=True,
+                                             prefix_token_sampler_scheme="speculative_jacobi")),
     # LlamaGen processors with a real nucleus: TopK(100) then TopPLogitsWarper3d(0.8) (a10)
     "plain_topk_topp_spec_w16": dict(V=1024, sharp=12.0, grammar="plain", image_top_k=100, text_top_k=10, top_p=0.8,
                                      prompt=[207], img_vocab=[0, 1024], do_sample=True, eos=[], max_length=100,

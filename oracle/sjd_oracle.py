@@ -149,12 +149,19 @@ class AnoleGrammar:
     max_length: int = 0           # generation_config.max_length (prompt + max_new_tokens)
     begin_index: int = 0          # prompt length (SuppressTokensAtBegin)
     top_k: int = 50               # HF default top_k when do_sample=True
+    mode: str = "image-only"      # multimodal_generation_mode (jacobi_iteration_anhole.py:170-265)
 
     def disallowed(self, ids: list[int]) -> np.ndarray:
         V, S, cur = self.vocab, self.image_seq_length, len(ids)
         img = np.zeros(V, bool)
         img[self.image_lo:self.image_hi] = True
         dis = np.zeros(V, bool)
+        if self.mode == "text-only":   # SuppressTokensLogitsProcessor3d(image ids + [boi, eoi])  (:190-198)
+            dis |= img
+            dis[[self.boi, self.eoi]] = True
+            return dis
+        if self.mode == "unrestricted":
+            return dis
         # AllowOnlyTokensAtRelativeOffsetLogitsProcessor3d(boi, [eoi], offset=S+1, exclusive=True)  (:242-256)
         not_eoi = np.ones(V, bool)
         not_eoi[self.eoi] = False
@@ -169,6 +176,8 @@ class AnoleGrammar:
         # SuppressTokensInIndexRangeLogitsProcessor3d([boi], start=max_length - S - 1)  (:280-286)
         if not (self.max_length - S - 1 > cur):
             dis[self.boi] = True
+        if self.mode == "interleaved-text-image":   # only the three processors above (:241-248)
+            return dis
         # SuppressTokensLogitsProcessor3d(everything but image ids, eos, boi, eoi)
         ok = img.copy()
         ok[[self.eos, self.boi, self.eoi]] = True

@@ -270,7 +270,8 @@ def _engine_for_case(env, case, noise_dev="cpu"):
     elif case["grammar"] == "anole":
         a = case["anole"]
         grammar = engine.AnoleGrammarState(a["boi"], a["eoi"], a["eos"], a["image"][0], a["image"][1], a["image_seq_length"],
-                                           case["max_length"], len(case["prompt"]), top_k=case["image_top_k"])
+                                           case["max_length"], len(case["prompt"]), top_k=case["image_top_k"],
+                                           mode=a.get("mode", "image-only"))
     else:
         grammar = engine.PlainTopKState(top_k=case["image_top_k"], top_p=case.get("top_p", 1.0))
 

@@ -44,8 +44,8 @@ def test_library_is_built_for_sm100a_with_tcgen05_and_tma(lib):
 def test_stream_k_workspace_is_host_computable(lib):
     L = lib.lib()
     # 2 KB of counters + 32 B of {arrived, done} per tile + per-tile row statistics + two segments of tpu fp32 partial
-    # tiles per CTA (tpu = weight tiles per stream-K unit, 2 unless SJD_GEMM_TPU says otherwise)
-    tpu = int(os.environ.get("SJD_GEMM_TPU", "2"))
+    # tiles per CTA (tpu = weight tiles per stream-K unit, 1 unless SJD_GEMM_TPU says otherwise)
+    tpu = int(os.environ.get("SJD_GEMM_TPU", "1"))
     assert L.sjd_gemm_workspace_bytes(4096, 4096, 64, 148) == 2048 + 32 * 32 + 32 * 64 * 4 + 2 * tpu * 148 * 64 * 128 * 4
     assert L.sjd_gemm_workspace_bytes(184622, 4096, 128, 148) == 2048 + 1443 * 32 + 1443 * 128 * 4 + 2 * tpu * 148 * 128 * 128 * 4
 
@@ -171,11 +171,16 @@ def _anole_pair(S=12, P=5, extra=2, top_k=50, V=9216):
 
 
 def _allowed_from_desc(d, V):
-    """allowed-id set of window position 0 as the verify kernel will see it"""
+    """allowed-id set of window position 0 as the verify kernel will see it (sjd_verify_args: allow range, allow_mode, ban)"""
     if d["forced"][0] >= 0:
         return {d["forced"][0]}
-    lo, hi = d["allow"]
-    return set(range(lo, hi))
+    mode, ban = d.get("allow_mode", 0), [b for b in d.get("ban", (-1, -1))]
+    if mode == 3:
+        return set(ban)
+    lo, hi = d["allow"] if d["allow"] else (0, V)
+    if mode == 2:
+        return set(range(V)) - set(range(lo, hi)) - set(ban)
+    return set(range(lo, hi)) - (set(ban) if mode in (1, 4) else set())
 
 
 def test_anole_grammar_state_matches_oracle_masks():
@@ -212,11 +217,47 @@ def test_anole_grammar_state_matches_oracle_masks():
             assert ids[P + S + 1] == 8196, "with single-token accepts end-of-image is forced at the offset"
 
 
-def test_anole_grammar_refuses_inexpressible_sets():
-    o, e = _anole_pair(S=4, P=2, extra=12)   # room for a second image: {eos, boi} after the first one
-    e.observe([0, 1, 8197, 10, 11, 12, 13, 8196])
-    with pytest.raises(NotImplementedError, match="not expressible"):
-        e.describe(1)
+def test_anole_two_id_sets_are_expressible_now():
+    """Round 1 refused the {eos, boi} set that appears when max_new_tokens leaves room for a second image; the verify
+    kernel now takes a one-or-two-id candidate set (allow_mode 3)."""
+    o, e = _anole_pair(S=4, P=2, extra=12)
+    ids = [0, 1, 8197, 10, 11, 12, 13, 8196]
+    e.observe(ids)
+    d = e.describe(1)
+    assert d["allow_mode"] == 3 and _allowed_from_desc(d, 9216) == set(np.flatnonzero(~o.disallowed(ids)).tolist()) == {2, 8197}
+
+
+@pytest.mark.parametrize("mode", ["text-only", "interleaved-text-image"])
+def test_anole_other_modes_match_oracle_masks(mode):
+    """a12 (round 2): the candidate set engine.AnoleGrammarState(mode) hands to sjd_verify == the reference's processors
+    for that multimodal_generation_mode restated as masks (oracle.AnoleGrammar(mode), itself pinned to the reference by
+    the goldens anole_text_only_w8 / anole_interleaved_w6), for every prefix of a run that crosses text -> begin-of-image
+    -> S image tokens -> forced end-of-image -> text -> the index from which begin-of-image is suppressed."""
+    from oracle import sjd_oracle as O
+    from sjd_b200 import engine
+    V, S, P = 9216, 6, 3
+    max_length = P + 30
+    o = O.AnoleGrammar(vocab=V, boi=8197, eoi=8196, eos=2, image_lo=4, image_hi=8196, image_seq_length=S,
+                       max_length=max_length, begin_index=P, top_k=50, mode=mode)
+    e = engine.AnoleGrammarState(8197, 8196, 2, 4, 8196, S, max_length, P, top_k=50, mode=mode)
+    ids = [0, 300, 400]
+    e.observe(ids)
+    script = [9000, 9001, 8197] + [10, 11, 12, 13, 14, 15] + [8196] + [9100 + i for i in range(16)]
+    for tok in script:
+        d = e.describe(3)
+        want = set(np.flatnonzero(~o.disallowed(ids)).tolist())
+        assert _allowed_from_desc(d, V) == want, (mode, len(ids), d["allow_mode"], d["ban"])
+        if mode == "interleaved-text-image" or tok not in (8197, 8196) and not (4 <= tok < 8196):
+            assert tok in want or mode == "text-only", (mode, len(ids), tok)
+        ids.append(tok)
+        e.observe([tok])
+    # residual decisions inside a text window: same set unless a draft is begin-of-image (then the kernel cannot express it)
+    e2 = engine.AnoleGrammarState(8197, 8196, 2, 4, 8196, S, max_length, P, top_k=50, mode=mode)
+    e2.observe([0, 300, 400])
+    assert e2.describe_residual(3, [400, 9000, 9001]) == [-1, -1, -1]
+    if mode == "interleaved-text-image":
+        with pytest.raises(NotImplementedError):
+            e2.describe_residual(3, [400, 8197, 9001])
 
 
 def test_anole_processors_translate_to_grammar_state():
@@ -238,6 +279,12 @@ def test_anole_processors_translate_to_grammar_state():
         procs[0](torch.zeros(1, 3, dtype=torch.long), torch.zeros(1, 2, V))
     with pytest.raises(NotImplementedError):
         H.grammar_from_processors(procs[:2] + procs[3:], vocab=V)      # one processor of the set missing
+    # the other modes of renew_pipeline_anole.generate (a12, round 2)
+    gi = H.grammar_from_processors(procs[:3] + procs[5:], vocab=V)     # interleaved-text-image: the first three + TopK
+    assert gi.mode == "interleaved-text-image" and (gi.boi, gi.eoi, gi.allow, gi.S) == (8197, 8196, (4, 8196), S)
+    gt = H.grammar_from_processors([H.SuppressTokensLogitsProcessor3d(image + [8197, 8196]), procs[5]], vocab=V)
+    assert gt.mode == "text-only" and gt.allow == (4, 8196) and {gt.boi, gt.eoi} == {8197, 8196}
+    assert gt.describe(2)["allow_mode"] == 2 and sorted(gt.describe(2)["ban"]) == [8196, 8197]
     procs[1] = H.AllowOnlyTokensInRelativeWindowLogitsProcessor3d(8197, image, window_width=S, exclusive=False)
     with pytest.raises(NotImplementedError):
         H.grammar_from_processors(procs, vocab=V)

@@ -28,7 +28,8 @@ def run_oracle(case, max_trips=None):
         a = case["anole"]
         grammar = O.AnoleGrammar(vocab=V, boi=a["boi"], eoi=a["eoi"], eos=a["eos"], image_lo=a["image"][0],
                                  image_hi=a["image"][1], image_seq_length=a["image_seq_length"],
-                                 max_length=case["max_length"], begin_index=len(case["prompt"]), top_k=case["image_top_k"])
+                                 max_length=case["max_length"], begin_index=len(case["prompt"]), top_k=case["image_top_k"],
+                                 mode=a.get("mode", "image-only"))
     else:
         grammar = O.PlainTopK(top_k=case["image_top_k"], top_p=case.get("top_p", 1.0))
     trace = []
