@@ -283,8 +283,8 @@ def test_anole_processors_translate_to_grammar_state():
     gi = H.grammar_from_processors(procs[:3] + procs[5:], vocab=V)     # interleaved-text-image: the first three + TopK
     assert gi.mode == "interleaved-text-image" and (gi.boi, gi.eoi, gi.allow, gi.S) == (8197, 8196, (4, 8196), S)
     gt = H.grammar_from_processors([H.SuppressTokensLogitsProcessor3d(image + [8197, 8196]), procs[5]], vocab=V)
-    assert gt.mode == "text-only" and gt.allow == (4, 8196) and {gt.boi, gt.eoi} == {8197, 8196}
-    assert gt.describe(2)["allow_mode"] == 2 and sorted(gt.describe(2)["ban"]) == [8196, 8197]
+    assert gt.mode == "text-only" and gt.describe(2)["allow_mode"] == 2
+    assert _allowed_from_desc(gt.describe(2), V) == set(range(V)) - set(image) - {8197, 8196}   # ([4, 8198) is one run here)
     procs[1] = H.AllowOnlyTokensInRelativeWindowLogitsProcessor3d(8197, image, window_width=S, exclusive=False)
     with pytest.raises(NotImplementedError):
         H.grammar_from_processors(procs, vocab=V)
