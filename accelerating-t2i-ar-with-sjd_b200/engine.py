@@ -24,7 +24,7 @@ def verify_call(logits: torch.Tensor, W: int, V: int, desc: dict, draft: torch.T
                 p_prev: torch.Tensor | None, *, has_uncond: bool, apply_cfg: bool, guidance: float,
                 temperature: float, do_sample: bool, scheme: int, noise_e1=None, noise_u=None, noise_e2=None,
                 eoi_token: int = -1, text_top_k: int = 0, p_cur: torch.Tensor | None = None,
-                sync: bool = True) -> dict:
+                sync: bool = True, rng: "PhiloxNoise | None" = None) -> dict:
     """Run the device verify step on fp32 logits [(2|1)*W, V].  `desc` carries the grammar decision for this
     window: {'allow': (lo, hi) | None, 'forced': [W ints], 'top_k': int}.  Returns device tensors and, when
     `sync`, the host ints `matched` / `rejected`."""
@@ -51,6 +51,11 @@ def verify_call(logits: torch.Tensor, W: int, V: int, desc: dict, draft: torch.T
     a.noise_e1 = noise_e1.data_ptr() if noise_e1 is not None else None
     a.noise_u = noise_u.data_ptr() if noise_u is not None else None
     a.noise_e2 = noise_e2.data_ptr() if noise_e2 is not None else None
+    if rng is not None:   # device-side noise: the three draws of one trip, in the reference's order
+        a.rng_mode, a.rng_seed = 1, rng.seed
+        a.rng_off[0], a.rng_span[0] = rng.draw(W * V)
+        a.rng_off[1], a.rng_span[1] = rng.draw(W * V)
+        a.rng_off[2], a.rng_span[2] = rng.draw(V)
     a.eoi_token, a.text_top_k = int(eoi_token), int(text_top_k)
     resid = _buf("resid", (V,), torch.float32, dev)
     nxt = torch.empty(W, dtype=torch.int32, device=dev)

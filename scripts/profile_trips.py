@@ -20,6 +20,7 @@ ap.add_argument("--window", type=int, default=32)
 ap.add_argument("--kv-len", type=int, default=1200)
 ap.add_argument("--layers", type=int, default=32)
 ap.add_argument("--time", action="store_true")
+ap.add_argument("--host-noise", action="store_true", help="round-1 form: torch generator kernels fill the noise tensors")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -42,19 +43,22 @@ p_prev = torch.softmax(torch.randn(W, V, device=dev), -1)
 draft = ids[:W].clone()
 q_row = torch.tensor([-1] + list(range(1, W // 2)) + [-1] * (W - W // 2), dtype=torch.int32, device=dev)
 gen = torch.Generator(dev).manual_seed(0)
+philox = engine.PhiloxNoise(0, dev)
 
 
 def trip(ev=None):
     if ev: ev[0].record()
     logits = stack.forward(W, rope, cpos, L, [0, P - 1], ids=ids, n_logit_tokens=W)
     if ev: ev[1].record()
-    e1 = torch.empty((W, V), device=dev).exponential_(1.0, generator=gen)
-    u = torch.rand((1, W, V), device=dev, generator=gen)[0].gather(1, draft.long()[:, None]).squeeze(1).contiguous()
-    e2 = torch.empty((1, V), device=dev).exponential_(1.0, generator=gen)
+    e1 = u = e2 = None
+    if args.host_noise:
+        e1 = torch.empty((W, V), device=dev).exponential_(1.0, generator=gen)
+        u = torch.rand((1, W, V), device=dev, generator=gen)[0].gather(1, draft.long()[:, None]).squeeze(1).contiguous()
+        e2 = torch.empty((1, V), device=dev).exponential_(1.0, generator=gen)
     if ev: ev[2].record()
     out = engine.verify_call(logits, W, V, desc, draft, q_row, p_prev, has_uncond=True, apply_cfg=True, guidance=3.0,
                              temperature=1.0, do_sample=True, scheme=0, noise_e1=e1, noise_u=u, noise_e2=e2,
-                             eoi_token=8196, text_top_k=10, sync=True)
+                             eoi_token=8196, text_top_k=10, sync=True, rng=None if args.host_noise else philox)
     if ev: ev[3].record()
     return out
 
