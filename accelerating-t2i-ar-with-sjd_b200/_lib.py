@@ -68,11 +68,13 @@ class VerifyArgs(C.Structure):
         ("sync_ws", C.c_void_p),
         ("rng_mode", C.c_int32), ("rng_seed", C.c_uint64), ("rng_off", C.c_uint64 * 3), ("rng_span", C.c_uint32 * 3),
         ("allow_mode", C.c_int32), ("ban", C.c_int32 * 2),
+        ("resid_set", C.c_int32), ("resid_allow_mode", C.c_int32), ("resid_allow_lo", C.c_int32),
+        ("resid_allow_hi", C.c_int32), ("resid_ban", C.c_int32 * 2), ("resid_from", C.c_int32),
     ]
 
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
-        self.ban[0] = self.ban[1] = -1      # "no extra removed id"
+        self.ban[0] = self.ban[1] = self.resid_ban[0] = self.resid_ban[1] = -1      # "no extra removed id"
 
 
 class ModelCfg(C.Structure):

@@ -251,6 +251,10 @@ int sjd_verify(const sjd_verify_args* a, void* stream) {
       (a->allow_mode == 2 && a->allow_hi < a->allow_lo))
     return fail(SJD_E_ARG, "sjd_verify: allow_mode / ban");
   p.allow_mode = a->allow_mode; p.ban[0] = a->ban[0]; p.ban[1] = a->ban[1];
+  if (a->resid_set && (a->resid_allow_mode < 0 || a->resid_allow_mode > 4)) return fail(SJD_E_ARG, "sjd_verify: resid_allow_mode");
+  p.resid_set = a->resid_set; p.resid_allow_mode = a->resid_allow_mode; p.resid_allow_lo = a->resid_allow_lo;
+  p.resid_allow_hi = a->resid_allow_hi; p.resid_ban[0] = a->resid_ban[0]; p.resid_ban[1] = a->resid_ban[1];
+  p.resid_from = a->resid_from;
   p.rng_mode = a->rng_mode; p.rng_seed = a->rng_seed;
   for (int k = 0; k < 3; ++k) { p.rng_off[k] = a->rng_off[k]; p.rng_span[k] = a->rng_span[k]; }
   g_launches += a->sync_ws ? 1 : 2;

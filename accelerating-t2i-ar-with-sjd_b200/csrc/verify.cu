@@ -31,6 +31,8 @@ struct VerifyParams {
   int allow_mode;          // 0: [lo,hi) if hi > lo (ban ignored); 1: same minus ban[]; 2: complement of [lo,hi) minus ban[];
                            // 3: only the ids ban[0], ban[1]; 4: everything minus ban[]
   int ban[2];              // removed ids (-1 = none); mode 3: the kept ids
+  int resid_set;           // 1: the residual (positions whose forced_resid is -1) uses the candidate set below instead
+  int resid_allow_mode, resid_allow_lo, resid_allow_hi, resid_ban[2], resid_from;   // ... from reject position resid_from on
   const int* forced;     // [W] forced token id per window position, or -1
   const int* forced_resid;  // [W] forced id of the residual distribution at reject position j; null = forced
   int top_k;             // 0 = off
@@ -135,19 +137,29 @@ struct Cand {
     return kind == 1 ? in : (kind == 2 ? !in : true);
   }
 };
-__device__ __forceinline__ Cand make_cand(const VerifyParams& p, bool text_mode) {
+__device__ __forceinline__ Cand make_cand_from(int m, int alo, int ahi, int b0, int b1, int V, bool text_mode) {
   Cand c;
-  const bool ranged = !text_mode && (p.allow_hi > p.allow_lo);
-  const int m = text_mode ? 0 : p.allow_mode;
+  const bool ranged = !text_mode && (ahi > alo);
+  if (text_mode) m = 0;
   c.kind = m == 2 ? 2 : (m == 3 ? 3 : ((m == 4 || !ranged) ? 0 : 1));
-  c.lo = ranged ? max(p.allow_lo, 0) : 0;
-  c.hi = ranged ? min(p.allow_hi, p.V) : p.V;
+  c.lo = ranged ? max(alo, 0) : 0;
+  c.hi = ranged ? min(ahi, V) : V;
   const bool bans = !text_mode && m >= 1;     // mode 0 = the zero-initialised legacy form: ban[] is not looked at
-  c.b0 = bans ? p.ban[0] : -1;
-  c.b1 = bans ? p.ban[1] : -1;
+  c.b0 = bans ? b0 : -1;
+  c.b1 = bans ? b1 : -1;
   c.span_lo = c.kind == 1 ? c.lo : 0;
-  c.span_hi = c.kind == 1 ? c.hi : p.V;
+  c.span_hi = c.kind == 1 ? c.hi : V;
   return c;
+}
+__device__ __forceinline__ Cand make_cand(const VerifyParams& p, bool text_mode) {
+  return make_cand_from(p.allow_mode, p.allow_lo, p.allow_hi, p.ban[0], p.ban[1], p.V, text_mode);
+}
+// the residual's candidate set: the window's, unless the caller gave another one (a grammar whose decision changes with
+// the drafts accepted inside the window, e.g. Anole right after a forced begin- / end-of-image)
+__device__ __forceinline__ Cand make_cand_resid(const VerifyParams& p, bool text_mode, int j) {
+  if (p.resid_set && !text_mode && j >= p.resid_from)
+    return make_cand_from(p.resid_allow_mode, p.resid_allow_lo, p.resid_allow_hi, p.resid_ban[0], p.resid_ban[1], p.V, false);
+  return make_cand(p, text_mode);
 }
 
 __device__ __forceinline__ NoiseRow noise_row_e1(const VerifyParams& p, int i) {
@@ -704,7 +716,7 @@ __device__ void verify_accept(const VerifyParams& p, BlockScratch& sc, TopPScrat
     int forced = (!text && fr) ? fr[j] : -1;
     bool mask_forced = false;
     if (forced <= -2) { forced = -2 - forced; mask_forced = true; }
-    const Cand cd = make_cand(p, text);
+    const Cand cd = make_cand_resid(p, text, j);
     const int lo = cd.span_lo, hi = cd.span_hi;
     const int v0 = (lo / int(blockDim.x)) * int(blockDim.x);
     const int top_k = text ? p.text_top_k : p.top_k;

@@ -327,10 +327,12 @@ class AnoleGrammarState:
     def describe_residual(self, n: int, drafts=None) -> list:
         """Forced id (encoded -2 - id, see below) of the residual at reject position j: the processors are re-run on the
         prefix plus the j drafts accepted before it (jacobi_iteration_lumina_mgpt.py:297-306).  `drafts` = the window's
-        tokens ([0] = last accepted token); only begin-of-image among them moves the triggers.  The kernel applies the
-        WINDOW's candidate set to the residual unless a forced id is given, so a residual set that differs from the
-        window's and is not a single id cannot be expressed and is refused."""
-        out = []
+        tokens ([0] = last accepted token); only begin-of-image among them moves the triggers.  Positions whose residual
+        set is the window's return -1; a single id returns the "mask-forced" code; ONE other multi-id set per window is
+        handed to the kernel through `self.resid_desc` (sjd_verify_args.resid_*): the positions after a forced
+        begin-of-image (image ids) or after a forced end-of-image (text).  Two different other sets in one window are
+        refused."""
+        out, other, other_from = [], None, 0
         d0 = self._decide(self.n)
         keep = list(self.boi_at)
         try:
@@ -340,22 +342,24 @@ class AnoleGrammarState:
                     if tok == self.boi:
                         self.boi_at.append(self.n + j - 1)
                 d = self._decide(self.n + j)
-                if d == d0 and d[0] != "forced":
-                    out.append(-1)
-                elif d[0] == "forced":
+                if d[0] == "forced":
                     out.append(-2 - d[1])   # "mask-forced" code of sjd_verify (include/sjd_b200.h, forced_resid): these
                     # processors fill the other ids with finfo.min rather than writing a one-hot row, which matters when
                     # the forced id has no residual mass
+                elif d == d0 and other is None:
+                    out.append(-1)
                 else:
-                    out.append(None)        # a different multi-id set: not expressible
+                    if other is None:
+                        other, other_from = d, j
+                    elif other != d:   # (also: back to the window's set after another one)
+                        raise NotImplementedError("Anole grammar: the residual candidate set changes twice inside one "
+                                                  "window (e.g. it straddles index max_length - image_seq_length - 1 right "
+                                                  "after an image); use a smaller window there")
+                    out.append(-1)
         finally:
             self.boi_at = keep
-        if any(t is None for t in out[1:]) and n > 1:
-            raise NotImplementedError("Anole grammar: the candidate set changes inside this window in a way the verify "
-                                      "kernel cannot express (a window right at begin-of-image, or one that straddles "
-                                      "index max_length - image_seq_length - 1 in interleaved mode); use "
-                                      "jacobi_loop_interval_l >= 1 / a window of 1 there")
-        return [(-1 if t is None else t) for t in out]
+        self.resid_desc = dict(self._desc(other, 1), resid_from=other_from) if other is not None else None
+        return out
 
 
 @dataclass
@@ -663,6 +667,12 @@ class SJDEngine:
             a.ban[0], a.ban[1] = desc.get("ban", (-1, -1))
             a.forced = ds[base + 2 * self.Wmax:].data_ptr()
             a.forced_resid = ds[base + 3 * self.Wmax:].data_ptr() if resid_forced is not None else None
+            rd = getattr(grammar, "resid_desc", None) if resid_forced is not None else None
+            if rd is not None:   # the residual's own candidate set (Anole: after a forced begin- / end-of-image)
+                a.resid_set, a.resid_allow_mode = 1, int(rd.get("allow_mode", 0))
+                a.resid_allow_lo, a.resid_allow_hi = rd["allow"] if rd["allow"] else (0, 0)
+                a.resid_ban[0], a.resid_ban[1] = rd.get("ban", (-1, -1))
+                a.resid_from = int(rd.get("resid_from", 0))
             a.top_k, a.do_sample, a.scheme = int(desc["top_k"]), int(do_sample), scheme
             a.top_p_thresh = top_p_threshold(desc.get("top_p", 1.0))
             a.draft = d_draft.data_ptr()

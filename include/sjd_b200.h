@@ -113,6 +113,11 @@ typedef struct sjd_verify_args {
    * 4: every id except ban[]. */
   int32_t allow_mode;
   int32_t ban[2];
+  /* resid_set = 1: residual positions j >= resid_from whose forced_resid is -1 use THIS candidate set (same encoding)
+   * instead of the window's — for grammars whose decision changes with the drafts accepted inside the window (Anole: the
+   * positions after a forced begin-of-image are image ids, the positions after a forced end-of-image are text). */
+  int32_t resid_set;
+  int32_t resid_allow_mode, resid_allow_lo, resid_allow_hi, resid_ban[2], resid_from;
 } sjd_verify_args;
 
 int sjd_verify(const sjd_verify_args* args, void* stream);

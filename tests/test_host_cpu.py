@@ -254,10 +254,14 @@ def test_anole_other_modes_match_oracle_masks(mode):
     # residual decisions inside a text window: same set unless a draft is begin-of-image (then the kernel cannot express it)
     e2 = engine.AnoleGrammarState(8197, 8196, 2, 4, 8196, S, max_length, P, top_k=50, mode=mode)
     e2.observe([0, 300, 400])
-    assert e2.describe_residual(3, [400, 9000, 9001]) == [-1, -1, -1]
+    assert e2.describe_residual(3, [400, 9000, 9001]) == [-1, -1, -1] and e2.resid_desc is None
     if mode == "interleaved-text-image":
-        with pytest.raises(NotImplementedError):
-            e2.describe_residual(3, [400, 8197, 9001])
+        # an accepted begin-of-image draft switches the residual of the positions behind it to image ids: handed to the
+        # kernel as its second candidate set (sjd_verify_args.resid_*, from position 1 on)
+        assert e2.describe_residual(3, [400, 8197, 9001]) == [-1, -1, -1]
+        assert e2.resid_desc["allow"] == (4, 8196) and e2.resid_desc["allow_mode"] == 1 and e2.resid_desc["resid_from"] == 1
+        want = set(np.flatnonzero(~o.disallowed([0, 300, 400, 8197, 9001][:4] + [])).tolist())
+        assert want == set(range(4, 8196))
 
 
 def test_anole_processors_translate_to_grammar_state():
