@@ -67,13 +67,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 constexpr int kAttnHalf = kAttnSub / 2;   // keys per warp per sub-chunk
 constexpr int kAttnMaxTiles = 4;          // query tiles per CTA (8 warps)
 
-template <int DH, int NTHREADS, int MINB>
+// STAGES = depth of the cp.async ring (2: the load of sub-chunk s+1 overlaps the math of s; 3: two sub-chunks in flight —
+// the round-2 ncu capture shows the 2-stage form waiting on global memory, long_scoreboard being its top stall reason)
+template <int DH, int NTHREADS, int MINB, int STAGES = 2>
 __global__ void __launch_bounds__(NTHREADS, MINB) attn_window_kernel(AttnParams p) {
   constexpr int ROWB = DH * 2 + 16;  // padded smem row (bytes): conflict-free ldmatrix
   constexpr int STAGE = kAttnSub * ROWB;
   extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t* sKb = smem;               // [2][kAttnSub][ROWB]
-  uint8_t* sVb = smem + 2 * STAGE;   // [2][kAttnSub][ROWB]
+  uint8_t* sKb = smem;                    // [STAGES][kAttnSub][ROWB]
+  uint8_t* sVb = smem + STAGES * STAGE;   // [STAGES][kAttnSub][ROWB]
 
   const int split = blockIdx.x, hkv = blockIdx.y % p.Hkv, tgroup = blockIdx.y / p.Hkv, b = blockIdx.z;
   if (p.l2_prefetch && threadIdx.x == 0) {
@@ -114,8 +116,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB) attn_window_kernel(AttnParams 
   auto load_sub = [&](int s) {
     constexpr int VEC_PER_ROW = DH / 8;
     const int key0 = k_begin + s * kAttnSub, nkeys = min(kAttnSub, k_end - key0);
-    uint8_t* dK = sKb + (s & 1) * STAGE;
-    uint8_t* dV = sVb + (s & 1) * STAGE;
+    uint8_t* dK = sKb + (s % STAGES) * STAGE;
+    uint8_t* dV = sVb + (s % STAGES) * STAGE;
     for (int idx = threadIdx.x; idx < kAttnSub * VEC_PER_ROW; idx += blockDim.x) {
       const int r = idx / VEC_PER_ROW, c = idx - r * VEC_PER_ROW;
       const int nb = r < nkeys ? 16 : 0;   // rows past the end are zero-filled
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) attn_window_kernel(AttnParams 
   uint32_t qf[DH / 16][4];
   if (n_sub > 0) {
     load_sub(0);
+    if (STAGES > 2 && n_sub > 1) load_sub(1);
     // Q fragments straight from global memory
     const __nv_bfloat16* q0 = p.q + (size_t(b * p.W + min(r0, p.W - 1)) * p.H + hq) * DH;
     const __nv_bfloat16* q1 = p.q + (size_t(b * p.W + min(r1, p.W - 1)) * p.H + hq) * DH;
@@ -147,18 +150,29 @@ __global__ void __launch_bounds__(NTHREADS, MINB) attn_window_kernel(AttnParams 
   }
 #pragma unroll 1
   for (int s = 0; s < n_sub; ++s) {
-    if (s + 1 < n_sub) {
-      load_sub(s + 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (STAGES == 2) {
+      if (s + 1 < n_sub) {
+        load_sub(s + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+    } else {   // sub-chunk s + 2 goes into the stage that iteration s - 1 released at its closing barrier
+      if (s + 2 < n_sub) {
+        load_sub(s + 2);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+      } else if (s + 1 < n_sub) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
     }
     __syncthreads();
     const int key0 = k_begin + s * kAttnSub + kh * kAttnHalf;   // first key of this warp's half
     // causal skip: every key of this half is beyond the last query of the tile, or past the end of the span
     if (has_tile && key0 < k_end && key0 <= p.kv_len + min(i0 + 15, p.W - 1)) {
-      const uint8_t* sK = sKb + (s & 1) * STAGE + kh * kAttnHalf * ROWB;
-      const uint8_t* sV = sVb + (s & 1) * STAGE + kh * kAttnHalf * ROWB;
+      const uint8_t* sK = sKb + (s % STAGES) * STAGE + kh * kAttnHalf * ROWB;
+      const uint8_t* sV = sVb + (s % STAGES) * STAGE + kh * kAttnHalf * ROWB;
       float sc[kAttnHalf / 8][4];
 #pragma unroll
       for (int n = 0; n < kAttnHalf / 8; ++n) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
@@ -366,13 +380,24 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(AttnCombine c) {
 }
 
 // Chooses the key split: as many CTAs as fit in ONE wave of three per SM, spans in whole 64-key sub-chunks.
+// (stages 3: two CTAs of 104 KB per SM instead of three of 70 KB)
+int attn_stages() {
+  static int st = 0;
+  if (!st) {
+    st = 2;
+    if (const char* e = getenv("SJD_ATTN_STAGES")) st = atoi(e) == 3 ? 3 : 2;
+  }
+  return st;
+}
+
 void attn_plan(AttnParams* p, int sm_count) {
   const int T = p->kv_len + p->W;
   const int G = p->H / p->Hkv;
   const int n_tiles = G * ((p->W + 15) / 16);
   const int tgroups = (n_tiles + kAttnMaxTiles - 1) / kAttnMaxTiles;
   const int base_ctas = p->rows * p->Hkv * tgroups;
-  int want = (3 * sm_count) / base_ctas;   // splits wanted: never more CTAs than the 3-per-SM slots (no second wave)
+  const int per_sm = (attn_stages() == 3 && n_tiles <= 2) ? 2 : 3;
+  int want = (per_sm * sm_count) / base_ctas;   // splits wanted: never more CTAs than the resident slots (no second wave)
   const int n_sub = (T + kAttnSub - 1) / kAttnSub;
   if (want > n_sub) want = n_sub;
   if (want < 1) want = 1;
@@ -412,6 +437,22 @@ int attn_launch(const AttnParams& p, int head_dim, bool with_combine, cudaStream
     rc |= launch_pdl(attn_window_kernel<DH_, NT_, MINB_>, grid, dim3(NT_), smem, stream, p);                      \
   } while (0)
   const int nt = nwarps * 32;
+#define SJD_ATTN_LAUNCH3(DH_, NT_)                                                                                 \
+  do {                                                                                                            \
+    constexpr int smem = 6 * kAttnSub * (DH_ * 2 + 16);                                                           \
+    static bool set = false;                                                                                      \
+    if (!set) {                                                                                                   \
+      cudaFuncSetAttribute(attn_window_kernel<DH_, NT_, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+      set = true;                                                                                                 \
+    }                                                                                                             \
+    rc |= launch_pdl(attn_window_kernel<DH_, NT_, 2, 3>, grid, dim3(NT_), smem, stream, p);                       \
+  } while (0)
+  if (attn_stages() == 3 && head_dim == 128 && n_tiles <= 2) {   // small windows of an MHA model: deeper ring, 2 CTAs / SM
+    if (nt == 64) SJD_ATTN_LAUNCH3(128, 64);
+    else SJD_ATTN_LAUNCH3(128, 128);
+    if (with_combine) rc |= launch_pdl(attn_combine_kernel<128>, cgrid, dim3(256), 0, stream, attn_combine_desc(p, 128));
+    return rc;
+  }
   if (head_dim == 128) {
     if (nt == 64) SJD_ATTN_LAUNCH(128, 64, 3);
     else if (nt == 128) SJD_ATTN_LAUNCH(128, 128, 3);
@@ -428,6 +469,7 @@ int attn_launch(const AttnParams& p, int head_dim, bool with_combine, cudaStream
     return -3;
   }
 #undef SJD_ATTN_LAUNCH
+#undef SJD_ATTN_LAUNCH3
   return rc;
 }
 

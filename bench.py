@@ -243,7 +243,7 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         achieved = alg / t_launch / 1e9
         traffic = None
-        tp = ROOT / "profiles" / "r01_gemm_traffic.json"
+        tp = ROOT / "profiles" / "r02_gemm_traffic.json"
         if tp.exists():
             try:
                 traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
