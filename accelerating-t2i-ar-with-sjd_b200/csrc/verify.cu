@@ -185,6 +185,57 @@ struct BlockScratch {
   uint32_t sel_above;
 };
 
+
+// Radix-select step shared by the two k-th-key routines: given hist[0..nb) (nb = 1024 or 2048 <= 2 * blockDim), find the
+// LARGEST bin b whose suffix count sum_{i >= b} hist[i] reaches `remaining`; sel_bin = b, sel_above = sum_{i > b} hist[i].
+// Every thread owns nb / blockDim consecutive bins in DESCENDING order; one block-wide exclusive scan of the per-thread
+// sums (warp shuffles + 32 warp totals) replaces the serial walk a single warp used to do while 31 others waited at the
+// barrier (30 % of the kernel's stall samples in the round-2 ncu capture, profiles/r02d_full_verify_summary.csv).
+// Integer arithmetic: the result does not depend on the order of anything.
+__device__ __forceinline__ void block_select_bin(uint32_t nb, uint32_t remaining, BlockScratch& sc) {
+  const uint32_t per = (nb + blockDim.x - 1) / blockDim.x;        // 1 or 2 (kVerifyThreads = 1024)
+  const uint32_t t = threadIdx.x, lane = t & 31u, wid = t >> 5;
+  uint32_t local = 0;
+  for (uint32_t j = 0; j < per; ++j) {
+    const uint32_t d = t * per + j;                                // d-th bin from the top
+    if (d < nb) local += sc.hist[nb - 1 - d];
+  }
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= uint32_t(o)) incl += v;
+  }
+  if (lane == 31) sc.redi[wid] = int(incl);
+  __syncthreads();
+  uint32_t wbase = 0;
+  {
+    const uint32_t nw = blockDim.x >> 5;
+    uint32_t wt = lane < nw ? uint32_t(sc.redi[lane]) : 0u, wincl = wt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, wincl, o);
+      if (lane >= uint32_t(o)) wincl += v;
+    }
+    wbase = __shfl_sync(0xffffffffu, wincl - wt, int(wid));        // exclusive total of the warps above this one
+  }
+  const uint32_t excl = wbase + incl - local;
+  if (excl < remaining && excl + local >= remaining) {             // exactly one thread
+    uint32_t run = excl;
+    for (uint32_t j = 0; j < per; ++j) {
+      const uint32_t d = t * per + j;
+      const uint32_t c = d < nb ? sc.hist[nb - 1 - d] : 0u;
+      if (run + c >= remaining) {
+        sc.sel_bin = nb - 1 - d;
+        sc.sel_above = run;
+        break;
+      }
+      run += c;
+    }
+  }
+  __syncthreads();
+}
+
 // k-th largest key among the finite entries of row[0..V); caller guarantees k <= #finite.
 __device__ uint32_t block_kth_key(const float* __restrict__ row, int vb, int V, int k, BlockScratch& sc) {
   uint32_t prefix = 0, mask = 0;
@@ -203,34 +254,7 @@ __device__ uint32_t block_kth_key(const float* __restrict__ row, int vb, int V, 
       if ((key & mask) == prefix) atomicAdd(&sc.hist[(key >> shift) & (nb - 1)], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-      const uint32_t lane = threadIdx.x;
-      const uint32_t per = nb / 32;
-      const uint32_t hi = nb - lane * per;  // exclusive top of this lane's chunk (lane 0 = largest keys)
-      uint32_t csum = 0;
-      for (uint32_t j = 0; j < per; ++j) csum += sc.hist[hi - 1 - j];
-      uint32_t incl = csum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= uint32_t(o)) incl += t;
-      }
-      const uint32_t excl = incl - csum;
-      const bool mine = (excl < remaining) && (incl >= remaining);
-      if (mine) {
-        uint32_t run = excl;
-        for (uint32_t j = 0; j < per; ++j) {
-          const uint32_t c = sc.hist[hi - 1 - j];
-          if (run + c >= remaining) {
-            sc.sel_bin = hi - 1 - j;
-            sc.sel_above = run;
-            break;
-          }
-          run += c;
-        }
-      }
-    }
-    __syncthreads();
+    block_select_bin(nb, remaining, sc);
     prefix |= sc.sel_bin << shift;
     mask |= (nb - 1) << shift;
     remaining -= sc.sel_above;
@@ -359,34 +383,7 @@ __device__ uint32_t block_kth_key_regs(const float (&s)[VPT], int k, BlockScratc
       }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-      const uint32_t lane = threadIdx.x;
-      const uint32_t per = nb / 32;
-      const uint32_t hi = nb - lane * per;  // exclusive top of this lane's chunk (lane 0 = largest keys)
-      uint32_t csum = 0;
-      for (uint32_t j = 0; j < per; ++j) csum += sc.hist[hi - 1 - j];
-      uint32_t incl = csum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= uint32_t(o)) incl += t;
-      }
-      const uint32_t excl = incl - csum;
-      const bool mine = (excl < remaining) && (incl >= remaining);
-      if (mine) {
-        uint32_t run = excl;
-        for (uint32_t j = 0; j < per; ++j) {
-          const uint32_t c = sc.hist[hi - 1 - j];
-          if (run + c >= remaining) {
-            sc.sel_bin = hi - 1 - j;
-            sc.sel_above = run;
-            break;
-          }
-          run += c;
-        }
-      }
-    }
-    __syncthreads();
+    block_select_bin(nb, remaining, sc);
     prefix |= sc.sel_bin << shift;
     mask |= (nb - 1) << shift;
     remaining -= sc.sel_above;
@@ -590,6 +587,20 @@ __device__ int block_top_p(float* __restrict__ row, int V, float thresh, int do_
   return do_sample ? tok : greedy_tok;
 }
 
+// row[a, b) = 0 with 16-byte stores where the alignment allows (V and the row base are multiples of 4 floats in every
+// shipped vocabulary; the scalar head / tail covers the rest)
+__device__ __forceinline__ void zero_fill(float* __restrict__ row, int a, int b) {
+  if (b <= a) return;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(row + a);
+  int head = int(((16 - (addr & 15)) & 15) >> 2);
+  if (head > b - a) head = b - a;
+  for (int v = a + threadIdx.x; v < a + head; v += blockDim.x) row[v] = 0.f;
+  const int a4 = a + head, n4 = (b - a4) >> 2;
+  float4* p4 = reinterpret_cast<float4*>(row + a4);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = a4 + 4 * n4 + threadIdx.x; v < b; v += blockDim.x) row[v] = 0.f;
+}
+
 constexpr int kRegVPT = 16;   // ids per thread held in registers: candidate ranges spanning up to 16 384 ids
 
 // One CTA per window position.
@@ -626,8 +637,8 @@ __device__ void verify_row(const VerifyParams& p, int i, BlockScratch& sc, TopPS
       s[j] = sv;
     }
     // everything outside the candidate range has probability zero
-    for (int v = threadIdx.x; v < lo; v += blockDim.x) row[v] = 0.f;
-    for (int v = hi + threadIdx.x; v < V; v += blockDim.x) row[v] = 0.f;
+    zero_fill(row, 0, lo);
+    zero_fill(row, hi, V);
     int tok = block_topk_softmax_sample_regs<kRegVPT>(s, v0, lo, hi, p.top_k, p.do_sample, noise_row_e1(p, i), row, V, sc);
     if (p.top_p_thresh > 0.f) {
       __syncthreads();   // the whole row of probabilities is in global memory
@@ -639,8 +650,8 @@ __device__ void verify_row(const VerifyParams& p, int i, BlockScratch& sc, TopPS
   // candidate range too wide for registers (Emu3: 32 768 visual ids of 184 622): same passes over the row in global
   // memory, but only over the blockDim-aligned span that covers [lo, hi); the rest of the row is probability 0
   const int ve = min(V, ((hi + int(blockDim.x) - 1) / int(blockDim.x)) * int(blockDim.x));
-  for (int v = threadIdx.x; v < v0; v += blockDim.x) row[v] = 0.f;
-  for (int v = ve + threadIdx.x; v < V; v += blockDim.x) row[v] = 0.f;
+  zero_fill(row, 0, v0);
+  zero_fill(row, ve, V);
   for (int v = v0 + threadIdx.x; v < ve; v += blockDim.x) {
     float s = -INFINITY;
     if (v >= lo && v < hi && cd.ok(v)) {

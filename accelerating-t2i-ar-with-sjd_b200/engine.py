@@ -528,12 +528,20 @@ class SJDEngine:
         self.d_stage = torch.empty(n_i32, dtype=torch.int32, device=self.dev)
         self.d_out = torch.empty(4 + Wmax, dtype=torch.int32, device=self.dev)
         self.h_out = torch.empty(4 + Wmax, dtype=torch.int32).pin_memory()
+        self.h_out_np = self.h_out.numpy()
+        self._views = {}                    # cached slices of the staging buffers per token-row count
         self.d_nxt = torch.empty(Wmax, dtype=torch.int32, device=self.dev)
         self.resid = torch.empty(self.V, dtype=torch.float32, device=self.dev)
         self.d_sync = torch.zeros(1, dtype=torch.int32, device=self.dev)   # sjd_verify's last-CTA counter (stays zero)
         self.noise_factory = noise_factory or default_noise
         self.lib = _lib.lib()
         self.stats = SJDStats()
+
+    def _img_vocab_np(self):
+        iv = self.img_vocab
+        if getattr(self, "_ivn_src", None) is not iv:      # hf_api swaps img_vocab between calls
+            self._ivn, self._ivn_src = iv.numpy(), iv
+        return self._ivn
 
     # -- one forward over `tokens` per row starting at cache slot kv_len -----------------------------------
     def _forward(self, row_tokens, kv_len, kv_lo, n_logit, embeds=None):
@@ -549,14 +557,17 @@ class SJDEngine:
             hn[b * W:(b + 1) * W] = row_tokens[b]
             _np.maximum(pos - kv_lo[b], 0, out=hn[M + b * W:M + (b + 1) * W])   # RoPE position = slot - first visible key
             hn[2 * M + b * W:2 * M + (b + 1) * W] = pos
-        self.d_stage[:3 * M].copy_(self.h_stage[:3 * M], non_blocking=True)
+        v = self._views.get(M)
+        if v is None:
+            ds = self.d_stage
+            v = self._views[M] = (ds[:3 * M], self.h_stage[:3 * M], ds[:M], ds[M:2 * M], ds[2 * M:3 * M])
+        v[0].copy_(v[1], non_blocking=True)
         if self._stage_copied is None:
             self._stage_copied = torch.cuda.Event()
         self._stage_copied.record(torch.cuda.current_stream(self.dev))
         self.stats.h2d_bytes += 12 * M
-        ds = self.d_stage
-        return self.stack.forward(W, ds[M:2 * M], ds[2 * M:3 * M], kv_len, kv_lo,
-                                  ids=None if embeds is not None else ds[:M], embeds=embeds, n_logit_tokens=n_logit)
+        return self.stack.forward(W, v[3], v[4], kv_len, kv_lo, ids=None if embeds is not None else v[2], embeds=embeds,
+                                  n_logit_tokens=n_logit)
 
     @torch.no_grad()
     def generate(self, input_ids, *, max_length: int, eos_token_ids=(), do_sample=True, temperature=1.0,
@@ -609,7 +620,7 @@ class SJDEngine:
                 fresh = []
                 if n_rand > 0:
                     r = torch.randint(0, len(self.img_vocab), (1, n_rand))   # CPU global RNG, like :505-509
-                    fresh = self.img_vocab[r[0]].tolist()
+                    fresh = self._img_vocab_np()[r.numpy()[0]].tolist()
                     fresh = horizon_init(fresh, p.multi_token_init_scheme, ids, carried, getattr(grammar, "w", None),
                                          prefill_num)
                 window = [ids[-1]] + keep + fresh
@@ -710,7 +721,7 @@ class SJDEngine:
             self.h_out[:4 + Wv].copy_(self.d_out[:4 + Wv], non_blocking=True)
             stats.d2h_bytes += 4 * (4 + Wv)
             stream.synchronize()
-            res = self.h_out[:4 + Wv].tolist()
+            res = self.h_out_np[:4 + Wv].tolist()
             matched, rejected = res[0], bool(res[1])
             toks = res[4:4 + Wv]
             if undo is not None and not rejected:
