@@ -545,6 +545,14 @@ int sjd_ctx_forward(sjd_ctx* c, const sjd_forward_args* a, void* stream) {
   if (a->kv_len < 0 || a->kv_len + W > g.max_len) return fail(SJD_E_ARG, "sjd_ctx_forward: KV cache overflow");
   if (a->n_logit_tokens < 1 || a->n_logit_tokens > W || !a->logits || !a->rope_pos || !a->cache_pos)
     return fail(SJD_E_ARG, "sjd_ctx_forward: bad logits/pos args");
+  {
+    // rope_pos lives on the device; under the engine's convention (position = cache slot - first visible key) the
+    // largest index of this call is kv_len + W - 1 - min(kv_lo): reject calls that would read past the RoPE table
+    // (the reference fails loudly on freqs_cis[input_pos], llamagen/llamagen.py:386)
+    int lo = a->kv_lo[0];
+    for (int b = 1; b < g.rows; ++b) lo = a->kv_lo[b] < lo ? a->kv_lo[b] : lo;
+    if (lo < 0 || a->kv_len + W - lo > g.n_rope_pos) return fail(SJD_E_ARG, "sjd_ctx_forward: RoPE table too small for these positions");
+  }
   if (ctx_ready(c)) return SJD_E_STATE;
   if (!a->ids && !a->embeds) return fail(SJD_E_ARG, "sjd_ctx_forward: ids or embeds required");
   if (a->ids && !c->have_embed) return fail(SJD_E_STATE, "sjd_ctx_forward: no embedding table");

@@ -172,7 +172,9 @@ typedef struct sjd_forward_args {
   int32_t W;                 /* tokens per row in this call; rows*W <= SJD_MAX_TOKENS */
   const int32_t* ids;        /* device [rows*W] token ids (row-major), or NULL when embeds is given */
   const void* embeds;        /* device bf16 [rows*W, d] input embeddings, or NULL */
-  const int32_t* rope_pos;   /* device [rows*W] index into the rope tables */
+  const int32_t* rope_pos;   /* device [rows*W] index into the rope tables, < n_rope_pos (the call is rejected when
+                              * kv_len + W - min(kv_lo) > n_rope_pos, i.e. when slot - first-visible-key positions would
+                              * run past the table) */
   const int32_t* cache_pos;  /* device [rows*W] KV slot written by each token */
   int32_t kv_len;            /* keys already valid in the cache; this call's tokens sit at kv_len .. kv_len+W-1 */
   int32_t kv_lo[SJD_MAX_ROWS]; /* first visible key per row (CFG hidden prefix / left padding) */
