@@ -260,6 +260,27 @@ __device__ __forceinline__ void epi_apply(const GemmEpi& ep, const EpiTileConst&
   }
 }
 
+// Sum of the parked partials of one (token row, tile) over its contributing CTAs c_first..c_last, in CTA order
+// (bit-reproducible), C loads in flight: a tile of o_proj / down is split over 5-6 CTAs, so C = 8 fetches them in one
+// L2 round trip where C = 4 needs two.
+template <int C>
+__device__ __forceinline__ void row_partial_sum(float (&v)[4], const float* __restrict__ pbase, int c_first, int c_last,
+                                                bool first_uses_last_slot, int tpu, int hh, size_t slot_floats) {
+#pragma unroll 1
+  for (int cb = c_first; cb <= c_last; cb += C) {
+    float4 pv[C];
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc) {
+      const int c = min(cb + cc, c_last);
+      const int slot = (2 * c + ((c == c_first && first_uses_last_slot) ? 1 : 0)) * tpu + hh;
+      pv[cc] = __ldcg(reinterpret_cast<const float4*>(pbase + size_t(slot) * slot_floats));
+    }
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc)   // CTA order: bit-reproducible
+      if (cb + cc <= c_last) { v[0] += pv[cc].x; v[1] += pv[cc].y; v[2] += pv[cc].z; v[3] += pv[cc].w; }
+  }
+}
+
 // ---- a chain of GEMMs executed by one persistent kernel ---------------------------------------------------
 constexpr int kMaxChainOps = 4;
 struct TmapSet {
@@ -287,6 +308,7 @@ struct KvPrefetch {
 struct Chain {
   int n_ops, num_stages;
   int lookahead;   // weight units prefetched into L2 beyond the ring
+  int row_c8;      // 1: the row owners fetch 8 partials per L2 round trip (SJD_GEMM_ROWC8)
   int epi_rows2;   // 1: the finisher epilogue keeps two token rows per warp in flight (SJD_GEMM_EPI2)
   int pf_always;   // 1: keep the L2 prefetch frontier `lookahead` units ahead in steady state too (0: only while the ring is blocked)
   uint32_t tmem_cols;
@@ -745,20 +767,9 @@ gemm_chain_kernel(const __grid_constant__ TmapSet maps, const Chain ch) {
                 const size_t off = size_t(m) * ep.N + size_t(t) * kBlockN + 4 * lane;
                 const uint2 hraw = *reinterpret_cast<const uint2*>(ep.h + off);
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
-                constexpr int C = 4;
-#pragma unroll 1
-                for (int cb = c_first; cb <= c_last; cb += C) {
-                  float4 pv[C];
-#pragma unroll
-                  for (int cc = 0; cc < C; ++cc) {
-                    const int c = min(cb + cc, c_last);
-                    const int slot = (2 * c + ((c == c_first && first_uses_last_slot) ? 1 : 0)) * tpu + hh;
-                    pv[cc] = __ldcg(reinterpret_cast<const float4*>(ep.ws + size_t(slot) * slot_floats + size_t(m) * 128 + 4 * lane));
-                  }
-#pragma unroll
-                  for (int cc = 0; cc < C; ++cc)   // CTA order: bit-reproducible
-                    if (cb + cc <= c_last) { v[0] += pv[cc].x; v[1] += pv[cc].y; v[2] += pv[cc].z; v[3] += pv[cc].w; }
-                }
+                const float* pbase = ep.ws + size_t(m) * 128 + 4 * lane;
+                if (ch.row_c8) row_partial_sum<8>(v, pbase, c_first, c_last, first_uses_last_slot, tpu, hh, slot_floats);
+                else row_partial_sum<4>(v, pbase, c_first, c_last, first_uses_last_slot, tpu, hh, slot_floats);
                 float hv[4];
                 unpack4(hraw, hv);
 #pragma unroll
@@ -1001,6 +1012,8 @@ int chain_launch(const TmapSet& maps, Chain ch, cudaStream_t stream) {
   // measured (profiles/r02g_epi2.txt): +1.4 % / +2.4 % chain throughput at 64 / 128 token rows, two runs each
   static const int epi2 = getenv("SJD_GEMM_EPI2") ? atoi(getenv("SJD_GEMM_EPI2")) : 1;
   ch.epi_rows2 = epi2;
+  static const int rowc8 = getenv("SJD_GEMM_ROWC8") ? atoi(getenv("SJD_GEMM_ROWC8")) : 1;   // +0.3 % (profiles/r02h_rowc8.txt)
+  ch.row_c8 = rowc8;
   int grid = 0;
   for (int i = 0; i < ch.n_ops; ++i) {
     if (ch.ops[i].sk.m_tile != ch.ops[0].sk.m_tile || ch.ops[i].sk.grid < 1) return -3;
