@@ -186,7 +186,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
     // Everything this CTA will stream goes to L2 now (fire and forget; L2 is the coherence point, so rows the previous
     // kernel is still writing are simply written into the prefetched lines): HBM works through the whole K/V span
     // from the first microsecond, the pipeline below then loads from L2 with a third of the latency.
-    {
+    if (a.l2_prefetch) {
       int i = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const TcUnit t = tc_unit(p, u, 0);

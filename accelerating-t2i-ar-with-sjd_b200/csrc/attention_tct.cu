@@ -86,7 +86,7 @@ attn_tct_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcParams p) {
   int early = 0;
   if (warp == 4) {
     // whole K/V span of this CTA to L2 now, first two units' K/V into smem now (see attention_tc.cu)
-    {
+    if (a.l2_prefetch) {
       int i = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const TcUnit t = tc_unit(p, u, 0);

@@ -458,6 +458,10 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
   memset(&tp, 0, sizeof(tp));
   if (use_tc || use_tct) {
     tp.a = ap;
+    // the tcgen05 kernels' "whole span to L2 first" pass is neutral to slightly negative on the B200
+    // (profiles/r02k_attn_tc_l2pf.txt): off unless asked for
+    static const int tc_l2pf = getenv("SJD_ATTN_TC_L2PF") ? atoi(getenv("SJD_ATTN_TC_L2PF")) : 0;
+    tp.a.l2_prefetch = tc_l2pf;
     if (use_tct) attn_tct_plan(&tp);
     else attn_tc_plan(&tp, g.head_dim);
     if (tp.a.n_chunks > c->max_chunks || ensure_tcmaps(c, tp.Wp)) return SJD_E_TMAP;
