@@ -320,6 +320,8 @@ struct AttnCombine {
   const float* part_ml;   // [splits][rows][H][W][2]
   __nv_bfloat16* out;     // [rows*W][H*Dh]
   int rows, W, H, n_chunks, head_dim;
+  int sparse;             // 1: most slots hold the empty marker {-inf, 0} (attention_sw.cu writes one partial per SEGMENT):
+                          //    read the 8-byte {m, sum} pairs first and fetch only the live partial rows
 };
 
 // one warp: merge the split partials of row `widx` = ((b * H + h) * W + i), normalise, write bf16
@@ -333,6 +335,53 @@ __device__ __forceinline__ void attn_combine_row(const AttnCombine& p, int widx,
 #pragma unroll
   for (int e = 0; e < PER; ++e) acc[e] = 0.f;
   float mrun = -INFINITY, lsum = 0.f;
+  if (p.sparse) {
+    constexpr int SB = 4;   // live partials merged per round trip
+    for (int cb = 0; cb < p.n_chunks; cb += 32) {
+      const int c = cb + lane;
+      float2 mine = make_float2(-INFINITY, 0.f);
+      if (c < p.n_chunks) mine = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (c * stride + idx) * 2));
+      unsigned live = __ballot_sync(0xffffffffu, mine.x != -INFINITY);   // ascending slot order = ascending key order
+      while (live) {
+        int src[SB];
+        bool on[SB];
+        const int first = __ffs(live) - 1;
+#pragma unroll
+        for (int k = 0; k < SB; ++k) {
+          on[k] = live != 0;
+          src[k] = on[k] ? __ffs(live) - 1 : first;
+          if (on[k]) live &= live - 1;
+        }
+        float2 ml[SB];
+        float po[SB][PER];
+#pragma unroll
+        for (int k = 0; k < SB; ++k) {
+          ml[k].x = __shfl_sync(0xffffffffu, mine.x, src[k]);
+          ml[k].y = __shfl_sync(0xffffffffu, mine.y, src[k]);
+#pragma unroll
+          for (int e = 0; e < PER; ++e) po[k][e] = __ldcg(p.part_o + ((cb + src[k]) * stride + idx) * DH + lane + 32 * e);
+        }
+        float mb = mrun;
+#pragma unroll
+        for (int k = 0; k < SB; ++k)
+          if (on[k]) mb = fmaxf(mb, ml[k].x);
+        const float rescale = exp2f(mrun - mb);   // mrun == -inf -> 0
+        lsum *= rescale;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) acc[e] *= rescale;
+        mrun = mb;
+#pragma unroll
+        for (int k = 0; k < SB; ++k) {
+          if (on[k]) {
+            const float w = exp2f(ml[k].x - mb);
+            lsum += w * ml[k].y;
+#pragma unroll
+            for (int e = 0; e < PER; ++e) acc[e] += w * po[k][e];
+          }
+        }
+      }
+    }
+  } else
   for (int c0 = 0; c0 < p.n_chunks; c0 += kCombBatch) {
     float2 ml[kCombBatch];
     float po[kCombBatch][PER];
@@ -410,6 +459,7 @@ AttnCombine attn_combine_desc(const AttnParams& p, int head_dim) {
   AttnCombine c;
   c.part_o = p.part_o; c.part_ml = p.part_ml; c.out = p.out;
   c.rows = p.rows; c.W = p.W; c.H = p.H; c.n_chunks = p.n_chunks; c.head_dim = head_dim;
+  c.sparse = 0;
   return c;
 }
 

@@ -1,0 +1,545 @@
+// Small-window Jacobi attention, round-2 form: the transposed tcgen05 formulation of attention_tct.cu
+//   S^T[128 keys x N q] = K Q^T,   O^T[128 d x N q] = V^T P^T,   L[128 x N q] = 1 P^T        (N = 32 | 64 query slots)
+// behind a pipeline built for the HBM stream instead of for the tensor core:
+//   * every CTA owns a CONTIGUOUS run of (CFG row, kv head, key tile) units, key tiles fastest, so it walks along the
+//     keys of one head: Q is loaded once per head (two 8/16 KB buffers), and the products of consecutive key tiles
+//     ACCUMULATE in TMEM (O^T and L) under one reference maximum per 8-column group — a "segment".  A segment ends when
+//     the head changes or when a tile's maximum exceeds the reference by more than 2^16 (then the probabilities of
+//     the new tile would grow past what fp32 sums should hold: a new segment starts from the new maximum).  One fp32
+//     partial {sum p v, m, sum p} is written per SEGMENT (slot = its first key tile; the other slots of the run get
+//     the empty marker {-inf, 0}) instead of one per tile: at 1 200 keys 2-3 partials per query row instead of 10,
+//     so the epilogue and the merge in the next chain kernel shrink with it;
+//   * K and V tiles arrive through separate TMA rings (K: 2 x 32 KB, released by the commit of S^T; V: 2-3 x 32 KB,
+//     released by the commit of O^T), P^T has its own two buffers: a K tile is free ~0.1 us after it landed, so
+//     the next K/V tiles stream while the softmax of this one runs — the two-stage form held 80 KB of smem through
+//     the whole softmax and exposed the load latency once per stage cycle;
+//   * softmax: thread = key (TMEM lane), two warps per lane quarter split the columns.  A probability only has to be
+//     scaled by a bound that is COMMON to the 128 keys of a column and recorded with the partial, not by the exact
+//     column maximum: each thread takes the max of 8 adjacent columns (draft positions i..i+7 of one head), one
+//     redux.sync per group gives the warp's value, the eight warps meet through 128 bytes of shared memory and ONE
+//     named barrier.  (attention_tct.cu parked all scores in a 17 KB staging tile and paid two barriers.)
+// Mask, partial format, merge and reference semantics as in attention_tc.cu (SDPA over the additive window mask,
+// modeling_chameleon.py:567-574, scheduler/jacobi_iteration_lumina_mgpt.py:1256-1336).  Head dim 128 only.
+#include "common.cuh"
+
+namespace sjd {
+
+constexpr int kSwThreads = 384;                          // warps 0-3 / 8-11: softmax + epilogue (lane quarter = warp & 3, column half = warp >> 3); 4: TMA; 5: MMA
+constexpr uint32_t kSwTileBytes = 2 * kTcKeys * 128;     // a K or V tile: two 64-wide head-dim boxes of [128 keys][128 B]
+constexpr uint32_t kSwPBytes = kTcKeys * 128;            // P^T: [128 keys][64 query slots] bf16
+
+struct AttnSwParams {
+  AttnTcParams t;   // geometry as attn_tct_plan leaves it
+  int ncols;        // accumulator columns per unit: 32 | 64
+  int nv;           // depth of the V ring
+  int grid_cap;     // > 0: at most this many CTAs (test knob: small shapes then exercise runs, ring wrap-around, segments)
+  float grow;       // a tile whose maximum exceeds the segment's reference by more than this (log2 units) starts a new segment
+};
+
+struct SwUnit {
+  int kt, b, hkv, h0, heads, key0, lo, run, R;
+  bool hidden;
+};
+
+__device__ __forceinline__ SwUnit sw_unit(const AttnTcParams& p, int u) {
+  const AttnParams& a = p.a;
+  SwUnit t;
+  const int G = a.H / a.Hkv;
+  t.run = tc_div(u, p.m_chunks, a.n_chunks);                 // (CFG row, kv head, row tile): what shares Q
+  t.kt = u - t.run * a.n_chunks;
+  t.b = tc_div(t.run, p.m_ny, p.ny);
+  const int y = t.run - t.b * p.ny;
+  t.hkv = tc_div(y, p.m_mtiles, p.mtiles);
+  const int mt = y - t.hkv * p.mtiles;
+  t.h0 = t.hkv * G + mt * p.hpc;
+  t.heads = min(p.hpc, G - mt * p.hpc);
+  t.key0 = t.kt * kTcKeys;
+  t.lo = a.kv_lo[t.b];
+  t.hidden = t.key0 + kTcKeys <= t.lo;                       // whole tile inside the hidden prefix
+  t.R = t.heads * p.Wp;
+  return t;
+}
+
+__device__ __forceinline__ int redux_max_s32(int v) {
+  int r;
+  asm volatile("redux.sync.max.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+template <int NCOLS>
+__global__ void __launch_bounds__(kSwThreads, 1)
+attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
+  constexpr int DH = 128;
+  constexpr int NC = NCOLS / 2;     // columns per softmax thread
+  constexpr int NG = NC / 8;        // 8-column groups per softmax thread
+  constexpr int NGT = NCOLS / 8;    // 8-column groups per unit
+  constexpr uint32_t kQBytes = 2 * NCOLS * 128;              // Q rows of one run: two head-dim atoms of [NCOLS slots][128 B]
+  const AttnTcParams& p = sp.t;
+  const AttnParams& a = p.a;
+  const int NV = sp.nv;
+  extern __shared__ uint8_t smem_raw[];
+  enum { FK = 0, EK = 2, FV = 4, EV = 8, FQ = 12, SD = 14, PR = 16, SG = 18, OD = 20, NBARS = 22 };
+  __shared__ __align__(8) uint64_t bars[NBARS];
+  __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float xw[2][4][8];                // [unit parity][lane quarter][column group]: the warps' group maxima
+  __shared__ int fresh_flag[2];                              // [unit parity] 1: this unit starts a segment (softmax -> MMA issuer)
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = base, sV = sK + 2 * kSwTileBytes, sP = sV + uint32_t(NV) * kSwTileBytes, sQ = sP + 2 * kSwPBytes,
+                 sOnes = sQ + 2 * kQBytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+  const int n_units = a.n_chunks * a.Hkv * p.mtiles * a.rows;
+  const int u0 = int((long long)blockIdx.x * n_units / gridDim.x), u1 = int((long long)(blockIdx.x + 1) * n_units / gridDim.x);
+  auto skip_hidden = [&](int u) {
+    while (u < u1 && sw_unit(p, u).hidden) ++u;
+    return u;
+  };
+
+  // the ones tile (A operand of the column-sum product): swizzling a constant is a no-op
+  {
+    uint4* ones = reinterpret_cast<uint4*>(smem_raw + (sOnes - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < int(kTcRows * 128 / 16); i += blockDim.x)
+      ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.q);
+      tma_prefetch_desc(&maps.k);
+      tma_prefetch_desc(&maps.v);
+      for (int i = 0; i < NBARS; ++i) mbar_init(bar(i), (i >= PR && i < SG) || i >= OD ? 8 : 1);
+      fence_barrier_init();
+    }
+  } else if (warp == 5) {
+    tmem_alloc(smem_u32(&tmem_holder), 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_holder;   // columns: S^T 0 | 64, O^T 128 | 192, L 256 | 320
+
+  // ---- producer helpers (warp 4, all lanes) ----
+  auto issue_k = [&](const SwUnit& t, int n) {
+    const int st = n & 1;
+    const int krow = p.k_row0 + (t.b * a.Hkv + t.hkv) * a.Lmax + t.key0;
+    if (lane == 0) mbar_arrive_expect_tx(bar(FK + st), kSwTileBytes);
+    __syncwarp();
+    if (lane < 2)
+      tma_load_2d(sK + uint32_t(st) * kSwTileBytes + uint32_t(lane) * kTcKeys * 128, &maps.k, lane * 64, krow, bar(FK + st),
+                  kPolicyEvictFirst);
+  };
+  auto issue_v = [&](const SwUnit& t, int n) {
+    const int st = n % NV;
+    const int krow = p.k_row0 + (t.b * a.Hkv + t.hkv) * a.Lmax + t.key0;
+    if (lane == 0) mbar_arrive_expect_tx(bar(FV + st), kSwTileBytes);
+    __syncwarp();
+    if (lane < 2)
+      tma_load_2d(sV + uint32_t(st) * kSwTileBytes + uint32_t(lane) * kTcKeys * 128, &maps.v, lane * 64, krow, bar(FV + st),
+                  kPolicyEvictFirst);
+  };
+  auto issue_q = [&](const SwUnit& t, int r) {   // r: CTA-local run counter -> buffer r & 1
+    const int qb = r & 1, nq = t.heads * 2;
+    if (lane == 0) mbar_arrive_expect_tx(bar(FQ + qb), uint32_t(nq) * uint32_t(p.Wp) * 128u);
+    __syncwarp();
+    for (int l = lane; l < nq; l += 32) {
+      const int d = l & 1, hs = l >> 1;
+      tma_load_2d(sQ + uint32_t(qb) * kQBytes + uint32_t(d) * NCOLS * 128 + uint32_t(hs * p.Wp) * 128, &maps.q,
+                  (t.h0 + hs) * DH + d * 64, t.b * a.W, bar(FQ + qb), kPolicyEvictLast);
+    }
+  };
+
+  // Keys below kv_len were cached by earlier forwards: their tiles may stream while the previous kernel finishes
+  // (q, the window's own K/V rows and the partial buffers are that kernel's until griddepcontrol.wait returns).
+  int early_k = 0, early_v = 0, uk = u0, uv = u0;
+  if (warp == 4) {
+    while (early_k < 2) {
+      uk = skip_hidden(uk);
+      if (uk >= u1) break;
+      const SwUnit t = sw_unit(p, uk);
+      if (t.key0 + kTcKeys > a.kv_len) break;
+      issue_k(t, early_k);
+      ++early_k;
+      ++uk;
+    }
+    while (early_v < NV) {
+      uv = skip_hidden(uv);
+      if (uv >= u1) break;
+      const SwUnit t = sw_unit(p, uv);
+      if (t.key0 + kTcKeys > a.kv_len) break;
+      issue_v(t, early_v);
+      ++early_v;
+      ++uv;
+    }
+  }
+  pdl_wait();                 // wait, THEN release the dependents (attention_tc.cu explains the order)
+  pdl_launch_dependents();
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[15] = clock64();
+
+  if (warp == 4) {
+    // ===== TMA producer: two cursors (K ring, V ring), whichever has a free stage goes =====
+    int q_runs = 0, last_run = -1;
+    {   // Q of the runs whose K tiles went out early (at most two units: both Q buffers are still untouched)
+      int u = u0;
+      for (int i = 0; i < early_k; ++i) {
+        u = skip_hidden(u);
+        const SwUnit t = sw_unit(p, u);
+        if (t.run != last_run) {
+          issue_q(t, q_runs++);
+          last_run = t.run;
+        }
+        ++u;
+      }
+    }
+    int nk = early_k, nv = early_v;
+    uk = skip_hidden(uk);
+    uv = skip_hidden(uv);
+    while (uk < u1 || uv < u1) {
+      bool did = false;
+      if (uk < u1) {
+        int ok = 1;
+        if (nk >= 2) {
+          if (lane == 0) ok = mbar_test_wait(bar(EK + (nk & 1)), uint32_t((nk >> 1) - 1) & 1u);
+          ok = __shfl_sync(0xffffffffu, ok, 0);
+        }
+        if (ok) {
+          const SwUnit t = sw_unit(p, uk);
+          // a third run's Q overwrites the buffer of run r-2: every S^T of that run precedes unit nk-2, whose commit
+          // the stage test above has just seen
+          if (t.run != last_run) {
+            issue_q(t, q_runs++);
+            last_run = t.run;
+          }
+          issue_k(t, nk);
+          if (p.dbg && blockIdx.x == 0 && lane == 0 && nk < 8) p.dbg[nk * 16 + 0] = clock64();
+          ++nk;
+          uk = skip_hidden(uk + 1);
+          did = true;
+        }
+      }
+      if (uv < u1) {
+        int ok = 1;
+        if (nv >= NV) {
+          if (lane == 0) ok = mbar_test_wait(bar(EV + nv % NV), uint32_t(nv / NV - 1) & 1u);
+          ok = __shfl_sync(0xffffffffu, ok, 0);
+        }
+        if (ok) {
+          issue_v(sw_unit(p, uv), nv);
+          ++nv;
+          uv = skip_hidden(uv + 1);
+          did = true;
+        }
+      }
+      if (!did) __nanosleep(32);
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16_f32(kTcKeys, NCOLS);                 // A = K, B = Q: both K-major
+      const uint32_t idesc_o = umma_idesc_bf16_f32_amn_bmn(DH, NCOLS);              // A = V (MN-major), B = P^T (MN-major)
+      const uint32_t idesc_l = umma_idesc_bf16_f32_bmn(kTcRows, NCOLS);             // A = ones (K-major), B = P^T
+      int N = 0;
+      for (int u = u0; u < u1; ++u) N += sw_unit(p, u).hidden ? 0 : 1;
+      int ns = 0, np = 0, us = skip_hidden(u0), s_last_run = -1, s_runs = 0, seg = -1;
+      while (np < N) {
+        bool did = false;
+        if (np < ns) {
+          const int ts = np & 1, vst = np % NV;
+          if (mbar_test_wait(bar(PR + ts), uint32_t(np >> 1) & 1u) && mbar_test_wait(bar(FV + vst), uint32_t(np / NV) & 1u)) {
+            const int fresh = *reinterpret_cast<volatile int*>(&fresh_flag[ts]);
+            if (fresh) {
+              if (seg >= 0) umma_commit(bar(SG + (seg & 1)));      // the segment that just ended: its products are all issued
+              ++seg;
+              if (seg >= 2) mbar_wait_backoff(bar(OD + (seg & 1)), uint32_t((seg >> 1) - 1) & 1u);   // accumulators drained
+            }
+            tcgen05_fence_after();
+            if (p.dbg && blockIdx.x == 0 && np < 8) p.dbg[np * 16 + 3] = clock64();
+            const uint32_t sPb = sP + uint32_t(ts) * kSwPBytes, sVb = sV + uint32_t(vst) * kSwTileBytes;
+            const uint32_t tO = tmem_base + 128 + uint32_t(seg & 1) * 64, tL = tmem_base + 256 + uint32_t(seg & 1) * 64;
+            const uint64_t d1 = umma_desc_sw128_kmajor(sOnes);
+            uint32_t acc = fresh ? 0u : 1u;
+#pragma unroll
+            for (int k = 0; k < kTcKeys / 16; ++k) {   // 16 keys per step = two 8-row groups = 2 048 bytes of either tile
+              const uint64_t dv = umma_desc_sw128_mnmajor(sVb + uint32_t(k) * 2048, kTcKeys * 128);
+              const uint64_t dp = umma_desc_sw128_mnmajor(sPb + uint32_t(k) * 2048, kTcKeys * 128);
+              umma_bf16_ss(tO, dv, dp, idesc_o, acc);
+              umma_bf16_ss(tL, d1, dp, idesc_l, acc);
+              acc = 1;
+            }
+            umma_commit(bar(EV + vst));
+            ++np;
+            if (np == N) umma_commit(bar(SG + (seg & 1)));
+            if (p.dbg && blockIdx.x == 0 && np <= 8) p.dbg[(np - 1) * 16 + 4] = clock64();
+            did = true;
+          }
+        }
+        if (ns < N && ns - np < 2) {
+          const SwUnit t = sw_unit(p, us);
+          const bool new_run = t.run != s_last_run;
+          const int r = new_run ? s_runs : s_runs - 1, qb = r & 1;
+          if (mbar_test_wait(bar(FK + (ns & 1)), uint32_t(ns >> 1) & 1u) &&
+              (!new_run || mbar_test_wait(bar(FQ + qb), uint32_t(r >> 1) & 1u))) {
+            if (new_run) {
+              s_last_run = t.run;
+              ++s_runs;
+            }
+            if (p.dbg && blockIdx.x == 0 && ns < 8) p.dbg[ns * 16 + 1] = clock64();
+            tcgen05_fence_after();
+            const uint32_t sKb = sK + uint32_t(ns & 1) * kSwTileBytes, sQb = sQ + uint32_t(qb) * kQBytes;
+            const uint32_t tS = tmem_base + uint32_t(ns & 1) * 64;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+              const uint64_t da = umma_desc_sw128_kmajor(sKb + uint32_t(d) * kTcKeys * 128);
+              const uint64_t db = umma_desc_sw128_kmajor(sQb + uint32_t(d) * NCOLS * 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_ss(tS, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc_s, acc);
+                acc = 1;
+              }
+            }
+            umma_commit(bar(EK + (ns & 1)));     // the K tile is free
+            umma_commit(bar(SD + (ns & 1)));     // S^T is there
+            if (p.dbg && blockIdx.x == 0 && ns < 8) p.dbg[ns * 16 + 2] = clock64();
+            ++ns;
+            us = skip_hidden(us + 1);
+            did = true;
+          }
+        }
+        if (!did) __nanosleep(20);
+      }
+    }
+  } else if (warp < 4 || warp >= 8) {
+    // ===== softmax + epilogue.  Thread = TMEM lane = KEY of the tile (softmax) / head-dim element (epilogue); the two
+    // warps of a lane quarter take the column halves =====
+    const int wq = warp & 3, half = warp >> 3;
+    const int kl = wq * 32 + lane;
+    const uint32_t t_row = uint32_t(wq * 32) << 16;
+    const float sc = a.scale_log2e;
+    const int cbase = half * NC;                                      // first column of this thread
+    const int hs_start = tc_div(cbase, p.m_wp, p.Wp), qi_start = cbase - hs_start * p.Wp;
+    float mref[NGT];                                                  // the running segment's reference maxima (scaled log2 domain)
+#pragma unroll
+    for (int g = 0; g < NGT; ++g) mref[g] = -INFINITY;
+    int seg = -1, last_run = -1, n = 0;
+    int s_R = 0, s_h0 = 0;                                            // the running segment's geometry
+    size_t s_base = 0;
+    // drains segment `e_seg` (accumulators of buffer e_seg & 1) into its partial slot
+    auto epilogue = [&](int e_seg, int e_R, int e_h0, size_t e_base, const float (&e_m)[NGT]) __attribute__((always_inline)) {
+      const int ob = e_seg & 1;
+      mbar_wait(bar(SG + ob), uint32_t(e_seg >> 1) & 1u);
+      tcgen05_fence_after();
+      if (p.dbg && blockIdx.x == 0 && wq == 0 && half == 0 && lane == 0 && e_seg < 8) p.dbg[e_seg * 16 + 8] = clock64();
+      const uint32_t tO = tmem_base + 128 + uint32_t(ob) * 64, tL = tmem_base + 256 + uint32_t(ob) * 64;
+      {
+        // slot c -> partial row: rows of one head are consecutive (512 bytes apart for this lane's element), the next
+        // head starts W rows later: one pointer walked with adds
+        float* pcol = a.part_o + (e_base + size_t(e_h0 + hs_start) * a.W + qi_start) * DH + kl;
+        int qi = qi_start;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NC; c0 += 16) {
+          if (cbase + c0 >= e_R) break;                               // warp-uniform
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tO + t_row + uint32_t(cbase + c0), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            if (qi < a.W && cbase + c0 + e < e_R) *pcol = __uint_as_float(v[e]);   // a warp writes 128 contiguous bytes
+            pcol += DH;
+            if (++qi == p.Wp) {
+              qi = 0;
+              pcol -= (p.Wp - a.W) * DH;
+            }
+          }
+        }
+      }
+      if (wq == 0 && half == 0) {   // {m, sum p}: every lane of L holds the sums; lane (c & 15) of the matching half-warp writes column c
+#pragma unroll 1
+        for (int c0 = 0; c0 < e_R; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tL + uint32_t(c0), v);
+          tmem_ld_wait();
+          const int c = c0 + (lane & 15);
+          if ((lane >> 4) == ((c0 >> 4) & 1) && c < e_R) {
+            float l = 0.f, m = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if ((lane & 15) == e) l = __uint_as_float(v[e]);
+#pragma unroll
+            for (int g = 0; g < NGT; ++g)
+              if ((c >> 3) == g) m = e_m[g];
+            const int hs2 = tc_div(c, p.m_wp, p.Wp), qi2 = c - hs2 * p.Wp;
+            if (qi2 < a.W) {
+              const size_t pr = e_base + size_t(e_h0 + hs2) * a.W + qi2;
+              *reinterpret_cast<float2*>(a.part_ml + pr * 2) = make_float2(m, l);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(OD + ob));
+      if (p.dbg && blockIdx.x == 0 && wq == 0 && half == 0 && lane == 0 && e_seg < 8) p.dbg[e_seg * 16 + 9] = clock64();
+    };
+    auto mark_empty = [&](const SwUnit& t, size_t ubase) {   // slot (key tile, rows of this unit) contributes nothing
+      if (wq == 0 && half == 0) {
+        for (int c = lane; c < t.R; c += 32) {
+          const int hs2 = tc_div(c, p.m_wp, p.Wp), qi2 = c - hs2 * p.Wp;
+          if (qi2 < a.W)
+            *reinterpret_cast<float2*>(a.part_ml + (ubase + size_t(t.h0 + hs2) * a.W + qi2) * 2) = make_float2(-INFINITY, 0.f);
+        }
+      }
+    };
+
+    for (int u = u0; u < u1; ++u) {
+      const SwUnit t = sw_unit(p, u);
+      const size_t ubase = (size_t(t.kt) * a.rows + t.b) * a.H * size_t(a.W);
+      if (t.hidden) {   // uniform per CTA
+        mark_empty(t, ubase);
+        continue;
+      }
+      const int ts = n & 1, j = n >> 1;
+      const uint32_t tS = tmem_base + uint32_t(ts) * 64;
+      mbar_wait(bar(SD + ts), uint32_t(j) & 1u);
+      tcgen05_fence_after();
+      if (p.dbg && blockIdx.x == 0 && wq == 0 && half == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 5] = clock64();
+      uint32_t v[NC];
+#pragma unroll
+      for (int c0 = 0; c0 < NC; c0 += 16)
+        tmem_ld_32x32b_x16(tS + t_row + uint32_t(cbase + c0), *reinterpret_cast<uint32_t(*)[16]>(&v[c0]));
+      tmem_ld_wait();
+      // visibility of (this key, column): bit e of okm
+      const int jk = t.key0 + kl, dk = jk - a.kv_len;               // visible to query i iff lo <= jk and dk <= i
+      const bool interior = (t.key0 >= t.lo) && (t.key0 + kTcKeys - 1 <= a.kv_len);
+      const bool key_ok = jk >= t.lo;
+      uint32_t okm = 0;
+      float gm[NG];
+      {
+        int qi = qi_start;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          float m = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const bool ok = (qi < a.W) && (cbase + 8 * g + e < t.R) && (interior || (key_ok && dk <= qi));
+            okm |= uint32_t(ok) << (8 * g + e);
+            m = fmaxf(m, ok ? __uint_as_float(v[8 * g + e]) : -INFINITY);
+            if (++qi == p.Wp) qi = 0;
+          }
+          gm[g] = ord2f(redux_max_s32(f2ord(m))) * sc;               // scale > 0: max commutes with it
+        }
+      }
+      if (lane < NG) {
+        float x = gm[0];
+#pragma unroll
+        for (int g = 1; g < NG; ++g)
+          if (lane == g) x = gm[g];
+        xw[ts][wq][half * NG + lane] = x;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float tmax[NGT];
+#pragma unroll
+      for (int g4 = 0; g4 < NGT / 4; ++g4) {
+        float4 x = *reinterpret_cast<const float4*>(&xw[ts][0][4 * g4]);
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+          const float4 y = *reinterpret_cast<const float4*>(&xw[ts][q][4 * g4]);
+          x.x = fmaxf(x.x, y.x); x.y = fmaxf(x.y, y.y); x.z = fmaxf(x.z, y.z); x.w = fmaxf(x.w, y.w);
+        }
+        tmax[4 * g4] = x.x; tmax[4 * g4 + 1] = x.y; tmax[4 * g4 + 2] = x.z; tmax[4 * g4 + 3] = x.w;
+      }
+      if (p.dbg && blockIdx.x == 0 && wq == 0 && half == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 6] = clock64();
+      // segment decision: identical in every thread (same inputs)
+      bool brk = t.run != last_run;
+#pragma unroll
+      for (int g = 0; g < NGT; ++g) brk = brk || (tmax[g] > mref[g] + sp.grow);
+      last_run = t.run;
+      float e_m[NGT];
+      const int e_seg = seg, e_R = s_R, e_h0 = s_h0;
+      const size_t e_base = s_base;
+      if (brk) {
+#pragma unroll
+        for (int g = 0; g < NGT; ++g) {
+          e_m[g] = mref[g];
+          mref[g] = tmax[g];
+        }
+        ++seg;
+        s_R = t.R; s_h0 = t.h0; s_base = ubase;
+      } else {
+        mark_empty(t, ubase);
+      }
+      // probabilities of this key for its columns (bf16, q contiguous) -> 16-byte chunks of its P^T row
+      {
+        uint8_t* const rowp = smem_raw + (sP + uint32_t(ts) * kSwPBytes - smem_u32(smem_raw)) + kl * 128;
+        uint32_t pk[NC / 2];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          float ms = half ? mref[(NG + g) % NGT] : mref[g];
+          if (ms == -INFINITY) ms = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const int i = 8 * g + e;
+            const float p0 = (okm >> i) & 1u ? ex2_approx(fmaf(__uint_as_float(v[i]), sc, -ms)) : 0.f;
+            const float p1 = (okm >> (i + 1)) & 1u ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -ms)) : 0.f;
+            const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+          *reinterpret_cast<uint4*>(rowp + (((half * NG + g) ^ (kl & 7)) << 4)) =
+              make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      }
+      tcgen05_fence_before();
+      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+      if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(&fresh_flag[ts]) = brk ? 1 : 0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(PR + ts));
+      if (p.dbg && blockIdx.x == 0 && wq == 0 && half == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 7] = clock64();
+      if (brk && e_seg >= 0) epilogue(e_seg, e_R, e_h0, e_base, e_m);
+      ++n;
+    }
+    if (seg >= 0) epilogue(seg, s_R, s_h0, s_base, mref);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Geometry: up to 64 / Wp heads of a kv head per unit; 32 accumulator columns when they suffice.
+void attn_sw_plan(AttnSwParams* sp, int force_ncols) {
+  attn_tct_plan(&sp->t);
+  const int R = sp->t.hpc * sp->t.Wp;
+  sp->ncols = (R <= 32 && force_ncols != 64) ? 32 : 64;
+  sp->nv = sp->ncols == 32 ? 3 : 2;
+}
+
+constexpr int attn_sw_smem(int ncols, int nv) {   // K ring, V ring, two P^T buffers, two Q buffers, the ones tile
+  return 1024 + 2 * int(kSwTileBytes) + nv * int(kSwTileBytes) + 2 * int(kSwPBytes) + 2 * (2 * ncols * 128) + kTcRows * 128;
+}
+
+int attn_sw_launch(const AttnTcMaps& maps, const AttnSwParams& sp, cudaStream_t stream) {
+  const AttnTcParams& p = sp.t;
+  const AttnParams& a = p.a;
+  if (p.hpc * p.Wp > 64 || p.head_dim != 128) return -3;
+  const int n_units = a.n_chunks * a.Hkv * p.mtiles * a.rows;
+  if (n_units >= 65536) return -3;   // tc_div's exact range
+  const int sms = device_num_sms();
+  int ng = n_units < sms ? n_units : sms;
+  if (sp.grid_cap > 0 && sp.grid_cap < ng) ng = sp.grid_cap;
+  dim3 grid(ng);
+  static bool set = false;
+  if (!set) {
+    if (cudaFuncSetAttribute(attn_sw_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_sw_smem(32, 3)) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_sw_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_sw_smem(64, 2)) != cudaSuccess)
+      return -5;
+    set = true;
+  }
+  if (sp.ncols == 32) return launch_pdl(attn_sw_kernel<32>, grid, dim3(kSwThreads), attn_sw_smem(32, sp.nv), stream, maps, sp);
+  return launch_pdl(attn_sw_kernel<64>, grid, dim3(kSwThreads), attn_sw_smem(64, sp.nv), stream, maps, sp);
+}
+
+}  // namespace sjd

@@ -14,6 +14,7 @@
 #include "gemm_fused.cu"
 #include "attention_tc.cu"
 #include "attention_tct.cu"
+#include "attention_sw.cu"
 #include "verify.cu"
 
 namespace sjd {
@@ -64,7 +65,11 @@ struct sjd_ctx {
   // tensor-core attention (attention_tc.cu): K / V cache maps (box 128 keys), q maps per row-slot count Wp (index Wp/8)
   sjd::AttnTcMaps tcmaps[17];
   bool tcmap_ok[17] = {false};
-  int attn_mode = 0;   // 0: pick per window (see forward_chain); SJD_ATTN = tc -> 1, mma -> 2, tct -> 3 force one kernel
+  int attn_mode = 0;   // 0: pick per window (see forward_chain); SJD_ATTN = tc -> 1, mma -> 2, tct -> 3, sw -> 4 force one kernel
+  int sw_grid = 0;       // developer/test knob SJD_ATTN_SW_GRID: cap on the kernel's CTAs (tiny shapes then walk runs, rings and segments)
+  float sw_grow = 16.f;  // developer/test knob SJD_ATTN_SW_GROW: log2 growth over the reference maximum that ends a segment
+  int sw_ncols = 0;      // developer/test knob SJD_ATTN_SW_NCOLS=64: always the 64-column instantiation
+  bool sw_auto = true;   // whether mode 0 may pick the segment-accumulating small-window kernel (SJD_ATTN_SW_AUTO=0: round-1 rule)
   bool tct_auto = false;   // whether mode 0 may pick the transposed small-window kernel
   bool attn_tc_ok = true;
 };
@@ -327,7 +332,11 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
   c->max_chunks = (g.max_len + kAttnSub - 1) / kAttnSub;   // upper bound on key splits
   {
     const char* e = getenv("SJD_ATTN");   // "tc": tcgen05 attention (attention_tc.cu); "mma": mma.sync kernel (attention.cu)
-    c->attn_mode = !e ? 0 : (strcmp(e, "tc") == 0 ? 1 : (strcmp(e, "mma") == 0 ? 2 : (strcmp(e, "tct") == 0 ? 3 : 0)));
+    c->attn_mode = !e ? 0 : (strcmp(e, "tc") == 0 ? 1 : (strcmp(e, "mma") == 0 ? 2 : (strcmp(e, "tct") == 0 ? 3 : (strcmp(e, "sw") == 0 ? 4 : 0))));
+    if (const char* e2 = getenv("SJD_ATTN_SW_AUTO")) c->sw_auto = atoi(e2) != 0;
+    if (const char* e2 = getenv("SJD_ATTN_SW_GRID")) c->sw_grid = atoi(e2);
+    if (const char* e2 = getenv("SJD_ATTN_SW_NCOLS")) c->sw_ncols = atoi(e2);
+    if (const char* e2 = getenv("SJD_ATTN_SW_GROW")) c->sw_grow = float(atof(e2));
     if (uint64_t(g.n_layers) * g.rows * g.n_kv_heads * uint64_t(g.max_len) >= (1ull << 31)) c->attn_tc_ok = false;
   }
   rc |= dmalloc(c, &c->part_o, size_t(c->max_chunks) * T * hd * sizeof(float));
@@ -447,22 +456,30 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
   // Two attention kernels.  The tcgen05 one wins when the query rows that share a kv head fill
   // between half and all of one 128-row UMMA tile (measured: Lumina W=64, Emu3 W=32, profiles/r01g_config_sweep*); with
   // fewer rows its softmax threads idle or duplicate work, with more the K/V tile is streamed once per row tile.
-  bool use_tc = false, use_tct = false;
+  bool use_tc = false, use_tct = false, use_sw = false;
   if (!gemm_only && c->attn_tc_ok && W <= kTcRows) {
     const int rows_per_kv = (g.n_heads / g.n_kv_heads) * ((W + 7) & ~7);
     const bool tct_fits = g.head_dim == 128 && ((W + 7) & ~7) <= kTctCols;
-    use_tct = tct_fits && (c->attn_mode == 3 || (c->attn_mode == 0 && rows_per_kv <= kTctCols && c->tct_auto));
-    use_tc = !use_tct && (c->attn_mode == 1 || (c->attn_mode == 0 && rows_per_kv >= 64 && rows_per_kv <= kTcRows));
+    // round 2: the segment-accumulating small-window kernel (attention_sw.cu) takes every shape whose query rows per kv
+    // head fit its 64 accumulator columns (Lumina / Chameleon up to window 64, Emu3 up to window 16)
+    use_sw = tct_fits && (c->attn_mode == 4 || (c->attn_mode == 0 && rows_per_kv <= kTctCols && c->sw_auto));
+    use_tct = !use_sw && tct_fits && (c->attn_mode == 3 || (c->attn_mode == 0 && rows_per_kv <= kTctCols && c->tct_auto));
+    use_tc = !use_sw && !use_tct && (c->attn_mode == 1 || (c->attn_mode == 0 && rows_per_kv >= 64 && rows_per_kv <= kTcRows));
   }
-  AttnTcParams tp;
-  memset(&tp, 0, sizeof(tp));
-  if (use_tc || use_tct) {
+  AttnSwParams swp;
+  memset(&swp, 0, sizeof(swp));
+  AttnTcParams& tp = swp.t;
+  if (use_tc || use_tct || use_sw) {
     tp.a = ap;
     // the tcgen05 kernels' "whole span to L2 first" pass is neutral to slightly negative on the B200
     // (profiles/r02k_attn_tc_l2pf.txt): off unless asked for
     static const int tc_l2pf = getenv("SJD_ATTN_TC_L2PF") ? atoi(getenv("SJD_ATTN_TC_L2PF")) : 0;
     tp.a.l2_prefetch = tc_l2pf;
-    if (use_tct) attn_tct_plan(&tp);
+    if (use_sw) {
+      attn_sw_plan(&swp, c->sw_ncols);
+      swp.grid_cap = c->sw_grid;
+      swp.grow = c->sw_grow;
+    } else if (use_tct) attn_tct_plan(&tp);
     else attn_tc_plan(&tp, g.head_dim);
     if (tp.a.n_chunks > c->max_chunks || ensure_tcmaps(c, tp.Wp)) return SJD_E_TMAP;
   }
@@ -506,12 +523,14 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
       // which separates the cost of the two kernel boundaries from the cost of the attention kernel itself
       static const int dbg_attn = getenv("SJD_DEBUG_ATTN") ? atoi(getenv("SJD_DEBUG_ATTN")) : 0;
       if (dbg_attn != 1) {
-        if (use_tc || use_tct) {
+        if (use_tc || use_tct || use_sw) {
           tp.a.k = ap.k; tp.a.v = ap.v;
           tp.k_row0 = int(size_t(l) * g.rows * g.n_kv_heads * size_t(g.max_len));
           tp.dbg = g_attn_dbg;
-          rc |= use_tct ? attn_tct_launch(c->tcmaps[tp.Wp / 8], tp, s) : attn_tc_launch(c->tcmaps[tp.Wp / 8], tp, s);
+          rc |= use_sw ? attn_sw_launch(c->tcmaps[tp.Wp / 8], swp, s)
+                       : (use_tct ? attn_tct_launch(c->tcmaps[tp.Wp / 8], tp, s) : attn_tc_launch(c->tcmaps[tp.Wp / 8], tp, s));
           cb.ch.pre = attn_combine_desc(tp.a, g.head_dim);
+          cb.ch.pre.sparse = use_sw ? 1 : 0;
         } else {
           rc |= attn_launch(ap, g.head_dim, false, s);   // the split merge rides in the next chain kernel (pre-op)
           cb.ch.pre = attn_combine_desc(ap, g.head_dim);

@@ -25,3 +25,31 @@ def load_loop_goldens():
 @pytest.fixture(scope="session")
 def loop_goldens():
     return load_loop_goldens()
+
+
+# Attention kernels a forward test can force (the context reads these variables when it is created).  "sw" = the
+# segment-accumulating small-window tcgen05 kernel (attention_sw.cu); its suffixes turn the developer knobs that make
+# SMALL test shapes walk what the bench shape walks: g<N> caps the grid at N CTAs (one CTA then runs several heads, wraps
+# its K / V rings, rotates its Q buffers and accumulates several key tiles per segment), grow<X> ends a segment whenever a
+# tile's maximum exceeds the reference by X (0: nearly every tile -> accumulator rotation), n64 forces the 64-column
+# instantiation.
+ATTN_MODES = ["auto", "tc", "tct", "mma", "sw", "sw:g1", "sw:g3:grow0", "sw:g2:n64"]
+_ATTN_KNOBS = ("SJD_ATTN", "SJD_ATTN_SW_GRID", "SJD_ATTN_SW_GROW", "SJD_ATTN_SW_NCOLS")
+
+
+def set_attn(monkeypatch, attn):
+    for k in _ATTN_KNOBS:
+        monkeypatch.delenv(k, raising=False)
+    if attn == "auto":
+        return
+    parts = attn.split(":")
+    monkeypatch.setenv("SJD_ATTN", parts[0])
+    for kn in parts[1:]:
+        if kn.startswith("grow"):
+            monkeypatch.setenv("SJD_ATTN_SW_GROW", kn[4:])
+        elif kn.startswith("g"):
+            monkeypatch.setenv("SJD_ATTN_SW_GRID", kn[1:])
+        elif kn.startswith("n"):
+            monkeypatch.setenv("SJD_ATTN_SW_NCOLS", kn[1:])
+        else:
+            raise ValueError(attn)

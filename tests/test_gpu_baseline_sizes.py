@@ -7,6 +7,8 @@ Everything goes through the C ABI of libsjd_b200.so; oracle/ is only the checker
 import pytest
 import torch
 
+from conftest import ATTN_MODES, set_attn
+
 pytestmark = pytest.mark.gpu
 
 
@@ -44,7 +46,7 @@ def _full_width(env, family):
     return _WEIGHTS[family]
 
 
-@pytest.mark.parametrize("attn", ["auto", "tc", "tct", "mma"])
+@pytest.mark.parametrize("attn", ATTN_MODES)
 @pytest.mark.parametrize("family", ["lumina7b", "emu3gen"])
 def test_full_width_forward_matches_reference_stack(env, family, attn, monkeypatch):
     """Prefill with a hidden CFG prefix / left padding, an AR step, windows of 32 and 64 with a 20-token roll-back in
@@ -55,10 +57,7 @@ def test_full_width_forward_matches_reference_stack(env, family, attn, monkeypat
     here runs over up to 2.4e7 logits (64 x 2 x 184 622) instead of 1e5 (first GPU run: 2.56 ulp at Emu3 width, W = 64).  A head-index, GQA-stacking (32:8) or vocabulary-tiling bug shared by all
     of the repo's kernels cannot pass this one."""
     RF, model, dev = env["RF"], env["model"], env["dev"]
-    if attn == "auto":
-        monkeypatch.delenv("SJD_ATTN", raising=False)
-    else:
-        monkeypatch.setenv("SJD_ATTN", attn)
+    set_attn(monkeypatch, attn)
     shape, w, w32, cos, sin, kv_lo = _full_width(env, family)
     cfg = RF.StackConfig(shape.n_layers, shape.d_model, shape.n_heads, shape.n_kv_heads, shape.head_dim, shape.d_ff,
                          shape.vocab, shape.rms_eps, qk_norm=shape.qk_norm, rope_interleaved=False)

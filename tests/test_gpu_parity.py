@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_loop_goldens
+from conftest import ATTN_MODES, load_loop_goldens, set_attn
 
 pytestmark = pytest.mark.gpu
 
@@ -313,7 +313,7 @@ def _family(env, name):
         RF.rope_tables_rotate_half(128, 512, 1e6, True), [0, 5]
 
 
-@pytest.mark.parametrize("attn", ["auto", "tc", "tct", "mma"])
+@pytest.mark.parametrize("attn", ATTN_MODES)
 @pytest.mark.parametrize("family", ["chameleon", "llamagen", "emu3"])
 def test_window_forward_matches_reference_stack(env, family, attn, monkeypatch):
     """Prefill, an AR step, two Jacobi windows with a 9-token roll-back in between, and a short window —
@@ -323,10 +323,7 @@ def test_window_forward_matches_reference_stack(env, family, attn, monkeypatch):
     # every attention kernel on every shape it supports (the context reads SJD_ATTN when it is created): "tc" = tcgen05 +
     # TMEM (attention_tc.cu), "tct" = its transposed small-window variant (attention_tct.cu; head dim 128, windows <= 64,
     # else the next choice), "mma" = mma.sync (attention.cu), "auto" = the per-window choice the product makes
-    if attn == "auto":
-        monkeypatch.delenv("SJD_ATTN", raising=False)
-    else:
-        monkeypatch.setenv("SJD_ATTN", attn)
+    set_attn(monkeypatch, attn)
     cfg, (cos, sin), kv_lo = _family(env, family)
     w = RF.random_weights(cfg, seed=1, device=dev)
     rows, max_len = 2, 320
