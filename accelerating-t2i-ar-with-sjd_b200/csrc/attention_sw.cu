@@ -24,7 +24,9 @@
 
 namespace sjd {
 
-constexpr int kSwThreads = 384;                          // warps 0-3 / 8-11: softmax + epilogue (lane quarter = warp & 3, column half = warp >> 3); 4: TMA; 5: MMA
+constexpr int kSwThreads = 576;                          // warps 0-15: softmax + epilogue (lane quarter = warp & 3, column quarter = warp >> 2); 16: TMA; 17: MMA
+constexpr int kSwTmaWarp = 16, kSwMmaWarp = 17;
+constexpr int kSwSoftThreads = 512;
 constexpr uint32_t kSwTileBytes = 2 * kTcKeys * 128;     // a K or V tile: two 64-wide head-dim boxes of [128 keys][128 B]
 constexpr uint32_t kSwPBytes = kTcKeys * 128;            // P^T: [128 keys][64 query slots] bf16
 
@@ -60,6 +62,21 @@ __device__ __forceinline__ SwUnit sw_unit(const AttnTcParams& p, int u) {
   return t;
 }
 
+// Units of a CTA are consecutive: walking them costs an add and a compare (a full decode is ~40 dependent
+// instructions, 0.1-0.3 us for a lone warp — measured on the producer's path right after the dependency wait).
+__device__ __forceinline__ void sw_next(const AttnTcParams& p, SwUnit& t, int& u) {
+  ++u;
+  if (++t.kt == p.a.n_chunks) {
+    t = sw_unit(p, u);
+  } else {
+    t.key0 += kTcKeys;
+    t.hidden = t.key0 + kTcKeys <= t.lo;
+  }
+}
+__device__ __forceinline__ void sw_skip_hidden(const AttnTcParams& p, SwUnit& t, int& u, int u1) {
+  while (u < u1 && t.hidden) sw_next(p, t, u);
+}
+
 __device__ __forceinline__ int redux_max_s32(int v) {
   int r;
   asm volatile("redux.sync.max.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
@@ -70,7 +87,7 @@ template <int NCOLS>
 __global__ void __launch_bounds__(kSwThreads, 1)
 attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
   constexpr int DH = 128;
-  constexpr int NC = NCOLS / 2;     // columns per softmax thread
+  constexpr int NC = NCOLS / 4;     // columns per softmax thread (8 | 16)
   constexpr int NG = NC / 8;        // 8-column groups per softmax thread
   constexpr int NGT = NCOLS / 8;    // 8-column groups per unit
   constexpr uint32_t kQBytes = 2 * NCOLS * 128;              // Q rows of one run: two head-dim atoms of [NCOLS slots][128 B]
@@ -83,6 +100,7 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
   __shared__ uint32_t tmem_holder;
   __shared__ __align__(16) float xw[2][4][8];                // [unit parity][lane quarter][column group]: the warps' group maxima
   __shared__ int fresh_flag[2];                              // [unit parity] 1: this unit starts a segment (softmax -> MMA issuer)
+  __shared__ float seg_m[2][8];                              // [segment parity][column group]: reference maxima of a segment awaiting its epilogue
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = base, sV = sK + 2 * kSwTileBytes, sP = sV + uint32_t(NV) * kSwTileBytes, sQ = sP + 2 * kSwPBytes,
                  sOnes = sQ + 2 * kQBytes;
@@ -90,10 +108,6 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   const int n_units = a.n_chunks * a.Hkv * p.mtiles * a.rows;
   const int u0 = int((long long)blockIdx.x * n_units / gridDim.x), u1 = int((long long)(blockIdx.x + 1) * n_units / gridDim.x);
-  auto skip_hidden = [&](int u) {
-    while (u < u1 && sw_unit(p, u).hidden) ++u;
-    return u;
-  };
 
   // the ones tile (A operand of the column-sum product): swizzling a constant is a no-op
   {
@@ -102,15 +116,15 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
       ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async();
   }
-  if (warp == 4) {
+  if (warp == kSwTmaWarp) {
     if (lane == 0) {
       tma_prefetch_desc(&maps.q);
       tma_prefetch_desc(&maps.k);
       tma_prefetch_desc(&maps.v);
-      for (int i = 0; i < NBARS; ++i) mbar_init(bar(i), (i >= PR && i < SG) || i >= OD ? 8 : 1);
+      for (int i = 0; i < NBARS; ++i) mbar_init(bar(i), (i >= PR && i < SG) || i >= OD ? 16 : 1);
       fence_barrier_init();
     }
-  } else if (warp == 5) {
+  } else if (warp == kSwMmaWarp) {
     tmem_alloc(smem_u32(&tmem_holder), 512);
     tmem_relinquish();
   }
@@ -119,232 +133,290 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_holder;   // columns: S^T 0 | 64, O^T 128 | 192, L 256 | 320
 
-  // ---- producer helpers (warp 4, all lanes) ----
+  // ---- producer helpers (warp 4, all lanes, warp-uniform arguments; the TMA instructions sit under elect.sync so that
+  // their operands stay in uniform registers) ----
   auto issue_k = [&](const SwUnit& t, int n) {
     const int st = n & 1;
     const int krow = p.k_row0 + (t.b * a.Hkv + t.hkv) * a.Lmax + t.key0;
-    if (lane == 0) mbar_arrive_expect_tx(bar(FK + st), kSwTileBytes);
+    const uint32_t dst = sK + uint32_t(st) * kSwTileBytes;
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(bar(FK + st), kSwTileBytes);
+      tma_load_2d(dst, &maps.k, 0, krow, bar(FK + st), kPolicyEvictFirst);
+      tma_load_2d(dst + kTcKeys * 128, &maps.k, 64, krow, bar(FK + st), kPolicyEvictFirst);
+    }
     __syncwarp();
-    if (lane < 2)
-      tma_load_2d(sK + uint32_t(st) * kSwTileBytes + uint32_t(lane) * kTcKeys * 128, &maps.k, lane * 64, krow, bar(FK + st),
-                  kPolicyEvictFirst);
   };
   auto issue_v = [&](const SwUnit& t, int n) {
     const int st = n % NV;
     const int krow = p.k_row0 + (t.b * a.Hkv + t.hkv) * a.Lmax + t.key0;
-    if (lane == 0) mbar_arrive_expect_tx(bar(FV + st), kSwTileBytes);
+    const uint32_t dst = sV + uint32_t(st) * kSwTileBytes;
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(bar(FV + st), kSwTileBytes);
+      tma_load_2d(dst, &maps.v, 0, krow, bar(FV + st), kPolicyEvictFirst);
+      tma_load_2d(dst + kTcKeys * 128, &maps.v, 64, krow, bar(FV + st), kPolicyEvictFirst);
+    }
     __syncwarp();
-    if (lane < 2)
-      tma_load_2d(sV + uint32_t(st) * kSwTileBytes + uint32_t(lane) * kTcKeys * 128, &maps.v, lane * 64, krow, bar(FV + st),
-                  kPolicyEvictFirst);
   };
-  auto issue_q = [&](const SwUnit& t, int r) {   // r: CTA-local run counter -> buffer r & 1
-    const int qb = r & 1, nq = t.heads * 2;
-    if (lane == 0) mbar_arrive_expect_tx(bar(FQ + qb), uint32_t(nq) * uint32_t(p.Wp) * 128u);
-    __syncwarp();
-    for (int l = lane; l < nq; l += 32) {
-      const int d = l & 1, hs = l >> 1;
-      tma_load_2d(sQ + uint32_t(qb) * kQBytes + uint32_t(d) * NCOLS * 128 + uint32_t(hs * p.Wp) * 128, &maps.q,
-                  (t.h0 + hs) * DH + d * 64, t.b * a.W, bar(FQ + qb), kPolicyEvictLast);
-    }
-  };
-
-  // Keys below kv_len were cached by earlier forwards: their tiles may stream while the previous kernel finishes
-  // (q, the window's own K/V rows and the partial buffers are that kernel's until griddepcontrol.wait returns).
-  int early_k = 0, early_v = 0, uk = u0, uv = u0;
-  if (warp == 4) {
-    while (early_k < 2) {
-      uk = skip_hidden(uk);
-      if (uk >= u1) break;
-      const SwUnit t = sw_unit(p, uk);
-      if (t.key0 + kTcKeys > a.kv_len) break;
-      issue_k(t, early_k);
-      ++early_k;
-      ++uk;
-    }
-    while (early_v < NV) {
-      uv = skip_hidden(uv);
-      if (uv >= u1) break;
-      const SwUnit t = sw_unit(p, uv);
-      if (t.key0 + kTcKeys > a.kv_len) break;
-      issue_v(t, early_v);
-      ++early_v;
-      ++uv;
-    }
-  }
-  pdl_wait();                 // wait, THEN release the dependents (attention_tc.cu explains the order)
-  pdl_launch_dependents();
-  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[15] = clock64();
-
-  if (warp == 4) {
-    // ===== TMA producer: two cursors (K ring, V ring), whichever has a free stage goes =====
-    int q_runs = 0, last_run = -1;
-    {   // Q of the runs whose K tiles went out early (at most two units: both Q buffers are still untouched)
-      int u = u0;
-      for (int i = 0; i < early_k; ++i) {
-        u = skip_hidden(u);
-        const SwUnit t = sw_unit(p, u);
-        if (t.run != last_run) {
-          issue_q(t, q_runs++);
-          last_run = t.run;
-        }
-        ++u;
+  auto issue_q = [&](int b, int h0, int heads, int r) {   // r: CTA-local run counter -> buffer r & 1
+    const int qb = r & 1;
+    const uint32_t dst = sQ + uint32_t(qb) * kQBytes;
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(bar(FQ + qb), uint32_t(heads) * 2u * uint32_t(p.Wp) * 128u);
+      for (int hs = 0; hs < heads; ++hs) {
+        tma_load_2d(dst + uint32_t(hs * p.Wp) * 128, &maps.q, (h0 + hs) * DH, b * a.W, bar(FQ + qb), kPolicyEvictLast);
+        tma_load_2d(dst + NCOLS * 128 + uint32_t(hs * p.Wp) * 128, &maps.q, (h0 + hs) * DH + 64, b * a.W, bar(FQ + qb), kPolicyEvictLast);
       }
     }
-    int nk = early_k, nv = early_v;
-    uk = skip_hidden(uk);
-    uv = skip_hidden(uv);
+    __syncwarp();
+  };
+
+  if (sp.grid_cap < 0) {   // developer timing (SJD_DEBUG_ATTN=2|4): the cost of the kernel boundaries alone
+    pdl_wait();
+    pdl_launch_dependents();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == kSwMmaWarp) tmem_dealloc(tmem_base, 512);
+    return;
+  }
+  // Every role decodes what it needs BEFORE the dependency wait and then waits inside its own branch (the per-role
+  // state must not be live across a common wait: registers).  Order: wait, THEN release the dependents
+  // (attention_tc.cu explains why).
+  auto dep_wait = [&]() {
+    pdl_wait();
+    pdl_launch_dependents();
+  };
+
+  if (warp == kSwTmaWarp) {
+    // ===== TMA producer: two cursors (K ring, V ring), whichever has a free stage goes =====
+    // Keys below kv_len were cached by earlier forwards: their tiles may stream while the previous kernel finishes
+    // (q, the window's own K/V rows and the partial buffers are that kernel's until griddepcontrol.wait returns).
+    // What the producer needs right after the wait — the first two runs' Q loads — is decoded before it.
+    int nk = 0, nv = 0, uk = u0, uv = u0, k_runs = 0, k_last_run = -1;
+    SwUnit tk = sw_unit(p, u0 < u1 ? u0 : 0), tv = tk;
+    int q_have = 0, qa_b = 0, qa_h0 = 0, qa_heads = 0, qb_b = 0, qb_h0 = 0, qb_heads = 0;
+    {
+      SwUnit tq = tk;
+      int uq = u0, last = -1;
+      while (q_have < 2) {
+        sw_skip_hidden(p, tq, uq, u1);
+        if (uq >= u1) break;
+        if (tq.run != last) {
+          if (q_have == 0) { qa_b = tq.b; qa_h0 = tq.h0; qa_heads = tq.heads; }
+          else { qb_b = tq.b; qb_h0 = tq.h0; qb_heads = tq.heads; }
+          ++q_have;
+          last = tq.run;
+        }
+        sw_next(p, tq, uq);
+      }
+    }
+    sw_skip_hidden(p, tk, uk, u1);
+    sw_skip_hidden(p, tv, uv, u1);
+    while (nk < 2 && uk < u1 && tk.key0 + kTcKeys <= a.kv_len) {
+      if (tk.run != k_last_run) {
+        ++k_runs;
+        k_last_run = tk.run;
+      }
+      issue_k(tk, nk);
+      ++nk;
+      sw_next(p, tk, uk);
+      sw_skip_hidden(p, tk, uk, u1);
+    }
+    while (nv < NV && uv < u1 && tv.key0 + kTcKeys <= a.kv_len) {
+      issue_v(tv, nv);
+      ++nv;
+      sw_next(p, tv, uv);
+      sw_skip_hidden(p, tv, uv, u1);
+    }
+    dep_wait();
+    // the head of the critical path: Q of the first two runs (both buffers are untouched)
+    if (q_have > 0) issue_q(qa_b, qa_h0, qa_heads, 0);
+    if (q_have > 1) issue_q(qb_b, qb_h0, qb_heads, 1);
+    if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[10] = clock64();
     while (uk < u1 || uv < u1) {
       bool did = false;
       if (uk < u1) {
-        int ok = 1;
-        if (nk >= 2) {
-          if (lane == 0) ok = mbar_test_wait(bar(EK + (nk & 1)), uint32_t((nk >> 1) - 1) & 1u);
-          ok = __shfl_sync(0xffffffffu, ok, 0);
-        }
+        bool ok = true;
+        if (nk >= 2) ok = __all_sync(0xffffffffu, mbar_test_wait(bar(EK + (nk & 1)), uint32_t((nk >> 1) - 1) & 1u)) != 0;
         if (ok) {
-          const SwUnit t = sw_unit(p, uk);
           // a third run's Q overwrites the buffer of run r-2: every S^T of that run precedes unit nk-2, whose commit
           // the stage test above has just seen
-          if (t.run != last_run) {
-            issue_q(t, q_runs++);
-            last_run = t.run;
+          if (tk.run != k_last_run) {
+            ++k_runs;
+            k_last_run = tk.run;
+            if (k_runs > 2) issue_q(tk.b, tk.h0, tk.heads, k_runs - 1);
           }
-          issue_k(t, nk);
+          issue_k(tk, nk);
           if (p.dbg && blockIdx.x == 0 && lane == 0 && nk < 8) p.dbg[nk * 16 + 0] = clock64();
           ++nk;
-          uk = skip_hidden(uk + 1);
+          sw_next(p, tk, uk);
+          sw_skip_hidden(p, tk, uk, u1);
           did = true;
         }
       }
       if (uv < u1) {
-        int ok = 1;
-        if (nv >= NV) {
-          if (lane == 0) ok = mbar_test_wait(bar(EV + nv % NV), uint32_t(nv / NV - 1) & 1u);
-          ok = __shfl_sync(0xffffffffu, ok, 0);
-        }
+        bool ok = true;
+        if (nv >= NV) ok = __all_sync(0xffffffffu, mbar_test_wait(bar(EV + nv % NV), uint32_t(nv / NV - 1) & 1u)) != 0;
         if (ok) {
-          issue_v(sw_unit(p, uv), nv);
+          issue_v(tv, nv);
           ++nv;
-          uv = skip_hidden(uv + 1);
+          sw_next(p, tv, uv);
+          sw_skip_hidden(p, tv, uv, u1);
           did = true;
         }
       }
       if (!did) __nanosleep(32);
     }
-  } else if (warp == 5) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+  } else if (warp == kSwMmaWarp) {
+    // ===== MMA issuer.  Everything it does sits on the per-unit critical path.  The WHOLE warp runs the loop with
+    // warp-uniform state and only the tcgen05 instructions sit under elect.sync: issued from a lane-divergent branch
+    // (`if (lane == 0)`) every UTCHMMA is wrapped in a broadcast loop of ~15 instructions (0.6-1.0 us per 16-MMA product
+    // in the first version's stamps).  Descriptors are built once (a k-step only adds to the start-address field) and a
+    // barrier that has been seen complete is not polled again (a test_wait costs ~150 cycles) =====
+    {
       const uint32_t idesc_s = umma_idesc_bf16_f32(kTcKeys, NCOLS);                 // A = K, B = Q: both K-major
       const uint32_t idesc_o = umma_idesc_bf16_f32_amn_bmn(DH, NCOLS);              // A = V (MN-major), B = P^T (MN-major)
       const uint32_t idesc_l = umma_idesc_bf16_f32_bmn(kTcRows, NCOLS);             // A = ones (K-major), B = P^T
-      int N = 0;
-      for (int u = u0; u < u1; ++u) N += sw_unit(p, u).hidden ? 0 : 1;
-      int ns = 0, np = 0, us = skip_hidden(u0), s_last_run = -1, s_runs = 0, seg = -1;
+      const uint64_t d_ones = umma_desc_sw128_kmajor(sOnes);
+      const uint64_t d_k0 = umma_desc_sw128_kmajor(sK), d_q0 = umma_desc_sw128_kmajor(sQ);
+      const uint64_t d_v0 = umma_desc_sw128_mnmajor(sV, kTcKeys * 128), d_p0 = umma_desc_sw128_mnmajor(sP, kTcKeys * 128);
+      auto all_ok = [&](uint32_t b, uint32_t parity) { return __all_sync(0xffffffffu, mbar_test_wait(b, parity)) != 0; };
+      int N = 0, mma_us = u0;       // real units of this CTA; the S cursor
+      SwUnit mma_t = sw_unit(p, u0 < u1 ? u0 : 0);
+      {
+        SwUnit t = mma_t;
+        for (int u = u0; u < u1;) {
+          N += t.hidden ? 0 : 1;
+          sw_next(p, t, u);
+        }
+      }
+      sw_skip_hidden(p, mma_t, mma_us, u1);
+      dep_wait();
+      int ns = 0, np = 0, s_last_run = -1, s_runs = 0, seg = -1;
+      bool fv_ok = false, fk_ok = false, fq_ok = false;   // sticky: landed V of unit np / K of unit ns / Q of unit ns' run
+      int s_new_run = -1, s_r = 0;                        // decoded once per S unit
       while (np < N) {
         bool did = false;
         if (np < ns) {
           const int ts = np & 1, vst = np % NV;
-          if (mbar_test_wait(bar(PR + ts), uint32_t(np >> 1) & 1u) && mbar_test_wait(bar(FV + vst), uint32_t(np / NV) & 1u)) {
-            const int fresh = *reinterpret_cast<volatile int*>(&fresh_flag[ts]);
+          if (!fv_ok) fv_ok = all_ok(bar(FV + vst), uint32_t(np / NV) & 1u);
+          if (fv_ok && all_ok(bar(PR + ts), uint32_t(np >> 1) & 1u)) {
+            const bool fresh = __any_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&fresh_flag[ts]) != 0) != 0;
             if (fresh) {
-              if (seg >= 0) umma_commit(bar(SG + (seg & 1)));      // the segment that just ended: its products are all issued
+              if (seg >= 0 && elect_one_sync()) umma_commit(bar(SG + (seg & 1)));   // the segment that just ended: its products are all issued
+              __syncwarp();
               ++seg;
               if (seg >= 2) mbar_wait_backoff(bar(OD + (seg & 1)), uint32_t((seg >> 1) - 1) & 1u);   // accumulators drained
             }
             tcgen05_fence_after();
-            if (p.dbg && blockIdx.x == 0 && np < 8) p.dbg[np * 16 + 3] = clock64();
-            const uint32_t sPb = sP + uint32_t(ts) * kSwPBytes, sVb = sV + uint32_t(vst) * kSwTileBytes;
+            if (p.dbg && blockIdx.x == 0 && lane == 0 && np < 8) p.dbg[np * 16 + 3] = clock64();
             const uint32_t tO = tmem_base + 128 + uint32_t(seg & 1) * 64, tL = tmem_base + 256 + uint32_t(seg & 1) * 64;
-            const uint64_t d1 = umma_desc_sw128_kmajor(sOnes);
-            uint32_t acc = fresh ? 0u : 1u;
-#pragma unroll
-            for (int k = 0; k < kTcKeys / 16; ++k) {   // 16 keys per step = two 8-row groups = 2 048 bytes of either tile
-              const uint64_t dv = umma_desc_sw128_mnmajor(sVb + uint32_t(k) * 2048, kTcKeys * 128);
-              const uint64_t dp = umma_desc_sw128_mnmajor(sPb + uint32_t(k) * 2048, kTcKeys * 128);
-              umma_bf16_ss(tO, dv, dp, idesc_o, acc);
-              umma_bf16_ss(tL, d1, dp, idesc_l, acc);
-              acc = 1;
-            }
-            umma_commit(bar(EV + vst));
+            const uint64_t dv0 = d_v0 + uint64_t(uint32_t(vst) * (kSwTileBytes >> 4));
+            const uint64_t dp0 = d_p0 + uint64_t(uint32_t(ts) * (kSwPBytes >> 4));
             ++np;
-            if (np == N) umma_commit(bar(SG + (seg & 1)));
-            if (p.dbg && blockIdx.x == 0 && np <= 8) p.dbg[(np - 1) * 16 + 4] = clock64();
+            if (elect_one_sync()) {
+              uint32_t acc = fresh ? 0u : 1u;
+#pragma unroll
+              for (int k = 0; k < kTcKeys / 16; ++k) {   // 16 keys per step = two 8-row groups = 2 048 bytes of either tile
+                umma_bf16_ss(tO, dv0 + uint64_t(k * 128), dp0 + uint64_t(k * 128), idesc_o, acc);
+                umma_bf16_ss(tL, d_ones, dp0 + uint64_t(k * 128), idesc_l, acc);
+                acc = 1;
+              }
+              umma_commit(bar(EV + vst));
+              if (np == N) umma_commit(bar(SG + (seg & 1)));
+            }
+            __syncwarp();
+            fv_ok = false;
+            if (p.dbg && blockIdx.x == 0 && lane == 0 && np <= 8) p.dbg[(np - 1) * 16 + 4] = clock64();
             did = true;
           }
         }
         if (ns < N && ns - np < 2) {
-          const SwUnit t = sw_unit(p, us);
-          const bool new_run = t.run != s_last_run;
-          const int r = new_run ? s_runs : s_runs - 1, qb = r & 1;
-          if (mbar_test_wait(bar(FK + (ns & 1)), uint32_t(ns >> 1) & 1u) &&
-              (!new_run || mbar_test_wait(bar(FQ + qb), uint32_t(r >> 1) & 1u))) {
-            if (new_run) {
-              s_last_run = t.run;
-              ++s_runs;
-            }
-            if (p.dbg && blockIdx.x == 0 && ns < 8) p.dbg[ns * 16 + 1] = clock64();
+          if (s_new_run < 0) {
+            s_new_run = mma_t.run != s_last_run ? 1 : 0;
+            s_last_run = mma_t.run;
+            if (s_new_run) ++s_runs;
+            s_r = s_runs - 1;
+            fq_ok = !s_new_run;
+          }
+          const int qb = s_r & 1;
+          if (!fk_ok) fk_ok = all_ok(bar(FK + (ns & 1)), uint32_t(ns >> 1) & 1u);
+          if (fk_ok && !fq_ok) fq_ok = all_ok(bar(FQ + qb), uint32_t(s_r >> 1) & 1u);
+          if (fk_ok && fq_ok) {
+            if (p.dbg && blockIdx.x == 0 && lane == 0 && ns < 8) p.dbg[ns * 16 + 1] = clock64();
             tcgen05_fence_after();
-            const uint32_t sKb = sK + uint32_t(ns & 1) * kSwTileBytes, sQb = sQ + uint32_t(qb) * kQBytes;
             const uint32_t tS = tmem_base + uint32_t(ns & 1) * 64;
-            uint32_t acc = 0;
+            const uint64_t dk = d_k0 + uint64_t(uint32_t(ns & 1) * (kSwTileBytes >> 4));
+            const uint64_t dq = d_q0 + uint64_t(uint32_t(qb) * (kQBytes >> 4));
+            if (elect_one_sync()) {
+              uint32_t acc = 0;
 #pragma unroll
-            for (int d = 0; d < 2; ++d) {
-              const uint64_t da = umma_desc_sw128_kmajor(sKb + uint32_t(d) * kTcKeys * 128);
-              const uint64_t db = umma_desc_sw128_kmajor(sQb + uint32_t(d) * NCOLS * 128);
+              for (int d = 0; d < 2; ++d) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16_ss(tS, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc_s, acc);
-                acc = 1;
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16_ss(tS, dk + uint64_t(d * (kTcKeys * 128 >> 4) + 2 * k), dq + uint64_t(d * (NCOLS * 128 >> 4) + 2 * k), idesc_s, acc);
+                  acc = 1;
+                }
               }
+              umma_commit(bar(EK + (ns & 1)));     // the K tile is free
+              umma_commit(bar(SD + (ns & 1)));     // S^T is there
             }
-            umma_commit(bar(EK + (ns & 1)));     // the K tile is free
-            umma_commit(bar(SD + (ns & 1)));     // S^T is there
-            if (p.dbg && blockIdx.x == 0 && ns < 8) p.dbg[ns * 16 + 2] = clock64();
+            __syncwarp();
+            if (p.dbg && blockIdx.x == 0 && lane == 0 && ns < 8) p.dbg[ns * 16 + 2] = clock64();
             ++ns;
-            us = skip_hidden(us + 1);
+            sw_next(p, mma_t, mma_us);
+            sw_skip_hidden(p, mma_t, mma_us, u1);
+            fk_ok = false;
+            s_new_run = -1;
             did = true;
           }
         }
         if (!did) __nanosleep(20);
       }
     }
-  } else if (warp < 4 || warp >= 8) {
-    // ===== softmax + epilogue.  Thread = TMEM lane = KEY of the tile (softmax) / head-dim element (epilogue); the two
-    // warps of a lane quarter take the column halves =====
-    const int wq = warp & 3, half = warp >> 3;
+  } else if (warp < 16) {
+    // ===== softmax + epilogue: 16 warps.  Thread = TMEM lane = KEY of the tile (softmax) / head-dim element
+    // (epilogue); the four warps of a lane quarter take a quarter of the columns each.  These warps run one dependent
+    // chain per unit (a lone warp issues an instruction every ~5 cycles), so the common case — a tile every query of
+    // the window sees completely, no padded columns — takes a path without mask arithmetic =====
+    const int wq = warp & 3, cq = warp >> 2;
     const int kl = wq * 32 + lane;
     const uint32_t t_row = uint32_t(wq * 32) << 16;
     const float sc = a.scale_log2e;
-    const int cbase = half * NC;                                      // first column of this thread
+    const int cbase = cq * NC;                                        // first column of this thread
     const int hs_start = tc_div(cbase, p.m_wp, p.Wp), qi_start = cbase - hs_start * p.Wp;
+    constexpr uint32_t kFull = (1u << NC) - 1u;
+    const bool dense = p.Wp == a.W;                                   // no padded rows between the heads of a unit
     float mref[NGT];                                                  // the running segment's reference maxima (scaled log2 domain)
 #pragma unroll
     for (int g = 0; g < NGT; ++g) mref[g] = -INFINITY;
     int seg = -1, last_run = -1, n = 0;
     int s_R = 0, s_h0 = 0;                                            // the running segment's geometry
     size_t s_base = 0;
-    // drains segment `e_seg` (accumulators of buffer e_seg & 1) into its partial slot
-    auto epilogue = [&](int e_seg, int e_R, int e_h0, size_t e_base, const float (&e_m)[NGT]) __attribute__((always_inline)) {
+    uint32_t colmask = 0;                                             // bit e: column cbase + e is a real query row of the run
+    // drains segment `e_seg` (accumulators of buffer e_seg & 1; reference maxima in seg_m[e_seg & 1]) into its partial slot
+    auto epilogue = [&](int e_seg, int e_R, int e_h0, size_t e_base) __attribute__((always_inline)) {
       const int ob = e_seg & 1;
       mbar_wait(bar(SG + ob), uint32_t(e_seg >> 1) & 1u);
       tcgen05_fence_after();
-      if (p.dbg && blockIdx.x == 0 && wq == 0 && half == 0 && lane == 0 && e_seg < 8) p.dbg[e_seg * 16 + 8] = clock64();
+      if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && e_seg < 8) p.dbg[e_seg * 16 + 8] = clock64();
       const uint32_t tO = tmem_base + 128 + uint32_t(ob) * 64, tL = tmem_base + 256 + uint32_t(ob) * 64;
-      {
-        // slot c -> partial row: rows of one head are consecutive (512 bytes apart for this lane's element), the next
-        // head starts W rows later: one pointer walked with adds
-        float* pcol = a.part_o + (e_base + size_t(e_h0 + hs_start) * a.W + qi_start) * DH + kl;
-        int qi = qi_start;
-#pragma unroll 1
-        for (int c0 = 0; c0 < NC; c0 += 16) {
-          if (cbase + c0 >= e_R) break;                               // warp-uniform
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tO + t_row + uint32_t(cbase + c0), v);
-          tmem_ld_wait();
+      if (cbase < e_R) {   // warp-uniform
+        uint32_t v[NC];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            if (qi < a.W && cbase + c0 + e < e_R) *pcol = __uint_as_float(v[e]);   // a warp writes 128 contiguous bytes
+        for (int c0 = 0; c0 < NC; c0 += 8) tmem_ld_32x32b_x8(tO + t_row + uint32_t(cbase + c0), *reinterpret_cast<uint32_t(*)[8]>(&v[c0]));
+        tmem_ld_wait();
+        if (dense && cbase + NC <= e_R) {
+          // rows of consecutive heads are consecutive: column c -> partial row e_h0 * W + c; a warp writes 128 contiguous bytes
+          float* pcol = a.part_o + (e_base + size_t(e_h0) * a.W + cbase) * DH + kl;
+#pragma unroll
+          for (int e = 0; e < NC; ++e) pcol[e * DH] = __uint_as_float(v[e]);
+        } else {
+          // the next head starts W rows later: one pointer walked with adds
+          float* pcol = a.part_o + (e_base + size_t(e_h0 + hs_start) * a.W + qi_start) * DH + kl;
+          int qi = qi_start;
+#pragma unroll
+          for (int e = 0; e < NC; ++e) {
+            if (qi < a.W && cbase + e < e_R) *pcol = __uint_as_float(v[e]);
             pcol += DH;
             if (++qi == p.Wp) {
               qi = 0;
@@ -353,7 +425,7 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
           }
         }
       }
-      if (wq == 0 && half == 0) {   // {m, sum p}: every lane of L holds the sums; lane (c & 15) of the matching half-warp writes column c
+      if (warp == 0) {   // {m, sum p}: every lane of L holds the sums; lane (c & 15) of the matching half-warp writes column c
 #pragma unroll 1
         for (int c0 = 0; c0 < e_R; c0 += 16) {
           uint32_t v[16];
@@ -361,13 +433,11 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
           tmem_ld_wait();
           const int c = c0 + (lane & 15);
           if ((lane >> 4) == ((c0 >> 4) & 1) && c < e_R) {
-            float l = 0.f, m = -INFINITY;
+            float l = 0.f;
 #pragma unroll
             for (int e = 0; e < 16; ++e)
               if ((lane & 15) == e) l = __uint_as_float(v[e]);
-#pragma unroll
-            for (int g = 0; g < NGT; ++g)
-              if ((c >> 3) == g) m = e_m[g];
+            const float m = seg_m[ob][c >> 3];
             const int hs2 = tc_div(c, p.m_wp, p.Wp), qi2 = c - hs2 * p.Wp;
             if (qi2 < a.W) {
               const size_t pr = e_base + size_t(e_h0 + hs2) * a.W + qi2;
@@ -379,10 +449,10 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(OD + ob));
-      if (p.dbg && blockIdx.x == 0 && wq == 0 && half == 0 && lane == 0 && e_seg < 8) p.dbg[e_seg * 16 + 9] = clock64();
+      if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && e_seg < 8) p.dbg[e_seg * 16 + 9] = clock64();
     };
     auto mark_empty = [&](const SwUnit& t, size_t ubase) {   // slot (key tile, rows of this unit) contributes nothing
-      if (wq == 0 && half == 0) {
+      if (warp == 0) {
         for (int c = lane; c < t.R; c += 32) {
           const int hs2 = tc_div(c, p.m_wp, p.Wp), qi2 = c - hs2 * p.Wp;
           if (qi2 < a.W)
@@ -391,52 +461,83 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
       }
     };
 
+    SwUnit sm_t = sw_unit(p, u0 < u1 ? u0 : 0);
+    dep_wait();
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[15] = clock64();
+    if (p.dbg && threadIdx.x == 0) {   // per-CTA wall-clock (ns): [128 + 4 cta] = dependency wait returned, [+1] = end of work, [+2] = units
+      long long tns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+      p.dbg[128 + 4 * blockIdx.x] = tns;
+      p.dbg[128 + 4 * blockIdx.x + 2] = u1 - u0;
+    }
     for (int u = u0; u < u1; ++u) {
-      const SwUnit t = sw_unit(p, u);
+      const SwUnit t = sm_t;
+      if (u + 1 < u1) {
+        int uu = u;
+        sw_next(p, sm_t, uu);
+      }
       const size_t ubase = (size_t(t.kt) * a.rows + t.b) * a.H * size_t(a.W);
       if (t.hidden) {   // uniform per CTA
         mark_empty(t, ubase);
         continue;
       }
+      const bool new_run = t.run != last_run;
+      last_run = t.run;
+      if (new_run) {   // which of this thread's columns are query rows (R can shrink on the last row tile of a kv head)
+        colmask = 0;
+        int qi = qi_start;
+#pragma unroll
+        for (int e = 0; e < NC; ++e) {
+          colmask |= uint32_t(qi < a.W && cbase + e < t.R) << e;
+          if (++qi == p.Wp) qi = 0;
+        }
+      }
       const int ts = n & 1, j = n >> 1;
       const uint32_t tS = tmem_base + uint32_t(ts) * 64;
       mbar_wait(bar(SD + ts), uint32_t(j) & 1u);
       tcgen05_fence_after();
-      if (p.dbg && blockIdx.x == 0 && wq == 0 && half == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 5] = clock64();
+      if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 5] = clock64();
       uint32_t v[NC];
 #pragma unroll
-      for (int c0 = 0; c0 < NC; c0 += 16)
-        tmem_ld_32x32b_x16(tS + t_row + uint32_t(cbase + c0), *reinterpret_cast<uint32_t(*)[16]>(&v[c0]));
+      for (int c0 = 0; c0 < NC; c0 += 8) tmem_ld_32x32b_x8(tS + t_row + uint32_t(cbase + c0), *reinterpret_cast<uint32_t(*)[8]>(&v[c0]));
       tmem_ld_wait();
-      // visibility of (this key, column): bit e of okm
-      const int jk = t.key0 + kl, dk = jk - a.kv_len;               // visible to query i iff lo <= jk and dk <= i
+      // visibility of (this key, column e): bit e of okm.  Interior tile: every key is visible to every query row
       const bool interior = (t.key0 >= t.lo) && (t.key0 + kTcKeys - 1 <= a.kv_len);
-      const bool key_ok = jk >= t.lo;
-      uint32_t okm = 0;
-      float gm[NG];
-      {
+      uint32_t okm = colmask;
+      if (!interior) {
+        const int jk = t.key0 + kl, dk = jk - a.kv_len;             // visible to query i iff lo <= jk and dk <= i
+        uint32_t vis = 0;
         int qi = qi_start;
+#pragma unroll
+        for (int e = 0; e < NC; ++e) {
+          vis |= uint32_t(dk <= qi) << e;
+          if (++qi == p.Wp) qi = 0;
+        }
+        okm = jk >= t.lo ? (okm & vis) : 0u;
+      }
+      float gm[NG];
+      if (okm == kFull) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const float m0 = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                                 fmaxf(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])));
+          const float m1 = fmaxf(fmaxf(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                                 fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+          gm[g] = fmaxf(m0, m1);
+        }
+      } else {
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           float m = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const bool ok = (qi < a.W) && (cbase + 8 * g + e < t.R) && (interior || (key_ok && dk <= qi));
-            okm |= uint32_t(ok) << (8 * g + e);
-            m = fmaxf(m, ok ? __uint_as_float(v[8 * g + e]) : -INFINITY);
-            if (++qi == p.Wp) qi = 0;
-          }
-          gm[g] = ord2f(redux_max_s32(f2ord(m))) * sc;               // scale > 0: max commutes with it
+          for (int e = 0; e < 8; ++e) m = fmaxf(m, (okm >> (8 * g + e)) & 1u ? __uint_as_float(v[8 * g + e]) : -INFINITY);
+          gm[g] = m;
         }
       }
-      if (lane < NG) {
-        float x = gm[0];
 #pragma unroll
-        for (int g = 1; g < NG; ++g)
-          if (lane == g) x = gm[g];
-        xw[ts][wq][half * NG + lane] = x;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int g = 0; g < NG; ++g) gm[g] = ord2f(redux_max_s32(f2ord(gm[g]))) * sc;   // scale > 0: max commutes with it
+      if (lane < NG) xw[ts][wq][cq * NG + lane] = (NG == 2 && lane == 1) ? gm[NG - 1] : gm[0];
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       float tmax[NGT];
 #pragma unroll
       for (int g4 = 0; g4 < NGT / 4; ++g4) {
@@ -448,21 +549,20 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
         }
         tmax[4 * g4] = x.x; tmax[4 * g4 + 1] = x.y; tmax[4 * g4 + 2] = x.z; tmax[4 * g4 + 3] = x.w;
       }
-      if (p.dbg && blockIdx.x == 0 && wq == 0 && half == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 6] = clock64();
+      if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 6] = clock64();
       // segment decision: identical in every thread (same inputs)
-      bool brk = t.run != last_run;
+      bool brk = new_run;
 #pragma unroll
       for (int g = 0; g < NGT; ++g) brk = brk || (tmax[g] > mref[g] + sp.grow);
-      last_run = t.run;
-      float e_m[NGT];
       const int e_seg = seg, e_R = s_R, e_h0 = s_h0;
       const size_t e_base = s_base;
       if (brk) {
+        if (threadIdx.x == 0 && seg >= 0) {   // the ended segment's maxima, for its epilogue (read by this warp only)
 #pragma unroll
-        for (int g = 0; g < NGT; ++g) {
-          e_m[g] = mref[g];
-          mref[g] = tmax[g];
+          for (int g = 0; g < NGT; ++g) seg_m[seg & 1][g] = mref[g];
         }
+#pragma unroll
+        for (int g = 0; g < NGT; ++g) mref[g] = tmax[g];
         ++seg;
         s_R = t.R; s_h0 = t.h0; s_base = ubase;
       } else {
@@ -474,20 +574,33 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
         uint32_t pk[NC / 2];
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-          float ms = half ? mref[(NG + g) % NGT] : mref[g];
-          if (ms == -INFINITY) ms = 0.f;
+          float ms = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            const int i = 8 * g + e;
-            const float p0 = (okm >> i) & 1u ? ex2_approx(fmaf(__uint_as_float(v[i]), sc, -ms)) : 0.f;
-            const float p1 = (okm >> (i + 1)) & 1u ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -ms)) : 0.f;
-            const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+          for (int x = 0; x < 4; ++x)
+            if (cq == x) ms = mref[(x * NG + g) % NGT];
+          if (ms == -INFINITY) ms = 0.f;
+          if (okm == kFull) {
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              const int i = 8 * g + e;
+              const __nv_bfloat162 pb = __floats2bfloat162_rn(ex2_approx(fmaf(__uint_as_float(v[i]), sc, -ms)),
+                                                              ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -ms)));
+              pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              const int i = 8 * g + e;
+              const float p0 = (okm >> i) & 1u ? ex2_approx(fmaf(__uint_as_float(v[i]), sc, -ms)) : 0.f;
+              const float p1 = (okm >> (i + 1)) & 1u ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -ms)) : 0.f;
+              const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+              pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+            }
           }
         }
 #pragma unroll
         for (int g = 0; g < NG; ++g)
-          *reinterpret_cast<uint4*>(rowp + (((half * NG + g) ^ (kl & 7)) << 4)) =
+          *reinterpret_cast<uint4*>(rowp + (((cq * NG + g) ^ (kl & 7)) << 4)) =
               make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       }
       tcgen05_fence_before();
@@ -495,15 +608,27 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
       if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(&fresh_flag[ts]) = brk ? 1 : 0;
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(PR + ts));
-      if (p.dbg && blockIdx.x == 0 && wq == 0 && half == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 7] = clock64();
-      if (brk && e_seg >= 0) epilogue(e_seg, e_R, e_h0, e_base, e_m);
+      if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 7] = clock64();
+      if (brk && e_seg >= 0) epilogue(e_seg, e_R, e_h0, e_base);
       ++n;
     }
-    if (seg >= 0) epilogue(seg, s_R, s_h0, s_base, mref);
+    if (seg >= 0) {
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int g = 0; g < NGT; ++g) seg_m[seg & 1][g] = mref[g];
+      }
+      __syncwarp();
+      epilogue(seg, s_R, s_h0, s_base);
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (p.dbg && threadIdx.x == 0) {
+    long long tns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+    p.dbg[128 + 4 * blockIdx.x + 1] = tns;
+  }
+  if (warp == kSwMmaWarp) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

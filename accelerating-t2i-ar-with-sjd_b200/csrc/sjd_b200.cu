@@ -527,10 +527,12 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
           tp.a.k = ap.k; tp.a.v = ap.v;
           tp.k_row0 = int(size_t(l) * g.rows * g.n_kv_heads * size_t(g.max_len));
           tp.dbg = g_attn_dbg;
+          if (use_sw && (dbg_attn == 2 || dbg_attn == 4)) swp.grid_cap = -1;   // (developer timing: the kernel returns after its dependency wait)
           rc |= use_sw ? attn_sw_launch(c->tcmaps[tp.Wp / 8], swp, s)
                        : (use_tct ? attn_tct_launch(c->tcmaps[tp.Wp / 8], tp, s) : attn_tc_launch(c->tcmaps[tp.Wp / 8], tp, s));
           cb.ch.pre = attn_combine_desc(tp.a, g.head_dim);
           cb.ch.pre.sparse = use_sw ? 1 : 0;
+          if (dbg_attn == 3 || dbg_attn == 4) cb.ch.pre.n_chunks = 0;   // (developer timing: no split merge)
         } else {
           rc |= attn_launch(ap, g.head_dim, false, s);   // the split merge rides in the next chain kernel (pre-op)
           cb.ch.pre = attn_combine_desc(ap, g.head_dim);
