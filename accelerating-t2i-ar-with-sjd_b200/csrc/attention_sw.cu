@@ -15,7 +15,7 @@
 //     the whole softmax and exposed the load latency once per stage cycle;
 //   * softmax: thread = key (TMEM lane), two warps per lane quarter split the columns.  A probability only has to be
 //     scaled by a bound that is COMMON to the 128 keys of a column and recorded with the partial, not by the exact
-//     column maximum: each thread takes the max of 8 adjacent columns (draft positions i..i+7 of one head), one
+//     column maximum (and rounded up to an integer in the log2 domain, which makes the result independent of it): each thread takes the max of 8 adjacent columns (draft positions i..i+7 of one head), one
 //     redux.sync per group gives the warp's value, the eight warps meet through 128 bytes of shared memory and ONE
 //     named barrier.  (attention_tct.cu parked all scores in a 17 KB staging tile and paid two barriers.)
 // Mask, partial format, merge and reference semantics as in attention_tc.cu (SDPA over the additive window mask,
@@ -547,7 +547,11 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
           const float4 y = *reinterpret_cast<const float4*>(&xw[ts][q][4 * g4]);
           x.x = fmaxf(x.x, y.x); x.y = fmaxf(x.y, y.y); x.z = fmaxf(x.z, y.z); x.w = fmaxf(x.w, y.w);
         }
-        tmax[4 * g4] = x.x; tmax[4 * g4 + 1] = x.y; tmax[4 * g4 + 2] = x.z; tmax[4 * g4 + 3] = x.w;
+        // INTEGER references (log2 domain): probabilities scaled against two different integers differ by an exact
+        // power of two, so their bf16 roundings, the fp32 products and the merge weights are the same numbers up to the
+        // exponent — the result does not depend on which 8-column group, key tile or segment supplied the reference,
+        // i.e. not on the window a token happens to share (tests: ..._logits_do_not_depend_on_the_window)
+        tmax[4 * g4] = ceilf(x.x); tmax[4 * g4 + 1] = ceilf(x.y); tmax[4 * g4 + 2] = ceilf(x.z); tmax[4 * g4 + 3] = ceilf(x.w);
       }
       if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 6] = clock64();
       // segment decision: identical in every thread (same inputs)

@@ -460,9 +460,11 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
   if (!gemm_only && c->attn_tc_ok && W <= kTcRows) {
     const int rows_per_kv = (g.n_heads / g.n_kv_heads) * ((W + 7) & ~7);
     const bool tct_fits = g.head_dim == 128 && ((W + 7) & ~7) <= kTctCols;
-    // round 2: the segment-accumulating small-window kernel (attention_sw.cu) takes every shape whose query rows per kv
-    // head fit its 64 accumulator columns (Lumina / Chameleon up to window 64, Emu3 up to window 16)
-    use_sw = tct_fits && (c->attn_mode == 4 || (c->attn_mode == 0 && rows_per_kv <= kTctCols && c->sw_auto));
+    // round 2: the segment-accumulating small-window kernel (attention_sw.cu) takes every head-dim-128 window of up to
+    // 64 tokens: Lumina / Chameleon (18.5 vs 22.7 us per layer at window 32, 24.4 vs 28.9 at 64) and the GQA shapes too,
+    // although a kv head's query rows then need several row tiles that re-stream the K/V tile from L2 (Emu3 window 64
+    // over 4 096 / 8 000 keys: 5.58 / 6.25 ms per forward vs 6.52 / 7.93; profiles/r02u_attn_sw.txt)
+    use_sw = tct_fits && (c->attn_mode == 4 || (c->attn_mode == 0 && c->sw_auto));
     use_tct = !use_sw && tct_fits && (c->attn_mode == 3 || (c->attn_mode == 0 && rows_per_kv <= kTctCols && c->tct_auto));
     use_tc = !use_sw && !use_tct && (c->attn_mode == 1 || (c->attn_mode == 0 && rows_per_kv >= 64 && rows_per_kv <= kTcRows));
   }

@@ -23,7 +23,7 @@ def ev_time(fn, n=10):
     return e0.elapsed_time(e1) / n
 Ws = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [32, 16, 64]
 for W in Ws:
-    L, P = int(os.environ.get('SJD_BENCH_L', '1200')), 67
+    L, P = int(os.environ.get("SJD_BENCH_L", "1200")), 67
     ids = torch.randint(4, 8196, (2 * W,), dtype=torch.int32).to(dev)
     pos = torch.arange(L, L + W, dtype=torch.int32)
     rope = torch.cat([pos, pos - (P - 1)]).to(dev); cpos = torch.cat([pos, pos]).to(dev)

