@@ -36,7 +36,12 @@ struct AttnSwParams {
   int nv;           // depth of the V ring
   int grid_cap;     // > 0: at most this many CTAs (test knob: small shapes then exercise runs, ring wrap-around, segments)
   float grow;       // a tile whose maximum exceeds the segment's reference by more than this (log2 units) starts a new segment
+  // CTA c owns units [ub[c], ub[c + 1]).  Not an equal split: per-CTA stamps (profiles/r02aa_attn_sw_classes.txt) show a
+  // CTA pays ~1.5 us per key tile (the HBM stream) and ~1.3 us more when its range crosses from one head to the next (the
+  // old segment's epilogue, a new Q), so the host balances  units + run_cost * crossings  (attn_sw_split)
+  uint16_t ub[150];
 };
+constexpr int kSwMaxGrid = 148;
 
 struct SwUnit {
   int kt, b, hkv, h0, heads, key0, lo, run, R;
@@ -106,8 +111,7 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
                  sOnes = sQ + 2 * kQBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
-  const int n_units = a.n_chunks * a.Hkv * p.mtiles * a.rows;
-  const int u0 = int((long long)blockIdx.x * n_units / gridDim.x), u1 = int((long long)(blockIdx.x + 1) * n_units / gridDim.x);
+  const int u0 = sp.ub[blockIdx.x], u1 = sp.ub[blockIdx.x + 1];
 
   // the ones tile (A operand of the column-sum product): swizzling a constant is a no-op
   {
@@ -211,6 +215,21 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
     }
     sw_skip_hidden(p, tk, uk, u1);
     sw_skip_hidden(p, tv, uv, u1);
+    // A range that STARTS with the tile holding this window's keys (the last tile of a head) must not keep the old
+    // tiles behind it from streaming early (such CTAs ended 2.5-3 us after their peers): its ring slot 0 is filled
+    // right after the wait, slots 1.. now
+    const bool defer0 = uk < u1 && tk.key0 + kTcKeys > a.kv_len;
+    const SwUnit t0 = tk;
+    if (defer0) {
+      k_runs = 1;
+      k_last_run = tk.run;
+      nk = 1;
+      nv = 1;
+      sw_next(p, tk, uk);
+      sw_skip_hidden(p, tk, uk, u1);
+      sw_next(p, tv, uv);
+      sw_skip_hidden(p, tv, uv, u1);
+    }
     while (nk < 2 && uk < u1 && tk.key0 + kTcKeys <= a.kv_len) {
       if (tk.run != k_last_run) {
         ++k_runs;
@@ -231,6 +250,10 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
     // the head of the critical path: Q of the first two runs (both buffers are untouched)
     if (q_have > 0) issue_q(qa_b, qa_h0, qa_heads, 0);
     if (q_have > 1) issue_q(qb_b, qb_h0, qb_heads, 1);
+    if (defer0) {
+      issue_k(t0, 0);
+      issue_v(t0, 0);
+    }
     if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[10] = clock64();
     while (uk < u1 || uv < u1) {
       bool did = false;
@@ -469,6 +492,7 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
       p.dbg[128 + 4 * blockIdx.x] = tns;
       p.dbg[128 + 4 * blockIdx.x + 2] = u1 - u0;
+      p.dbg[128 + 4 * blockIdx.x + 3] = u0;
     }
     for (int u = u0; u < u1; ++u) {
       const SwUnit t = sm_t;
@@ -646,11 +670,49 @@ void attn_sw_plan(AttnSwParams* sp, int force_ncols) {
   sp->nv = sp->ncols == 32 ? 3 : 2;
 }
 
+// Contiguous split of the units over `grid` CTAs that balances the modelled time  (real units) + run_cost * (head
+// changes inside the range)  instead of the unit count: smallest common deadline by bisection over a greedy sweep.
+// Hidden tiles (whole tile inside a row's hidden prefix) cost nothing.
+void attn_sw_split(AttnSwParams* sp, int grid, float run_cost) {
+  const AttnParams& a = sp->t.a;
+  const int nc = a.n_chunks, n_runs = a.Hkv * sp->t.mtiles * a.rows, n_units = nc * n_runs;
+  auto hidden = [&](int u) {
+    const int run = u / nc, kt = u - run * nc, b = run / sp->t.ny;
+    return (kt + 1) * kTcKeys <= a.kv_lo[b];
+  };
+  auto sweep = [&](float deadline, bool write) {
+    int u = 0;
+    for (int c = 0; c < grid; ++c) {
+      if (write) sp->ub[c] = uint16_t(u);
+      float cost = 0.f;
+      int last_run = -1;
+      while (u < n_units) {
+        const int run = u / nc;
+        float add = hidden(u) ? 0.f : 1.f;
+        if (add > 0.f && last_run >= 0 && run != last_run) add += run_cost;
+        if (cost + add > deadline && cost > 0.f) break;
+        cost += add;
+        if (add > 0.f) last_run = run;
+        ++u;
+      }
+    }
+    if (write) sp->ub[grid] = uint16_t(n_units);
+    return u >= n_units;
+  };
+  float lo = 0.f, hi = float(n_units) + run_cost * n_runs + 1.f;
+  for (int it = 0; it < 30; ++it) {
+    const float mid = 0.5f * (lo + hi);
+    if (sweep(mid, false)) hi = mid;
+    else lo = mid;
+  }
+  sweep(hi, true);
+}
+
 constexpr int attn_sw_smem(int ncols, int nv) {   // K ring, V ring, two P^T buffers, two Q buffers, the ones tile
   return 1024 + 2 * int(kSwTileBytes) + nv * int(kSwTileBytes) + 2 * int(kSwPBytes) + 2 * (2 * ncols * 128) + kTcRows * 128;
 }
 
-int attn_sw_launch(const AttnTcMaps& maps, const AttnSwParams& sp, cudaStream_t stream) {
+int attn_sw_launch(const AttnTcMaps& maps, AttnSwParams& sp, cudaStream_t stream) {
   const AttnTcParams& p = sp.t;
   const AttnParams& a = p.a;
   if (p.hpc * p.Wp > 64 || p.head_dim != 128) return -3;
@@ -658,8 +720,13 @@ int attn_sw_launch(const AttnTcMaps& maps, const AttnSwParams& sp, cudaStream_t 
   if (n_units >= 65536) return -3;   // tc_div's exact range
   const int sms = device_num_sms();
   int ng = n_units < sms ? n_units : sms;
+  if (ng > kSwMaxGrid) ng = kSwMaxGrid;
   if (sp.grid_cap > 0 && sp.grid_cap < ng) ng = sp.grid_cap;
   dim3 grid(ng);
+  if (sp.ub[ng] != uint16_t(n_units)) {   // (the same split serves every layer of a forward)
+    static const float run_cost = getenv("SJD_ATTN_SW_RUNCOST") ? float(atof(getenv("SJD_ATTN_SW_RUNCOST"))) : 0.5f;
+    attn_sw_split(&sp, ng, run_cost);
+  }
   static bool set = false;
   if (!set) {
     if (cudaFuncSetAttribute(attn_sw_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_sw_smem(32, 3)) != cudaSuccess ||

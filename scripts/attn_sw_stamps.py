@@ -35,6 +35,7 @@ for n in range(8):
 print("producer (us): after wait %.2f, early-Q done %.2f, cursors ready %.2f, first post-wait Q issued %.2f" % tuple(((int(b[0, k]) - t0) / 1.9e3 if int(b[0, k]) else float('nan')) for k in (10, 11, 12, 13)))
 c = full[128:].view(160, 4)
 c = c[c[:, 0] > 0]
+c = c[c[:, 2] > 0]
 if len(c):
     s0 = int(c[:, 0].min())
     st_, en_ = (c[:, 0] - s0).float() / 1e3, (c[:, 1] - s0).float() / 1e3
@@ -44,3 +45,26 @@ if len(c):
     for nu in sorted(set(c[:, 2].tolist())):
         m = c[:, 2] == nu
         print(f"  CTAs with {nu} units: {int(m.sum())}, busy (end - own wait) median {(en_[m] - st_[m]).median():.2f} max {(en_[m] - st_[m]).max():.2f} us")
+
+# what makes a CTA slow?  classify by the units it owns (contiguous split of runs x key tiles, key tiles fastest)
+if len(c) and os.environ.get("SJD_STAMPS_CLASSES"):
+    n_chunks = (L + W + 127) // 128
+    n_units = n_chunks * 32 * 2
+    G = len(c)
+    rows = []
+    for cta in range(G):
+        u0 = int(c[cta, 3]); u1 = u0 + int(c[cta, 2])
+        if u1 == u0:
+            continue
+        kts = [u % n_chunks for u in range(u0, u1)]
+        runs = len({u // n_chunks for u in range(u0, u1)})
+        rows.append((u1 - u0, int((n_chunks - 1) in kts), int(any(kt == 0 and (u // n_chunks) >= 32 for kt, u in zip(kts, range(u0, u1)))), runs,
+                     kts[0] == n_chunks - 1, float(en_[cta] - st_[cta])))
+    import collections
+    agg = collections.defaultdict(list)
+    for r in rows:
+        agg[r[:5]].append(r[5])
+    print("class (units, has window tile, has hidden-prefix tile, runs, STARTS with the window tile): n, median busy us, max")
+    for k in sorted(agg):
+        v = sorted(agg[k])
+        print(f"  {k}: n={len(v)} median {v[len(v) // 2]:.2f} max {v[-1]:.2f}")
