@@ -133,6 +133,9 @@ def lib() -> C.CDLL:
     L.sjd_verify.argtypes = [C.POINTER(VerifyArgs), C.c_void_p]
     L.sjd_debug_philox.restype = C.c_int
     L.sjd_debug_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
+    L.sjd_vq_lookup.restype = C.c_int
+    L.sjd_vq_lookup.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_int, C.c_void_p, C.c_void_p]
     L.sjd_ctx_create.restype = C.c_int
     L.sjd_ctx_create.argtypes = [C.POINTER(ModelCfg), C.POINTER(C.c_void_p)]
     L.sjd_ctx_destroy.restype = None

@@ -16,6 +16,7 @@
 #include "attention_tct.cu"
 #include "attention_sw.cu"
 #include "verify.cu"
+#include "vq_lookup.cu"
 
 namespace sjd {
 
@@ -190,6 +191,16 @@ void sjd_debug_gemm_stamps(void* device_buf, int n_launches) {
   g_dbg_buf = static_cast<long long*>(device_buf);
   g_dbg_cap = n_launches;
   g_dbg_idx = 0;
+}
+
+int sjd_vq_lookup(const int32_t* codes, int n_pix, int hw, const float* codebook, int n_e, int e_dim, int l2_norm,
+                  const float* w, const float* bias, int z, float* out, void* stream) {
+  if (!codes || !codebook || !w || !bias || !out || n_pix < 1 || hw < 1 || n_pix % hw || n_e < 1 || e_dim < 1 || z < 1)
+    return fail(SJD_E_ARG, "sjd_vq_lookup: bad argument");
+  const int rc = vq_lookup_launch(codes, n_pix, hw, codebook, n_e, e_dim, l2_norm, w, bias, z, out, static_cast<cudaStream_t>(stream));
+  if (rc) return fail(rc == -3 ? SJD_E_ARG : SJD_E_LAUNCH, "sjd_vq_lookup: launch");
+  g_launches++;
+  return 0;
 }
 
 size_t sjd_gemm_workspace_bytes(int N, int K, int m_tile, int grid_limit) {

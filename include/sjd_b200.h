@@ -192,6 +192,18 @@ void sjd_debug_gemm_stamps(void* device_buf, int n_launches);
 /* Developer timing of the tensor-core attention: CTA 0 of every following launch writes clock64 stamps of its pipeline
  * stages to device_buf[unit < 8][16] (int64; the last launch wins).  NULL switches it off. */
 void sjd_debug_attn_stamps(void* device_buf);
+/* ------------------------------------------------------------------------------------------------
+ * Output side of the loop: image-token ids -> the latent feature map a VQGAN decoder starts from.
+ * Replaces, in one launch, get_codebook_entry + post_quant_conv of the reference's decode_code:
+ *   LlamaGen   llamagen/tokenizer/tokenizer_image/vq_model.py:52-55, :261-275 (L2-normalised codebook), :39, :47-49
+ *   Chameleon  lumina_mgpt/model/chameleon_vae_ori/vqgan.py:594-597, :131-146, :589-592
+ * codes: device int32 [n_pix] (n_pix = batch * hw, row-major latent grid); codebook: device fp32 [n_e, e_dim];
+ * w / bias: post_quant_conv weight [z, e_dim] (its 1x1 kernel squeezed) and bias [z]; out: device fp32 [batch, z, hw]
+ * (NCHW).  l2_norm = 1 normalises every codebook row like F.normalize (eps 1e-12).  Ids outside [0, n_e) are clamped.
+ * ---------------------------------------------------------------------------------------------- */
+int sjd_vq_lookup(const int32_t* codes, int n_pix, int hw, const float* codebook, int n_e, int e_dim, int l2_norm,
+                  const float* w, const float* bias, int z, float* out, void* stream);
+
 /* counts kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t sjd_launch_count(void);
 

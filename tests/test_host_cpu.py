@@ -604,3 +604,40 @@ def test_model_loader_dispatch_and_names():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             ML.load_pretrained_model("synthetic/llamagen-gpt-b", device="cpu", n_layers=1)
+
+
+# ------------------------------------------------------------------------ f3: VQ decoders (token ids -> pixels)
+@pytest.mark.parametrize("family", ["llamagen", "chameleon"])
+def test_vq_decoder_plan_and_conv_stack_match_reference_golden_on_cpu(family):
+    """The decoder's structure is read from the state dict's keys (two naming schemes); its convolution stack (library
+    calls) on the latents the reference formula gives must reproduce the pixels the UNMODIFIED reference module produced
+    (tests/golden/vq_decode_*.json, oracle/mint_vq_golden.py).  The token-side kernel (sjd_vq_lookup) is checked on the
+    GPU; constructing the decoder without a GPU must fail loudly."""
+    import json
+    import torch
+    import torch.nn.functional as F
+    from sjd_b200 import vq_decode
+    from oracle.vq_case import fill_state
+    g = json.loads((ROOT / "tests" / "golden" / f"vq_decode_{family}.json").read_text())
+    sd = fill_state(g["shapes"], g["seed"])
+    with pytest.raises(RuntimeError):
+        vq_decode.VQDecoder(sd, "cpu")
+    dec = vq_decode.VQDecoder.__new__(vq_decode.VQDecoder)
+    dec.sd = {k: v.float() for k, v in sd.items()}
+    dec.layout = "llamagen" if any(k.startswith("decoder.conv_blocks.") for k in sd) else "chameleon"
+    assert dec.layout == family
+    dec.program = dec._plan()
+    ops = [op for op, _ in dec.program]
+    assert ops.count("up") == 2 and ops.count("attn") >= 1 and ops[:3] == ["res", "attn", "res"]
+    cb = sd["quantize.embedding.weight"]
+    if g["l2_norm"]:
+        cb = F.normalize(cb, p=2, dim=-1)
+    codes = torch.tensor(g["codes"])
+    B, h, w = g["batch"], g["h"], g["w"]
+    zq = cb[codes].reshape(B, h, w, -1).permute(0, 3, 1, 2).contiguous()
+    lat = F.conv2d(zq, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+    with torch.no_grad():
+        px = dec.decode_latents(lat)
+    ref = torch.tensor(g["pixels"]).reshape(g["out_shape"])
+    assert list(px.shape) == g["out_shape"]
+    assert (px - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
