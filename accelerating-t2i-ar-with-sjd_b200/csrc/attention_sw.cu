@@ -40,6 +40,13 @@ struct AttnSwParams {
   // CTA pays ~1.5 us per key tile (the HBM stream) and ~1.3 us more when its range crosses from one head to the next (the
   // old segment's epilogue, a new Q), so the host balances  units + run_cost * crossings  (attn_sw_split)
   uint16_t ub[150];
+  // Cluster mode (cluster >= 1): every run (CFG row, kv head, row tile) belongs to ONE thread-block cluster of `cluster`
+  // CTAs, each walking a contiguous slice of the run's key tiles into a single TMEM accumulator (a tile whose maximum
+  // outgrows the reference rescales the accumulator in place instead of starting a segment).  At the end the CTAs stage
+  // their {O^T, L, m} in their own shared memory, the cluster leader reads them through distributed shared memory, merges
+  // and writes the NORMALISED bf16 attention rows: no fp32 partials in global memory, no merge pre-op and no grid-wide
+  // wait for it in the chain kernel that follows.  0: the segment / partial-slot form above (runs > SMs, test knobs).
+  int cluster;
 };
 constexpr int kSwMaxGrid = 148;
 
@@ -174,6 +181,12 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
     __syncwarp();
   };
 
+  const int cl = sp.cluster;
+  float fin_o[NC], fin_l[NC], fin_m[NG];   // cluster mode, softmax warps: this thread's columns of the CTA's O^T / L, their references
+#pragma unroll
+  for (int e = 0; e < NC; ++e) fin_o[e] = fin_l[e] = 0.f;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) fin_m[g] = -INFINITY;
   if (sp.grid_cap < 0) {   // developer timing (SJD_DEBUG_ATTN=2|4): the cost of the kernel boundaries alone
     pdl_wait();
     pdl_launch_dependents();
@@ -502,7 +515,7 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
       }
       const size_t ubase = (size_t(t.kt) * a.rows + t.b) * a.H * size_t(a.W);
       if (t.hidden) {   // uniform per CTA
-        mark_empty(t, ubase);
+        if (!cl) mark_empty(t, ubase);
         continue;
       }
       const bool new_run = t.run != last_run;
@@ -579,9 +592,41 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
       }
       if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && n < 8) p.dbg[n * 16 + 6] = clock64();
       // segment decision: identical in every thread (same inputs)
-      bool brk = new_run;
+      bool grew = false;
 #pragma unroll
-      for (int g = 0; g < NGT; ++g) brk = brk || (tmax[g] > mref[g] + sp.grow);
+      for (int g = 0; g < NGT; ++g) grew = grew || (tmax[g] > mref[g] + sp.grow);
+      bool brk = cl ? seg < 0 : (new_run || grew);
+      if (cl && seg >= 0 && grew) {
+        // cluster mode keeps ONE accumulator per CTA: a tile that outgrows the reference rescales O^T and L in place.
+        // Every product issued so far has completed once the commit behind PV(n-1) has arrived (its V stage's barrier).
+        mbar_wait(bar(EV + (n - 1) % NV), uint32_t((n - 1) / NV) & 1u);
+        tcgen05_fence_after();
+        float nm[NGT];
+#pragma unroll
+        for (int g = 0; g < NGT; ++g) nm[g] = fmaxf(mref[g], tmax[g]);
+        const uint32_t tO = tmem_base + 128 + t_row + uint32_t(cbase), tL = tmem_base + 256 + t_row + uint32_t(cbase);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          float f = 1.f;
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            if (cq == x) f = nm[(x * NG + g) % NGT] == -INFINITY ? 1.f : exp2f(mref[(x * NG + g) % NGT] - nm[(x * NG + g) % NGT]);
+          uint32_t vo[8], vl[8];
+          tmem_ld_32x32b_x8(tO + uint32_t(8 * g), vo);
+          tmem_ld_32x32b_x8(tL + uint32_t(8 * g), vl);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            vo[e] = __float_as_uint(__uint_as_float(vo[e]) * f);
+            vl[e] = __float_as_uint(__uint_as_float(vl[e]) * f);
+          }
+          tmem_st_32x32b_x8(tO + uint32_t(8 * g), vo);
+          tmem_st_32x32b_x8(tL + uint32_t(8 * g), vl);
+        }
+        tmem_st_wait();
+#pragma unroll
+        for (int g = 0; g < NGT; ++g) mref[g] = nm[g];
+      }
       const int e_seg = seg, e_R = s_R, e_h0 = s_h0;
       const size_t e_base = s_base;
       if (brk) {
@@ -593,7 +638,7 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
         for (int g = 0; g < NGT; ++g) mref[g] = tmax[g];
         ++seg;
         s_R = t.R; s_h0 = t.h0; s_base = ubase;
-      } else {
+      } else if (!cl) {
         mark_empty(t, ubase);
       }
       // probabilities of this key for its columns (bf16, q contiguous) -> 16-byte chunks of its P^T row
@@ -640,7 +685,32 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
       if (brk && e_seg >= 0) epilogue(e_seg, e_R, e_h0, e_base);
       ++n;
     }
-    if (seg >= 0) {
+    if (cl) {
+      // this thread's columns of the CTA's accumulators (lane = head-dim element; every lane of L holds the sums)
+      if (seg >= 0) {
+        mbar_wait(bar(SG), 0u);
+        tcgen05_fence_after();
+        uint32_t vo[NC], vl[NC];
+#pragma unroll
+        for (int c0 = 0; c0 < NC; c0 += 8) {
+          tmem_ld_32x32b_x8(tmem_base + 128 + t_row + uint32_t(cbase + c0), *reinterpret_cast<uint32_t(*)[8]>(&vo[c0]));
+          tmem_ld_32x32b_x8(tmem_base + 256 + t_row + uint32_t(cbase + c0), *reinterpret_cast<uint32_t(*)[8]>(&vl[c0]));
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < NC; ++e) {
+          fin_o[e] = __uint_as_float(vo[e]);
+          fin_l[e] = __uint_as_float(vl[e]);
+        }
+        tcgen05_fence_before();
+      }
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          if (cq == x) fin_m[g] = mref[(x * NG + g) % NGT];
+      }
+    } else if (seg >= 0) {
       if (threadIdx.x == 0) {
 #pragma unroll
         for (int g = 0; g < NGT; ++g) seg_m[seg & 1][g] = mref[g];
@@ -648,6 +718,81 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
       __syncwarp();
       epilogue(seg, s_R, s_h0, s_base);
     }
+  }
+  if (cl) {
+    // ===== cluster merge: peers stage {O^T [col][d], L [col], m [group]} in their own K ring (free by now), one cluster
+    // barrier, the leader reads them through distributed shared memory, merges in rank order (fixed: reproducible) and
+    // writes the normalised bf16 rows; a second barrier keeps the peers' shared memory alive until it has =====
+    const uint32_t rank = cl > 1 ? cluster_ctarank() : 0u;
+    float* const stO = reinterpret_cast<float*>(smem_raw + (sK - smem_u32(smem_raw)));   // [NCOLS][128]
+    float* const stL = stO + NCOLS * 128;                                                 // [NCOLS]
+    float* const stM = stL + NCOLS;                                                       // [NGT]
+    const int wq = warp & 3, cq = warp >> 2, kl = wq * 32 + lane, cbase = cq * NC;
+    if (cl > 1) {
+      if (warp < 16 && rank != 0) {
+#pragma unroll
+        for (int e = 0; e < NC; ++e) stO[(cbase + e) * 128 + kl] = fin_o[e];
+        if (kl == 0) {
+#pragma unroll
+          for (int e = 0; e < NC; ++e) stL[cbase + e] = fin_l[e];
+#pragma unroll
+          for (int g = 0; g < NG; ++g) stM[cq * NG + g] = fin_m[g];
+        }
+      }
+      cluster_sync_all();
+    }
+    if (warp < 16 && rank == 0 && u0 < u1) {
+      const SwUnit tr = sw_unit(p, u0);
+      float M[NG], num[NC], den[NC];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) M[g] = fin_m[g];
+#pragma unroll 1
+      for (int r = 1; r < cl; ++r) {
+        const uint32_t bm = dsmem_addr(smem_u32(stM), uint32_t(r));
+#pragma unroll
+        for (int g = 0; g < NG; ++g) M[g] = fmaxf(M[g], ld_dsmem_f32(bm + uint32_t(cq * NG + g) * 4u));
+      }
+      {
+        float w0[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) w0[g] = fin_m[g] == -INFINITY ? 0.f : exp2f(fin_m[g] - M[g]);
+#pragma unroll
+        for (int e = 0; e < NC; ++e) {
+          num[e] = fin_o[e] * w0[e >> 3];
+          den[e] = fin_l[e] * w0[e >> 3];
+        }
+      }
+#pragma unroll 1
+      for (int r = 1; r < cl; ++r) {
+        const uint32_t bm = dsmem_addr(smem_u32(stM), uint32_t(r)), bo = dsmem_addr(smem_u32(stO), uint32_t(r)),
+                       bl = dsmem_addr(smem_u32(stL), uint32_t(r));
+        float wr[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const float m = ld_dsmem_f32(bm + uint32_t(cq * NG + g) * 4u);
+          wr[g] = m == -INFINITY ? 0.f : exp2f(m - M[g]);
+        }
+#pragma unroll
+        for (int e = 0; e < NC; ++e) {
+          num[e] += ld_dsmem_f32(bo + uint32_t((cbase + e) * 128 + kl) * 4u) * wr[e >> 3];
+          den[e] += ld_dsmem_f32(bl + uint32_t(cbase + e) * 4u) * wr[e >> 3];
+        }
+      }
+      int hs = tc_div(cbase, p.m_wp, p.Wp), qi = cbase - hs * p.Wp;
+#pragma unroll
+      for (int e = 0; e < NC; ++e) {
+        // same arithmetic as attn_combine_row (reciprocal, then multiply): a token's attention row must not depend on
+        // whether its window took this path or the partial-slot path
+        const float inv = den[e] > 0.f ? 1.f / den[e] : 0.f;               // fully masked query (CFG hidden prefix) -> 0
+        if (qi < a.W && cbase + e < tr.R)
+          a.out[(size_t(tr.b * a.W + qi) * a.H + tr.h0 + hs) * DH + kl] = __float2bfloat16_rn(num[e] * inv);
+        if (++qi == p.Wp) {
+          qi = 0;
+          ++hs;
+        }
+      }
+    }
+    if (cl > 1) cluster_sync_all();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -663,11 +808,22 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
 }
 
 // Geometry: up to 64 / Wp heads of a kv head per unit; 32 accumulator columns when they suffice.
-void attn_sw_plan(AttnSwParams* sp, int force_ncols) {
+void attn_sw_plan(AttnSwParams* sp, int force_ncols, int max_cluster) {
   attn_tct_plan(&sp->t);
   const int R = sp->t.hpc * sp->t.Wp;
   sp->ncols = (R <= 32 && force_ncols != 64) ? 32 : 64;
   sp->nv = sp->ncols == 32 ? 3 : 2;
+  // cluster mode: as many CTAs per run (1, 2 or 4) as fit one wave and have a key tile each
+  const AttnParams& a = sp->t.a;
+  const int runs = a.Hkv * sp->t.mtiles * a.rows, sms = device_num_sms() < kSwMaxGrid ? device_num_sms() : kSwMaxGrid;
+  int k = 0;
+  // (measured, profiles/r02ah_attn_sw_cluster.txt: 18.8 -> 18.0 us per layer at window 32, 24.3 -> 22.9 at 64, 36.8 -> 31.3 at
+  // 64 over 2 400 keys; at window 16 the two cluster barriers cost more than the merge pre-op they replace: 18.5 -> 19.0)
+  if (max_cluster > 0 && runs <= sms && R >= 32) {
+    k = 1;
+    while (k * 2 <= max_cluster && k * 2 <= 4 && runs * k * 2 <= sms && k * 2 <= a.n_chunks) k *= 2;
+  }
+  sp->cluster = k;
 }
 
 // Contiguous split of the units over `grid` CTAs that balances the modelled time  (real units) + run_cost * (head
@@ -721,12 +877,20 @@ int attn_sw_launch(const AttnTcMaps& maps, AttnSwParams& sp, cudaStream_t stream
   const int sms = device_num_sms();
   int ng = n_units < sms ? n_units : sms;
   if (ng > kSwMaxGrid) ng = kSwMaxGrid;
-  if (sp.grid_cap > 0 && sp.grid_cap < ng) ng = sp.grid_cap;
-  dim3 grid(ng);
-  if (sp.ub[ng] != uint16_t(n_units)) {   // (the same split serves every layer of a forward)
+  if (sp.grid_cap > 0) {
+    sp.cluster = 0;
+    if (sp.grid_cap < ng) ng = sp.grid_cap;
+  }
+  if (sp.cluster > 0) {   // CTA r * k + j: slice j of run r's key tiles
+    const int k = sp.cluster, runs = a.Hkv * p.mtiles * a.rows, nc = a.n_chunks;
+    ng = runs * k;
+    if (sp.ub[ng] != uint16_t(n_units) || sp.ub[1] != uint16_t(nc / k))
+      for (int c = 0; c <= ng; ++c) sp.ub[c] = uint16_t((c / k) * nc + ((c % k) * nc) / k);
+  } else if (sp.ub[ng] != uint16_t(n_units)) {   // (the same split serves every layer of a forward)
     static const float run_cost = getenv("SJD_ATTN_SW_RUNCOST") ? float(atof(getenv("SJD_ATTN_SW_RUNCOST"))) : 0.5f;
     attn_sw_split(&sp, ng, run_cost);
   }
+  dim3 grid(ng);
   static bool set = false;
   if (!set) {
     if (cudaFuncSetAttribute(attn_sw_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_sw_smem(32, 3)) != cudaSuccess ||
@@ -734,8 +898,10 @@ int attn_sw_launch(const AttnTcMaps& maps, AttnSwParams& sp, cudaStream_t stream
       return -5;
     set = true;
   }
-  if (sp.ncols == 32) return launch_pdl(attn_sw_kernel<32>, grid, dim3(kSwThreads), attn_sw_smem(32, sp.nv), stream, maps, sp);
-  return launch_pdl(attn_sw_kernel<64>, grid, dim3(kSwThreads), attn_sw_smem(64, sp.nv), stream, maps, sp);
+  const int k = sp.cluster > 1 ? sp.cluster : 1;
+  if (sp.ncols == 32)
+    return launch_pdl_cluster(attn_sw_kernel<32>, grid, dim3(kSwThreads), attn_sw_smem(32, sp.nv), stream, k, maps, sp);
+  return launch_pdl_cluster(attn_sw_kernel<64>, grid, dim3(kSwThreads), attn_sw_smem(64, sp.nv), stream, k, maps, sp);
 }
 
 }  // namespace sjd

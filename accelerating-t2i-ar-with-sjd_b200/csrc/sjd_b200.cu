@@ -69,6 +69,7 @@ struct sjd_ctx {
   int attn_mode = 0;   // 0: pick per window (see forward_chain); SJD_ATTN = tc -> 1, mma -> 2, tct -> 3, sw -> 4 force one kernel
   int sw_grid = 0;       // developer/test knob SJD_ATTN_SW_GRID: cap on the kernel's CTAs (tiny shapes then walk runs, rings and segments)
   float sw_grow = 16.f;  // developer/test knob SJD_ATTN_SW_GROW: log2 growth over the reference maximum that ends a segment
+  int sw_cluster = 4;    // SJD_ATTN_SW_CLUSTER: largest cluster (CTAs per run) of the in-kernel merge; 0 = partial slots + merge pre-op
   int sw_ncols = 0;      // developer/test knob SJD_ATTN_SW_NCOLS=64: always the 64-column instantiation
   bool sw_auto = true;   // whether mode 0 may pick the segment-accumulating small-window kernel (SJD_ATTN_SW_AUTO=0: round-1 rule)
   bool tct_auto = false;   // whether mode 0 may pick the transposed small-window kernel
@@ -346,6 +347,7 @@ int sjd_ctx_create(const sjd_model_cfg* cfg, sjd_ctx** out) {
     c->attn_mode = !e ? 0 : (strcmp(e, "tc") == 0 ? 1 : (strcmp(e, "mma") == 0 ? 2 : (strcmp(e, "tct") == 0 ? 3 : (strcmp(e, "sw") == 0 ? 4 : 0))));
     if (const char* e2 = getenv("SJD_ATTN_SW_AUTO")) c->sw_auto = atoi(e2) != 0;
     if (const char* e2 = getenv("SJD_ATTN_SW_GRID")) c->sw_grid = atoi(e2);
+    if (const char* e2 = getenv("SJD_ATTN_SW_CLUSTER")) c->sw_cluster = atoi(e2);
     if (const char* e2 = getenv("SJD_ATTN_SW_NCOLS")) c->sw_ncols = atoi(e2);
     if (const char* e2 = getenv("SJD_ATTN_SW_GROW")) c->sw_grow = float(atof(e2));
     if (uint64_t(g.n_layers) * g.rows * g.n_kv_heads * uint64_t(g.max_len) >= (1ull << 31)) c->attn_tc_ok = false;
@@ -489,7 +491,7 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
     static const int tc_l2pf = getenv("SJD_ATTN_TC_L2PF") ? atoi(getenv("SJD_ATTN_TC_L2PF")) : 0;
     tp.a.l2_prefetch = tc_l2pf;
     if (use_sw) {
-      attn_sw_plan(&swp, c->sw_ncols);
+      attn_sw_plan(&swp, c->sw_ncols, c->sw_grid > 0 ? 0 : c->sw_cluster);
       swp.grid_cap = c->sw_grid;
       swp.grow = c->sw_grow;
     } else if (use_tct) attn_tct_plan(&tp);
@@ -545,6 +547,7 @@ static int forward_chain(sjd_ctx* c, int W, const sjd_forward_args* a, bool gemm
                        : (use_tct ? attn_tct_launch(c->tcmaps[tp.Wp / 8], tp, s) : attn_tc_launch(c->tcmaps[tp.Wp / 8], tp, s));
           cb.ch.pre = attn_combine_desc(tp.a, g.head_dim);
           cb.ch.pre.sparse = use_sw ? 1 : 0;
+          if (use_sw && swp.cluster > 0) cb.ch.pre.n_chunks = 0;   // merged and normalised by the attention kernel's cluster leaders
           if (dbg_attn == 3 || dbg_attn == 4) cb.ch.pre.n_chunks = 0;   // (developer timing: no split merge)
         } else {
           rc |= attn_launch(ap, g.head_dim, false, s);   // the split merge rides in the next chain kernel (pre-op)

@@ -32,9 +32,10 @@ def loop_goldens():
 # SMALL test shapes walk what the bench shape walks: g<N> caps the grid at N CTAs (one CTA then runs several heads, wraps
 # its K / V rings, rotates its Q buffers and accumulates several key tiles per segment), grow<X> ends a segment whenever a
 # tile's maximum exceeds the reference by X (0: nearly every tile -> accumulator rotation), n64 forces the 64-column
-# instantiation.
-ATTN_MODES = ["auto", "tc", "tct", "mma", "sw", "sw:g1", "sw:g3:grow0", "sw:g2:n64"]
-_ATTN_KNOBS = ("SJD_ATTN", "SJD_ATTN_SW_GRID", "SJD_ATTN_SW_GROW", "SJD_ATTN_SW_NCOLS")
+# instantiation, c<K> caps the cluster size of the in-kernel merge (c0: partial slots + merge pre-op in the next chain kernel;
+# default: clusters of up to 4 CTAs per head — with grow0 the accumulators are rescaled in place at nearly every tile).
+ATTN_MODES = ["auto", "tc", "tct", "mma", "sw", "sw:grow0", "sw:c2:n64:grow0", "sw:c0", "sw:g1", "sw:g3:grow0", "sw:g2:n64"]
+_ATTN_KNOBS = ("SJD_ATTN", "SJD_ATTN_SW_GRID", "SJD_ATTN_SW_GROW", "SJD_ATTN_SW_NCOLS", "SJD_ATTN_SW_CLUSTER")
 
 
 def set_attn(monkeypatch, attn):
@@ -47,6 +48,8 @@ def set_attn(monkeypatch, attn):
     for kn in parts[1:]:
         if kn.startswith("grow"):
             monkeypatch.setenv("SJD_ATTN_SW_GROW", kn[4:])
+        elif kn.startswith("c"):
+            monkeypatch.setenv("SJD_ATTN_SW_CLUSTER", kn[1:])
         elif kn.startswith("g"):
             monkeypatch.setenv("SJD_ATTN_SW_GRID", kn[1:])
         elif kn.startswith("n"):
