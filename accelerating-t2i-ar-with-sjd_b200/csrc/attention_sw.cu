@@ -877,9 +877,10 @@ int attn_sw_launch(const AttnTcMaps& maps, AttnSwParams& sp, cudaStream_t stream
   const int sms = device_num_sms();
   int ng = n_units < sms ? n_units : sms;
   if (ng > kSwMaxGrid) ng = kSwMaxGrid;
-  if (sp.grid_cap > 0) {
+  static bool cluster_refused = false;   // a cluster launch failed once on this device (e.g. a partitioned GPU): stay in the segment form
+  if (sp.grid_cap > 0 || cluster_refused) {
     sp.cluster = 0;
-    if (sp.grid_cap < ng) ng = sp.grid_cap;
+    if (sp.grid_cap > 0 && sp.grid_cap < ng) ng = sp.grid_cap;
   }
   if (sp.cluster > 0) {   // CTA r * k + j: slice j of run r's key tiles
     const int k = sp.cluster, runs = a.Hkv * p.mtiles * a.rows, nc = a.n_chunks;
@@ -899,9 +900,20 @@ int attn_sw_launch(const AttnTcMaps& maps, AttnSwParams& sp, cudaStream_t stream
     set = true;
   }
   const int k = sp.cluster > 1 ? sp.cluster : 1;
-  if (sp.ncols == 32)
-    return launch_pdl_cluster(attn_sw_kernel<32>, grid, dim3(kSwThreads), attn_sw_smem(32, sp.nv), stream, k, maps, sp);
-  return launch_pdl_cluster(attn_sw_kernel<64>, grid, dim3(kSwThreads), attn_sw_smem(64, sp.nv), stream, k, maps, sp);
+  const int rc = sp.ncols == 32
+      ? launch_pdl_cluster(attn_sw_kernel<32>, grid, dim3(kSwThreads), attn_sw_smem(32, sp.nv), stream, k, maps, sp)
+      : launch_pdl_cluster(attn_sw_kernel<64>, grid, dim3(kSwThreads), attn_sw_smem(64, sp.nv), stream, k, maps, sp);
+  if (rc && k > 1 && !cluster_refused) {
+    // the cluster could not be placed: fall back to the segment form (fp32 partial slots + merge pre-op in the next chain
+    // kernel — the caller looks at sp.cluster after this call) instead of failing the forward
+    cudaGetLastError();
+    cluster_refused = true;
+    sp.cluster = 0;
+    sp.ub[0] = sp.ub[1] = 0;
+    for (int c = 2; c < 150; ++c) sp.ub[c] = 0;
+    return attn_sw_launch(maps, sp, stream);
+  }
+  return rc;
 }
 
 }  // namespace sjd
