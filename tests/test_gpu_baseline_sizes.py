@@ -291,3 +291,47 @@ def test_vq_decoder_matches_reference_golden(env, family):
             dec.latents(torch.full((B * h * w,), cb.shape[0]), B, h, w)      # id outside the codebook
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+# ------------------------------------------------------------------------ long caches at full width (clusters of 2 / 4 CTAs)
+@pytest.mark.parametrize("attn", ["auto", "sw:c0", "sw:c4:grow0", "mma"])
+def test_long_cache_full_width_forward_matches_reference_stack(env, attn, monkeypatch):
+    """The bench shape's regime: Lumina-mGPT-7B width (2 layers), a cache of 1 500 keys built by chunked prefill with a
+    hidden CFG prefix, then windows of 32, 64 and 16 — 12 to 13 key tiles per head, i.e. attention_sw.cu's clusters of two
+    CTAs with several tiles accumulated per CTA (default), its partial-slot form (c0), in-place rescaling at nearly every
+    tile (grow0) and the mma.sync kernel, all against the bf16-emulating oracle with the bounds of the short-cache test."""
+    RF, model, dev = env["RF"], env["model"], env["dev"]
+    set_attn(monkeypatch, attn)
+    shape, w, w32, cos0, sin0, _ = _full_width(env, "lumina7b")
+    families = env["families"]
+    cos, sin = families.rope_rotate_half(128, 2048, 10000.0, True)
+    cfg = RF.StackConfig(shape.n_layers, shape.d_model, shape.n_heads, shape.n_kv_heads, shape.head_dim, shape.d_ff,
+                         shape.vocab, shape.rms_eps, qk_norm=shape.qk_norm, rope_interleaved=False)
+    rows, max_len, kv_lo = 2, 1792, [0, 130]          # row 1 hides a whole key tile and a bit
+    ds = model.DeviceStack(shape, w, cos, sin, rows, max_len, dev)
+    ref = RF.RefStack(cfg, w32, cos.to(dev), sin.to(dev), rows, max_len, emulate_bf16=True)
+    g = torch.Generator().manual_seed(23)
+    kv_len = 0
+
+    def step(W, n):
+        nonlocal kv_len
+        ids = torch.randint(0, shape.vocab, (rows, W), generator=g).to(dev)
+        pos = torch.arange(kv_len, kv_len + W, device=dev)[None].repeat(rows, 1)
+        rope_pos = torch.stack([(pos[b] - kv_lo[b]).clamp(min=0) for b in range(rows)])
+        lg = ds.forward(W, rope_pos.int().flatten().contiguous(), pos.int().flatten().contiguous(), kv_len, kv_lo,
+                        ids=ids.int().flatten().contiguous(), n_logit_tokens=n).clone()
+        lr = ref.forward(ids=ids, rope_pos=rope_pos, kv_len=kv_len, kv_lo=kv_lo, cache_pos=pos, n_logit_tokens=n)
+        torch.cuda.synchronize()
+        kv_len += W
+        return lg, lr
+
+    for _ in range(12):                                # 1 536 cached keys, 128 per call
+        step(128, 1)
+    for W in (32, 64, 16):
+        lg, lr = step(W, W)
+        assert torch.isfinite(lg).all()
+        ulp = 2.0 ** (torch.floor(torch.log2(lr.abs().max())).item() - 7)
+        d = (lg - lr).abs()
+        assert d.max().item() <= 3.0 * ulp, f"{attn} W={W}: max {d.max().item()} ulp {ulp}"
+        assert d.mean().item() < 0.5 * ulp, (attn, W, d.mean().item(), ulp)
+    ds.close()
