@@ -72,8 +72,40 @@ def mint_chameleon():
                 out_shape=list(px.shape), pixels=[round(float(x), 7) for x in px.flatten().tolist()])
 
 
+def mint_emu3():
+    """emu3/tokenizer/modeling_emu3visionvq.py: Emu3VisionVQModel(config).decode(codes [B, h, w]) on a narrow config."""
+    import types
+    pkg = types.ModuleType("ref_emu3_tok")
+    pkg.__path__ = [str(REF / "emu3" / "tokenizer")]
+    sys.modules["ref_emu3_tok"] = pkg
+    cfgm = load(REF / "emu3/tokenizer/configuration_emu3visionvq.py", "ref_emu3_tok.configuration_emu3visionvq")
+    sys.modules["ref_emu3_tok.configuration_emu3visionvq"] = cfgm
+    spec = importlib.util.spec_from_file_location("ref_emu3_tok.modeling_emu3visionvq",
+                                                  REF / "emu3/tokenizer/modeling_emu3visionvq.py")
+    vq = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = vq
+    spec.loader.exec_module(vq)
+    torch.manual_seed(0)
+    cfg = cfgm.Emu3VisionVQConfig(codebook_size=72, embed_dim=4, z_channels=4, ch=32, ch_mult=[1, 2, 2], num_res_blocks=1,
+                                  attn_resolutions=[2], temporal_downsample_factor=4)
+    m = vq.Emu3VisionVQModel(cfg)
+    m.eval()
+    full = m.state_dict()
+    shapes = {k: list(v.shape) for k, v in full.items()
+              if k.startswith(("decoder.", "post_quant_conv.", "quantize.embedding."))}
+    full.update(fill_state(shapes, 13))
+    m.load_state_dict(full)
+    g = torch.Generator().manual_seed(7)
+    B, h, w = 2, 5, 4
+    codes = torch.randint(0, 72, (B, h, w), generator=g)
+    with torch.no_grad():
+        px = m.decode(codes)
+    return dict(family="emu3", seed=13, shapes=shapes, codes=codes.flatten().tolist(), batch=B, h=h, w=w, l2_norm=False,
+                out_shape=list(px.shape), pixels=[round(float(x), 7) for x in px.flatten().tolist()])
+
+
 if __name__ == "__main__":
-    for fn in (mint_llamagen, mint_chameleon):
+    for fn in (mint_llamagen, mint_chameleon, mint_emu3):
         g = fn()
         p = ROOT / "tests" / "golden" / f"vq_decode_{g['family']}.json"
         p.write_text(json.dumps(g))

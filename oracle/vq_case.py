@@ -10,8 +10,17 @@ def fill_state(shapes: dict, seed: int) -> dict:
     sd = {}
     for k in sorted(shapes):
         shp = tuple(shapes[k])
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros(shp, dtype=torch.long)
+            continue
         t = torch.randn(shp, generator=g)
-        if k.endswith("norm.weight") or ".norm1.weight" in k or ".norm2.weight" in k or k.endswith("norm_out.weight"):
+        if k.endswith("running_var"):
+            t = 0.5 + t.abs()
+        elif k.endswith("running_mean"):
+            t = 0.1 * t
+        elif k.endswith("norm_layer.weight"):
+            t = 1.0 + 0.2 * t
+        elif k.endswith("norm.weight") or ".norm1.weight" in k or ".norm2.weight" in k or k.endswith("norm_out.weight"):
             t = 1.0 + 0.2 * t                                  # GroupNorm scales around one
         elif k.endswith(".bias"):
             t = 0.1 * t

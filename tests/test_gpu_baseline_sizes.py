@@ -335,3 +335,30 @@ def test_long_cache_full_width_forward_matches_reference_stack(env, attn, monkey
         assert d.max().item() <= 3.0 * ulp, f"{attn} W={W}: max {d.max().item()} ulp {ulp}"
         assert d.mean().item() < 0.5 * ulp, (attn, W, d.mean().item(), ulp)
     ds.close()
+
+
+def test_emu3_vq_decoder_matches_reference_golden(env):
+    """Emu3 image tokens -> pixels on the GPU: two sjd_vq_lookup launches (post_quant_conv of the codebook rows, and the rows
+    themselves for the latent-conditioned normalisations), the temporal stack and the 2-D decoder, against the unmodified
+    Emu3VisionVQModel.decode (oracle/mint_vq_golden.py).  fp32, TF32 off for the comparison."""
+    import json
+    from conftest import GOLDEN
+    from sjd_b200 import vq_decode
+    from oracle.vq_case import fill_state
+    dev = env["dev"]
+    g = json.loads((GOLDEN / "vq_decode_emu3.json").read_text())
+    sd = fill_state(g["shapes"], g["seed"])
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        dec = vq_decode.Emu3VQDecoder(sd, dev)
+        B, h, w = g["batch"], g["h"], g["w"]
+        px = dec.decode(torch.tensor(g["codes"]).reshape(B, h, w))
+        ref = torch.tensor(g["pixels"]).reshape(g["out_shape"]).to(dev)
+        assert list(px.shape) == g["out_shape"]
+        assert (px - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+        with pytest.raises(NotImplementedError):
+            dec.decode(torch.zeros(1, 2, h, w, dtype=torch.long))               # video codes stay with the reference
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

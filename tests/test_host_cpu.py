@@ -641,3 +641,34 @@ def test_vq_decoder_plan_and_conv_stack_match_reference_golden_on_cpu(family):
     ref = torch.tensor(g["pixels"]).reshape(g["out_shape"])
     assert list(px.shape) == g["out_shape"]
     assert (px - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_emu3_vq_decoder_stack_matches_reference_golden_on_cpu():
+    """Emu3's vision-tokenizer decoder for images: temporal stack (inference BatchNorm3d, causal 3-D convolutions, x2 up-sampling
+    in time) + latent-conditioned 2-D decoder, driven from the latents the reference formula gives, must reproduce the pixels
+    of the unmodified Emu3VisionVQModel.decode (tests/golden/vq_decode_emu3.json).  For one frame the causal (3, 1, 1)
+    post_quant_conv reduces to its last temporal tap — asserted here against F.conv3d with the reference's padding."""
+    import json
+    import torch
+    import torch.nn.functional as F
+    from sjd_b200 import vq_decode
+    from oracle.vq_case import fill_state
+    g = json.loads((ROOT / "tests" / "golden" / "vq_decode_emu3.json").read_text())
+    sd = fill_state(g["shapes"], g["seed"])
+    with pytest.raises(RuntimeError):
+        vq_decode.Emu3VQDecoder(sd, "cpu")
+    dec = vq_decode.Emu3VQDecoder.__new__(vq_decode.Emu3VQDecoder)
+    dec.sd = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
+    dec.program = dec._plan()
+    assert dec.n_time_res == 1 and dec.n_time_up == 2
+    B, h, w = g["batch"], g["h"], g["w"]
+    codes = torch.tensor(g["codes"])
+    zq = sd["quantize.embedding.weight"][codes].reshape(B, h, w, -1).permute(0, 3, 1, 2).contiguous()
+    pq_w, pq_b = sd["post_quant_conv.conv.weight"], sd["post_quant_conv.conv.bias"]
+    z_ref = F.conv3d(F.pad(zq.unsqueeze(2), (0, 0, 0, 0, 2, 0)), pq_w, pq_b)[:, :, 0]
+    z = F.conv2d(zq, pq_w[:, :, -1], pq_b)
+    assert (z - z_ref).abs().max().item() < 1e-6
+    px = dec.decode_latents(z, zq)
+    ref = torch.tensor(g["pixels"]).reshape(g["out_shape"])
+    assert list(px.shape) == g["out_shape"]
+    assert (px - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
