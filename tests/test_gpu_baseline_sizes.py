@@ -362,3 +362,42 @@ def test_emu3_vq_decoder_matches_reference_golden(env):
             dec.decode(torch.zeros(1, 2, h, w, dtype=torch.long))               # video codes stay with the reference
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+# ------------------------------------------------------------------------ f4: T5 encoder on the tcgen05 GEMM
+def test_t5_encoder_on_the_gemm_kernel_matches_hf(env):
+    """T5Embedder's model call (llamagen/language/t5.py:78-83) with every linear layer on sjd_gemm_bf16: last_hidden_state of a
+    small gated-gelu T5 encoder (two captions, one padded) against HF's own T5EncoderModel in fp32 on the same
+    bf16-representable weights — within bf16 activation error — and at flan-t5-xl's layer width (d 2048, 32 heads x 64,
+    d_ff 5120, 120 tokens x 2 captions = 240 token rows, one layer) against the same."""
+    from transformers import T5Config, T5EncoderModel
+    from sjd_b200 import t5_encoder
+    dev = env["dev"]
+    for cfg_kw, B, T, tol_max, tol_mean in ((dict(d_model=128, d_kv=64, num_heads=2, d_ff=256, num_layers=2, vocab_size=100), 2, 24, 3e-2, 5e-3),
+                                            (dict(d_model=2048, d_kv=64, num_heads=32, d_ff=5120, num_layers=1, vocab_size=512), 2, 120, 6e-2, 6e-3)):
+        torch.manual_seed(1)
+        cfg = T5Config(feed_forward_proj="gated-gelu", dropout_rate=0.0, **cfg_kw)
+        m = T5EncoderModel(cfg).eval()
+        with torch.no_grad():
+            for p in m.parameters():
+                p.copy_(p.bfloat16().float())
+        m = m.to(dev)
+        g = torch.Generator().manual_seed(3)
+        ids = torch.randint(0, cfg.vocab_size, (B, T), generator=g).to(dev)
+        mask = torch.ones(B, T, dtype=torch.long, device=dev)
+        mask[1, T // 2:] = 0
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.no_grad():
+                ref = m(input_ids=ids, attention_mask=mask)["last_hidden_state"]
+            enc = t5_encoder.T5EncoderB200.from_module(m)
+            out, msk = enc.get_text_embeddings(ids, mask)
+            out2 = enc.forward(ids, mask)                      # second call captures a CUDA graph,
+            out3 = enc.forward(ids.flip(0), mask.flip(0))      # third replays it on new inputs
+            assert torch.equal(out, out2) and torch.equal(out3, enc.forward(ids.flip(0), mask.flip(0), graph=False))
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+        assert out.shape == ref.shape and torch.isfinite(out).all() and torch.equal(msk, mask)
+        d = (out - ref).abs()[mask.bool()]
+        assert d.max().item() < tol_max and d.mean().item() < tol_mean, (cfg_kw["d_model"], d.max().item(), d.mean().item())

@@ -672,3 +672,71 @@ def test_emu3_vq_decoder_stack_matches_reference_golden_on_cpu():
     ref = torch.tensor(g["pixels"]).reshape(g["out_shape"])
     assert list(px.shape) == g["out_shape"]
     assert (px - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+
+
+# ------------------------------------------------------------------------ f4: T5 encoder (LlamaGen text-to-image captions)
+def _t5_case():
+    import torch
+    from transformers import T5Config, T5EncoderModel
+    torch.manual_seed(0)
+    cfg = T5Config(d_model=128, d_kv=64, num_heads=2, d_ff=256, num_layers=2, vocab_size=100,
+                   feed_forward_proj="gated-gelu", dropout_rate=0.0)
+    m = T5EncoderModel(cfg).eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(p.bfloat16().float())          # bf16-representable weights: only activation rounding can differ
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, 100, (2, 24), generator=g)
+    mask = torch.ones(2, 24, dtype=torch.long)
+    mask[1, 15:] = 0                               # a padded caption
+    with torch.no_grad():
+        ref = m(input_ids=ids, attention_mask=mask)["last_hidden_state"]
+    return m, ids, mask, ref
+
+
+def test_t5_encoder_structure_matches_hf_on_cpu(monkeypatch):
+    """llamagen/language/t5.py:78-83 calls HF's T5EncoderModel; sjd_b200.t5_encoder restates its stack (T5LayerNorm, unscaled
+    attention with bucketed relative position bias shared from block 0, padding mask, gated gelu_new FFN, final norm) around
+    ONE primitive, y = x W^T.  With that primitive in fp32 torch the restatement must equal HF to rounding; with bf16 operands
+    (what sjd_gemm_bf16 computes, checked on the GPU) it must stay within bf16 activation error.  No GPU -> construction raises."""
+    import torch
+    from sjd_b200 import t5_encoder
+    m, ids, mask, ref = _t5_case()
+    with pytest.raises(RuntimeError):
+        t5_encoder.T5EncoderB200.from_module(m, device="cpu")
+    monkeypatch.setattr(t5_encoder.T5EncoderB200, "__init__", _t5_cpu_init)
+    enc = t5_encoder.T5EncoderB200.from_module(m, device="cpu")
+    enc._linear = lambda x, w: x @ w.float().T
+    out = enc.forward(ids, mask, graph=False)
+    assert (out - ref).abs().max().item() < 2e-5
+    enc._linear = lambda x, w: x.bfloat16().float() @ w.float().T
+    out = enc.forward(ids, mask, graph=False)
+    d = (out - ref).abs()
+    assert d.max().item() < 3e-2 and d.mean().item() < 5e-3, (d.max().item(), d.mean().item())
+
+
+def _t5_cpu_init(self, state_dict, *, num_heads, d_kv, relative_attention_num_buckets=32, relative_attention_max_distance=128,
+                 layer_norm_epsilon=1e-6, gated=None, act="gelu_new", device="cuda"):
+    """Test-only constructor: the product's __init__ minus the CUDA-only parts (workspace, staging buffer, device check)."""
+    import torch
+    if str(device) != "cpu":
+        raise AssertionError("test helper")
+    sd = {k[len("encoder."):] if k.startswith("encoder.") else k: v for k, v in state_dict.items()}
+    self.device, self.H, self.dkv = torch.device("cpu"), num_heads, d_kv
+    self.n_buckets, self.max_dist, self.eps, self.act = relative_attention_num_buckets, relative_attention_max_distance, layer_norm_epsilon, act
+    self.embed = sd["embed_tokens.weight" if "embed_tokens.weight" in sd else "shared.weight"].float()
+    self.d = self.embed.shape[1]
+    self.gated = bool(gated)
+    self.rel_bias = sd["block.0.layer.0.SelfAttention.relative_attention_bias.weight"].float()
+    self.layers = []
+    n_layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("block."))
+    for i in range(n_layers):
+        a, f = f"block.{i}.layer.0.", f"block.{i}.layer.1."
+        self.layers.append(dict(
+            ln1=sd[a + "layer_norm.weight"].float(),
+            qkv=torch.cat([sd[a + "SelfAttention.q.weight"], sd[a + "SelfAttention.k.weight"], sd[a + "SelfAttention.v.weight"]], 0).bfloat16(),
+            o=sd[a + "SelfAttention.o.weight"].bfloat16(), ln2=sd[f + "layer_norm.weight"].float(),
+            wi=torch.cat([sd[f + "DenseReluDense.wi_0.weight"], sd[f + "DenseReluDense.wi_1.weight"]], 0).bfloat16(),
+            wo=sd[f + "DenseReluDense.wo.weight"].bfloat16()))
+    self.final_ln = sd["final_layer_norm.weight"].float()
+    self.inner, self.d_ff = self.H * self.dkv, self.layers[0]["wo"].shape[1]
