@@ -724,17 +724,22 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
     // barrier, the leader reads them through distributed shared memory, merges in rank order (fixed: reproducible) and
     // writes the normalised bf16 rows; a second barrier keeps the peers' shared memory alive until it has =====
     const uint32_t rank = cl > 1 ? cluster_ctarank() : 0u;
-    float* const stO = reinterpret_cast<float*>(smem_raw + (sK - smem_u32(smem_raw)));   // [NCOLS][128]
-    float* const stL = stO + NCOLS * 128;                                                 // [NCOLS]
+    // staging layout: O^T as [d][NCOLS + 4] (a thread's columns are contiguous: 16-byte stores here, 16-byte distributed
+    // shared memory loads in the leader), then L [NCOLS], then m [NGT]
+    constexpr int kPitch = NCOLS + 4;
+    float* const stO = reinterpret_cast<float*>(smem_raw + (sK - smem_u32(smem_raw)));   // [128][kPitch]
+    float* const stL = stO + 128 * kPitch;                                                // [NCOLS]
     float* const stM = stL + NCOLS;                                                       // [NGT]
     const int wq = warp & 3, cq = warp >> 2, kl = wq * 32 + lane, cbase = cq * NC;
     if (cl > 1) {
       if (warp < 16 && rank != 0) {
 #pragma unroll
-        for (int e = 0; e < NC; ++e) stO[(cbase + e) * 128 + kl] = fin_o[e];
+        for (int e = 0; e < NC; e += 4)
+          *reinterpret_cast<float4*>(stO + kl * kPitch + cbase + e) = make_float4(fin_o[e], fin_o[e + 1], fin_o[e + 2], fin_o[e + 3]);
         if (kl == 0) {
 #pragma unroll
-          for (int e = 0; e < NC; ++e) stL[cbase + e] = fin_l[e];
+          for (int e = 0; e < NC; e += 4)
+            *reinterpret_cast<float4*>(stL + cbase + e) = make_float4(fin_l[e], fin_l[e + 1], fin_l[e + 2], fin_l[e + 3]);
 #pragma unroll
           for (int g = 0; g < NG; ++g) stM[cq * NG + g] = fin_m[g];
         }
@@ -772,23 +777,41 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
           const float m = ld_dsmem_f32(bm + uint32_t(cq * NG + g) * 4u);
           wr[g] = m == -INFINITY ? 0.f : exp2f(m - M[g]);
         }
+        float4 po[NC / 4], pl[NC / 4];
 #pragma unroll
-        for (int e = 0; e < NC; ++e) {
-          num[e] += ld_dsmem_f32(bo + uint32_t((cbase + e) * 128 + kl) * 4u) * wr[e >> 3];
-          den[e] += ld_dsmem_f32(bl + uint32_t(cbase + e) * 4u) * wr[e >> 3];
+        for (int e4 = 0; e4 < NC / 4; ++e4) {
+          po[e4] = ld_dsmem_v4(bo + uint32_t(kl * kPitch + cbase + 4 * e4) * 4u);
+          pl[e4] = ld_dsmem_v4(bl + uint32_t(cbase + 4 * e4) * 4u);
+        }
+#pragma unroll
+        for (int e4 = 0; e4 < NC / 4; ++e4) {
+          const float w = wr[(4 * e4) >> 3];
+          num[4 * e4] += po[e4].x * w; num[4 * e4 + 1] += po[e4].y * w; num[4 * e4 + 2] += po[e4].z * w; num[4 * e4 + 3] += po[e4].w * w;
+          den[4 * e4] += pl[e4].x * w; den[4 * e4 + 1] += pl[e4].y * w; den[4 * e4 + 2] += pl[e4].z * w; den[4 * e4 + 3] += pl[e4].w * w;
         }
       }
-      int hs = tc_div(cbase, p.m_wp, p.Wp), qi = cbase - hs * p.Wp;
+      // same arithmetic as attn_combine_row (reciprocal, then multiply): a token's attention row must not depend on
+      // whether its window took this path or the partial-slot path
+      if (tr.heads == 1 && p.Wp == a.W) {
+        // one head, no padded rows: column c is query row c of head h0, a constant stride apart
+        __nv_bfloat16* o = a.out + (size_t(tr.b * a.W + cbase) * a.H + tr.h0) * DH + kl;
+        const size_t stride = size_t(a.H) * DH;
 #pragma unroll
-      for (int e = 0; e < NC; ++e) {
-        // same arithmetic as attn_combine_row (reciprocal, then multiply): a token's attention row must not depend on
-        // whether its window took this path or the partial-slot path
-        const float inv = den[e] > 0.f ? 1.f / den[e] : 0.f;               // fully masked query (CFG hidden prefix) -> 0
-        if (qi < a.W && cbase + e < tr.R)
-          a.out[(size_t(tr.b * a.W + qi) * a.H + tr.h0 + hs) * DH + kl] = __float2bfloat16_rn(num[e] * inv);
-        if (++qi == p.Wp) {
-          qi = 0;
-          ++hs;
+        for (int e = 0; e < NC; ++e) {
+          const float inv = den[e] > 0.f ? 1.f / den[e] : 0.f;             // fully masked query (CFG hidden prefix) -> 0
+          if (cbase + e < tr.R) o[e * stride] = __float2bfloat16_rn(num[e] * inv);
+        }
+      } else {
+        int hs = tc_div(cbase, p.m_wp, p.Wp), qi = cbase - hs * p.Wp;
+#pragma unroll
+        for (int e = 0; e < NC; ++e) {
+          const float inv = den[e] > 0.f ? 1.f / den[e] : 0.f;
+          if (qi < a.W && cbase + e < tr.R)
+            a.out[(size_t(tr.b * a.W + qi) * a.H + tr.h0 + hs) * DH + kl] = __float2bfloat16_rn(num[e] * inv);
+          if (++qi == p.Wp) {
+            qi = 0;
+            ++hs;
+          }
         }
       }
     }

@@ -221,6 +221,11 @@ __device__ __forceinline__ uint32_t dsmem_addr(uint32_t smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
