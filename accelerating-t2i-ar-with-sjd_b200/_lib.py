@@ -70,6 +70,7 @@ class VerifyArgs(C.Structure):
         ("allow_mode", C.c_int32), ("ban", C.c_int32 * 2),
         ("resid_set", C.c_int32), ("resid_allow_mode", C.c_int32), ("resid_allow_lo", C.c_int32),
         ("resid_allow_hi", C.c_int32), ("resid_ban", C.c_int32 * 2), ("resid_from", C.c_int32),
+        ("done_flag", C.c_void_p), ("done_seq", C.c_int32),
     ]
 
     def __init__(self, *a, **k):

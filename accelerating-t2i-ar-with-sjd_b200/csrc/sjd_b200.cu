@@ -272,6 +272,8 @@ int sjd_verify(const sjd_verify_args* a, void* stream) {
   p.resid_set = a->resid_set; p.resid_allow_mode = a->resid_allow_mode; p.resid_allow_lo = a->resid_allow_lo;
   p.resid_allow_hi = a->resid_allow_hi; p.resid_ban[0] = a->resid_ban[0]; p.resid_ban[1] = a->resid_ban[1];
   p.resid_from = a->resid_from;
+  if (a->done_flag && !a->sync_ws) return fail(SJD_E_ARG, "sjd_verify: done_flag needs sync_ws (the one-launch form)");
+  p.done_flag = a->done_flag; p.done_seq = a->done_seq;
   p.rng_mode = a->rng_mode; p.rng_seed = a->rng_seed;
   for (int k = 0; k < 3; ++k) { p.rng_off[k] = a->rng_off[k]; p.rng_span[k] = a->rng_span[k]; }
   g_launches += a->sync_ws ? 1 : 2;

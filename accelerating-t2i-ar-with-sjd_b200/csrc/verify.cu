@@ -33,6 +33,8 @@ struct VerifyParams {
   int ban[2];              // removed ids (-1 = none); mode 3: the kept ids
   int resid_set;           // 1: the residual (positions whose forced_resid is -1) uses the candidate set below instead
   int resid_allow_mode, resid_allow_lo, resid_allow_hi, resid_ban[2], resid_from;   // ... from reject position resid_from on
+  int* done_flag;          // optional (mapped host memory): receives done_seq once the result is written (system-scope fence)
+  int done_seq;
   const int* forced;     // [W] forced token id per window position, or -1
   const int* forced_resid;  // [W] forced id of the residual distribution at reject position j; null = forced
   int top_k;             // 0 = off
@@ -789,6 +791,11 @@ __device__ void verify_accept(const VerifyParams& p, BlockScratch& sc, TopPScrat
     p.out_info[1] = rejected ? 1 : 0;
     p.out_info[2] = first;
     p.out_info[3] = s_text_mode;
+    if (p.done_flag) {
+      // every thread's out_tokens store precedes the last __syncthreads this thread passed: the fence is cumulative
+      __threadfence_system();
+      *reinterpret_cast<volatile int*>(p.done_flag) = p.done_seq;
+    }
   }
 }
 

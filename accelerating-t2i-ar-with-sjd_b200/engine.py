@@ -1,6 +1,7 @@
 """Host side of the SJD loop.  (verify_call: thin wrapper over sjd_verify; the decode loop follows below.)"""
 from __future__ import annotations
 
+import os
 import ctypes as C
 
 import numpy as _np
@@ -527,8 +528,15 @@ class SJDEngine:
         self._stage_copied = None          # event: the last H2D copy out of h_stage[:3M] has completed
         self.d_stage = torch.empty(n_i32, dtype=torch.int32, device=self.dev)
         self.d_out = torch.empty(4 + Wmax, dtype=torch.int32, device=self.dev)
-        self.h_out = torch.empty(4 + Wmax, dtype=torch.int32).pin_memory()
+        # result of a verify step: {matched, rejected, first, text_mode, tokens[Wmax], done flag}.  Pinned host memory the
+        # verify kernel writes DIRECTLY (mapped under unified addressing) and flags with a sequence number behind a
+        # system-scope fence: the loop polls the flag instead of copying device -> host and synchronising the stream
+        # (SJD_ZERO_COPY=0 restores copy + synchronize)
+        self.h_out = torch.zeros(5 + Wmax, dtype=torch.int32).pin_memory()
         self.h_out_np = self.h_out.numpy()
+        self._flag_idx = 4 + Wmax
+        self._seq = 0
+        self._zero_copy = os.environ.get("SJD_ZERO_COPY", "1") != "0"
         self._views = {}                    # cached slices of the staging buffers per token-row count
         self.d_nxt = torch.empty(Wmax, dtype=torch.int32, device=self.dev)
         self.resid = torch.empty(self.V, dtype=torch.float32, device=self.dev)
@@ -714,13 +722,28 @@ class SJDEngine:
                     a.noise_u, a.noise_e2 = u.data_ptr(), e2.data_ptr()
             a.eoi_token, a.text_top_k = int(grammar.eoi_token), int(grammar.text_top_k)
             a.resid, a.next_tokens = self.resid.data_ptr(), self.d_nxt.data_ptr()
-            a.out_info, a.out_tokens = self.d_out.data_ptr(), self.d_out[4:].data_ptr()
             a.sync_ws = self.d_sync.data_ptr()
             stream = torch.cuda.current_stream(dev)
-            _lib.check(self.lib.sjd_verify(C.byref(a), C.c_void_p(stream.cuda_stream)), "sjd_verify")
-            self.h_out[:4 + Wv].copy_(self.d_out[:4 + Wv], non_blocking=True)
-            stats.d2h_bytes += 4 * (4 + Wv)
-            stream.synchronize()
+            if self._zero_copy:
+                self._seq = (self._seq % 0x3FFFFFFF) + 1
+                a.out_info, a.out_tokens = self.h_out.data_ptr(), self.h_out[4:].data_ptr()
+                a.done_flag, a.done_seq = self.h_out[self._flag_idx:].data_ptr(), self._seq
+                _lib.check(self.lib.sjd_verify(C.byref(a), C.c_void_p(stream.cuda_stream)), "sjd_verify")
+                stats.d2h_bytes += 4 * (5 + Wv)
+                flag, fi, seq = self.h_out_np, self._flag_idx, self._seq
+                spins = 0
+                while flag[fi] != seq:
+                    spins += 1
+                    if spins > 2_000_000:            # ~ seconds: something is wrong on the device; surface it
+                        stream.synchronize()
+                        if flag[fi] != seq:
+                            raise RuntimeError("sjd_verify finished without publishing its result")
+            else:
+                a.out_info, a.out_tokens = self.d_out.data_ptr(), self.d_out[4:].data_ptr()
+                _lib.check(self.lib.sjd_verify(C.byref(a), C.c_void_p(stream.cuda_stream)), "sjd_verify")
+                self.h_out[:4 + Wv].copy_(self.d_out[:4 + Wv], non_blocking=True)
+                stats.d2h_bytes += 4 * (4 + Wv)
+                stream.synchronize()
             res = self.h_out_np[:4 + Wv].tolist()
             matched, rejected = res[0], bool(res[1])
             toks = res[4:4 + Wv]

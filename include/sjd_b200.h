@@ -118,6 +118,14 @@ typedef struct sjd_verify_args {
    * positions after a forced begin-of-image are image ids, the positions after a forced end-of-image are text). */
   int32_t resid_set;
   int32_t resid_allow_mode, resid_allow_lo, resid_allow_hi, resid_ban[2], resid_from;
+  /* Completion flag for a caller that reads the result without a stream synchronisation: when done_flag != NULL the kernel
+   * stores done_seq to *done_flag after out_tokens / out_info are written, behind a system-scope fence.  Meant for
+   * out_tokens / out_info / done_flag in mapped pinned HOST memory (device-accessible under unified addressing): the host
+   * polls the flag and finds the result next to it — no device-to-host copy, no cudaStreamSynchronize on the per-iteration
+   * path (the reference reads `.item()`s, i.e. synchronises, several times per iteration:
+   * scheduler/jacobi_iteration_lumina_mgpt.py:335-376).  Needs sync_ws (the one-launch form). */
+  int32_t* done_flag;
+  int32_t done_seq;
 } sjd_verify_args;
 
 int sjd_verify(const sjd_verify_args* args, void* stream);
