@@ -1,23 +1,32 @@
 // Small-window Jacobi attention, round-2 form: the transposed tcgen05 formulation of attention_tct.cu
 //   S^T[128 keys x N q] = K Q^T,   O^T[128 d x N q] = V^T P^T,   L[128 x N q] = 1 P^T        (N = 32 | 64 query slots)
-// behind a pipeline built for the HBM stream instead of for the tensor core:
-//   * every CTA owns a CONTIGUOUS run of (CFG row, kv head, key tile) units, key tiles fastest, so it walks along the
-//     keys of one head: Q is loaded once per head (two 8/16 KB buffers), and the products of consecutive key tiles
-//     ACCUMULATE in TMEM (O^T and L) under one reference maximum per 8-column group — a "segment".  A segment ends when
-//     the head changes or when a tile's maximum exceeds the reference by more than 2^16 (then the probabilities of
-//     the new tile would grow past what fp32 sums should hold: a new segment starts from the new maximum).  One fp32
-//     partial {sum p v, m, sum p} is written per SEGMENT (slot = its first key tile; the other slots of the run get
-//     the empty marker {-inf, 0}) instead of one per tile: at 1 200 keys 2-3 partials per query row instead of 10,
-//     so the epilogue and the merge in the next chain kernel shrink with it;
+// behind a pipeline built for the HBM stream and for the latency of lone warps instead of for the tensor core
+// (DESIGN.md 3.2a has the measurements behind every choice):
+//   * every CTA owns a CONTIGUOUS range of (CFG row, kv head [x row tile], key tile) units, key tiles fastest, so it walks
+//     along the keys of one head: Q is loaded once per head (two buffers), and the products of consecutive key tiles
+//     ACCUMULATE in TMEM (O^T and L) under one reference maximum per 8-column group;
+//   * CLUSTER MODE (default when a kv head has >= 32 query rows): a head belongs to one thread-block cluster of 1, 2 or 4
+//     CTAs, each with ONE accumulator (a tile that outgrows the reference rescales it in place through tcgen05.ld / .st);
+//     at the end the peers stage {O^T, L, m} in their own shared memory and the cluster leader merges them through
+//     distributed shared memory and writes the NORMALISED bf16 attention rows — no fp32 partials in global memory, no
+//     merge pre-op in the chain kernel that follows;
+//   * SEGMENT FORM (narrow windows, runs > SMs, test knobs): a tile that outgrows the reference by more than 2^grow, or a
+//     new head, starts a new "segment" in the other accumulator; one fp32 partial {sum p v, m, sum p} per segment goes to
+//     the partial slot of its first key tile (the other slots get the empty marker {-inf, 0}) and the next chain kernel's
+//     pre-op merges them (attn_combine_row, sparse form);
 //   * K and V tiles arrive through separate TMA rings (K: 2 x 32 KB, released by the commit of S^T; V: 2-3 x 32 KB,
-//     released by the commit of O^T), P^T has its own two buffers: a K tile is free ~0.1 us after it landed, so
-//     the next K/V tiles stream while the softmax of this one runs — the two-stage form held 80 KB of smem through
-//     the whole softmax and exposed the load latency once per stage cycle;
-//   * softmax: thread = key (TMEM lane), two warps per lane quarter split the columns.  A probability only has to be
-//     scaled by a bound that is COMMON to the 128 keys of a column and recorded with the partial, not by the exact
-//     column maximum (and rounded up to an integer in the log2 domain, which makes the result independent of it): each thread takes the max of 8 adjacent columns (draft positions i..i+7 of one head), one
-//     redux.sync per group gives the warp's value, the eight warps meet through 128 bytes of shared memory and ONE
-//     named barrier.  (attention_tct.cu parked all scores in a 17 KB staging tile and paid two barriers.)
+//     released by the commit of O^T), P^T has its own two buffers: a K tile is free ~0.1 us after it landed, so the
+//     next tiles stream while the softmax of this one runs; tiles of old keys are requested before griddepcontrol.wait;
+//   * softmax: thread = key (TMEM lane), 16 warps (four per lane quarter, 8-16 columns each), a mask-free path for tiles
+//     every query sees completely.  A probability only has to be scaled by a bound that is COMMON to the 128 keys of a
+//     column and recorded with the result, not by the exact column maximum: each thread takes the max of 8 adjacent
+//     columns (draft positions i..i+7 of one head), one redux.sync per group, the warps meet through 128 bytes of shared
+//     memory and ONE named barrier, and the bound is rounded up to an INTEGER in the log2 domain — probabilities scaled
+//     against different integers differ by exact powers of two, so the result does not depend on the reference (nor,
+//     therefore, on the window a token shares);
+//   * the MMA warp runs its issue loop warp-uniformly with only tcgen05.mma / commit under elect.sync, descriptors are
+//     built once, barriers seen complete are not polled again, units are walked incrementally, every role decodes what
+//     it needs before the dependency wait and waits inside its own branch.
 // Mask, partial format, merge and reference semantics as in attention_tc.cu (SDPA over the additive window mask,
 // modeling_chameleon.py:567-574, scheduler/jacobi_iteration_lumina_mgpt.py:1256-1336).  Head dim 128 only.
 #include "common.cuh"
