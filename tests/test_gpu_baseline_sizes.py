@@ -294,17 +294,19 @@ def test_vq_decoder_matches_reference_golden(env, family):
 
 
 # ------------------------------------------------------------------------ long caches at full width (clusters of 2 / 4 CTAs)
-@pytest.mark.parametrize("attn", ["auto", "sw:c0", "sw:c4:grow0", "mma"])
-def test_long_cache_full_width_forward_matches_reference_stack(env, attn, monkeypatch):
+@pytest.mark.parametrize("attn,family", [("auto", "lumina7b"), ("sw:c0", "lumina7b"), ("sw:c4:grow0", "lumina7b"),
+                                         ("mma", "lumina7b"), ("auto", "emu3gen"), ("sw:c0", "emu3gen")])
+def test_long_cache_full_width_forward_matches_reference_stack(env, attn, family, monkeypatch):
     """The bench shape's regime: Lumina-mGPT-7B width (2 layers), a cache of 1 500 keys built by chunked prefill with a
     hidden CFG prefix, then windows of 32, 64 and 16 — 12 to 13 key tiles per head, i.e. attention_sw.cu's clusters of two
     CTAs with several tiles accumulated per CTA (default), its partial-slot form (c0), in-place rescaling at nearly every
-    tile (grow0) and the mma.sync kernel, all against the bf16-emulating oracle with the bounds of the short-cache test."""
+    tile (grow0) and the mma.sync kernel, all against the bf16-emulating oracle with the bounds of the short-cache test.
+    Emu3-Gen's width (GQA 32 : 8, V = 184 622: BASELINE config 4's regime — four row tiles per kv head at window 64) as well."""
     RF, model, dev = env["RF"], env["model"], env["dev"]
     set_attn(monkeypatch, attn)
-    shape, w, w32, cos0, sin0, _ = _full_width(env, "lumina7b")
+    shape, w, w32, cos0, sin0, _ = _full_width(env, family)
     families = env["families"]
-    cos, sin = families.rope_rotate_half(128, 2048, 10000.0, True)
+    cos, sin = families.rope_rotate_half(128, 2048, 10000.0 if family == "lumina7b" else 1e6, True)
     cfg = RF.StackConfig(shape.n_layers, shape.d_model, shape.n_heads, shape.n_kv_heads, shape.head_dim, shape.d_ff,
                          shape.vocab, shape.rms_eps, qk_norm=shape.qk_norm, rope_interleaved=False)
     rows, max_len, kv_lo = 2, 1792, [0, 130]          # row 1 hides a whole key tile and a bit
