@@ -733,6 +733,7 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
     // barrier, the leader reads them through distributed shared memory, merges in rank order (fixed: reproducible) and
     // writes the normalised bf16 rows; a second barrier keeps the peers' shared memory alive until it has =====
     const uint32_t rank = cl > 1 ? cluster_ctarank() : 0u;
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[16 + 10] = clock64();   // (developer stamps: scripts/attn_sw_stamps.py)
     // staging layout: O^T as [d][NCOLS + 4] (a thread's columns are contiguous: 16-byte stores here, 16-byte distributed
     // shared memory loads in the leader), then L [NCOLS], then m [NGT]
     constexpr int kPitch = NCOLS + 4;
@@ -740,6 +741,7 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
     float* const stL = stO + 128 * kPitch;                                                // [NCOLS]
     float* const stM = stL + NCOLS;                                                       // [NGT]
     const int wq = warp & 3, cq = warp >> 2, kl = wq * 32 + lane, cbase = cq * NC;
+    const SwUnit tr = sw_unit(p, u0 < u1 ? u0 : 0);   // this CTA's run (decoded before the barrier: off the merge's path)
     if (cl > 1) {
       if (warp < 16 && rank != 0) {
 #pragma unroll
@@ -755,51 +757,56 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
       }
       cluster_sync_all();
     }
-    if (warp < 16 && rank == 0 && u0 < u1) {
-      const SwUnit tr = sw_unit(p, u0);
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[16 + 11] = clock64();
+    const bool merger = warp < 16 && rank == 0 && u0 < u1;
+    // second barrier, split: everybody except the leader's merging warps arrives at once; those arrive when their
+    // distributed-shared-memory loads have returned; all wait at the very end (the peers' shared memory stays alive)
+    if (cl > 1 && !merger) cluster_arrive_relaxed();
+    if (merger) {
+      // online merge in rank order (own accumulators first).  The references are integers in the log2 domain, so every
+      // rescale is an exact power of two and the result equals attn_combine_row's batch form bit for bit; one DSMEM round
+      // trip per peer (m, O^T and L requested together)
       float M[NG], num[NC], den[NC];
 #pragma unroll
       for (int g = 0; g < NG; ++g) M[g] = fin_m[g];
-#pragma unroll 1
-      for (int r = 1; r < cl; ++r) {
-        const uint32_t bm = dsmem_addr(smem_u32(stM), uint32_t(r));
 #pragma unroll
-        for (int g = 0; g < NG; ++g) M[g] = fmaxf(M[g], ld_dsmem_f32(bm + uint32_t(cq * NG + g) * 4u));
-      }
-      {
-        float w0[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) w0[g] = fin_m[g] == -INFINITY ? 0.f : exp2f(fin_m[g] - M[g]);
-#pragma unroll
-        for (int e = 0; e < NC; ++e) {
-          num[e] = fin_o[e] * w0[e >> 3];
-          den[e] = fin_l[e] * w0[e >> 3];
-        }
+      for (int e = 0; e < NC; ++e) {
+        num[e] = fin_m[e >> 3] == -INFINITY ? 0.f : fin_o[e];
+        den[e] = fin_m[e >> 3] == -INFINITY ? 0.f : fin_l[e];
       }
 #pragma unroll 1
       for (int r = 1; r < cl; ++r) {
         const uint32_t bm = dsmem_addr(smem_u32(stM), uint32_t(r)), bo = dsmem_addr(smem_u32(stO), uint32_t(r)),
                        bl = dsmem_addr(smem_u32(stL), uint32_t(r));
-        float wr[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          const float m = ld_dsmem_f32(bm + uint32_t(cq * NG + g) * 4u);
-          wr[g] = m == -INFINITY ? 0.f : exp2f(m - M[g]);
-        }
+        float mr[NG];
         float4 po[NC / 4], pl[NC / 4];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) mr[g] = ld_dsmem_f32(bm + uint32_t(cq * NG + g) * 4u);
 #pragma unroll
         for (int e4 = 0; e4 < NC / 4; ++e4) {
           po[e4] = ld_dsmem_v4(bo + uint32_t(kl * kPitch + cbase + 4 * e4) * 4u);
           pl[e4] = ld_dsmem_v4(bl + uint32_t(cbase + 4 * e4) * 4u);
         }
+        float so[NG], sr[NG];   // scale of what has been merged so far / of peer r
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const float mn = fmaxf(M[g], mr[g]);
+          so[g] = M[g] == -INFINITY ? 0.f : exp2f(M[g] - mn);
+          sr[g] = mr[g] == -INFINITY ? 0.f : exp2f(mr[g] - mn);
+          M[g] = mn;
+        }
 #pragma unroll
         for (int e4 = 0; e4 < NC / 4; ++e4) {
-          const float w = wr[(4 * e4) >> 3];
-          num[4 * e4] += po[e4].x * w; num[4 * e4 + 1] += po[e4].y * w; num[4 * e4 + 2] += po[e4].z * w; num[4 * e4 + 3] += po[e4].w * w;
-          den[4 * e4] += pl[e4].x * w; den[4 * e4 + 1] += pl[e4].y * w; den[4 * e4 + 2] += pl[e4].z * w; den[4 * e4 + 3] += pl[e4].w * w;
+          const float a0 = so[(4 * e4) >> 3], a1 = sr[(4 * e4) >> 3];
+          num[4 * e4] = num[4 * e4] * a0 + po[e4].x * a1; num[4 * e4 + 1] = num[4 * e4 + 1] * a0 + po[e4].y * a1;
+          num[4 * e4 + 2] = num[4 * e4 + 2] * a0 + po[e4].z * a1; num[4 * e4 + 3] = num[4 * e4 + 3] * a0 + po[e4].w * a1;
+          den[4 * e4] = den[4 * e4] * a0 + pl[e4].x * a1; den[4 * e4 + 1] = den[4 * e4 + 1] * a0 + pl[e4].y * a1;
+          den[4 * e4 + 2] = den[4 * e4 + 2] * a0 + pl[e4].z * a1; den[4 * e4 + 3] = den[4 * e4 + 3] * a0 + pl[e4].w * a1;
         }
       }
-      // same arithmetic as attn_combine_row (reciprocal, then multiply): a token's attention row must not depend on
+      if (cl > 1) cluster_arrive_relaxed();   // the peers' shared memory has been read (the arithmetic above consumed every load)
+      if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[16 + 12] = clock64();
+      // same final arithmetic as attn_combine_row (reciprocal, then multiply): a token's attention row must not depend on
       // whether its window took this path or the partial-slot path
       if (tr.heads == 1 && p.Wp == a.W) {
         // one head, no padded rows: column c is query row c of head h0, a constant stride apart
@@ -824,7 +831,9 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
         }
       }
     }
-    if (cl > 1) cluster_sync_all();
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[16 + 13] = clock64();
+    if (cl > 1) cluster_wait();
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[16 + 14] = clock64();
   }
   tcgen05_fence_before();
   __syncthreads();

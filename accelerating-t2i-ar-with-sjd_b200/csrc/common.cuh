@@ -210,6 +210,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(uint32_t M, uint32_t 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split form: the second barrier of a hand-off only has to keep the peers alive until somebody has READ their shared memory,
+// so the reader arrives (relaxed: nothing it wrote has to be visible to the others) as soon as its loads have returned and
+// everybody waits at the very end
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -33,6 +33,7 @@ for n in range(8):
     print(f"unit {n}: " + "  ".join(f"{names[k]} {((int(b[n, k]) - t0) / 1.9e3 if int(b[n, k]) else float('nan')):6.2f}" for k in range(10)))
 
 print("producer (us): after wait %.2f, early-Q done %.2f, cursors ready %.2f, first post-wait Q issued %.2f" % tuple(((int(b[0, k]) - t0) / 1.9e3 if int(b[0, k]) else float('nan')) for k in (10, 11, 12, 13)))
+print("cluster tail of CTA 0 (us): tail entered %.2f, first cluster barrier passed %.2f, merged %.2f, rows stored %.2f, second barrier passed %.2f" % tuple(((int(b[1, k]) - t0) / 1.9e3 if int(b[1, k]) else float('nan')) for k in (10, 11, 12, 13, 14)))
 c = full[128:].view(160, 4)
 c = c[c[:, 0] > 0]
 c = c[c[:, 2] > 0]
