@@ -5,12 +5,12 @@
 //   * every CTA owns a CONTIGUOUS range of (CFG row, kv head [x row tile], key tile) units, key tiles fastest, so it walks
 //     along the keys of one head: Q is loaded once per head (two buffers), and the products of consecutive key tiles
 //     ACCUMULATE in TMEM (O^T and L) under one reference maximum per 8-column group;
-//   * CLUSTER MODE (default when a kv head has >= 32 query rows): a head belongs to one thread-block cluster of 1, 2 or 4
+//   * CLUSTER MODE (default): a head belongs to one thread-block cluster of 1, 2 or 4
 //     CTAs, each with ONE accumulator (a tile that outgrows the reference rescales it in place through tcgen05.ld / .st);
 //     at the end the peers stage {O^T, L, m} in their own shared memory and the cluster leader merges them through
 //     distributed shared memory and writes the NORMALISED bf16 attention rows — no fp32 partials in global memory, no
 //     merge pre-op in the chain kernel that follows;
-//   * SEGMENT FORM (narrow windows, runs > SMs, test knobs): a tile that outgrows the reference by more than 2^grow, or a
+//   * SEGMENT FORM (runs > SMs, SJD_ATTN_SW_CLUSTER=0, test knobs): a tile that outgrows the reference by more than 2^grow, or a
 //     new head, starts a new "segment" in the other accumulator; one fp32 partial {sum p v, m, sum p} per segment goes to
 //     the partial slot of its first key tile (the other slots get the empty marker {-inf, 0}) and the next chain kernel's
 //     pre-op merges them (attn_combine_row, sparse form);
@@ -562,7 +562,10 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
         okm = jk >= t.lo ? (okm & vis) : 0u;
       }
       float gm[NG];
-      if (okm == kFull) {
+      if (okm == 0u) {   // none of this thread's (key, column) pairs is visible (padded columns of a narrow window, masked keys)
+#pragma unroll
+        for (int g = 0; g < NG; ++g) gm[g] = -INFINITY;
+      } else if (okm == kFull) {
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           const float m0 = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
@@ -661,7 +664,10 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
           for (int x = 0; x < 4; ++x)
             if (cq == x) ms = mref[(x * NG + g) % NGT];
           if (ms == -INFINITY) ms = 0.f;
-          if (okm == kFull) {
+          if (okm == 0u) {
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) pk[(8 * g + e) >> 1] = 0u;
+          } else if (okm == kFull) {
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
               const int i = 8 * g + e;
@@ -858,9 +864,10 @@ void attn_sw_plan(AttnSwParams* sp, int force_ncols, int max_cluster) {
   const AttnParams& a = sp->t.a;
   const int runs = a.Hkv * sp->t.mtiles * a.rows, sms = device_num_sms() < kSwMaxGrid ? device_num_sms() : kSwMaxGrid;
   int k = 0;
-  // (measured, profiles/r02ah_attn_sw_cluster.txt: 18.8 -> 18.0 us per layer at window 32, 24.3 -> 22.9 at 64, 36.8 -> 31.3 at
-  // 64 over 2 400 keys; at window 16 the two cluster barriers cost more than the merge pre-op they replace: 18.5 -> 19.0)
-  if (max_cluster > 0 && runs <= sms && R >= 32) {
+  // (measured, profiles/r02ba_attn_sw_cluster_tail.txt, r02bc_cluster_minr.txt: 17.1 -> 15.5 us per layer at window 32,
+  // 24.3 -> 21.4 at 64, 19.0 -> 18.3 at 16, 19.2 -> 18.5 at 8; the first form of the cluster tail lost at window 16)
+  static const int min_r = getenv("SJD_ATTN_SW_CLUSTER_MINR") ? atoi(getenv("SJD_ATTN_SW_CLUSTER_MINR")) : 8;
+  if (max_cluster > 0 && runs <= sms && R >= min_r) {
     k = 1;
     while (k * 2 <= max_cluster && k * 2 <= 4 && runs * k * 2 <= sms && k * 2 <= a.n_chunks) k *= 2;
   }
