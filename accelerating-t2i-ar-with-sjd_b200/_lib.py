@@ -134,6 +134,8 @@ def lib() -> C.CDLL:
     L.sjd_verify.argtypes = [C.POINTER(VerifyArgs), C.c_void_p]
     L.sjd_debug_philox.restype = C.c_int
     L.sjd_debug_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
+    L.sjd_debug_attn_sw_split.restype = C.c_int
+    L.sjd_debug_attn_sw_split.argtypes = [C.c_int] * 5 + [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p, C.c_void_p]
     L.sjd_vq_lookup.restype = C.c_int
     L.sjd_vq_lookup.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p, C.c_void_p]

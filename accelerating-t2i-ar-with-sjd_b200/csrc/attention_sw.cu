@@ -855,14 +855,15 @@ attn_sw_kernel(const __grid_constant__ AttnTcMaps maps, const AttnSwParams sp) {
 }
 
 // Geometry: up to 64 / Wp heads of a kv head per unit; 32 accumulator columns when they suffice.
-void attn_sw_plan(AttnSwParams* sp, int force_ncols, int max_cluster) {
+void attn_sw_plan(AttnSwParams* sp, int force_ncols, int max_cluster, int sm_count = 0) {
   attn_tct_plan(&sp->t);
   const int R = sp->t.hpc * sp->t.Wp;
   sp->ncols = (R <= 32 && force_ncols != 64) ? 32 : 64;
   sp->nv = sp->ncols == 32 ? 3 : 2;
   // cluster mode: as many CTAs per run (1, 2 or 4) as fit one wave and have a key tile each
   const AttnParams& a = sp->t.a;
-  const int runs = a.Hkv * sp->t.mtiles * a.rows, sms = device_num_sms() < kSwMaxGrid ? device_num_sms() : kSwMaxGrid;
+  if (sm_count <= 0) sm_count = device_num_sms();
+  const int runs = a.Hkv * sp->t.mtiles * a.rows, sms = sm_count < kSwMaxGrid ? sm_count : kSwMaxGrid;
   int k = 0;
   // (measured, profiles/r02ba_attn_sw_cluster_tail.txt, r02bc_cluster_minr.txt: 17.1 -> 15.5 us per layer at window 32,
   // 24.3 -> 21.4 at 64, 19.0 -> 18.3 at 16, 19.2 -> 18.5 at 8; the first form of the cluster tail lost at window 16)
@@ -916,21 +917,19 @@ constexpr int attn_sw_smem(int ncols, int nv) {   // K ring, V ring, two P^T buf
   return 1024 + 2 * int(kSwTileBytes) + nv * int(kSwTileBytes) + 2 * int(kSwPBytes) + 2 * (2 * ncols * 128) + kTcRows * 128;
 }
 
-int attn_sw_launch(const AttnTcMaps& maps, AttnSwParams& sp, cudaStream_t stream) {
+// Grid size and the unit table sp.ub for the mode sp.cluster says (0: cost-balanced contiguous split; k >= 1: CTA r * k + j
+// walks slice j of run r's key tiles).  Pure host arithmetic (tests/test_host_cpu.py checks it through sjd_debug_attn_sw_split).
+int attn_sw_grid(AttnSwParams& sp, int sms) {
   const AttnTcParams& p = sp.t;
   const AttnParams& a = p.a;
-  if (p.hpc * p.Wp > 64 || p.head_dim != 128) return -3;
   const int n_units = a.n_chunks * a.Hkv * p.mtiles * a.rows;
-  if (n_units >= 65536) return -3;   // tc_div's exact range
-  const int sms = device_num_sms();
   int ng = n_units < sms ? n_units : sms;
   if (ng > kSwMaxGrid) ng = kSwMaxGrid;
-  static bool cluster_refused = false;   // a cluster launch failed once on this device (e.g. a partitioned GPU): stay in the segment form
-  if (sp.grid_cap > 0 || cluster_refused) {
+  if (sp.grid_cap > 0) {
     sp.cluster = 0;
-    if (sp.grid_cap > 0 && sp.grid_cap < ng) ng = sp.grid_cap;
+    if (sp.grid_cap < ng) ng = sp.grid_cap;
   }
-  if (sp.cluster > 0) {   // CTA r * k + j: slice j of run r's key tiles
+  if (sp.cluster > 0) {
     const int k = sp.cluster, runs = a.Hkv * p.mtiles * a.rows, nc = a.n_chunks;
     ng = runs * k;
     if (sp.ub[ng] != uint16_t(n_units) || sp.ub[1] != uint16_t(nc / k))
@@ -939,7 +938,18 @@ int attn_sw_launch(const AttnTcMaps& maps, AttnSwParams& sp, cudaStream_t stream
     static const float run_cost = getenv("SJD_ATTN_SW_RUNCOST") ? float(atof(getenv("SJD_ATTN_SW_RUNCOST"))) : 0.5f;
     attn_sw_split(&sp, ng, run_cost);
   }
-  dim3 grid(ng);
+  return ng;
+}
+
+int attn_sw_launch(const AttnTcMaps& maps, AttnSwParams& sp, cudaStream_t stream) {
+  const AttnTcParams& p = sp.t;
+  const AttnParams& a = p.a;
+  if (p.hpc * p.Wp > 64 || p.head_dim != 128) return -3;
+  const int n_units = a.n_chunks * a.Hkv * p.mtiles * a.rows;
+  if (n_units >= 65536) return -3;   // tc_div's exact range
+  static bool cluster_refused = false;   // a cluster launch failed once on this device (e.g. a partitioned GPU): stay in the segment form
+  if (cluster_refused) sp.cluster = 0;
+  dim3 grid(attn_sw_grid(sp, device_num_sms()));
   static bool set = false;
   if (!set) {
     if (cudaFuncSetAttribute(attn_sw_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_sw_smem(32, 3)) != cudaSuccess ||

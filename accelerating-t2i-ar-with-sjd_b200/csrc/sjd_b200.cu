@@ -204,6 +204,27 @@ int sjd_vq_lookup(const int32_t* codes, int n_pix, int hw, const float* codebook
   return 0;
 }
 
+int sjd_debug_attn_sw_split(int W, int n_heads, int n_kv_heads, int rows, int kv_len, const int32_t* kv_lo, int sm_count,
+                            int max_cluster, int grid_cap, uint16_t* ub_out, int32_t* info_out) {
+  if (W < 1 || ((W + 7) & ~7) > kTctCols || n_heads < 1 || n_kv_heads < 1 || n_heads % n_kv_heads || rows < 1 ||
+      rows > kAttnMaxRows || kv_len < 0 || !kv_lo || sm_count < 1 || !ub_out || !info_out)
+    return fail(SJD_E_ARG, "sjd_debug_attn_sw_split: bad argument");
+  AttnSwParams sp;
+  memset(&sp, 0, sizeof(sp));
+  AttnParams& a = sp.t.a;
+  a.rows = rows; a.W = W; a.H = n_heads; a.Hkv = n_kv_heads; a.kv_len = kv_len;
+  for (int b = 0; b < kAttnMaxRows; ++b) a.kv_lo[b] = b < rows ? kv_lo[b] : 0;
+  attn_sw_plan(&sp, 0, max_cluster, sm_count);
+  sp.grid_cap = grid_cap;
+  const int n_units = a.n_chunks * a.Hkv * sp.t.mtiles * a.rows;
+  if (n_units >= 65536) return fail(SJD_E_ARG, "sjd_debug_attn_sw_split: too many units");
+  const int ng = attn_sw_grid(sp, sm_count);
+  for (int c = 0; c < 150; ++c) ub_out[c] = sp.ub[c];
+  info_out[0] = ng; info_out[1] = sp.cluster; info_out[2] = sp.ncols; info_out[3] = n_units;
+  info_out[4] = a.n_chunks; info_out[5] = sp.t.mtiles; info_out[6] = sp.t.hpc; info_out[7] = sp.nv;
+  return 0;
+}
+
 size_t sjd_gemm_workspace_bytes(int N, int K, int m_tile, int grid_limit) {
   return gemm_workspace(gemm_partition(N, K, m_tile, grid_limit)).bytes;
 }

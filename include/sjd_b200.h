@@ -212,6 +212,13 @@ void sjd_debug_attn_stamps(void* device_buf);
 int sjd_vq_lookup(const int32_t* codes, int n_pix, int hw, const float* codebook, int n_e, int e_dim, int l2_norm,
                   const float* w, const float* bias, int z, float* out, void* stream);
 
+/* Developer / test (pure host arithmetic, no GPU needed): the work split attention_sw.cu would use for a window of W tokens
+ * over kv_len cached keys — ub_out[150]: CTA c owns units [ub[c], ub[c+1]) (unit = (CFG row, kv head x row tile, 128-key tile),
+ * key tiles fastest); info_out[8] = {grid, cluster size (0: segment form), accumulator columns, units, key tiles per run,
+ * row tiles per kv head, heads per unit, V ring depth}.  grid_cap > 0 forces the segment form on at most that many CTAs. */
+int sjd_debug_attn_sw_split(int W, int n_heads, int n_kv_heads, int rows, int kv_len, const int32_t* kv_lo, int sm_count,
+                            int max_cluster, int grid_cap, uint16_t* ub_out, int32_t* info_out);
+
 /* counts kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t sjd_launch_count(void);
 

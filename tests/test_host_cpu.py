@@ -740,3 +740,44 @@ def _t5_cpu_init(self, state_dict, *, num_heads, d_kv, relative_attention_num_bu
             wo=sd[f + "DenseReluDense.wo.weight"].bfloat16()))
     self.final_ln = sd["final_layer_norm.weight"].float()
     self.inner, self.d_ff = self.H * self.dkv, self.layers[0]["wo"].shape[1]
+
+
+# ------------------------------------------------------------------------ attention_sw.cu: host-side work split
+@pytest.mark.parametrize("W,H,Hkv,rows,kv_len,kv_lo", [
+    (32, 32, 32, 2, 1200, [0, 66]),      # the bench shape: 64 heads x 10 key tiles
+    (32, 32, 32, 2, 2400, [0, 66]),
+    (64, 32, 8, 2, 4096, [0, 5]),        # Emu3-Gen window 64: four row tiles per kv head
+    (16, 32, 8, 2, 700, [0, 300]),       # GQA stacked into one unit; row 1 hides two whole key tiles
+    (1, 32, 32, 1, 90, [0]),             # a plain AR step, one key tile
+    (8, 2, 2, 2, 300, [0, 36]),          # toy shape
+])
+def test_attention_sw_work_split_covers_every_unit_once(lib, W, H, Hkv, rows, kv_len, kv_lo):
+    """The unit table attention_sw.cu's CTAs read (pure host arithmetic, sjd_debug_attn_sw_split): ranges are contiguous, cover
+    [0, units) exactly once; in cluster mode CTA r*k + j holds slice j of run r's key tiles, every CTA has a tile and the grid
+    is one wave; in the segment form (grid cap) the cost-balanced ranges differ by at most two units unless they cross heads."""
+    import ctypes as C
+    L = lib.lib()
+    kl = (C.c_int32 * len(kv_lo))(*kv_lo)
+    for sms, max_cluster, grid_cap in ((148, 4, 0), (148, 0, 0), (148, 4, 7), (132, 2, 0)):
+        ub = (C.c_uint16 * 150)()
+        info = (C.c_int32 * 8)()
+        assert L.sjd_debug_attn_sw_split(W, H, Hkv, rows, kv_len, kl, sms, max_cluster, grid_cap, ub, info) == 0
+        grid, k, ncols, n_units, n_chunks, mtiles, hpc, nv = list(info)
+        Wp = (W + 7) // 8 * 8
+        assert n_chunks == (kv_len + W + 127) // 128 and hpc * Wp <= 64 and ncols in (32, 64) and nv in (2, 3)
+        assert n_units == n_chunks * Hkv * mtiles * rows and hpc * mtiles >= H // Hkv
+        b = list(ub[:grid + 1])
+        assert b[0] == 0 and b[grid] == n_units and all(b[i] <= b[i + 1] for i in range(grid)), (b, n_units)
+        if grid_cap:
+            assert k == 0 and grid <= grid_cap
+        if k:
+            runs = Hkv * mtiles * rows
+            assert k in (1, 2, 4) and k <= max_cluster and grid == runs * k <= sms and k <= n_chunks
+            for c in range(grid):
+                r, j = divmod(c, k)
+                assert b[c] == r * n_chunks + j * n_chunks // k and b[c + 1] > b[c]
+        else:
+            assert grid <= sms
+            if grid == sms and n_units >= 4 * grid:
+                sizes = [b[i + 1] - b[i] for i in range(grid)]
+                assert max(sizes) - min(s for s in sizes if s) <= max(4, n_chunks // 2), sizes
