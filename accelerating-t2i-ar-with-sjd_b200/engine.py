@@ -538,6 +538,7 @@ class SJDEngine:
         self._seq = 0
         self._zero_copy = os.environ.get("SJD_ZERO_COPY", "1") != "0"
         self._views = {}                    # cached slices of the staging buffers per token-row count
+        self._stream = None                 # torch's current stream, looked up once per generate() (~8 us per look-up)
         self.d_nxt = torch.empty(Wmax, dtype=torch.int32, device=self.dev)
         self.resid = torch.empty(self.V, dtype=torch.float32, device=self.dev)
         self.d_sync = torch.zeros(1, dtype=torch.int32, device=self.dev)   # sjd_verify's last-CTA counter (stays zero)
@@ -572,8 +573,12 @@ class SJDEngine:
         v[0].copy_(v[1], non_blocking=True)
         if self._stage_copied is None:
             self._stage_copied = torch.cuda.Event()
-        self._stage_copied.record(torch.cuda.current_stream(self.dev))
+        stream = self._stream if self._stream is not None else torch.cuda.current_stream(self.dev)
+        self._stage_copied.record(stream)
         self.stats.h2d_bytes += 12 * M
+        if self._stream is not None and getattr(self.stack, "ctx", None) is not None:   # (test doubles of the stack take no handle)
+            return self.stack.forward(W, v[3], v[4], kv_len, kv_lo, ids=None if embeds is not None else v[2], embeds=embeds,
+                                      n_logit_tokens=n_logit, stream_handle=stream.cuda_stream)
         return self.stack.forward(W, v[3], v[4], kv_len, kv_lo, ids=None if embeds is not None else v[2], embeds=embeds,
                                   n_logit_tokens=n_logit)
 
@@ -615,6 +620,7 @@ class SJDEngine:
         first_trip = True
         finished = False
         torch.cuda.synchronize(dev)
+        self._stream = torch.cuda.current_stream(dev)
         t0 = _time.perf_counter()
         while not finished:
             # ---- window -------------------------------------------------------------------------------
@@ -723,7 +729,7 @@ class SJDEngine:
             a.eoi_token, a.text_top_k = int(grammar.eoi_token), int(grammar.text_top_k)
             a.resid, a.next_tokens = self.resid.data_ptr(), self.d_nxt.data_ptr()
             a.sync_ws = self.d_sync.data_ptr()
-            stream = torch.cuda.current_stream(dev)
+            stream = self._stream
             if self._zero_copy:
                 self._seq = (self._seq % 0x3FFFFFFF) + 1
                 a.out_info, a.out_tokens = self.h_out.data_ptr(), self.h_out[4:].data_ptr()
@@ -778,6 +784,7 @@ class SJDEngine:
             first_trip = False
             if (ids[-1] in eos) or cur_len >= max_length or (stop_fn is not None and stop_fn(ids)):
                 finished = True
+        self._stream = None
         torch.cuda.synchronize(dev)
         stats.t_inner = _time.perf_counter() - t0
         stats.new_tokens = len(ids) - len(input_ids)

@@ -82,9 +82,12 @@ class DeviceStack:
 
     def forward(self, W: int, rope_pos: torch.Tensor, cache_pos: torch.Tensor, kv_len: int, kv_lo,
                 ids: torch.Tensor | None = None, embeds: torch.Tensor | None = None,
-                n_logit_tokens: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+                n_logit_tokens: int | None = None, out: torch.Tensor | None = None,
+                stream_handle: int | None = None) -> torch.Tensor:
         """ids / rope_pos / cache_pos: int32 device tensors [rows*W] (row-major).  Returns fp32 logits
-        [rows, n_logit_tokens, vocab] (a view of an internal buffer unless ``out`` is given)."""
+        [rows, n_logit_tokens, vocab] (a view of an internal buffer unless ``out`` is given).  stream_handle: the raw
+        cudaStream_t to launch on (default: torch's current stream; looking it up costs ~8 us of host time per call, which
+        the decode loop — where it sits between one iteration's result and the next iteration's first kernel — avoids)."""
         n = W if n_logit_tokens is None else n_logit_tokens
         a = _lib.ForwardArgs()
         a.W = W
@@ -98,7 +101,7 @@ class DeviceStack:
         a.n_logit_tokens = n
         buf = self.logits_buf if out is None else out
         a.logits = buf.data_ptr()
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = torch.cuda.current_stream(self.device).cuda_stream if stream_handle is None else stream_handle
         _lib.check(self.lib.sjd_ctx_forward(self.ctx, C.byref(a), C.c_void_p(stream)), "sjd_ctx_forward")
         return buf[: self.rows * n].view(self.rows, n, self.shape.vocab)
 
