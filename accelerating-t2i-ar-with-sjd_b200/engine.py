@@ -539,6 +539,9 @@ class SJDEngine:
         self._zero_copy = os.environ.get("SJD_ZERO_COPY", "1") != "0"
         self._views = {}                    # cached slices of the staging buffers per token-row count
         self._stream = None                 # torch's current stream, looked up once per generate() (~8 us per look-up)
+        # SJD_NVTX=1: NVTX ranges "sjd.forward" / "sjd.verify" around the two C calls of an iteration (a timeline aid for
+        # nsys / ncu --nvtx; off by default: a push / pop pair costs host time on the per-iteration path)
+        self._nvtx = os.environ.get("SJD_NVTX", "0") == "1"
         self.d_nxt = torch.empty(Wmax, dtype=torch.int32, device=self.dev)
         self.resid = torch.empty(self.V, dtype=torch.float32, device=self.dev)
         self.d_sync = torch.zeros(1, dtype=torch.int32, device=self.dev)   # sjd_verify's last-CTA counter (stays zero)
@@ -662,7 +665,12 @@ class SJDEngine:
                     s = e
             else:
                 rt = [window] * rows
+                if self._nvtx:
+                    torch.cuda.nvtx.range_push("sjd.forward")
                 logits = self._forward(rt, kv_len, kv_lo, n_out)
+                if self._nvtx:
+                    torch.cuda.nvtx.range_pop()
+                    torch.cuda.nvtx.range_push("sjd.verify")
             # ---- verify ---------------------------------------------------------------------------------
             Wv = n_out
             desc = grammar.describe(Wv)
@@ -750,6 +758,8 @@ class SJDEngine:
                 self.h_out[:4 + Wv].copy_(self.d_out[:4 + Wv], non_blocking=True)
                 stats.d2h_bytes += 4 * (4 + Wv)
                 stream.synchronize()
+            if self._nvtx and not first_trip:
+                torch.cuda.nvtx.range_pop()
             res = self.h_out_np[:4 + Wv].tolist()
             matched, rejected = res[0], bool(res[1])
             toks = res[4:4 + Wv]

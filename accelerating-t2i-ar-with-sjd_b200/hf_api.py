@@ -20,6 +20,7 @@ class swapping exactly like the reference.
 """
 from __future__ import annotations
 
+import logging
 import math
 
 import torch
@@ -495,9 +496,13 @@ def renew_sampler(model_class):
             torch.cuda.synchronize()
             self.sjd_stats = eng.stats
             # the three lines drivers/logs rely on (jacobi_iteration_lumina_mgpt.py:1217-1220)
-            print("Time elapsed inner: ", t1.elapsed_time(t2) / 1000)
+            t_inner = t1.elapsed_time(t2) / 1000
+            print("Time elapsed inner: ", t_inner)
             print("gen loop num (NFE): ", eng.stats.nfe)
             print("tokens length: ", len(ids))
+            logging.info(f"Time elapsed inner: {t_inner}")              # (:1221-1223: the same three lines through logging)
+            logging.info(f"gen loop num (NFE): {eng.stats.nfe}")
+            logging.info(f"tokens length: {len(ids)}")
             if streamer is not None:
                 streamer.put(torch.tensor(ids[len(prompt):]))
                 streamer.end()
